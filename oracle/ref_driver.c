@@ -19,6 +19,7 @@
 #include "utils/arith/arith.h"
 #include "utils/arith/ntt.h"
 #include "utils/sampling/sampling.h"
+#include "utils/sampling/gaussian_cdf.h"
 #include "utils/sampling/gaussian_knuth_yao.h"
 #include "utils/sampling/gaussian_bernoulli.h"
 #include "utils/crypto/prng.h"

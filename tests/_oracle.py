@@ -1,0 +1,220 @@
+"""ctypes bindings for the two CPU checkers (TEST INFRASTRUCTURE ONLY).
+
+* ``port()``  -> oracle/libscoracle.so, our plain-C restatement (oracle/sc_oracle*.c)
+* ``ref()``   -> oracle/_ref/libscref.so, the unmodified reference compiled by oracle/Makefile
+                 (present only when it was built in the dev container; it travels to the GPU box)
+
+Both expose the same batch-driver calling convention (oracle/ref_driver.c, oracle/sc_oracle.h),
+so a test can run one input through either.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+# safecrypto_ntt_e, /root/reference/src/utils/arith/ntt.h:106-123
+REFERENCE, BARRETT, FP, AVX, SOLINAS_7681, SOLINAS_8380417 = range(6)
+VARIANT_NAMES = {REFERENCE: "reference", BARRETT: "barrett", FP: "fp", AVX: "avx",
+                 SOLINAS_7681: "7681", SOLINAS_8380417: "8380417"}
+
+(OP_FWD, OP_INV, OP_FWD_LARGE, OP_INV_LARGE, OP_FFT, OP_FFT_LARGE, OP_PW, OP_PW16, OP_NORMALIZE,
+ OP_CENTER, OP_POLYMUL, OP_TRIPLE16, OP_MODN, OP_MULN, OP_SQRN, OP_FLIP, OP_INVERT, OP_DIV,
+ OP_PWR, OP_SCALAR, OP_SPARSE32, OP_SPARSE16) = range(22)
+
+PRNG_AES_CTR_DRBG, PRNG_CHACHA = 0, 2
+SAMPLER_CDF, SAMPLER_KNUTH_YAO, SAMPLER_BERNOULLI = 0, 1, 5
+NORMAL_SAMPLES, BLINDING_SAMPLES, SHUFFLE_SAMPLES = 0, 1, 2
+
+# (tw_bits, q, n) of build_tools/ntt_table_gen/main.c:19-37
+TABLE_PARAMS = [(16, 7681, 256), (16, 12289, 512), (16, 12289, 1024), (16, 18433, 512), (16, 18433, 1024),
+                (32, 4206593, 512), (32, 4206593, 1024), (32, 5767169, 512), (32, 5767169, 1024),
+                (32, 8380417, 256), (32, 8399873, 512), (32, 10223617, 512), (32, 10223617, 1024),
+                (32, 16813057, 512), (32, 51750913, 512), (32, 51750913, 1024), (32, 134348801, 1024)]
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def aligned(a, dtype=None, align=64):
+    """Copy into a 64-byte aligned contiguous array: the reference's AVX2 variant uses aligned
+    loads on caller buffers (sc_malloc gives 32-byte alignment, safecrypto_private.c:82-96)."""
+    a = np.asarray(a, dtype=dtype)
+    buf = np.empty(a.nbytes + align, dtype=np.uint8)
+    off = (-buf.ctypes.data) % align
+    out = buf[off:off + a.nbytes].view(a.dtype).reshape(a.shape)
+    out[...] = a
+    return out
+
+
+class Checker:
+    def __init__(self, path, prefix):
+        self.lib = ctypes.CDLL(path)
+        self.prefix = prefix
+        self.path = path
+        f = self._fn("ntt_batch")
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_int32]
+        g = self._fn("gauss_streams")
+        g.restype = ctypes.c_int
+        g.argtypes = [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_float, ctypes.c_uint32, ctypes.c_void_p,
+                                           ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int32,
+                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t]
+        s = self._fn("prng_script")
+        s.restype = ctypes.c_int
+        s.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p,
+                      ctypes.c_size_t, ctypes.c_void_p]
+        self._fn("num_threads").restype = ctypes.c_int
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def num_threads(self):
+        return int(self._fn("num_threads")())
+
+    def ntt_batch(self, variant, op, n, q, tw_bits, a, b=None, w=None, r=None, scalar=0, threads=0,
+                  want_rc=False, a_dtype=np.int32):
+        a = aligned(np.asarray(a, dtype=a_dtype).reshape(-1, n))
+        count = a.shape[0]
+        out = aligned(np.zeros((count, n), dtype=np.int32))
+        w = None if w is None else aligned(w)
+        r = None if r is None else aligned(r)
+        b_stride = 0
+        if b is not None:
+            b = aligned(b)
+            # 1-D operand = one row shared by the whole batch; 2-D = one row per batch item
+            b_stride = 0 if b.ndim == 1 else b.shape[-1]
+        rc = np.zeros(count, dtype=np.int32)
+        ret = self._fn("ntt_batch")(variant, op, n, q, tw_bits, _vp(out), _vp(a), _vp(b), b_stride,
+                                    _vp(w), _vp(r), count, threads, _vp(rc), int(scalar))
+        if want_rc:
+            return out, rc, ret
+        return out
+
+    def prng_script(self, prng_type, seed, script, seed_period=0):
+        seed = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+        script = np.ascontiguousarray(script, dtype=np.int32).reshape(-1, 2)
+        nout = int(sum(2 if k == 64 else 1 for k in script[:, 0]))
+        out = np.zeros(nout, dtype=np.uint32)
+        got = self._fn("prng_script")(prng_type, _vp(seed), seed.size, seed_period, _vp(script),
+                                      script.shape[0], _vp(out))
+        assert got == nout, (got, nout)
+        return out
+
+    def prng_words(self, prng_type, seed, nwords, seed_period=0):
+        return self.prng_script(prng_type, seed, [(32, 0)] * nwords, seed_period)
+
+    def cdf_table(self, precision, blinding, tail, sigma):
+        f = self._fn("cdf_table")
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t]
+        cap = 1 << 16
+        buf = np.zeros(cap, dtype=np.uint64 if precision == 64 else np.uint32)
+        size = f(precision, blinding, tail, sigma, _vp(buf), cap)
+        assert 0 < size <= cap
+        return buf[:size].copy()
+
+    def ky_table(self, bitwidth, tail, sigma):
+        f = self._fn("ky_table")
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t,
+                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        cap = 1 << 22
+        buf = np.zeros(cap, dtype=np.uint8)
+        dims = np.zeros(3, dtype=np.int32)
+        sz = f(bitwidth, tail, sigma, _vp(buf), cap, dims[0:].ctypes.data, dims[1:].ctypes.data, dims[2:].ctypes.data)
+        assert 0 < sz <= cap
+        return buf[:sz].reshape(int(dims[0]), int(dims[1])).copy(), int(dims[2])
+
+    def ber_table(self, tail, sigma):
+        f = self._fn("ber_table")
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t,
+                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        buf = np.zeros(64 * 8, dtype=np.uint8)
+        dims = np.zeros(3, dtype=np.int32)
+        sz = f(tail, sigma, _vp(buf), buf.size, dims[0:].ctypes.data, dims[1:].ctypes.data, dims[2:].ctypes.data)
+        return buf[:sz].reshape(-1, 8).copy(), int(dims[1]), int(dims[2])
+
+    def gauss_streams(self, sampler, precision, blinding, prng_type, tail, sigma, seeds, n, discard=0,
+                      centre=0, threads=0, calls=1):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8)
+        nstreams, seed_len = seeds.shape
+        out = np.zeros((nstreams, calls * n), dtype=np.int32)
+        fail = self._fn("gauss_streams")(sampler, precision, blinding, prng_type, tail, sigma, discard,
+                                         _vp(seeds), seed_len, nstreams, n, centre, _vp(out), threads, calls)
+        assert fail == 0
+        return out
+
+
+class RefChecker(Checker):
+    """The reference library also exports its generated twiddle tables as data symbols."""
+
+    def table(self, kind, q, n, tw_bits):
+        ct = ctypes.c_int16 if tw_bits == 16 else ctypes.c_int32
+        size = n // 2 if kind == "inv_w" else n
+        arr = (ct * size).in_dll(self.lib, "%s%d_n%d" % (kind, q, n))
+        return np.ctypeslib.as_array(arr).copy()
+
+
+class PortChecker(Checker):
+    def roots_of_unity(self, q, n, tw_bits):
+        f = self.lib.orc_roots_of_unity
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        w = np.zeros(n, dtype=np.int32)
+        r = np.zeros(n, dtype=np.int32)
+        g = ctypes.c_int64(0)
+        assert f(q, n, _vp(w), _vp(r), ctypes.byref(g)) == 0
+        dt = np.int16 if tw_bits == 16 else np.int32
+        return w.astype(dt), r.astype(dt), int(g.value)
+
+    def scalar(self, name, variant, n, q, *args):
+        class P(ctypes.Structure):
+            _fields_ = [("n", ctypes.c_int32), ("q", ctypes.c_int32), ("m", ctypes.c_int32), ("k", ctypes.c_int32),
+                        ("inv_q_dbl", ctypes.c_double), ("inv_q_flt", ctypes.c_float)]
+        p = P()
+        self.lib.orc_init_reduce(ctypes.byref(p), n, q)
+        f = getattr(self.lib, "orc_" + name)
+        f.restype = ctypes.c_int32
+        return int(f(variant, *[ctypes.c_int32(int(x)) for x in args], ctypes.byref(p)))
+
+
+_cache = {}
+
+
+def build_port():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
+
+
+def port():
+    if "port" not in _cache:
+        path = os.path.join(ORACLE_DIR, "libscoracle.so")
+        srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.startswith("sc_oracle")]
+        if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(s) for s in srcs):
+            build_port()
+        _cache["port"] = PortChecker(path, "orc_")
+    return _cache["port"]
+
+
+def ref_available():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libscref.so"))
+
+
+def ref():
+    if "ref" not in _cache:
+        _cache["ref"] = RefChecker(os.path.join(ORACLE_DIR, "_ref", "libscref.so"), "ref_")
+    return _cache["ref"]
+
+
+def tables(q, n, tw_bits):
+    """(w, r) for a parameter set -- from the port's generator (validated against the reference's
+    generated ntt_tables.c in tests/test_oracle_vs_ref.py and tests/golden/tables.json)."""
+    w, r, _ = port().roots_of_unity(q, n, tw_bits)
+    return w, r
