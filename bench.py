@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native lattice hot path.
+
+Workload (BASELINE.json configs[1]): batched negacyclic polynomial multiplication, n = 512,
+q = 12289, 2^20 independent operand pairs per GPU, synthetic uniform coefficients.  One "step" is
+one pass of the fused polymul kernel over the whole batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by the driver under torch.distributed.run (one rank per GPU).  The batch shards by
+polynomial index with no data-path collective (weak scaling: 2^20 pairs per GPU); NCCL is used only for
+the barrier and the max-over-ranks of the device time.
+
+Prints ONE JSON line.  `value` = polymuls/s with operands resident in HBM (CUDA events on the launching
+stream); `e2e` = the same metric through scgpu_polymul_batch_host() with pinned HOST buffers, H2D and
+D2H inside the timed region; `roofline` = algorithmic bytes (12 n per product) / kernel time against
+the measured HBM copy bandwidth; `cpu_baseline` = the reference's own C code (oracle/_ref) on the
+host cores of this box.  `--impl reference` times that CPU path alone.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_COEF, Q = 512, 12289
+BATCH = 1 << 20                 # polynomial pairs per GPU per step (device-resident leg)
+E2E_BATCH = 1 << 18             # pairs per GPU per step through the host-buffer C-ABI call
+METRIC = "ntt_polymul_per_s_n512_q12289"
+UNIT = "polymul/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_run(count, threads=0, variant=None, repeats=1):
+    """Time the reference's CPU polymul (fwd, fwd, pointwise, inv per pair) on `count` pairs."""
+    import _oracle as O
+    if O.ref_available():
+        chk, kind = O.ref(), "reference"
+        variant = O.AVX if variant is None else variant        # what every scheme selects on an AVX2 host (bliss_b.c:273-277)
+    else:
+        chk, kind = O.port(), "port"
+        variant = O.FP if variant is None else variant
+    w, r = O.tables(Q, N_COEF, 16)
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, Q, size=(count, N_COEF)).astype(np.int32)
+    b = rng.integers(0, Q, size=(count, N_COEF)).astype(np.int32)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        chk.ntt_batch(variant, O.OP_POLYMUL, N_COEF, Q, 16, a, b, w, r, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    cores = chk.num_threads() if threads == 0 else threads
+    return count / best, cores, kind, O.VARIANT_NAMES[variant], best
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    # bounded sample per step, sized from a short calibration so the whole run stays within minutes
+    rate, cores, kind, vname, _ = cpu_reference_run(1 << 14)
+    per_step = int(min(1 << 20, max(1 << 14, rate * 1.5)))       # ~1.5 s of CPU work per step
+    per_step = 1 << (per_step.bit_length() - 1)
+    for _ in range(args.warmup):
+        cpu_reference_run(per_step)
+    t_total = 0.0
+    for _ in range(args.steps):
+        _, _, _, _, dt = cpu_reference_run(per_step)
+        t_total += dt
+    value = per_step * args.steps / t_total
+    sample = "%d polymul pairs per step (fwd,fwd,pointwise,inv; variant %s), OpenMP static over %d host threads" % (per_step, vname, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "batched NTT polymul n=512 q=12289 (BLISS-B / Falcon-512 shape), CPU reference on a bounded sample",
+                   "n": N_COEF, "q": Q, "pairs_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import libsafecrypto_b200 as sc
+    import _oracle as O
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w, r = O.tables(Q, N_COEF, 16)        # twiddle tables (host set-up; validated against the reference's generated ones)
+    plan = sc.NttPlan(N_COEF, Q, sc.REFERENCE, w, r, device=local_rank)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    a = torch.randint(0, Q, (BATCH, N_COEF), dtype=torch.int32, device=dev, generator=g)
+    b = torch.randint(0, Q, (BATCH, N_COEF), dtype=torch.int32, device=dev, generator=g)
+    out = torch.empty_like(a)
+
+    # ---- device-resident leg ---------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        plan.polymul(out, a, b)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sc.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    barrier()
+    ev0.record()
+    evs = []
+    for _ in range(args.steps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        plan.polymul(out, a, b)
+        e.record()
+        evs.append((s, e))
+    ev1.record()
+    barrier()
+    launches = sc.launch_count() - launches0
+    sampler.stop_flag.set()
+    sampler.join()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kernel_ms = [s.elapsed_time(e) for s, e in evs]
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * BATCH / (ms_per_step * 1e-3)
+
+    # spot-check the timed output against the oracle (parity is the gate, tests/ hold the full suite)
+    sl = slice(4321, 4321 + 16)
+    exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, N_COEF, Q, 16, a[sl].cpu().numpy(), b[sl].cpu().numpy(), w, r)
+    assert np.array_equal(out[sl].cpu().numpy(), exp), "polymul output differs from the oracle"
+
+    # ---- roofline of the dominant (only) kernel ------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    k_ms = float(np.mean(kernel_ms))
+    alg_bytes = 12 * N_COEF * BATCH                     # read a, b (4n each) + write out (4n) per product
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "k_polymul<9,MODE_POLYMUL>",
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes}
+    prof = os.path.join(ROOT, "profiles", "polymul_traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+    int_roof = None
+    if rank == 0:
+        # INT-issue roofline: the kernel is bound by the integer pipes, not HBM
+        mul_g = sc.int_peak_gops(0, 2048, local_rank)
+        bfly_g = sc.int_peak_gops(9, 2048, local_rank)
+        # 3 transforms x (n/2) log2 n butterflies + 2 n pointwise/scale products, 5 INT ops per butterfly-equivalent
+        int_ops = (3 * (N_COEF // 2) * 9 + 2 * N_COEF) * 5.0
+        int_roof = {"imad_gops": mul_g, "montgomery_butterfly_mix_gops": bfly_g,
+                    "achieved_gops": int_ops * BATCH / (k_ms * 1e-3) / 1e9,
+                    "frac_of_butterfly_mix_peak": int_ops * BATCH / (k_ms * 1e-3) / 1e9 / bfly_g if bfly_g > 0 else None}
+
+    # ---- end-to-end leg: host buffers through the C-ABI ----------------------------------------------------
+    ha = torch.randint(0, Q, (E2E_BATCH, N_COEF), dtype=torch.int32).pin_memory()
+    hb = torch.randint(0, Q, (E2E_BATCH, N_COEF), dtype=torch.int32).pin_memory()
+    ho = torch.empty((E2E_BATCH, N_COEF), dtype=torch.int32).pin_memory()
+    for _ in range(2):
+        plan.polymul_host(ho, ha, hb)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.polymul_host(ho, ha, hb)                    # blocks until the result is back in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * E2E_BATCH * e2e_steps / e2e_s
+    exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, N_COEF, Q, 16, ha[:8].numpy(), hb[:8].numpy(), w, r)
+    assert np.array_equal(ho[:8].numpy(), exp), "host-path output differs from the oracle"
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 4 * N_COEF * E2E_BATCH,
+           "d2h_bytes_per_step": 4 * N_COEF * E2E_BATCH, "pairs_per_step": E2E_BATCH, "steps": e2e_steps,
+           "api": "scgpu_polymul_batch_host (pinned host buffers, chunked 3-stream H2D/kernel/D2H pipeline)"}
+
+    # ---- secondary metric: Gaussian samples/s (BASELINE config 5 shape) -----------------------------------------
+    gauss = None
+    if rank == 0:
+        gp = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0, device=local_rank)
+        nstreams, n = 1 << 18, 512
+        seeds = torch.randint(0, 256, (nstreams, 40), dtype=torch.uint8, device=dev, generator=g)
+        smp = torch.empty((nstreams, n), dtype=torch.int32, device=dev)
+        gauss = {}
+        for name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
+            for _ in range(2):
+                gp.streams(prng, seeds, n, smp)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(3):
+                gp.streams(prng, seeds, n, smp)
+            e.record()
+            torch.cuda.synchronize()
+            gauss["cdf64_sigma215_%s_samples_per_s" % name] = 3 * nstreams * n / (s.elapsed_time(e) * 1e-3)
+        gauss["shape"] = "%d streams x %d samples, CDF-64, sigma 215, tail 13.42" % (nstreams, n)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cores, kind, vname, _ = cpu_reference_run(1 << 14)
+        count = int(min(1 << 20, max(1 << 14, rate * 12)))         # ~12 s of CPU work
+        rate, cores, kind, vname, dt = cpu_reference_run(count)
+        rate1, _, _, _, _ = cpu_reference_run(max(1 << 12, count // max(cores, 1)), threads=1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "%d pairs, variant %s (fwd,fwd,pointwise,inv), %.1f s wall; 1-thread rate %.0f/s" % (count, vname, dt, rate1)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "batched NTT polymul n=512 q=12289 (BASELINE configs[1]), 2^20 pairs per GPU, fused fwd/fwd/pointwise/inv, canonical output",
+                       "n": N_COEF, "q": Q, "pairs_per_gpu": BATCH, "parallelism": "shard by polynomial index, no collective",
+                       "cache": "operands 4 GiB + result 2 GiB per step >> 126 MB L2 (no flush needed)"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,214 @@
+"""ctypes binding of libscgpu.so (include/scgpu.h).  Plumbing only: pointers in, status out."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# safecrypto_ntt_e (reference src/utils/arith/ntt.h:106-123)
+REFERENCE, BARRETT, FP, AVX, SOLINAS_7681, SOLINAS_8380417 = range(6)
+(OP_FWD, OP_INV, OP_FWD_LARGE, OP_INV_LARGE, OP_FFT, OP_FFT_LARGE, OP_PW, OP_PW16, OP_NORMALIZE,
+ OP_CENTER, OP_POLYMUL, OP_TRIPLE16, OP_MODN, OP_MULN, OP_SQRN, OP_FLIP, OP_INVERT, OP_DIV,
+ OP_PWR, OP_SCALAR, OP_SPARSE32, OP_SPARSE16) = range(22)
+PRNG_AES_CTR_DRBG, PRNG_CHACHA = 0, 2
+SAMPLER_CDF, SAMPLER_KNUTH_YAO, SAMPLER_BERNOULLI = 0, 1, 5
+NORMAL_SAMPLES, BLINDING_SAMPLES, SHUFFLE_SAMPLES = 0, 1, 2
+
+
+class ScgpuError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libscgpu.so")
+
+
+_lib = None
+
+
+def lib():
+    """Load libscgpu.so.  Fails loudly: there is no other implementation to fall back to."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ScgpuError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(make -C libsafecrypto_b200/csrc). No CPU fallback exists." % path)
+        L = ctypes.CDLL(path)
+        vp, sz, i32, u32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_uint32
+        L.scgpu_last_error.restype = ctypes.c_char_p
+        L.scgpu_launch_count.restype = ctypes.c_uint64
+        L.scgpu_int_peak_gops.restype = ctypes.c_double
+        L.scgpu_int_peak_gops.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.scgpu_ntt_plan_create.argtypes = [ctypes.POINTER(vp), vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int]
+        L.scgpu_ntt_plan_destroy.argtypes = [vp]
+        L.scgpu_ntt_plan_destroy.restype = None
+        L.scgpu_ntt_batch.argtypes = [vp, ctypes.c_int, vp, vp, vp, sz, sz, i32, vp, vp]
+        L.scgpu_ntt_batch_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, sz, sz, i32, vp]
+        L.scgpu_polymul_batch.argtypes = [vp, vp, vp, vp, sz, sz, vp]
+        L.scgpu_polymul_batch_host.argtypes = [vp, vp, vp, vp, sz, sz]
+        L.scgpu_ntt_mul_key_batch.argtypes = [vp, vp, vp, vp, ctypes.c_int, sz, sz, vp]
+        L.scgpu_matvec_batch.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, sz, vp]
+        L.scgpu_gauss_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_float, ctypes.c_float, ctypes.c_int]
+        L.scgpu_gauss_plan_destroy.argtypes = [vp]
+        L.scgpu_gauss_plan_destroy.restype = None
+        L.scgpu_gauss_streams.argtypes = [vp, ctypes.c_int, vp, sz, sz, sz, sz, i32, u32, vp, vp]
+        L.scgpu_gauss_streams_host.argtypes = [vp, ctypes.c_int, vp, sz, sz, sz, sz, i32, u32, vp]
+        L.scgpu_prng_words.argtypes = [ctypes.c_int, vp, sz, sz, sz, sz, vp, vp]
+        L.init_reduce.argtypes = [vp, sz, i32]
+        L.init_reduce.restype = None
+        _lib = L
+    return _lib
+
+
+def _check(status, what):
+    if status < 0:
+        raise ScgpuError("%s: %s (status %d)" % (what, lib().scgpu_last_error().decode(), status))
+    return status
+
+
+def launch_count():
+    return int(lib().scgpu_launch_count())
+
+
+def int_peak_gops(kind, iters=4096, device=0):
+    return float(lib().scgpu_int_peak_gops(kind, iters, device))
+
+
+PARAMS_SIZE = 60   # sizeof(ntt_params_t), packed (reference src/utils/arith/ntt.h:91-103)
+
+
+def make_params(n, q):
+    """A reference-layout ntt_params_t filled by the library's init_reduce()."""
+    buf = ctypes.create_string_buffer(64)
+    lib().init_reduce(buf, n, q)
+    return buf
+
+
+def _ptr(t):
+    """Device or host pointer of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def _stream_handle(stream):
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    return stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+
+
+class NttPlan:
+    """scgpu_ntt_plan_t: one (q, n, variant) parameter set with the caller's w / r tables."""
+
+    def __init__(self, n, q, variant, w=None, r=None, device=0, params=None):
+        self.n, self.q, self.variant = n, q, variant
+        self.params = params if params is not None else make_params(n, q)
+        tw_bits = 0
+        self._w = self._r = None
+        if w is not None:
+            w = np.ascontiguousarray(w)
+            tw_bits = 16 if w.dtype == np.int16 else 32
+            self._w = w
+            if r is not None:
+                self._r = np.ascontiguousarray(r, dtype=w.dtype)
+        self.tw_bits = tw_bits
+        h = ctypes.c_void_p()
+        _check(lib().scgpu_ntt_plan_create(ctypes.byref(h), self.params, variant, _ptr(self._w), _ptr(self._r),
+                                           tw_bits, device), "scgpu_ntt_plan_create")
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().scgpu_ntt_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device buffers (torch CUDA tensors) -------------------------------------------------------
+    def batch(self, op, out, a, b=None, b_stride=None, count=None, scalar=0, rc=None, stream=None):
+        if count is None:
+            count = a.shape[0] if a.dim() > 1 else 1
+        if b_stride is None:
+            b_stride = 0 if (b is None or b.dim() == 1) else b.shape[-1]
+        return _check(lib().scgpu_ntt_batch(self.handle, op, _ptr(out), _ptr(a), _ptr(b), b_stride, count,
+                                            int(scalar), _ptr(rc), _stream_handle(stream)), "scgpu_ntt_batch")
+
+    def polymul(self, out, a, b, count=None, stream=None):
+        if count is None:
+            count = a.shape[0]
+        b_stride = 0 if b.dim() == 1 else b.shape[-1]
+        return _check(lib().scgpu_polymul_batch(self.handle, _ptr(out), _ptr(a), _ptr(b), b_stride, count,
+                                                _stream_handle(stream)), "scgpu_polymul_batch")
+
+    def mul_key(self, out, t, key, count=None, stream=None):
+        if count is None:
+            count = t.shape[0]
+        key_bits = key.element_size() * 8
+        key_stride = 0 if key.dim() == 1 else key.shape[-1]
+        return _check(lib().scgpu_ntt_mul_key_batch(self.handle, _ptr(out), _ptr(t), _ptr(key), key_bits, key_stride,
+                                                    count, _stream_handle(stream)), "scgpu_ntt_mul_key_batch")
+
+    def matvec(self, out, A, s, k, l, count=None, stream=None):
+        if count is None:
+            count = s.shape[0]
+        return _check(lib().scgpu_matvec_batch(self.handle, _ptr(out), _ptr(A), _ptr(s), k, l, count,
+                                               _stream_handle(stream)), "scgpu_matvec_batch")
+
+    # ---- host buffers (numpy arrays or pinned torch CPU tensors) -----------------------------------
+    def batch_host(self, op, out, a, b=None, b_stride=None, count=None, scalar=0, rc=None):
+        if count is None:
+            count = a.shape[0] if len(a.shape) > 1 else 1
+        if b_stride is None:
+            b_stride = 0 if (b is None or len(b.shape) == 1) else b.shape[-1]
+        return _check(lib().scgpu_ntt_batch_host(self.handle, op, _ptr(out), _ptr(a), _ptr(b), b_stride, count,
+                                                 int(scalar), _ptr(rc)), "scgpu_ntt_batch_host")
+
+    def polymul_host(self, out, a, b, count=None):
+        if count is None:
+            count = a.shape[0]
+        b_stride = 0 if len(b.shape) == 1 else b.shape[-1]
+        return _check(lib().scgpu_polymul_batch_host(self.handle, _ptr(out), _ptr(a), _ptr(b), b_stride, count),
+                      "scgpu_polymul_batch_host")
+
+
+class GaussPlan:
+    """scgpu_gauss_plan_t: sampler tables (built on the host with the reference's formulas) on the device."""
+
+    def __init__(self, sampler, precision, blinding, tail, sigma, device=0):
+        h = ctypes.c_void_p()
+        _check(lib().scgpu_gauss_plan_create(ctypes.byref(h), sampler, precision, blinding, tail, sigma, device),
+               "scgpu_gauss_plan_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().scgpu_gauss_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def streams(self, prng_type, seeds, n, out, calls=1, centre=0, discard=0, stream=None):
+        nstreams, seed_len = seeds.shape
+        return _check(lib().scgpu_gauss_streams(self.handle, prng_type, _ptr(seeds), seed_len, nstreams, n, calls,
+                                                centre, discard, _ptr(out), _stream_handle(stream)),
+                      "scgpu_gauss_streams")
+
+    def streams_host(self, prng_type, seeds, n, out, calls=1, centre=0, discard=0):
+        nstreams, seed_len = seeds.shape
+        return _check(lib().scgpu_gauss_streams_host(self.handle, prng_type, _ptr(seeds), seed_len, nstreams, n,
+                                                     calls, centre, discard, _ptr(out)), "scgpu_gauss_streams_host")

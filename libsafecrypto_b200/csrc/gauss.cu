@@ -1,0 +1,425 @@
+// gauss.cu -- discrete Gaussian sampling kernels (src/utils/sampling of the reference).
+//
+//   k_stream_seq   one thread per PRNG stream, any sampler / vector mode / discard setting: the exact
+//                  sequential semantics of sample_vector_32, shuffle_sample_vector_32,
+//                  blinding_sample_vector_32 (sampling.c:68-228) over gaussian_cdf_sample_32/64
+//                  (gaussian_cdf.c:536-553,639-659,661-677,760-774), gaussian_knuth_yao_sample
+//                  (gaussian_knuth_yao.c:301-364) and bernoulli_sample_64 (gaussian_bernoulli.c:161-280).
+//   k_cdf_aes      CDF + AES-CTR-DRBG, NORMAL_SAMPLES, no discard: sample j of a stream depends only on
+//                  DRBG block j/2 (64-bit) or j/4 (32-bit), so one thread produces one block's samples;
+//                  CDF table and AES tables in shared memory, coalesced 64/128-bit stores.
+//   k_cdf_chacha   CDF + ChaCha20-CSPRNG, NORMAL_SAMPLES, no discard: one warp per stream; each lane
+//                  encrypts a contiguous run of blocks, a warp XOR-scan rebuilds the running XOR the
+//                  reference's encrypt-in-place framing creates, samples go out through shared memory.
+#include "scgpu_internal.h"
+#include "csprng.cuh"
+#include "gauss_plan.h"
+#include "../../include/scgpu.h"
+
+namespace scgpu {
+
+namespace {
+
+// ---- samplers on a sequential stream ----------------------------------------------------------------
+
+// gaussian_cdf.c:536-553: fixed log2(size) probe steps, largest a with cdf[a] < x
+template <typename T>
+__device__ __forceinline__ uint32_t cdf_search(const T *cdf, uint32_t size, T x)
+{
+    uint32_t a = 0;
+    for (uint32_t st = size >> 1; st > 0; st >>= 1) {
+        uint32_t b = a + st;
+        a = (b < size && cdf[b] < x) ? b : a;
+    }
+    return a;
+}
+
+__device__ __forceinline__ int32_t sample_cdf(const GaussTablesDev &g, PrngStream &rng)
+{
+    if (g.precision == 64) {
+        uint64_t x = rng.next64();
+        uint32_t a = cdf_search<uint64_t>(g.cdf64, g.cdf_size, x);
+        return (x & 1) ? (int32_t)a : -(int32_t)a;
+    }
+    uint32_t x = rng.next32();
+    uint32_t a = cdf_search<uint32_t>(g.cdf32, g.cdf_size, x);
+    return (x & 1) ? (int32_t)a : -(int32_t)a;
+}
+
+// Knuth-Yao walk.  The reference scans row `row` of the probability matrix column by column and stops at
+// the first column where the running distance goes negative; with one-positions precomputed per row that
+// is "the (dist+1)-th one of the row, if the row has that many".  After the first hit the distance stays
+// negative, every later row contributes column 0, and only the fixed RNG consumption remains
+// (one word per 32 rows plus the trailing word).
+__device__ __forceinline__ int32_t sample_ky(const GaussTablesDev &g, PrngStream &rng)
+{
+    for (;;) {
+        int32_t dist = 0, sample = 0;
+        bool hit = false;
+        uint32_t rnd = rng.next32();
+        for (int row = 0; row < g.ky_rows; row++) {
+            dist = 2 * dist + (int32_t)(rnd & 1);
+            rnd >>= 1;
+            if ((row & 0x1F) == 0x1F) rnd = rng.next32();
+            if (!hit) {
+                int32_t ones = (int32_t)(g.ky_rowoff[row + 1] - g.ky_rowoff[row]);
+                if (dist < ones) {
+                    sample = g.ky_onepos[g.ky_rowoff[row] + dist];
+                    hit = true;
+                    dist = -1;
+                } else {
+                    dist -= ones;
+                }
+            } else {
+                dist = -1;             // any negative value: 2*dist + bit - {0,1} stays negative
+            }
+        }
+        rnd = rng.next32();
+        sample = sample % g.ky_bound;
+        if (sample == 0 && (rnd & 1)) continue;
+        return (rnd & 2) ? sample : -sample;
+    }
+}
+
+__device__ __forceinline__ int32_t sample_ber(const GaussTablesDev &g, PrngStream &rng)
+{
+    for (;;) {
+        uint32_t val;
+        for (;;) {                                               // gaussian_bernoulli.c:161-246
+            val = rng.var(g.ber_maxlog);
+            if (val >= (uint32_t)g.ber_maxval) continue;
+            uint32_t accept_mask = 0, x = val * val;
+            bool reject = false;
+            for (int j = 0; j < 8 && !reject; j++) {
+                for (int i = g.ber_entries; i--;) {
+                    uint32_t r = rng.var(8) & 0xFF;
+                    uint32_t tv = g.ber_tab[i * 8 + j];
+                    if (r < tv && ((accept_mask >> i) & 1) == 0) accept_mask |= (1u << i);
+                    if (r > tv && ((x >> i) & 1) == 1 && ((accept_mask >> i) & 1) == 0) { reject = true; break; }
+                }
+            }
+            if (!reject) break;
+        }
+        uint32_t rnd = rng.var(2);                               // :248-280
+        if (val == 0) { if (rnd < 2) continue; return 0; }
+        return (rnd & 1) ? -(int32_t)val : (int32_t)val;
+    }
+}
+
+__device__ __forceinline__ int32_t draw(const GaussTablesDev &g, PrngStream &rng)
+{
+    if (g.sampler == SCGPU_SAMPLER_CDF) return sample_cdf(g, rng);
+    if (g.sampler == SCGPU_SAMPLER_KNUTH_YAO) return sample_ky(g, rng);
+    return sample_ber(g, rng);
+}
+
+// sampling.c:68-83
+__device__ __forceinline__ uint32_t rand_range(PrngStream &rng, uint32_t x)
+{
+    uint32_t rem = 0xFFFFFFFFu % x;
+    for (;;) {
+        uint32_t y = rng.next32();
+        if (y >= (0xFFFFFFFFu - rem)) continue;
+        return y % x;
+    }
+}
+
+struct SeqArgs {
+    GaussTablesDev g;
+    const uint8_t *seeds;
+    PrngState *states;          // optional resumable states (drop-in prng_ctx_t); NULL = fresh streams from seeds
+    uint32_t seed_len, seed_period;
+    uint32_t prng_type;
+    size_t nstreams, n, calls;
+    int32_t centre;
+    uint32_t thresh;
+    int32_t *out;
+    int mode;                   // 0 sampler vector calls, 1 raw words, 2 single get_sample, 3 instantiate only
+};
+
+__global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
+{
+    __shared__ AesTables aes;
+    aes_tables_init(aes);
+    __syncthreads();
+    const size_t sidx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (sidx >= a.nstreams) return;
+    PrngStream rng;
+    rng.aes = &aes;
+    rng.seed = a.seeds + sidx * a.seed_len;
+    if (a.states && a.states[sidx].seed_len != 0) rng.s = a.states[sidx];
+    else rng.init(a.prng_type, a.seed_len, a.seed_period);
+
+    int32_t *v = a.out + sidx * a.n * a.calls;
+    if (a.mode == 1) {
+        for (size_t i = 0; i < a.n * a.calls; i++) v[i] = (int32_t)rng.next32();
+    } else if (a.mode == 2) {
+        v[0] = draw(a.g, rng);
+    } else if (a.mode == 3) {
+        // instantiate only: the state is written back below
+    } else {
+        for (size_t call = 0; call < a.calls; call++, v += a.n) {
+            const size_t n = a.n;
+            if (a.g.sampler != SCGPU_SAMPLER_CDF || a.g.blinding == SCGPU_NORMAL_SAMPLES) {
+                // sampling.c:211-228 (KY / Bernoulli are driven the same way: sample() + centre)
+                for (size_t i = 0; i < n;) {
+                    v[i] = draw(a.g, rng) + a.centre;
+                    bool discard = a.thresh && rng.next32() < a.thresh;
+                    if (!discard) i++;
+                }
+            } else {
+                // sampling.c:127-145: inside-out shuffle; v[0] is drawn without the centre
+                v[0] = draw(a.g, rng);
+                for (size_t i = 1; i < n;) {
+                    uint32_t j = rand_range(rng, (uint32_t)i);
+                    if (j != i) v[i] = v[j];
+                    v[j] = draw(a.g, rng) + a.centre;
+                    bool discard = a.thresh && rng.next32() < a.thresh;
+                    if (!discard) i++;
+                }
+                if (a.g.blinding == SCGPU_BLINDING_SAMPLES)      // sampling.c:170-191
+                    for (size_t i = 0; i < n; i++) v[i] -= draw(a.g, rng);
+            }
+        }
+    }
+    if (a.states) a.states[sidx] = rng.s;
+}
+
+// ---- fast path 1: CDF over the AES-CTR-DRBG ---------------------------------------------------------------
+struct FastArgs {
+    GaussTablesDev g;
+    const uint8_t *seeds;
+    uint32_t seed_len, seed_period;
+    size_t nstreams, per_stream;        // per_stream = calls * n samples
+    int32_t centre;
+    int32_t *out;
+    uint32_t *keys;                      // [nstreams][61]: 60 round-key words + initial counter
+};
+
+// one thread per stream: DRBG instantiation (zero-key block encryptions, entropy mix, key schedule)
+__global__ void __launch_bounds__(128) k_drbg_setup(FastArgs a)
+{
+    __shared__ AesTables aes;
+    aes_tables_init(aes);
+    __syncthreads();
+    const size_t sidx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (sidx >= a.nstreams) return;
+    PrngStream rng;
+    rng.aes = &aes;
+    rng.seed = a.seeds + sidx * a.seed_len;
+    rng.init(PRNG_AES, a.seed_len, a.seed_period);
+    uint32_t *k = a.keys + sidx * 61;
+    for (int i = 0; i < 60; i++) k[i] = rng.s.drbg_rk[i];
+    k[60] = rng.s.drbg_counter;
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(256) k_cdf_aes(FastArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AesTables *aes = reinterpret_cast<AesTables *>(smem_raw);
+    uint64_t *cdf64 = reinterpret_cast<uint64_t *>(smem_raw + 2048);
+    uint32_t *cdf32 = reinterpret_cast<uint32_t *>(smem_raw + 2048);
+    aes_tables_init(*aes);
+    if (PREC == 64) for (uint32_t i = threadIdx.x; i < a.g.cdf_size; i += blockDim.x) cdf64[i] = a.g.cdf64[i];
+    else            for (uint32_t i = threadIdx.x; i < a.g.cdf_size; i += blockDim.x) cdf32[i] = a.g.cdf32[i];
+    __syncthreads();
+    constexpr int SPB = PREC == 64 ? 2 : 4;                   // samples per 16-byte DRBG block
+    const size_t blocks_per_stream = (a.per_stream + SPB - 1) / SPB;
+    const size_t total = a.nstreams * blocks_per_stream;
+    for (size_t item = blockIdx.x * (size_t)blockDim.x + threadIdx.x; item < total; item += (size_t)gridDim.x * blockDim.x) {
+        const size_t sidx = item / blocks_per_stream, blk = item % blocks_per_stream;
+        const uint32_t *k = a.keys + sidx * 61;
+        uint32_t w[4];
+        drbg_block_words(*aes, k, k[60] + (uint32_t)blk, w);
+        int32_t res[4];
+        if (PREC == 64) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                uint64_t x = ((uint64_t)w[2 * i] << 32) | w[2 * i + 1];
+                uint32_t s = cdf_search<uint64_t>(cdf64, a.g.cdf_size, x);
+                res[i] = ((x & 1) ? (int32_t)s : -(int32_t)s) + a.centre;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t s = cdf_search<uint32_t>(cdf32, a.g.cdf_size, w[i]);
+                res[i] = ((w[i] & 1) ? (int32_t)s : -(int32_t)s) + a.centre;
+            }
+        }
+        int32_t *o = a.out + sidx * a.per_stream + blk * SPB;
+        const size_t left = a.per_stream - blk * SPB;
+        if (left >= SPB && ((reinterpret_cast<uintptr_t>(o) & (SPB * 4 - 1)) == 0)) {
+            if (PREC == 64) *reinterpret_cast<int2 *>(o) = make_int2(res[0], res[1]);
+            else            *reinterpret_cast<int4 *>(o) = make_int4(res[0], res[1], res[2], res[3]);
+        } else {
+            for (size_t i = 0; i < SPB && i < left; i++) o[i] = res[i];
+        }
+    }
+}
+
+// ---- fast path 2: CDF over the ChaCha20-CSPRNG ----------------------------------------------------------------
+// Word i of a fresh stream: 0 for i < 3, else word (i-3)%4 of D[(i-3)/4], D[j] = XOR_{k<=j} first16(block k),
+// byte-swapped.  One warp per stream; lane l owns blocks [l*C, (l+1)*C).
+template <int PREC>
+__global__ void __launch_bounds__(256) k_cdf_chacha(FastArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *cdf64 = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *cdf32 = reinterpret_cast<uint32_t *>(smem_raw);
+    if (PREC == 64) for (uint32_t i = threadIdx.x; i < a.g.cdf_size; i += blockDim.x) cdf64[i] = a.g.cdf64[i];
+    else            for (uint32_t i = threadIdx.x; i < a.g.cdf_size; i += blockDim.x) cdf32[i] = a.g.cdf32[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int WPS = PREC == 64 ? 2 : 1;                                   // words per sample
+    const size_t words = a.per_stream * WPS;
+    const size_t nblocks = words > 3 ? (words - 3 + 3) / 4 : 0;                // blocks D[0..nblocks)
+    const size_t C = (nblocks + 31) / 32;
+    for (size_t sidx = warp; sidx < a.nstreams; sidx += nwarps) {
+        const uint8_t *seed = a.seeds + sidx * a.seed_len;
+        // key / iv: first 40 entropy bytes (ring buffer)
+        uint32_t key[8], iv[2];
+        {
+            uint32_t e = 0;
+            auto le32 = [&]() {
+                uint32_t v = 0;
+                for (int b = 0; b < 4; b++) { v |= (uint32_t)seed[e] << (8 * b); if (++e == a.seed_len) e = 0; }
+                return v;
+            };
+            for (int i = 0; i < 8; i++) key[i] = le32();
+            iv[0] = le32(); iv[1] = le32();
+        }
+        // pass 1: XOR of this lane's blocks
+        uint32_t acc[4] = {0, 0, 0, 0};
+        const size_t b0 = (size_t)lane * C, b1 = (b0 + C < nblocks) ? b0 + C : nblocks;
+        for (size_t b = b0; b < b1; b++) {
+            uint32_t ks[4];
+            chacha20_first16(key, (uint32_t)b, (uint32_t)(b >> 32), iv[0], iv[1], ks);
+            acc[0] ^= ks[0]; acc[1] ^= ks[1]; acc[2] ^= ks[2]; acc[3] ^= ks[3];
+        }
+        // exclusive XOR scan over lanes
+        uint32_t pre[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t v = acc[i];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, off);
+                if (lane >= off) v ^= o;
+            }
+            pre[i] = v ^ acc[i];
+        }
+        // pass 2: regenerate the lane's blocks, emit its words -> samples
+        int32_t *orow = a.out + sidx * a.per_stream;
+        if (lane == 0) {
+            // words 0..2 are zero: samples built only from them
+            if (PREC == 64) { if (a.per_stream > 0) orow[0] = a.centre + 0; }     // x = 0 -> a = 0, sign -> -0
+            else for (size_t i = 0; i < 3 && i < a.per_stream; i++) orow[i] = a.centre;
+        }
+        uint32_t run[4] = {pre[0], pre[1], pre[2], pre[3]};
+        // the 64-bit sample that straddles two blocks needs the last word of the previous block:
+        // word index of D[j] word k is 3 + 4j + k; sample s (64-bit) uses words 2s, 2s+1.
+        uint32_t carry = 0;                                                        // word 4*b0+2 (= D[b0-1] word 3)
+        if (b0 > 0 && b0 <= nblocks) carry = bswap32(pre[3]);
+        for (size_t b = b0; b < b1; b++) {
+            uint32_t ks[4];
+            chacha20_first16(key, (uint32_t)b, (uint32_t)(b >> 32), iv[0], iv[1], ks);
+            run[0] ^= ks[0]; run[1] ^= ks[1]; run[2] ^= ks[2]; run[3] ^= ks[3];
+            const uint32_t w0 = bswap32(run[0]), w1 = bswap32(run[1]), w2 = bswap32(run[2]), w3 = bswap32(run[3]);
+            const size_t wi = 3 + 4 * b;                                           // index of w0
+            if (PREC == 64) {
+                // words wi-1 (carry), wi .. wi+3: samples (wi-1)/2 = 2b+1 and 2b+2
+                const size_t s0 = 2 * b + 1;
+                uint64_t x0 = ((uint64_t)carry << 32) | w0;
+                uint64_t x1 = ((uint64_t)w1 << 32) | w2;
+                if (s0 < a.per_stream) {
+                    uint32_t s = cdf_search<uint64_t>(cdf64, a.g.cdf_size, x0);
+                    orow[s0] = ((x0 & 1) ? (int32_t)s : -(int32_t)s) + a.centre;
+                }
+                if (s0 + 1 < a.per_stream) {
+                    uint32_t s = cdf_search<uint64_t>(cdf64, a.g.cdf_size, x1);
+                    orow[s0 + 1] = ((x1 & 1) ? (int32_t)s : -(int32_t)s) + a.centre;
+                }
+                carry = w3;
+            } else {
+                const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (wi + k < a.per_stream) {
+                        uint32_t s = cdf_search<uint32_t>(cdf32, a.g.cdf_size, w[k]);
+                        orow[wi + k] = ((w[k] & 1) ? (int32_t)s : -(int32_t)s) + a.centre;
+                    }
+                }
+            }
+        }
+    }
+}
+
+unsigned cap_grid(size_t want, int sms, int per_sm)
+{
+    size_t cap = (size_t)sms * per_sm;
+    if (want > cap) want = cap;
+    if (want == 0) want = 1;
+    return (unsigned)want;
+}
+
+}  // namespace
+
+int launch_gauss_seq(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
+                     uint32_t seed_period, PrngState *states, size_t nstreams, size_t n, size_t calls,
+                     int32_t centre, uint32_t discard, int32_t *out, int mode, cudaStream_t st)
+{
+    if (nstreams == 0 || (n * calls == 0 && mode != 2)) return SCGPU_OK;
+    SeqArgs a;
+    a.g = g; a.seeds = seeds; a.states = states; a.seed_len = (uint32_t)seed_len; a.seed_period = seed_period;
+    a.prng_type = (uint32_t)prng_type; a.nstreams = nstreams; a.n = n; a.calls = calls; a.centre = centre;
+    a.thresh = discard == 2 ? 1u << 28 : discard == 4 ? 1u << 30 : discard == 6 ? 1u << 31 : 0;   // sampling.c:85-92
+    a.out = out; a.mode = mode;
+    const unsigned grid = (unsigned)((nstreams + 127) / 128);
+    k_stream_seq<<<grid, 128, 0, st>>>(a);
+    count_launch();
+    SCGPU_CUDA_CHECK(cudaGetLastError());
+    return SCGPU_OK;
+}
+
+int launch_gauss_fast(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
+                      uint32_t seed_period, size_t nstreams, size_t per_stream, int32_t centre, int32_t *out,
+                      uint32_t *key_scratch, int sm_count, cudaStream_t st)
+{
+    if (nstreams == 0 || per_stream == 0) return SCGPU_OK;
+    FastArgs a;
+    a.g = g; a.seeds = seeds; a.seed_len = (uint32_t)seed_len; a.seed_period = seed_period;
+    a.nstreams = nstreams; a.per_stream = per_stream; a.centre = centre; a.out = out; a.keys = key_scratch;
+    const size_t table_bytes = (size_t)g.cdf_size * (g.precision == 64 ? 8 : 4);
+    if (prng_type == PRNG_AES) {
+        k_drbg_setup<<<(unsigned)((nstreams + 127) / 128), 128, 0, st>>>(a);
+        count_launch();
+        const size_t smem = 2048 + table_bytes;
+        const int spb = g.precision == 64 ? 2 : 4;
+        const size_t items = nstreams * ((per_stream + spb - 1) / spb);
+        const unsigned grid = cap_grid((items + 255) / 256, sm_count, 4);
+        if (g.precision == 64) {
+            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_cdf_aes<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_cdf_aes<64><<<grid, 256, smem, st>>>(a);
+        } else {
+            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_cdf_aes<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_cdf_aes<32><<<grid, 256, smem, st>>>(a);
+        }
+    } else {
+        const unsigned grid = cap_grid((nstreams + 7) / 8, sm_count, 4);
+        if (g.precision == 64) {
+            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_cdf_chacha<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+            k_cdf_chacha<64><<<grid, 256, table_bytes, st>>>(a);
+        } else {
+            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_cdf_chacha<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+            k_cdf_chacha<32><<<grid, 256, table_bytes, st>>>(a);
+        }
+    }
+    count_launch();
+    SCGPU_CUDA_CHECK(cudaGetLastError());
+    return SCGPU_OK;
+}
+
+}  // namespace scgpu

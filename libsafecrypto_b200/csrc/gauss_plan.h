@@ -1,0 +1,35 @@
+// gauss_plan.h -- device-side view of one sampler's tables (built on the host by host_sampling.cu).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cuda_runtime.h>
+
+namespace scgpu {
+
+struct PrngState;
+
+struct GaussTablesDev {
+    int sampler;            // random_sampling_e
+    int precision;          // 32 / 64
+    int blinding;           // sample_blinding_e
+    // CDF (gaussian_cdf.c:555-610, 679-728)
+    const uint64_t *cdf64;
+    const uint32_t *cdf32;
+    uint32_t cdf_size;
+    // Knuth-Yao (gaussian_knuth_yao.c:81-189): per-row positions of the one-bits of the probability matrix
+    int ky_rows, ky_bound;
+    const uint32_t *ky_rowoff;      // [rows + 1]
+    const uint16_t *ky_onepos;
+    // Bernoulli (gaussian_bernoulli.c:40-103): entries x 8 bytes, most significant byte first
+    const uint8_t *ber_tab;
+    int ber_entries, ber_maxval, ber_maxlog;
+};
+
+int launch_gauss_seq(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
+                     uint32_t seed_period, PrngState *states, size_t nstreams, size_t n, size_t calls,
+                     int32_t centre, uint32_t discard, int32_t *out, int mode, cudaStream_t st);
+int launch_gauss_fast(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
+                      uint32_t seed_period, size_t nstreams, size_t per_stream, int32_t centre, int32_t *out,
+                      uint32_t *key_scratch, int sm_count, cudaStream_t st);
+
+}  // namespace scgpu

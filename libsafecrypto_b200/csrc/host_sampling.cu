@@ -1,0 +1,649 @@
+// host_sampling.cu -- host side of the sampler path: table construction, the batch C-ABI and the
+// reference's drop-in create_sampler()/get_vector_32()/prng_*() surface.
+//
+// Tables are built on the HOST with the reference's own formulas and C library calls (x87 long double
+// expl for the CDF and Knuth-Yao tables, float expf/powf/log2f for Bernoulli), exactly as
+// gaussian_cdf_create_64 (gaussian_cdf.c:555-610), gaussian_cdf_create_32 (:679-728),
+// create_knuth_yao_table_32/64 (gaussian_knuth_yao.c:81-124) and gen_ber_table_64
+// (gaussian_bernoulli.c:61-103) do, then uploaded; they are never recomputed on the device
+// (SURVEY.md 7 "hard parts").  All random words and all samples are produced by kernels in gauss.cu.
+#include "scgpu_internal.h"
+#include "csprng.cuh"
+#include "gauss_plan.h"
+#include "../../include/scgpu.h"
+#include "../../include/scgpu_dropin.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+using namespace scgpu;
+
+struct scgpu_gauss_plan {
+    GaussTablesDev t;
+    int device, sm_count;
+    void *d_cdf = nullptr;
+    uint32_t *d_rowoff = nullptr;
+    uint16_t *d_onepos = nullptr;
+    uint8_t *d_ber = nullptr;
+    std::mutex mu;
+    uint32_t *d_keys = nullptr; size_t keys_cap = 0;        // DRBG round keys of the fast path
+    uint8_t *d_seeds = nullptr; size_t seeds_cap = 0;       // staging for *_host
+    int32_t *d_out = nullptr; size_t out_cap = 0;
+};
+
+namespace {
+
+// sc_math.c:447-452
+size_t ceil_log2_sz(size_t x)
+{
+    size_t l = 0;
+    while ((x >> (l + 1)) != 0) l++;
+    if (x & (x - 1)) l++;
+    return l;
+}
+
+// sc_math.c:1066-1100
+uint64_t bin_expansion(double x, int nbits)
+{
+    double val = 0, step = 0.5f;
+    uint64_t res = 0;
+    for (int i = 0; i < nbits; i++) {
+        res <<= 1;
+        if ((val + step) < x) { val += step; res |= 1; }
+        step = step / 2;
+    }
+    return res;
+}
+
+#define L_2_SQRTPI 1.128379167095512573896158903121545172L
+#define L_SQRT1_2  0.707106781186547524400844362104849039L
+
+std::vector<uint64_t> build_cdf64(int blinding, float tail, float sigma)
+{
+    int bits = (int)ceil_log2_sz((size_t)(tail * sigma));
+    int size = 1 << bits;
+    std::vector<uint64_t> cdf((size_t)size);
+    if (blinding == SCGPU_BLINDING_SAMPLES) sigma *= L_SQRT1_2;
+    long double d = L_2_SQRTPI * L_SQRT1_2 * 18446744073709551616.0L / sigma;
+    long double e = -0.5L / (sigma * sigma);
+    long double s = 0.5L * d;
+    int i;
+    cdf[0] = 0;
+    for (i = 1; i < size - 1; i++) {
+        cdf[i] = (uint64_t)s;
+        if (cdf[i] == 0) break;
+        s += d * expl(e * ((long double)(i * i)));
+    }
+    for (; i < size; i++) cdf[i] = 0xFFFFFFFFFFFFFFFFULL;
+    return cdf;
+}
+
+std::vector<uint32_t> build_cdf32(int blinding, float tail, float sigma)
+{
+    int bits = (int)ceil_log2_sz((size_t)(tail * sigma));
+    int size = 1 << bits;
+    std::vector<uint32_t> cdf((size_t)size);
+    if (blinding == SCGPU_BLINDING_SAMPLES) sigma *= M_SQRT1_2;
+    float d = M_2_SQRTPI * M_SQRT1_2 * 4294967296.0 / sigma;
+    float e = -0.5L / (sigma * sigma);
+    float s = 0.5L * d;
+    int i;
+    cdf[0] = 0;
+    for (i = 1; i < size - 1; i++) {
+        cdf[i] = (uint32_t)s;
+        if (cdf[i] == 0) break;
+        s += d * expl(e * ((float)(i * i)));
+    }
+    for (; i < size; i++) cdf[i] = 0xFFFFFFFFu;
+    return cdf;
+}
+
+template <typename T>
+int upload(T **dst, const std::vector<T> &src)
+{
+    SCGPU_CUDA_CHECK(cudaMalloc(dst, sizeof(T) * (src.size() ? src.size() : 1)));
+    SCGPU_CUDA_CHECK(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    return SCGPU_OK;
+}
+
+template <typename T>
+int ensure_cap(T **buf, size_t *cap, size_t want)
+{
+    if (*cap >= want) return SCGPU_OK;
+    cudaFree(*buf);
+    *buf = nullptr; *cap = 0;
+    SCGPU_CUDA_CHECK(cudaMalloc(buf, want * sizeof(T)));
+    *cap = want;
+    return SCGPU_OK;
+}
+
+const uint32_t kDefaultSeedPeriod = 0x00100000;     // safecrypto.c:379
+
+// Can the position-addressable kernels serve this request?  They assume no reseed inside a stream.
+bool fast_path_ok(const GaussTablesDev &t, int prng_type, size_t per_stream, uint32_t discard)
+{
+    if (t.sampler != SCGPU_SAMPLER_CDF || t.blinding != SCGPU_NORMAL_SAMPLES || discard != 0) return false;
+    const size_t words = per_stream * (t.precision == 64 ? 2 : 1);
+    if (prng_type == PRNG_CHACHA20) return words <= 2 * ((size_t)kDefaultSeedPeriod / 8 - 1);   // first reseed epoch
+    const size_t blocks = (words + 3) / 4;
+    return blocks <= (size_t)(kDefaultSeedPeriod >> 4) * 64;                                      // first DRBG epoch
+}
+
+}  // namespace
+
+extern "C" int scgpu_gauss_plan_create(scgpu_gauss_plan_t **out, int sampler, int precision, int blinding,
+                                       float tail, float sigma, int device)
+{
+    if (!out) { set_error("gauss_plan_create: null argument"); return SCGPU_ERR_ARG; }
+    if (!(sigma > 0) || !(tail > 0)) { set_error("gauss_plan_create: tail/sigma must be positive"); return SCGPU_ERR_ARG; }
+    if (blinding < 0 || blinding > 2) { set_error("gauss_plan_create: blinding %d", blinding); return SCGPU_ERR_ARG; }
+    int ndev = 0;
+    SCGPU_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("gauss_plan_create: device %d of %d", device, ndev); return SCGPU_ERR_ARG; }
+    SCGPU_CUDA_CHECK(cudaSetDevice(device));
+    scgpu_gauss_plan *p = new scgpu_gauss_plan();
+    memset(&p->t, 0, sizeof(p->t));
+    p->t.sampler = sampler; p->t.precision = precision; p->t.blinding = blinding;
+    p->device = device;
+    cudaDeviceProp prop;
+    SCGPU_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    p->sm_count = prop.multiProcessorCount;
+    int rc = SCGPU_OK;
+    if (sampler == SCGPU_SAMPLER_CDF && precision == 64) {
+        std::vector<uint64_t> cdf = build_cdf64(blinding, tail, sigma);
+        uint64_t *d = nullptr;
+        rc = upload(&d, cdf);
+        p->d_cdf = d; p->t.cdf64 = d; p->t.cdf_size = (uint32_t)cdf.size();
+    } else if (sampler == SCGPU_SAMPLER_CDF && precision == 32) {
+        std::vector<uint32_t> cdf = build_cdf32(blinding, tail, sigma);
+        uint32_t *d = nullptr;
+        rc = upload(&d, cdf);
+        p->d_cdf = d; p->t.cdf32 = d; p->t.cdf_size = (uint32_t)cdf.size();
+    } else if (sampler == SCGPU_SAMPLER_KNUTH_YAO && (precision == 32 || precision == 64) && blinding != SCGPU_BLINDING_SAMPLES) {
+        // gaussian_knuth_yao.c:126-189; the matrix is stored as per-row positions of its one-bits
+        const int rows = precision;
+        const int bound = (int32_t)ceil(tail * sigma);
+        const int cols = bound + 1;
+        if (cols > 65535) { delete p; set_error("Knuth-Yao table too wide (%d columns)", cols); return SCGPU_ERR_UNSUPPORTED; }
+        long double d = 0.7978845608028653558798L / sigma;
+        long double e = -0.5L / (sigma * sigma);
+        std::vector<uint64_t> colbits((size_t)cols);
+        for (int col = 0; col < cols; col++) {
+            long double pr = (col == 0) ? d : d * expl(e * ((long double)(col * col)));
+            colbits[col] = bin_expansion((double)pr, rows);
+        }
+        std::vector<uint32_t> rowoff((size_t)rows + 1);
+        std::vector<uint16_t> onepos;
+        for (int row = 0; row < rows; row++) {
+            rowoff[row] = (uint32_t)onepos.size();
+            for (int col = 0; col < cols; col++)
+                if ((colbits[col] >> (rows - 1 - row)) & 1) onepos.push_back((uint16_t)col);
+        }
+        rowoff[rows] = (uint32_t)onepos.size();
+        rc = upload(&p->d_rowoff, rowoff);
+        if (rc == SCGPU_OK) rc = upload(&p->d_onepos, onepos);
+        p->t.ky_rows = rows; p->t.ky_bound = bound; p->t.ky_rowoff = p->d_rowoff; p->t.ky_onepos = p->d_onepos;
+    } else if (sampler == SCGPU_SAMPLER_BERNOULLI && precision == 64) {
+        // gaussian_bernoulli.c:40-103
+        float max_gauss_val = ceil(tail * sigma);
+        p->t.ber_maxval = (uint16_t)(int32_t)max_gauss_val;
+        p->t.ber_maxlog = (uint16_t)(int32_t)ceil(log2f(max_gauss_val));
+        size_t max_val = ceil(log2f(tail * tail * sigma * sigma));
+        if (max_val > 32) { delete p; set_error("Bernoulli table needs %zu entries (accept mask is 32 bits)", max_val); return SCGPU_ERR_UNSUPPORTED; }
+        std::vector<uint8_t> tab(max_val * 8);
+        for (size_t i = 0; i < max_val; i++) {
+            double temp = expf(-powf(2, i) / (2 * sigma * sigma));
+            uint64_t bitsv = bin_expansion(temp, 64);
+            for (int j = 0; j < 8; j++) tab[i * 8 + j] = (uint8_t)(bitsv >> (56 - 8 * j));
+        }
+        rc = upload(&p->d_ber, tab);
+        p->t.ber_entries = (int)max_val; p->t.ber_tab = p->d_ber;
+    } else {
+        delete p;
+        set_error("gauss_plan_create: sampler %d at %d-bit precision (blinding %d) is not on the GPU path", sampler, precision, blinding);
+        return SCGPU_ERR_UNSUPPORTED;
+    }
+    if (rc != SCGPU_OK) { scgpu_gauss_plan_destroy(p); return rc; }
+    *out = p;
+    return SCGPU_OK;
+}
+
+extern "C" void scgpu_gauss_plan_destroy(scgpu_gauss_plan_t *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_cdf); cudaFree(p->d_rowoff); cudaFree(p->d_onepos); cudaFree(p->d_ber);
+    cudaFree(p->d_keys); cudaFree(p->d_seeds); cudaFree(p->d_out);
+    delete p;
+}
+
+static int gauss_dispatch(scgpu_gauss_plan *p, int prng_type, const uint8_t *d_seeds, size_t seed_len, size_t nstreams,
+                          size_t n, size_t calls, int32_t centre, uint32_t discard, int32_t *d_out, cudaStream_t st)
+{
+    if (prng_type != PRNG_AES && prng_type != PRNG_CHACHA20) { set_error("PRNG type %d is not on the GPU path (0 = AES-CTR-DRBG, 2 = ChaCha20)", prng_type); return SCGPU_ERR_UNSUPPORTED; }
+    if (seed_len == 0 || !d_seeds || !d_out) { set_error("gauss_streams: null/empty argument"); return SCGPU_ERR_ARG; }
+    if (discard != 0 && discard != 2 && discard != 4 && discard != 6) { set_error("gauss_streams: discard %u", discard); return SCGPU_ERR_ARG; }
+    if (fast_path_ok(p->t, prng_type, n * calls, discard)) {
+        if (prng_type == PRNG_AES) {
+            int e = ensure_cap(&p->d_keys, &p->keys_cap, nstreams * 61);
+            if (e != SCGPU_OK) return e;
+        }
+        return launch_gauss_fast(p->t, prng_type, d_seeds, seed_len, kDefaultSeedPeriod, nstreams, n * calls, centre,
+                                 d_out, p->d_keys, p->sm_count, st);
+    }
+    return launch_gauss_seq(p->t, prng_type, d_seeds, seed_len, kDefaultSeedPeriod, nullptr, nstreams, n, calls, centre,
+                            discard, d_out, 0, st);
+}
+
+extern "C" int scgpu_gauss_streams(const scgpu_gauss_plan_t *plan, int prng_type, const uint8_t *seeds,
+                                   size_t seed_len, size_t nstreams, size_t n, size_t calls, int32_t centre,
+                                   uint32_t discard, int32_t *out, void *stream)
+{
+    if (!plan) { set_error("gauss_streams: null plan"); return SCGPU_ERR_ARG; }
+    scgpu_gauss_plan *p = const_cast<scgpu_gauss_plan *>(plan);
+    std::lock_guard<std::mutex> lock(p->mu);
+    SCGPU_CUDA_CHECK(cudaSetDevice(p->device));
+    return gauss_dispatch(p, prng_type, seeds, seed_len, nstreams, n, calls, centre, discard, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int scgpu_gauss_streams_host(const scgpu_gauss_plan_t *plan, int prng_type, const uint8_t *seeds,
+                                        size_t seed_len, size_t nstreams, size_t n, size_t calls, int32_t centre,
+                                        uint32_t discard, int32_t *out)
+{
+    if (!plan || !seeds || !out) { set_error("gauss_streams_host: null argument"); return SCGPU_ERR_ARG; }
+    scgpu_gauss_plan *p = const_cast<scgpu_gauss_plan *>(plan);
+    std::lock_guard<std::mutex> lock(p->mu);
+    SCGPU_CUDA_CHECK(cudaSetDevice(p->device));
+    int e = ensure_cap(&p->d_seeds, &p->seeds_cap, nstreams * seed_len);
+    if (e != SCGPU_OK) return e;
+    e = ensure_cap(&p->d_out, &p->out_cap, nstreams * n * calls);
+    if (e != SCGPU_OK) return e;
+    SCGPU_CUDA_CHECK(cudaMemcpyAsync(p->d_seeds, seeds, nstreams * seed_len, cudaMemcpyHostToDevice, 0));
+    e = gauss_dispatch(p, prng_type, p->d_seeds, seed_len, nstreams, n, calls, centre, discard, p->d_out, 0);
+    if (e != SCGPU_OK) return e;
+    SCGPU_CUDA_CHECK(cudaMemcpyAsync(out, p->d_out, nstreams * n * calls * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
+    SCGPU_CUDA_CHECK(cudaStreamSynchronize(0));
+    return SCGPU_OK;
+}
+
+extern "C" int scgpu_prng_words(int prng_type, const uint8_t *seeds, size_t seed_len, size_t seed_period,
+                                size_t nstreams, size_t nwords, uint32_t *out, void *stream)
+{
+    if (prng_type != PRNG_AES && prng_type != PRNG_CHACHA20) { set_error("PRNG type %d is not on the GPU path", prng_type); return SCGPU_ERR_UNSUPPORTED; }
+    if (!seeds || !out || seed_len == 0) { set_error("prng_words: null/empty argument"); return SCGPU_ERR_ARG; }
+    GaussTablesDev none;
+    memset(&none, 0, sizeof(none));
+    return launch_gauss_seq(none, prng_type, seeds, seed_len, seed_period ? (uint32_t)seed_period : kDefaultSeedPeriod,
+                            nullptr, nstreams, nwords, 1, 0, 0, reinterpret_cast<int32_t *>(out), 1, static_cast<cudaStream_t>(stream));
+}
+
+// =======================================================================================================
+// Drop-in PRNG front end and sampler objects
+// =======================================================================================================
+//
+// prng_ctx_t here is libscgpu's own context: the generator state lives on the DEVICE (PrngState) and every
+// random word -- whether handed to host callers through prng_32()/prng_var() or consumed by a sampler
+// kernel -- is produced by the kernels in gauss.cu from that state.  Host callers are served from a
+// read-ahead pool of device-generated words; before a sampler kernel runs, the device state is advanced
+// by exactly the number of pool words the host has consumed, so host and device draws interleave in the
+// reference's order.  INTEGRATION.md describes how a build inside the reference tree maps its own
+// prng_ctx_t (prng_types.h:121-232) onto this.
+
+struct prng_ctx_t {
+    safecrypto_prng_e type;
+    safecrypto_entropy_e entropy;
+    size_t seed_period;
+    std::vector<uint8_t> seed;          // entropy ring buffer handed to the device
+    const UINT8 *user_entropy = nullptr; size_t user_len = 0;
+    bool inited = false;
+    int device = 0;
+    cudaStream_t st = nullptr;
+    uint8_t *d_seed = nullptr;
+    PrngState *d_state = nullptr;       // state at the START of the host pool
+    uint32_t *d_pool = nullptr;
+    int32_t *d_out = nullptr; size_t out_cap = 0;
+    static constexpr size_t kPool = 4096;
+    uint32_t pool[kPool];
+    size_t pool_fill = 0, pool_rd = 0;  // words valid / consumed
+    uint32_t var_buf = 0; size_t var_bits = 0;
+    UINT64 csprng_bytes = 0, out_bytes = 0;
+    std::mutex mu;
+};
+
+static prng_entropy_callback g_entropy_cb = nullptr;
+
+namespace {
+
+[[noreturn]] void prng_fatal(const char *what)
+{
+    fprintf(stderr, "libscgpu: %s: %s\n", what, scgpu_last_error());
+    abort();
+}
+
+#define PRNG_CUDA(expr) do { if ((expr) != cudaSuccess) { set_error("%s", #expr); prng_fatal("CUDA call failed"); } } while (0)
+
+GaussTablesDev no_tables()
+{
+    GaussTablesDev t;
+    memset(&t, 0, sizeof(t));
+    return t;
+}
+
+// advance the device state past the pool words the host already consumed and drop the pool
+void sync_device_position(prng_ctx_t *c)
+{
+    PRNG_CUDA(cudaSetDevice(c->device));
+    if (c->pool_rd > 0) {
+        if (launch_gauss_seq(no_tables(), c->type, c->d_seed, c->seed.size(), (uint32_t)c->seed_period, c->d_state, 1,
+                             c->pool_rd, 1, 0, 0, reinterpret_cast<int32_t *>(c->d_pool), 1, c->st) != SCGPU_OK)
+            prng_fatal("prng advance");
+    }
+    c->pool_fill = c->pool_rd = 0;
+    // the prng_var bit buffer travels with the state
+    PrngState hs;
+    PRNG_CUDA(cudaMemcpyAsync(&hs, c->d_state, sizeof(hs), cudaMemcpyDeviceToHost, c->st));
+    PRNG_CUDA(cudaStreamSynchronize(c->st));
+    hs.var_buf = c->var_buf; hs.var_bits = (uint32_t)c->var_bits;
+    PRNG_CUDA(cudaMemcpyAsync(c->d_state, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->st));
+    PRNG_CUDA(cudaStreamSynchronize(c->st));
+}
+
+void pull_var_state(prng_ctx_t *c)
+{
+    PrngState hs;
+    PRNG_CUDA(cudaMemcpyAsync(&hs, c->d_state, sizeof(hs), cudaMemcpyDeviceToHost, c->st));
+    PRNG_CUDA(cudaStreamSynchronize(c->st));
+    c->var_buf = hs.var_buf; c->var_bits = hs.var_bits;
+}
+
+void refill_pool(prng_ctx_t *c)
+{
+    PRNG_CUDA(cudaSetDevice(c->device));
+    // state := state advanced by the consumed words, then generate a fresh pool WITHOUT committing it:
+    // the committed state stays at the pool start, so run the generator on a scratch copy.
+    sync_device_position(c);
+    PrngState *scratch = nullptr;
+    PRNG_CUDA(cudaMalloc(&scratch, sizeof(PrngState)));
+    PRNG_CUDA(cudaMemcpyAsync(scratch, c->d_state, sizeof(PrngState), cudaMemcpyDeviceToDevice, c->st));
+    if (launch_gauss_seq(no_tables(), c->type, c->d_seed, c->seed.size(), (uint32_t)c->seed_period, scratch, 1,
+                         prng_ctx_t::kPool, 1, 0, 0, reinterpret_cast<int32_t *>(c->d_pool), 1, c->st) != SCGPU_OK)
+        prng_fatal("prng refill");
+    PRNG_CUDA(cudaMemcpyAsync(c->pool, c->d_pool, sizeof(c->pool), cudaMemcpyDeviceToHost, c->st));
+    PRNG_CUDA(cudaStreamSynchronize(c->st));
+    cudaFree(scratch);
+    c->pool_fill = prng_ctx_t::kPool;
+    c->pool_rd = 0;
+    c->csprng_bytes += 4 * prng_ctx_t::kPool;
+}
+
+uint32_t host_next32(prng_ctx_t *c)
+{
+    if (c->pool_rd >= c->pool_fill) refill_pool(c);
+    c->out_bytes += 4;
+    return c->pool[c->pool_rd++];
+}
+
+}  // namespace
+
+extern "C" {
+
+prng_ctx_t *prng_create(safecrypto_entropy_e entropy, safecrypto_prng_e type, safecrypto_prng_threading_e mt,
+                        size_t seed_period)
+{
+    (void)mt;
+    // prng.c:560-626: unknown types and a zero period are rejected; only the two generators whose byte
+    // stream is reproduced on the device are available here
+    if (type != SC_PRNG_AES_CTR_DRBG && type != SC_PRNG_CHACHA) return NULL;
+    if (seed_period == 0) return NULL;
+    prng_ctx_t *c = new prng_ctx_t();
+    c->type = type; c->entropy = entropy; c->seed_period = seed_period;
+    const char *env = getenv("SCGPU_DEVICE");
+    c->device = env ? atoi(env) : 0;
+    return c;
+}
+
+SINT32 prng_set_entropy(prng_ctx_t *ctx, const UINT8 *entropy, size_t len)
+{
+    if (!ctx) return SC_FUNC_FAILURE;
+    ctx->user_entropy = entropy; ctx->user_len = len;
+    return SC_FUNC_SUCCESS;
+}
+
+SINT32 prng_set_entropy_callback(prng_entropy_callback cb)
+{
+    g_entropy_cb = cb;
+    return SC_FUNC_SUCCESS;
+}
+
+SINT32 prng_init(prng_ctx_t *ctx, const UINT8 *nonce, size_t len_nonce)
+{
+    (void)nonce; (void)len_nonce;       // unused by these two generators (prng.c:219-262)
+    if (!ctx) return SC_FUNC_FAILURE;
+    // Entropy that the reference pulls lazily at every (re)seed is gathered up front into the ring the
+    // device reads: 64 reseeds' worth for callback / OS sources, the user's buffer as-is otherwise.
+    const size_t per_seed = ctx->type == SC_PRNG_CHACHA ? 40 : 36;
+    switch (ctx->entropy) {
+    case SC_ENTROPY_USER_PROVIDED:
+        if (!ctx->user_entropy || ctx->user_len == 0) return SC_FUNC_FAILURE;
+        ctx->seed.assign(ctx->user_entropy, ctx->user_entropy + ctx->user_len);
+        break;
+    case SC_ENTROPY_CALLBACK:
+        if (!g_entropy_cb) return SC_FUNC_FAILURE;
+        ctx->seed.resize(64 * per_seed);
+        for (size_t off = 0; off < ctx->seed.size(); off += per_seed) {
+            if (ctx->type == SC_PRNG_AES_CTR_DRBG) { g_entropy_cb(4, ctx->seed.data() + off); g_entropy_cb(32, ctx->seed.data() + off + 4); }
+            else g_entropy_cb(40, ctx->seed.data() + off);
+        }
+        break;
+    case SC_ENTROPY_RANDOM: case SC_ENTROPY_DEV_RANDOM: case SC_ENTROPY_DEV_URANDOM: {
+        ctx->seed.resize(64 * per_seed);
+        FILE *fp = fopen("/dev/urandom", "rb");
+        if (!fp || fread(ctx->seed.data(), 1, ctx->seed.size(), fp) != ctx->seed.size()) { if (fp) fclose(fp); return SC_FUNC_FAILURE; }
+        fclose(fp);
+    } break;
+    default:
+        return SC_FUNC_FAILURE;
+    }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SC_FUNC_FAILURE;
+    PRNG_CUDA(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    PRNG_CUDA(cudaMalloc(&ctx->d_seed, ctx->seed.size()));
+    PRNG_CUDA(cudaMalloc(&ctx->d_state, sizeof(PrngState)));
+    PRNG_CUDA(cudaMalloc(&ctx->d_pool, sizeof(uint32_t) * prng_ctx_t::kPool));
+    PRNG_CUDA(cudaMemcpyAsync(ctx->d_seed, ctx->seed.data(), ctx->seed.size(), cudaMemcpyHostToDevice, ctx->st));
+    PRNG_CUDA(cudaMemsetAsync(ctx->d_state, 0, sizeof(PrngState), ctx->st));      // seed_len == 0: "fresh stream"
+    // instantiate the generator on the device (zero words requested, state written back)
+    if (launch_gauss_seq(no_tables(), ctx->type, ctx->d_seed, ctx->seed.size(), (uint32_t)ctx->seed_period, ctx->d_state,
+                         1, 1, 1, 0, 0, reinterpret_cast<int32_t *>(ctx->d_pool), 3, ctx->st) != SCGPU_OK)
+        return SC_FUNC_FAILURE;
+    PRNG_CUDA(cudaStreamSynchronize(ctx->st));
+    ctx->inited = true;
+    return SC_FUNC_SUCCESS;
+}
+
+safecrypto_prng_e prng_get_type(prng_ctx_t *ctx) { return ctx ? ctx->type : SC_PRNG_MAX; }
+
+SINT32 prng_destroy(prng_ctx_t *ctx)
+{
+    if (!ctx) return SC_FUNC_FAILURE;
+    if (ctx->inited) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->st);
+        cudaFree(ctx->d_seed); cudaFree(ctx->d_state); cudaFree(ctx->d_pool); cudaFree(ctx->d_out);
+        cudaStreamDestroy(ctx->st);
+    }
+    delete ctx;
+    return SC_FUNC_SUCCESS;
+}
+
+UINT64 prng_get_csprng_bytes(prng_ctx_t *ctx) { return ctx->csprng_bytes; }
+UINT64 prng_get_out_bytes(prng_ctx_t *ctx) { return ctx->out_bytes; }
+
+UINT32 prng_32(prng_ctx_t *ctx)
+{
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return host_next32(ctx);
+}
+
+UINT64 prng_64(prng_ctx_t *ctx)
+{
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    UINT64 hi = host_next32(ctx);
+    return (hi << 32) | host_next32(ctx);
+}
+
+// prng.c:1017-1048: bit-buffer bookkeeping on words that came from the device
+UINT32 prng_var(prng_ctx_t *ctx, size_t n)
+{
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    UINT32 mask = n >= 32 ? 0xFFFFFFFFu : (1u << n) - 1u;
+    if (n > 32) n = 32;
+    UINT32 ret = ctx->var_buf;
+    if (ctx->var_bits < n) {
+        size_t need = n - ctx->var_bits;
+        ret = need >= 32 ? ret : ret << need;
+        ctx->var_buf = host_next32(ctx);
+        ret |= ctx->var_buf & (need >= 32 ? 0u : ((1u << need) - 1u));
+        ctx->var_buf = need >= 32 ? ctx->var_buf : ctx->var_buf >> need;
+        ctx->var_bits = 32 - need;
+    } else {
+        ctx->var_buf >>= n;
+        ctx->var_bits -= n;
+    }
+    return ret & mask;
+}
+
+SINT32 prng_bit(prng_ctx_t *ctx) { return (SINT32)prng_var(ctx, 1); }
+UINT16 prng_16(prng_ctx_t *ctx) { return (UINT16)prng_var(ctx, 16); }
+UINT8 prng_8(prng_ctx_t *ctx) { return (UINT8)prng_var(ctx, 8); }
+
+}  // extern "C"
+
+// ---- samplers ----------------------------------------------------------------------------------------------
+
+namespace {
+
+struct GaussObj {            // what utils_sampling_t::gauss points at
+    scgpu_gauss_plan *plan;
+    prng_ctx_t *prng;
+};
+
+void *gauss_create_stub(prng_ctx_t *, FLOAT, FLOAT, size_t, sample_blinding_e) { return nullptr; }
+
+SINT32 gauss_destroy(void **g)
+{
+    if (!g || !*g) return SC_FUNC_FAILURE;
+    GaussObj *o = static_cast<GaussObj *>(*g);
+    scgpu_gauss_plan_destroy(o->plan);
+    delete o;
+    *g = nullptr;
+    return SC_FUNC_SUCCESS;
+}
+
+prng_ctx_t *gauss_get_prng(void *g) { return g ? static_cast<GaussObj *>(g)->prng : nullptr; }
+
+// run `n` samples (vector mode) or one bare sample (mode 2) of the sampler on the context's device state
+void run_on_ctx(GaussObj *o, int32_t *host_out, size_t n, int32_t centre, uint32_t discard, int mode)
+{
+    prng_ctx_t *c = o->prng;
+    std::lock_guard<std::mutex> lock(c->mu);
+    sync_device_position(c);
+    if (c->out_cap < n) {
+        cudaFree(c->d_out);
+        PRNG_CUDA(cudaMalloc(&c->d_out, sizeof(int32_t) * n));
+        c->out_cap = n;
+    }
+    if (launch_gauss_seq(o->plan->t, c->type, c->d_seed, c->seed.size(), (uint32_t)c->seed_period, c->d_state, 1, n, 1,
+                         centre, discard, c->d_out, mode, c->st) != SCGPU_OK)
+        prng_fatal("sampler kernel");
+    PRNG_CUDA(cudaMemcpyAsync(host_out, c->d_out, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->st));
+    PRNG_CUDA(cudaStreamSynchronize(c->st));
+    pull_var_state(c);
+}
+
+SINT32 gauss_sample(void *g)
+{
+    int32_t v = 0;
+    run_on_ctx(static_cast<GaussObj *>(g), &v, 1, 0, 0, 2);
+    return v;
+}
+
+SINT32 vector_32(const utils_sampling_t *s, SINT32 *v, size_t n, SINT32 centre)
+{
+    run_on_ctx(static_cast<GaussObj *>(s->gauss), v, n, centre, s->discard, 0);
+    return SC_FUNC_SUCCESS;
+}
+
+SINT32 vector_16(const utils_sampling_t *s, SINT16 *v, size_t n, SINT32 centre)
+{
+    std::vector<int32_t> tmp(n);
+    run_on_ctx(static_cast<GaussObj *>(s->gauss), tmp.data(), n, centre, s->discard, 0);
+    for (size_t i = 0; i < n; i++) v[i] = (SINT16)tmp[i];        // the reference stores each sample into SINT16
+    return SC_FUNC_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+// sampling.c:425-469.  Unsupported combinations return NULL like the reference's configure_sampler.
+utils_sampling_t *create_sampler(random_sampling_e type, sample_precision_e precision, sample_blinding_e blinding,
+                                 SINT32 dimension, sample_bootstrap_e bootstrapped, prng_ctx_t *prng_ctx,
+                                 FLOAT tail, FLOAT sigma)
+{
+    if (!prng_ctx || !prng_ctx->inited) return NULL;
+    if (bootstrapped != SAMPLING_DISABLE_BOOTSTRAP) return NULL;      // MW bootstrap: SURVEY.md 8f rank 4
+    scgpu_gauss_plan *plan = nullptr;
+    if (scgpu_gauss_plan_create(&plan, (int)type, (int)precision, (int)blinding, tail, sigma, prng_ctx->device) != SCGPU_OK)
+        return NULL;
+    utils_sampling_t *s = static_cast<utils_sampling_t *>(calloc(1, sizeof(utils_sampling_t)));
+    if (!s) { scgpu_gauss_plan_destroy(plan); return NULL; }
+    GaussObj *o = new GaussObj{plan, prng_ctx};
+    s->create = gauss_create_stub;
+    s->destroy = gauss_destroy;
+    s->get_prng = gauss_get_prng;
+    s->sample = gauss_sample;
+    s->vector_16 = vector_16;
+    s->vector_32 = vector_32;
+    s->precision = precision;
+    s->dimension = dimension;
+    s->bootstrapped = bootstrapped;
+    s->tail = tail;
+    s->sigma = sigma;
+    s->gauss = o;
+    s->prng_ctx = prng_ctx;
+    s->discard = 0;
+    s->bootstrap = NULL;
+    return s;
+}
+
+SINT32 destroy_sampler(utils_sampling_t **sampler)
+{
+    if (!sampler || !*sampler) return SC_FUNC_FAILURE;
+    utils_sampling_t *s = *sampler;
+    if (s->destroy(&s->gauss) == SC_FUNC_FAILURE) return SC_FUNC_FAILURE;
+    free(s);
+    *sampler = NULL;
+    return SC_FUNC_SUCCESS;
+}
+
+SINT32 set_discard(utils_sampling_t *sampler, UINT32 discard) { sampler->discard = discard; return SC_FUNC_SUCCESS; }
+SINT32 get_sample(utils_sampling_t *sampler) { return sampler->sample(sampler->gauss); }
+SINT32 get_bootstrap_sample(utils_sampling_t *sampler, FLOAT sigma, FLOAT centre)
+{
+    (void)sampler; (void)sigma; (void)centre;
+    return 0;                                  // sampling.c:519-538: 0 unless a bootstrap sampler was requested
+}
+SINT32 get_vector_16(utils_sampling_t *sampler, SINT16 *v, size_t n, FLOAT centre)
+{
+    return sampler->vector_16(sampler, v, n, (SINT32)centre);
+}
+SINT32 get_vector_32(utils_sampling_t *sampler, SINT32 *v, size_t n, FLOAT centre)
+{
+    return sampler->vector_32(sampler, v, n, (SINT32)centre);
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// scgpu_internal.h -- shared between the translation units of libscgpu.so (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+
+#include "reduce.cuh"
+
+namespace scgpu {
+
+void set_error(const char *fmt, ...);
+void count_launch();
+
+#define SCGPU_CUDA_CHECK(expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ::scgpu::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SCGPU_ERR_CUDA;                                                          \
+        }                                                                                   \
+    } while (0)
+
+// Device-resident state of one (q, n, variant) parameter set.
+struct NttPlanDev {
+    int n, logn, variant, tw_bits, device;
+    RedConst rc;
+    int32_t *w;          // caller's w[n], sign-extended to 32 bits
+    int32_t *r;          // caller's r[n]
+    // fused-kernel constants (Montgomery domain, R = 2^32)
+    MontTw *zeta_fwd;    // [n]: index 2^s + b  -> psi^brv(.) * R
+    MontTw *zeta_inv;    // [n]: inverses, last-stage entries pre-multiplied by n^-1
+    MontTw ninv;         // n^-1 * R   (sum branch of the last inverse stage)
+    MontTw rsq;          // R^2 mod q  (brings one pointwise operand into Montgomery form)
+    int32_t qinv;        // q^-1 mod 2^32
+    int32_t fold;        // reserved
+    int sm_count;
+};
+
+struct ExactArgs {
+    int32_t *out;
+    const void *a;
+    const void *b;
+    size_t b_stride;
+    size_t count;
+    const int32_t *w;
+    const int32_t *r;
+    int32_t *rcodes;
+    RedConst rc;
+    int op;
+    int tw_bits;
+    int32_t scalar;
+};
+
+int launch_exact(const NttPlanDev &plan, const ExactArgs &args, cudaStream_t stream);
+int launch_polymul(const NttPlanDev &plan, int32_t *out, const int32_t *a, const int32_t *b,
+                   size_t b_stride, size_t count, cudaStream_t stream);
+int launch_mul_key(const NttPlanDev &plan, int32_t *out, const int32_t *t, const void *key,
+                   int key_bits, size_t key_stride, size_t count, cudaStream_t stream);
+int launch_matvec(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s,
+                  int k, int l, size_t count, cudaStream_t stream);
+int build_fast_tables(NttPlanDev &plan, const int32_t *w_host);
+void free_fast_tables(NttPlanDev &plan);
+
+}  // namespace scgpu

@@ -1,0 +1,611 @@
+// shim.cu -- the C-ABI of libscgpu.so: plans, batch entry points on device and host buffers,
+// and the reference's drop-in NTT surface (utils_arith_ntt / init_reduce / barrett_init /
+// roots_of_unity_s16/s32).  Host code only; every arithmetic result comes from a kernel in
+// ntt_exact.cu / ntt_fast.cu.  There is no CPU evaluation path here.
+#include "scgpu_internal.h"
+#include "../../include/scgpu.h"
+#include "../../include/scgpu_dropin.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+namespace scgpu {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+}  // namespace scgpu
+
+using namespace scgpu;
+
+struct scgpu_ntt_plan {
+    NttPlanDev dev;
+    // staging for the *_host entry points (lazily created, guarded by mu)
+    std::mutex mu;
+    static constexpr int kStreams = 3;
+    cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+    int32_t *d_a[kStreams] = {nullptr, nullptr, nullptr};
+    int32_t *d_b[kStreams] = {nullptr, nullptr, nullptr};
+    int32_t *d_o[kStreams] = {nullptr, nullptr, nullptr};
+    int32_t *d_rc[kStreams] = {nullptr, nullptr, nullptr};
+    void *d_shared = nullptr;      // a shared (b_stride == 0) second operand
+    size_t shared_cap = 0;
+    size_t chunk_rows = 0;
+};
+
+extern "C" const char *scgpu_last_error(void) { return g_err; }
+extern "C" uint64_t scgpu_launch_count(void) { return g_launches.load(); }
+extern "C" int scgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static int ilog2_exact(size_t n)
+{
+    int l = 0;
+    while (((size_t)1 << l) < n) l++;
+    return (((size_t)1 << l) == n) ? l : -1;
+}
+
+extern "C" int scgpu_ntt_plan_create(scgpu_ntt_plan_t **out, const void *params, int variant,
+                                     const void *w, const void *r, int tw_bits, int device)
+{
+    if (!out || !params) { set_error("plan_create: null argument"); return SCGPU_ERR_ARG; }
+    const ntt_params_t *p = static_cast<const ntt_params_t *>(params);
+    if (variant < SCGPU_NTT_REFERENCE || variant > SCGPU_NTT_SOLINAS_8380417) {
+        set_error("plan_create: reduction variant %d is not live in the reference (arith.c:360-396)", variant);
+        return SCGPU_ERR_UNSUPPORTED;
+    }
+    if (tw_bits != 16 && tw_bits != 32 && !(tw_bits == 0 && !w)) { set_error("plan_create: tw_bits must be 16 or 32"); return SCGPU_ERR_ARG; }
+    const int32_t q = p->u.ntt32.q;
+    if (q < 2) { set_error("plan_create: q=%d", q); return SCGPU_ERR_ARG; }
+    int ndev = 0;
+    SCGPU_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("plan_create: device %d of %d", device, ndev); return SCGPU_ERR_ARG; }
+    SCGPU_CUDA_CHECK(cudaSetDevice(device));
+
+    scgpu_ntt_plan *plan = new scgpu_ntt_plan();
+    NttPlanDev &d = plan->dev;
+    memset(&d, 0, sizeof(d));
+    d.n = (int)p->n;
+    d.logn = ilog2_exact(p->n);
+    d.variant = variant;
+    d.tw_bits = tw_bits;
+    d.device = device;
+    d.rc.q = q;
+    d.rc.m = p->u.ntt32.m;
+    d.rc.k = p->u.ntt32.k;
+    d.rc.inv_q_dbl = p->inv_q_dbl;
+    d.rc.qs_inv = (float)p->inv_q_dbl;
+    d.rc.recip64 = ~0ull / (uint64_t)q;
+    d.rc.recip32 = 0xFFFFFFFFu / (uint32_t)q;
+    cudaDeviceProp prop;
+    SCGPU_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    d.sm_count = prop.multiProcessorCount;
+    if (w) {
+        if (d.logn < 8 || d.logn > 10) {
+            set_error("plan_create: transforms support n = 256, 512, 1024 (got %zu)", p->n);
+            delete plan;
+            return SCGPU_ERR_UNSUPPORTED;
+        }
+        std::vector<int32_t> wh(d.n), rh(d.n);
+        for (int i = 0; i < d.n; i++) {
+            wh[i] = tw_bits == 16 ? (int32_t)static_cast<const int16_t *>(w)[i] : static_cast<const int32_t *>(w)[i];
+            if (r) rh[i] = tw_bits == 16 ? (int32_t)static_cast<const int16_t *>(r)[i] : static_cast<const int32_t *>(r)[i];
+        }
+        SCGPU_CUDA_CHECK(cudaMalloc(&d.w, sizeof(int32_t) * d.n));
+        SCGPU_CUDA_CHECK(cudaMemcpy(d.w, wh.data(), sizeof(int32_t) * d.n, cudaMemcpyHostToDevice));
+        if (r) {
+            SCGPU_CUDA_CHECK(cudaMalloc(&d.r, sizeof(int32_t) * d.n));
+            SCGPU_CUDA_CHECK(cudaMemcpy(d.r, rh.data(), sizeof(int32_t) * d.n, cudaMemcpyHostToDevice));
+        }
+        int rcode = build_fast_tables(d, wh.data());
+        if (rcode != SCGPU_OK) { delete plan; return rcode; }
+    }
+    *out = plan;
+    return SCGPU_OK;
+}
+
+extern "C" void scgpu_ntt_plan_destroy(scgpu_ntt_plan_t *plan)
+{
+    if (!plan) return;
+    cudaSetDevice(plan->dev.device);
+    for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) {
+        if (plan->streams[i]) { cudaStreamSynchronize(plan->streams[i]); cudaStreamDestroy(plan->streams[i]); }
+        cudaFree(plan->d_a[i]); cudaFree(plan->d_b[i]); cudaFree(plan->d_o[i]); cudaFree(plan->d_rc[i]);
+    }
+    cudaFree(plan->d_shared);
+    cudaFree(plan->dev.w);
+    cudaFree(plan->dev.r);
+    free_fast_tables(plan->dev);
+    delete plan;
+}
+
+static bool op_needs_w(int op)
+{
+    return op <= SCGPU_OP_FFT_LARGE || op == SCGPU_OP_POLYMUL || op == SCGPU_OP_TRIPLE16;
+}
+static bool op_needs_r(int op)
+{
+    return op == SCGPU_OP_INV || op == SCGPU_OP_INV_LARGE || op == SCGPU_OP_POLYMUL || op == SCGPU_OP_TRIPLE16;
+}
+static bool op_needs_b(int op)
+{
+    return op == SCGPU_OP_PW || op == SCGPU_OP_PW16 || op == SCGPU_OP_POLYMUL || op == SCGPU_OP_TRIPLE16 ||
+           op == SCGPU_OP_MULN || op == SCGPU_OP_DIV || op == SCGPU_OP_PWR || op == SCGPU_OP_SPARSE32 ||
+           op == SCGPU_OP_SPARSE16;
+}
+static size_t b_elem_size(int op) { return (op == SCGPU_OP_PW16 || op == SCGPU_OP_TRIPLE16) ? 2 : 4; }
+static size_t a_elem_size(int op) { return op == SCGPU_OP_SPARSE16 ? 2 : 4; }
+
+static int check_batch_args(const scgpu_ntt_plan_t *plan, int op, const void *out, const void *a, const void *b)
+{
+    if (!plan || !out || !a) { set_error("ntt_batch: null argument"); return SCGPU_ERR_ARG; }
+    if (op < 0 || op > SCGPU_OP_SPARSE16) { set_error("ntt_batch: unknown op %d", op); return SCGPU_ERR_ARG; }
+    if (op_needs_w(op) && !plan->dev.w) { set_error("ntt_batch: op %d needs the plan's w table", op); return SCGPU_ERR_ARG; }
+    if (op_needs_r(op) && !plan->dev.r) { set_error("ntt_batch: op %d needs the plan's r table", op); return SCGPU_ERR_ARG; }
+    if (op_needs_b(op) && !b) { set_error("ntt_batch: op %d needs a second operand", op); return SCGPU_ERR_ARG; }
+    if (op == SCGPU_OP_TRIPLE16 && plan->dev.tw_bits != 16) { set_error("TRIPLE16 needs 16-bit tables"); return SCGPU_ERR_ARG; }
+    return SCGPU_OK;
+}
+
+extern "C" int scgpu_ntt_batch(const scgpu_ntt_plan_t *plan, int op, int32_t *out, const void *a,
+                               const void *b, size_t b_stride, size_t count, int32_t scalar,
+                               int32_t *rc, void *stream)
+{
+    int e = check_batch_args(plan, op, out, a, b);
+    if (e != SCGPU_OK) return e;
+    SCGPU_CUDA_CHECK(cudaSetDevice(plan->dev.device));
+    ExactArgs g;
+    g.out = out; g.a = a; g.b = op_needs_b(op) ? b : nullptr; g.b_stride = b_stride; g.count = count;
+    g.w = plan->dev.w; g.r = plan->dev.r; g.rcodes = rc; g.rc = plan->dev.rc;
+    g.op = op; g.tw_bits = plan->dev.tw_bits; g.scalar = scalar;
+    return launch_exact(plan->dev, g, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int scgpu_polymul_batch(const scgpu_ntt_plan_t *plan, int32_t *out, const int32_t *a,
+                                   const int32_t *b, size_t b_stride, size_t count, void *stream)
+{
+    if (!plan || !out || !a || !b) { set_error("polymul_batch: null argument"); return SCGPU_ERR_ARG; }
+    SCGPU_CUDA_CHECK(cudaSetDevice(plan->dev.device));
+    return launch_polymul(plan->dev, out, a, b, b_stride, count, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int scgpu_ntt_mul_key_batch(const scgpu_ntt_plan_t *plan, int32_t *out, const int32_t *t,
+                                       const void *key, int key_bits, size_t key_stride, size_t count,
+                                       void *stream)
+{
+    if (!plan || !out || !t || !key) { set_error("ntt_mul_key_batch: null argument"); return SCGPU_ERR_ARG; }
+    SCGPU_CUDA_CHECK(cudaSetDevice(plan->dev.device));
+    return launch_mul_key(plan->dev, out, t, key, key_bits, key_stride, count, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int scgpu_matvec_batch(const scgpu_ntt_plan_t *plan, int32_t *out, const int32_t *A,
+                                  const int32_t *s, int k, int l, size_t count, void *stream)
+{
+    if (!plan || !out || !A || !s) { set_error("matvec_batch: null argument"); return SCGPU_ERR_ARG; }
+    SCGPU_CUDA_CHECK(cudaSetDevice(plan->dev.device));
+    return launch_matvec(plan->dev, out, A, s, k, l, count, static_cast<cudaStream_t>(stream));
+}
+
+// ---- host-buffer entry points: chunked three-stream pipeline -----------------------------------------
+
+static int ensure_staging(scgpu_ntt_plan *plan, size_t row_bytes_a, size_t row_bytes_b, size_t row_bytes_o, size_t count)
+{
+    // ~16 MiB of the widest operand per chunk keeps H2D, kernel and D2H of neighbouring chunks overlapped
+    size_t widest = row_bytes_a > row_bytes_o ? row_bytes_a : row_bytes_o;
+    if (row_bytes_b > widest) widest = row_bytes_b;
+    size_t rows = (16u << 20) / widest;
+    if (rows < 1) rows = 1;
+    if (rows > count) rows = count;
+    if (plan->chunk_rows >= rows && plan->streams[0]) return SCGPU_OK;
+    for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) {
+        if (!plan->streams[i]) SCGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->streams[i], cudaStreamNonBlocking));
+        cudaFree(plan->d_a[i]); cudaFree(plan->d_b[i]); cudaFree(plan->d_o[i]); cudaFree(plan->d_rc[i]);
+        // sized for the largest row any op uses: n SINT32
+        size_t rb = (size_t)plan->dev.n * 4;
+        if (rb < widest) rb = widest;
+        SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_a[i], rows * rb));
+        SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_b[i], rows * rb));
+        SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_o[i], rows * rb));
+        SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_rc[i], rows * sizeof(int32_t)));
+    }
+    plan->chunk_rows = rows;
+    return SCGPU_OK;
+}
+
+static int ensure_shared(scgpu_ntt_plan *plan, const void *host, size_t bytes)
+{
+    if (plan->shared_cap < bytes) {
+        cudaFree(plan->d_shared);
+        plan->d_shared = nullptr;
+        SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_shared, bytes));
+        plan->shared_cap = bytes;
+    }
+    SCGPU_CUDA_CHECK(cudaMemcpy(plan->d_shared, host, bytes, cudaMemcpyHostToDevice));
+    return SCGPU_OK;
+}
+
+// kind: 0 exact op, 1 fused polymul, 2 fused key product (key_bits in `op`)
+static int run_host_pipeline(scgpu_ntt_plan *plan, int kind, int op, int32_t *out, const void *a, const void *b,
+                             size_t b_stride, size_t count, int32_t scalar, int32_t *rc)
+{
+    if (count == 0) return SCGPU_OK;
+    std::lock_guard<std::mutex> lock(plan->mu);
+    SCGPU_CUDA_CHECK(cudaSetDevice(plan->dev.device));
+    const size_t n = (size_t)plan->dev.n;
+    const size_t ra = n * (kind == 0 ? a_elem_size(op) : 4);
+    const size_t belem = kind == 0 ? b_elem_size(op) : (kind == 2 ? (size_t)op / 8 : 4);
+    const bool has_b = kind != 0 || op_needs_b(op);
+    const size_t rb = has_b ? (b_stride ? b_stride : n) * belem : 0;
+    int e = ensure_staging(plan, ra, b_stride ? rb : 0, n * 4, count);
+    if (e != SCGPU_OK) return e;
+    const void *d_bshared = nullptr;
+    if (has_b && b_stride == 0) {
+        size_t bytes = (kind == 0 && (op == SCGPU_OP_SPARSE32 || op == SCGPU_OP_SPARSE16)) ? (size_t)(scalar & 0xFFFF) * 4 : n * belem;
+        e = ensure_shared(plan, b, bytes);
+        if (e != SCGPU_OK) return e;
+        d_bshared = plan->d_shared;
+    }
+    const size_t rows = plan->chunk_rows;
+    int status = SCGPU_OK;
+    for (size_t off = 0, ci = 0; off < count; off += rows, ci++) {
+        const int s = (int)(ci % scgpu_ntt_plan::kStreams);
+        cudaStream_t st = plan->streams[s];
+        const size_t cnt = (count - off < rows) ? count - off : rows;
+        SCGPU_CUDA_CHECK(cudaMemcpyAsync(plan->d_a[s], static_cast<const char *>(a) + off * ra, cnt * ra, cudaMemcpyHostToDevice, st));
+        const void *db = d_bshared;
+        if (has_b && b_stride) {
+            SCGPU_CUDA_CHECK(cudaMemcpyAsync(plan->d_b[s], static_cast<const char *>(b) + off * rb, cnt * rb, cudaMemcpyHostToDevice, st));
+            db = plan->d_b[s];
+        }
+        if (kind == 0) {
+            ExactArgs g;
+            g.out = plan->d_o[s]; g.a = plan->d_a[s]; g.b = has_b ? db : nullptr; g.b_stride = b_stride; g.count = cnt;
+            g.w = plan->dev.w; g.r = plan->dev.r; g.rcodes = rc ? plan->d_rc[s] : nullptr; g.rc = plan->dev.rc;
+            g.op = op; g.tw_bits = plan->dev.tw_bits; g.scalar = scalar;
+            status = launch_exact(plan->dev, g, st);
+        } else if (kind == 1) {
+            status = launch_polymul(plan->dev, plan->d_o[s], plan->d_a[s], static_cast<const int32_t *>(db), b_stride, cnt, st);
+        } else {
+            status = launch_mul_key(plan->dev, plan->d_o[s], plan->d_a[s], db, op, b_stride, cnt, st);
+        }
+        if (status != SCGPU_OK) break;
+        SCGPU_CUDA_CHECK(cudaMemcpyAsync(out + off * n, plan->d_o[s], cnt * n * 4, cudaMemcpyDeviceToHost, st));
+        if (rc && kind == 0) SCGPU_CUDA_CHECK(cudaMemcpyAsync(rc + off, plan->d_rc[s], cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) SCGPU_CUDA_CHECK(cudaStreamSynchronize(plan->streams[i]));
+    return status;
+}
+
+extern "C" int scgpu_ntt_batch_host(const scgpu_ntt_plan_t *plan, int op, int32_t *out, const void *a,
+                                    const void *b, size_t b_stride, size_t count, int32_t scalar, int32_t *rc)
+{
+    int e = check_batch_args(plan, op, out, a, b);
+    if (e != SCGPU_OK) return e;
+    return run_host_pipeline(const_cast<scgpu_ntt_plan *>(plan), 0, op, out, a, b, b_stride, count, scalar, rc);
+}
+
+extern "C" int scgpu_polymul_batch_host(const scgpu_ntt_plan_t *plan, int32_t *out, const int32_t *a,
+                                        const int32_t *b, size_t b_stride, size_t count)
+{
+    if (!plan || !out || !a || !b) { set_error("polymul_batch_host: null argument"); return SCGPU_ERR_ARG; }
+    return run_host_pipeline(const_cast<scgpu_ntt_plan *>(plan), 1, 0, out, a, b, b_stride, count, 0, nullptr);
+}
+
+// =======================================================================================================
+// Drop-in surface: utils_arith_ntt() and friends
+// =======================================================================================================
+
+extern "C" void barrett_init(ntt_params_t *p)
+{
+    // ntt.c:142-146
+    p->u.ntt32.k = 30;
+    p->u.ntt32.m = (1 << p->u.ntt32.k) / p->u.ntt32.q;
+}
+
+extern "C" void init_reduce(ntt_params_t *p, size_t n, SINT32 q)
+{
+    // ntt.c:132-140
+    p->n = n;
+    p->u.ntt32.q = q;
+    barrett_init(p);
+    p->q_dbl = (DOUBLE)q;
+    p->inv_q_dbl = 1.0 / p->q_dbl;
+    p->inv_q_flt = 1.0 / (FLOAT)q;
+}
+
+// roots_of_unity.c:141-207.  Table generation is host-side set-up (the reference does it at build
+// time with build_tools/ntt_table_gen or once per create() under USE_RUNTIME_NTT_TABLES).
+static uint64_t mulmod_u64(uint64_t a, uint64_t b, uint64_t q) { return (uint64_t)(((unsigned __int128)a * b) % q); }
+static uint64_t powmod_u64(uint64_t b, uint64_t e, uint64_t q)
+{
+    uint64_t r = 1;
+    b %= q;
+    while (e) { if (e & 1) r = mulmod_u64(r, b, q); b = mulmod_u64(b, b, q); e >>= 1; }
+    return r;
+}
+template <typename T>
+static SINT32 roots_of_unity_impl(T *fwd, T *inv, size_t n, uint64_t p, uint64_t prim)
+{
+    if (prim == 0) {
+        for (uint64_t m = 2; m + 1 < p; m++)
+            if (powmod_u64(m, n, p) == p - 1) { prim = m; break; }       // smallest m with m^n == -1
+    }
+    if (prim == 0) return SC_FUNC_FAILURE;
+    // inv[0] = |x| where n x + p y = 1; for the parameter sets of the reference this is -(n^-1) mod p
+    uint64_t ninv = powmod_u64(n % p, p - 2, p);
+    uint64_t acc = 1, racc = (p - ninv) % p;
+    for (size_t i = 0; i < n; i++) {
+        fwd[i] = (T)acc;
+        inv[i] = (T)racc;
+        acc = mulmod_u64(acc, prim, p);
+        racc = mulmod_u64(racc, prim, p);
+    }
+    return SC_FUNC_SUCCESS;
+}
+extern "C" SINT32 roots_of_unity_s32(SINT32 *fwd, SINT32 *inv, size_t n, sc_ulimb_t p, sc_ulimb_t prim, SINT32 ternary)
+{
+    (void)ternary;
+    return roots_of_unity_impl<SINT32>(fwd, inv, n, p, prim);
+}
+extern "C" SINT32 roots_of_unity_s16(SINT16 *fwd, SINT16 *inv, size_t n, sc_ulimb_t p, sc_ulimb_t prim, SINT32 ternary)
+{
+    (void)ternary;
+    return roots_of_unity_impl<SINT16>(fwd, inv, n, p, prim);
+}
+
+namespace {
+
+[[noreturn]] void dropin_fatal(const char *what)
+{
+    // The reference has no error channel on these void functions: log and abort.
+    fprintf(stderr, "libscgpu: %s: %s\n", what, scgpu_last_error());
+    abort();
+}
+
+uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull)
+{
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+struct PlanCache {
+    std::mutex mu;
+    std::unordered_map<uint64_t, scgpu_ntt_plan *> map;
+    scgpu_ntt_plan *get(int variant, const ntt_params_t *p, size_t n, const void *w, const void *r, int tw_bits)
+    {
+        // Keyed by the parameter values and the table CONTENTS (tables may be malloc'ed at run time and
+        // their address reused, bliss_b.c:365-374).
+        struct { int variant, tw_bits; int32_t q, m, k; uint64_t n; double inv; } key = {
+            variant, tw_bits, p->u.ntt32.q, p->u.ntt32.m, p->u.ntt32.k, (uint64_t)n, p->inv_q_dbl };
+        uint64_t h = fnv1a(&key, sizeof(key));
+        const size_t tb = (size_t)(tw_bits / 8) * n;
+        if (w) h = fnv1a(w, tb, h);
+        if (r) h = fnv1a(r, tb, h ^ 0x9E3779B97F4A7C15ull);
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = map.find(h);
+        if (it != map.end()) return it->second;
+        ntt_params_t q = *p;
+        q.n = n;
+        scgpu_ntt_plan *plan = nullptr;
+        int dev = 0;
+        const char *env = getenv("SCGPU_DEVICE");
+        if (env) dev = atoi(env);
+        if (scgpu_ntt_plan_create(&plan, &q, variant, w, r, w ? tw_bits : 0, dev) != SCGPU_OK) dropin_fatal("plan creation failed");
+        map[h] = plan;
+        return plan;
+    }
+};
+PlanCache g_cache;
+
+// Per-thread stream and scratch: the reference's functions are re-entrant and BLISS-B calls them from
+// worker threads (bliss_b.c:74-175).
+struct ThreadCtx {
+    cudaStream_t st = nullptr;
+    char *d[3] = {nullptr, nullptr, nullptr};
+    size_t cap[3] = {0, 0, 0};
+    int32_t *d_rc = nullptr;
+    void *ensure(int i, size_t bytes)
+    {
+        if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) dropin_fatal("stream");
+        if (!d_rc && cudaMalloc(&d_rc, sizeof(int32_t)) != cudaSuccess) dropin_fatal("cudaMalloc");
+        if (cap[i] < bytes) {
+            cudaFree(d[i]);
+            size_t want = bytes < 8192 ? 8192 : bytes;
+            if (cudaMalloc(&d[i], want) != cudaSuccess) dropin_fatal("cudaMalloc");
+            cap[i] = want;
+        }
+        return d[i];
+    }
+};
+thread_local ThreadCtx t_ctx;
+
+// One reference call = one row through the batch kernel.
+SINT32 run_one(int variant, int op, const ntt_params_t *p, size_t n, SINT32 *out, const void *a, const void *b,
+               size_t b_elems, const void *w, const void *r, int tw_bits, int32_t scalar)
+{
+    scgpu_ntt_plan *plan = g_cache.get(variant, p, n, w, r, tw_bits);
+    if (cudaSetDevice(plan->dev.device) != cudaSuccess) dropin_fatal("cudaSetDevice");
+    ThreadCtx &c = t_ctx;
+    const size_t abytes = n * a_elem_size(op), obytes = n * 4, bbytes = b_elems * b_elem_size(op);
+    void *da = c.ensure(0, abytes);
+    void *dout = c.ensure(1, obytes);
+    void *db = b ? c.ensure(2, bbytes) : nullptr;
+    bool ok = cudaMemcpyAsync(da, a, abytes, cudaMemcpyHostToDevice, c.st) == cudaSuccess;
+    if (b) ok = ok && cudaMemcpyAsync(db, b, bbytes, cudaMemcpyHostToDevice, c.st) == cudaSuccess;
+    if (!ok) dropin_fatal("H2D copy");
+    if (scgpu_ntt_batch(plan, op, static_cast<int32_t *>(dout), da, db, b_elems, 1, scalar, c.d_rc, c.st) != SCGPU_OK)
+        dropin_fatal("kernel launch");
+    int32_t rc = 0;
+    ok = cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, c.st) == cudaSuccess;
+    if (op == SCGPU_OP_INVERT || op == SCGPU_OP_DIV)
+        ok = ok && cudaMemcpyAsync(&rc, c.d_rc, sizeof(rc), cudaMemcpyDeviceToHost, c.st) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c.st) == cudaSuccess;
+    if (!ok) dropin_fatal("D2H copy");
+    return rc;
+}
+
+[[noreturn]] void not_on_hot_path(const char *member)
+{
+    fprintf(stderr, "libscgpu: utils_arith_ntt_t::%s is not GPU backed: no scheme of the reference calls the SINT16-data "
+                    "or limb-data members (SURVEY.md 3.6); use the *_32 members\n", member);
+    abort();
+}
+
+template <int V>
+struct DropIn {
+    // scalars: one-element rows
+    static SINT32 modn_32(SINT32 x, scP p) { SINT32 o; run_one(V, SCGPU_OP_MODN, p, 1, &o, &x, nullptr, 0, nullptr, nullptr, 0, 0); return o; }
+    static SINT32 muln_32(SINT32 x, SINT32 y, scP p) { SINT32 o; run_one(V, SCGPU_OP_MULN, p, 1, &o, &x, &y, 1, nullptr, nullptr, 0, 0); return o; }
+    static SINT32 sqrn_32(SINT32 x, scP p) { SINT32 o; run_one(V, SCGPU_OP_SQRN, p, 1, &o, &x, nullptr, 0, nullptr, nullptr, 0, 0); return o; }
+    static SINT32 pwr_32(SINT32 x, SINT32 e, scP p) { SINT32 o; run_one(V, SCGPU_OP_PWR, p, 1, &o, &x, &e, 1, nullptr, nullptr, 0, 0); return o; }
+    static void mul_32_sparse(SINT32 *v, size_t n, UINT16 omega, const SINT32 *t, const SINT32 *u)
+    {
+        ntt_params_t p; init_reduce(&p, n, 12289);      // the generic sparse product does not reduce (ntt.c:381-400)
+        run_one(V, SCGPU_OP_SPARSE32, &p, n, v, t, u, omega, nullptr, nullptr, 0, omega);
+    }
+    static void mul_32_sparse_16(SINT32 *v, size_t n, UINT16 omega, const SINT16 *t, const SINT32 *u)
+    {
+        ntt_params_t p; init_reduce(&p, n, 12289);
+        run_one(V, SCGPU_OP_SPARSE16, &p, n, v, t, u, omega, nullptr, nullptr, 0, omega);
+    }
+    static void mul_32_pointwise(SINT32 *v, scP p, const SINT32 *t, const SINT32 *u) { run_one(V, SCGPU_OP_PW, p, p->n, v, t, u, p->n, nullptr, nullptr, 0, 0); }
+    static void mul_32_pointwise_16(SINT32 *v, scP p, const SINT32 *t, const SINT16 *u) { run_one(V, SCGPU_OP_PW16, p, p->n, v, t, u, p->n, nullptr, nullptr, 0, 0); }
+    static void mul_32_scalar(SINT32 *v, scP p, const SINT32 *t, SINT32 c) { run_one(V, SCGPU_OP_SCALAR, p, p->n, v, t, nullptr, 0, nullptr, nullptr, 0, c); }
+    static void fft_32_32(SINT32 *v, scP p, const SINT32 *w) { run_one(V, SCGPU_OP_FFT, p, p->n, v, v, nullptr, 0, w, nullptr, 32, 0); }
+    static void fft_32_32_large(SINT32 *v, scP p, const SINT32 *w) { run_one(V, SCGPU_OP_FFT_LARGE, p, p->n, v, v, nullptr, 0, w, nullptr, 32, 0); }
+    static void fft_32_16(SINT32 *v, scP p, const SINT16 *w) { run_one(V, SCGPU_OP_FFT, p, p->n, v, v, nullptr, 0, w, nullptr, 16, 0); }
+    static void fft_32_16_large(SINT32 *v, scP p, const SINT16 *w) { run_one(V, SCGPU_OP_FFT_LARGE, p, p->n, v, v, nullptr, 0, w, nullptr, 16, 0); }
+    static SINT32 invert_32(SINT32 *v, scP p, size_t n) { return run_one(V, SCGPU_OP_INVERT, p, n, v, v, nullptr, 0, nullptr, nullptr, 0, 0); }
+    static SINT32 div_32(SINT32 *num, const SINT32 *den, scP p, size_t n) { return run_one(V, SCGPU_OP_DIV, p, n, num, num, den, n, nullptr, nullptr, 0, 0); }
+    static void flip_32(SINT32 *v, scP p) { run_one(V, SCGPU_OP_FLIP, p, p->n, v, v, nullptr, 0, nullptr, nullptr, 0, 0); }
+    static void center_32(SINT32 *v, size_t n, scP p) { run_one(V, SCGPU_OP_CENTER, p, n, v, v, nullptr, 0, nullptr, nullptr, 0, 0); }
+    static void normalize_32(SINT32 *v, size_t n, scP p) { run_one(V, SCGPU_OP_NORMALIZE, p, n, v, v, nullptr, 0, nullptr, nullptr, 0, 0); }
+    static void fwd_ntt_32_32(SINT32 *v, scP p, const SINT32 *t, const SINT32 *w) { run_one(V, SCGPU_OP_FWD, p, p->n, v, t, nullptr, 0, w, nullptr, 32, 0); }
+    static void inv_ntt_32_32(SINT32 *v, scP p, const SINT32 *t, const SINT32 *w, const SINT32 *r) { run_one(V, SCGPU_OP_INV, p, p->n, v, t, nullptr, 0, w, r, 32, 0); }
+    static void fwd_ntt_32_32_large(SINT32 *v, scP p, const SINT32 *t, const SINT32 *w) { run_one(V, SCGPU_OP_FWD_LARGE, p, p->n, v, t, nullptr, 0, w, nullptr, 32, 0); }
+    static void inv_ntt_32_32_large(SINT32 *v, scP p, const SINT32 *t, const SINT32 *w, const SINT32 *r) { run_one(V, SCGPU_OP_INV_LARGE, p, p->n, v, t, nullptr, 0, w, r, 32, 0); }
+    static void fwd_ntt_32_16(SINT32 *v, scP p, const SINT32 *t, const SINT16 *w) { run_one(V, SCGPU_OP_FWD, p, p->n, v, t, nullptr, 0, w, nullptr, 16, 0); }
+    static void inv_ntt_32_16(SINT32 *v, scP p, const SINT32 *t, const SINT16 *w, const SINT16 *r) { run_one(V, SCGPU_OP_INV, p, p->n, v, t, nullptr, 0, w, r, 16, 0); }
+    static void fwd_ntt_32_16_large(SINT32 *v, scP p, const SINT32 *t, const SINT16 *w) { run_one(V, SCGPU_OP_FWD_LARGE, p, p->n, v, t, nullptr, 0, w, nullptr, 16, 0); }
+    static void inv_ntt_32_16_large(SINT32 *v, scP p, const SINT32 *t, const SINT16 *w, const SINT16 *r) { run_one(V, SCGPU_OP_INV_LARGE, p, p->n, v, t, nullptr, 0, w, r, 16, 0); }
+};
+
+// stubs for the 51 members no scheme calls
+#define STUB(ret, name, args) static ret stub_##name args { not_on_hot_path(#name); }
+STUB(SINT16, modn_16, (SINT16, scP)) STUB(SINT16, muln_16, (SINT16, SINT16, scP)) STUB(SINT16, sqrn_16, (SINT16, scP))
+STUB(void, mul_16_sparse, (SINT16 *, size_t, UINT16, const SINT16 *, const SINT16 *))
+STUB(void, mul_16_pointwise, (SINT16 *, scP, const SINT16 *, const SINT16 *))
+STUB(void, mul_16_scalar, (SINT16 *, scP, const SINT16 *, SINT16))
+STUB(void, fft_16, (SINT16 *, scP, const SINT16 *))
+STUB(SINT32, pwr_16, (SINT16, SINT16, scP)) STUB(SINT32, invert_16, (SINT16 *, scP, size_t))
+STUB(SINT32, div_16, (SINT16 *, const SINT16 *, scP, size_t))
+STUB(void, flip_16, (SINT16 *, scP)) STUB(void, center_16, (SINT16 *, size_t, scP))
+STUB(void, fwd_ntt_16, (SINT16 *, scP, const SINT16 *, const SINT16 *))
+STUB(void, inv_ntt_16, (SINT16 *, scP, const SINT16 *, const SINT16 *, const SINT16 *))
+STUB(sc_slimb_t, modn_limb, (sc_slimb_t, scP)) STUB(sc_slimb_t, muln_limb, (sc_slimb_t, sc_slimb_t, scP))
+STUB(void, mul_limb_sparse, (sc_slimb_t *, size_t, UINT16, const SINT32 *, const sc_slimb_t *))
+STUB(void, mul_limb_sparse_16, (sc_slimb_t *, size_t, UINT16, const SINT16 *, const sc_slimb_t *))
+STUB(void, mul_limb_pointwise, (sc_slimb_t *, scP, const sc_slimb_t *, const sc_slimb_t *))
+STUB(void, mul_limb_pointwise_32, (sc_slimb_t *, scP, const sc_slimb_t *, const SINT32 *))
+STUB(void, mul_limb_pointwise_16, (sc_slimb_t *, scP, const sc_slimb_t *, const SINT16 *))
+STUB(void, mul_limb_scalar, (sc_slimb_t *, scP, const sc_slimb_t *, sc_slimb_t))
+STUB(void, fft_limb, (sc_slimb_t *, scP, const sc_slimb_t *))
+STUB(void, fft_limb_32, (sc_slimb_t *, scP, const SINT32 *))
+STUB(void, fft_limb_16, (sc_slimb_t *, scP, const SINT16 *))
+STUB(SINT32, invert_limb, (sc_slimb_t *, scP, size_t))
+STUB(SINT32, div_limb, (sc_slimb_t *, const sc_slimb_t *, scP, size_t))
+STUB(void, flip_limb, (sc_slimb_t *, scP)) STUB(void, center_limb, (sc_slimb_t *, size_t, scP))
+STUB(void, fwd_ntt_limb, (sc_slimb_t *, scP, const sc_slimb_t *, const sc_slimb_t *))
+STUB(void, inv_ntt_limb, (sc_slimb_t *, scP, const sc_slimb_t *, const sc_slimb_t *, const sc_slimb_t *))
+STUB(void, fwd_ntt_limb_32, (sc_slimb_t *, scP, const sc_slimb_t *, const SINT32 *))
+STUB(void, inv_ntt_limb_32, (sc_slimb_t *, scP, const sc_slimb_t *, const SINT32 *, const SINT32 *))
+STUB(void, fwd_ntt_limb_16, (sc_slimb_t *, scP, const sc_slimb_t *, const SINT16 *))
+STUB(void, inv_ntt_limb_16, (sc_slimb_t *, scP, const sc_slimb_t *, const SINT16 *, const SINT16 *))
+#undef STUB
+
+template <int V>
+utils_arith_ntt_t make_table()
+{
+    utils_arith_ntt_t t;
+    t.modn_16 = stub_modn_16; t.muln_16 = stub_muln_16; t.sqrn_16 = stub_sqrn_16;
+    t.mul_16_sparse = stub_mul_16_sparse; t.mul_16_pointwise = stub_mul_16_pointwise; t.mul_16_scalar = stub_mul_16_scalar;
+    t.fft_16 = stub_fft_16; t.large_fft_16 = stub_fft_16;
+    t.pwr_16 = stub_pwr_16; t.invert_16 = stub_invert_16; t.div_16 = stub_div_16; t.flip_16 = stub_flip_16;
+    t.center_16 = stub_center_16; t.normalize_16 = stub_center_16;
+    t.fwd_ntt_16 = stub_fwd_ntt_16; t.inv_ntt_16 = stub_inv_ntt_16; t.fwd_ntt_16_large = stub_fwd_ntt_16; t.inv_ntt_16_large = stub_inv_ntt_16;
+
+    using D = DropIn<V>;
+    t.modn_32 = D::modn_32; t.muln_32 = D::muln_32; t.sqrn_32 = D::sqrn_32;
+    t.mul_32_sparse = D::mul_32_sparse; t.mul_32_sparse_16 = D::mul_32_sparse_16;
+    t.mul_32_pointwise = D::mul_32_pointwise; t.mul_32_pointwise_16 = D::mul_32_pointwise_16; t.mul_32_scalar = D::mul_32_scalar;
+    t.fft_32_32 = D::fft_32_32; t.fft_32_32_large = D::fft_32_32_large; t.fft_32_16 = D::fft_32_16; t.fft_32_16_large = D::fft_32_16_large;
+    t.pwr_32 = D::pwr_32; t.invert_32 = D::invert_32; t.div_32 = D::div_32; t.flip_32 = D::flip_32;
+    t.center_32 = D::center_32; t.normalize_32 = D::normalize_32;
+    t.fwd_ntt_32_32 = D::fwd_ntt_32_32; t.inv_ntt_32_32 = D::inv_ntt_32_32;
+    t.fwd_ntt_32_32_large = D::fwd_ntt_32_32_large; t.inv_ntt_32_32_large = D::inv_ntt_32_32_large;
+    t.fwd_ntt_32_16 = D::fwd_ntt_32_16; t.inv_ntt_32_16 = D::inv_ntt_32_16;
+    t.fwd_ntt_32_16_large = D::fwd_ntt_32_16_large; t.inv_ntt_32_16_large = D::inv_ntt_32_16_large;
+
+    t.modn_limb = stub_modn_limb; t.muln_limb = stub_muln_limb; t.sqrn_limb = stub_modn_limb;
+    t.mul_limb_sparse = stub_mul_limb_sparse; t.mul_limb_sparse_16 = stub_mul_limb_sparse_16;
+    t.mul_limb_pointwise = stub_mul_limb_pointwise; t.mul_limb_pointwise_32 = stub_mul_limb_pointwise_32;
+    t.mul_limb_pointwise_16 = stub_mul_limb_pointwise_16; t.mul_limb_scalar = stub_mul_limb_scalar;
+    t.fft_limb = stub_fft_limb; t.fft_limb_large = stub_fft_limb; t.fft_limb_32 = stub_fft_limb_32; t.fft_limb_32_large = stub_fft_limb_32;
+    t.fft_limb_16 = stub_fft_limb_16; t.fft_limb_16_large = stub_fft_limb_16;
+    t.pwr_limb = stub_muln_limb; t.invert_limb = stub_invert_limb; t.div_limb = stub_div_limb; t.flip_limb = stub_flip_limb;
+    t.center_limb = stub_center_limb; t.normalize_limb = stub_center_limb;
+    t.fwd_ntt_limb = stub_fwd_ntt_limb; t.inv_ntt_limb = stub_inv_ntt_limb;
+    t.fwd_ntt_limb_large = stub_fwd_ntt_limb; t.inv_ntt_limb_large = stub_inv_ntt_limb;
+    t.fwd_ntt_limb_32 = stub_fwd_ntt_limb_32; t.inv_ntt_limb_32 = stub_inv_ntt_limb_32;
+    t.fwd_ntt_limb_32_large = stub_fwd_ntt_limb_32; t.inv_ntt_limb_32_large = stub_inv_ntt_limb_32;
+    t.fwd_ntt_limb_16 = stub_fwd_ntt_limb_16; t.inv_ntt_limb_16 = stub_inv_ntt_limb_16;
+    t.fwd_ntt_limb_16_large = stub_fwd_ntt_limb_16; t.inv_ntt_limb_16_large = stub_inv_ntt_limb_16;
+    return t;
+}
+
+const utils_arith_ntt_t g_tab_reference = make_table<V_REFERENCE>();
+const utils_arith_ntt_t g_tab_barrett = make_table<V_BARRETT>();
+const utils_arith_ntt_t g_tab_fp = make_table<V_FP>();
+const utils_arith_ntt_t g_tab_avx = make_table<V_AVX>();
+const utils_arith_ntt_t g_tab_7681 = make_table<V_SOL7681>();
+const utils_arith_ntt_t g_tab_8380417 = make_table<V_SOL8380417>();
+
+}  // namespace
+
+extern "C" {
+const utils_arith_ntt_t *ntt_table = nullptr;      // ntt.c:31
+
+// arith.c:360-396: unknown types select the reference table
+const utils_arith_ntt_t *utils_arith_ntt(safecrypto_ntt_e type)
+{
+    switch (type) {
+    case SC_NTT_BARRETT:         ntt_table = &g_tab_barrett; break;
+    case SC_NTT_FLOATING_POINT:  ntt_table = &g_tab_fp; break;
+    case SC_NTT_AVX:             ntt_table = &g_tab_avx; break;
+    case SC_NTT_SOLINAS_7681:    ntt_table = &g_tab_7681; break;
+    case SC_NTT_SOLINAS_8380417: ntt_table = &g_tab_8380417; break;
+    default:                     ntt_table = &g_tab_reference; break;
+    }
+    return ntt_table;
+}
+}

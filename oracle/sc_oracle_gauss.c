@@ -344,8 +344,9 @@ int orc_gauss_streams(int sampler, int precision, int blinding, int prng_type, f
         for (size_t c = 0; c < calls_per_stream; c++) {
             int32_t *v = out + (st * calls_per_stream + c) * n;
             if (sampler != ORC_SAMPLER_CDF) {
-                /* ref_driver.c calls sample() directly for KY / Bernoulli */
-                for (size_t i = 0; i < n; i++) v[i] = draw(&s) + centre;
+                /* ref_driver.c calls sample() directly for KY / Bernoulli (identical when discard == 0);
+                 * here they go through sample_vector_32 as a CONSTRAINED_SYSTEM build would */
+                vec_normal(&s, v, n, centre);
             } else if (blinding == ORC_SHUFFLE_SAMPLES) vec_shuffle(&s, v, n, centre);
             else if (blinding == ORC_BLINDING_SAMPLES)  vec_blinding(&s, v, n, centre);
             else                                         vec_normal(&s, v, n, centre);

@@ -1,0 +1,177 @@
+"""Parity of the CUDA sampler / CSPRNG path with the CPU oracle: bit-exact samples for the same seeds."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import libsafecrypto_b200 as sc  # noqa: E402
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+DEV = "cuda:0"
+
+
+def seeds_for(count, length=64, salt=0):
+    return np.array([[(s * 131 + j * 7 + 3 + salt) & 0xFF for j in range(length)] for s in range(count)], dtype=np.uint8)
+
+
+def gpu_words(prng, seeds, nwords, seed_period=0):
+    d_seeds = torch.from_numpy(seeds).to(DEV)
+    out = torch.zeros((seeds.shape[0], nwords), dtype=torch.int32, device=DEV)
+    st = sc.lib().scgpu_prng_words(prng, d_seeds.data_ptr(), seeds.shape[1], seed_period, seeds.shape[0], nwords,
+                                   out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert st == 0, sc.lib().scgpu_last_error()
+    torch.cuda.synchronize()
+    return out.cpu().numpy().view(np.uint32)
+
+
+def gpu_samples(sampler, precision, blinding, prng, tail, sigma, seeds, n, calls=1, centre=0, discard=0):
+    plan = sc.GaussPlan(sampler, precision, blinding, tail, sigma)
+    d_seeds = torch.from_numpy(seeds).to(DEV)
+    out = torch.full((seeds.shape[0], n * calls), 123456, dtype=torch.int32, device=DEV)
+    plan.streams(prng, d_seeds, n, out, calls=calls, centre=centre, discard=discard)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+def test_prng_word_stream(prng):
+    seeds = seeds_for(5)
+    got = gpu_words(prng, seeds, 10000)
+    for i in range(seeds.shape[0]):
+        assert np.array_equal(got[i], O.port().prng_words(prng, seeds[i].tobytes(), 10000))
+    name = "chacha" if prng == O.PRNG_CHACHA else "aes"
+    gold = G["prng_%s_words" % name]
+    assert np.array_equal(gpu_words(prng, G["prng_seed"].reshape(1, -1), gold.size)[0], gold)
+
+
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+def test_prng_reseed_boundaries(prng):
+    seeds = seeds_for(2, 48, salt=9)
+    got = gpu_words(prng, seeds, 3 * 4096 + 5, seed_period=64)
+    for i in range(2):
+        assert np.array_equal(got[i], O.port().prng_words(prng, seeds[i].tobytes(), 3 * 4096 + 5, seed_period=64))
+
+
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+@pytest.mark.parametrize("precision", [32, 64])
+@pytest.mark.parametrize("blinding", [O.NORMAL_SAMPLES, O.BLINDING_SAMPLES, O.SHUFFLE_SAMPLES])
+def test_cdf_vectors(prng, precision, blinding):
+    seeds = seeds_for(70)
+    for discard, n, calls, centre in ((0, 512, 2, 3), (2, 512, 1, 0), (6, 256, 2, -1), (0, 77, 3, 0), (0, 1, 1, 5)):
+        got = gpu_samples(O.SAMPLER_CDF, precision, blinding, prng, 13.42, 215.0, seeds, n, calls, centre, discard)
+        exp = O.port().gauss_streams(O.SAMPLER_CDF, precision, blinding, prng, 13.42, 215.0, seeds, n,
+                                     discard=discard, centre=centre, calls=calls)
+        assert np.array_equal(got, exp), (discard, n, calls)
+
+
+@pytest.mark.parametrize("pname,prng", [("chacha", O.PRNG_CHACHA), ("aes", O.PRNG_AES_CTR_DRBG)])
+def test_golden_samples_on_gpu(pname, prng):
+    seeds = G["gauss_seeds"]
+    for bl in (0, 1, 2):
+        for prec in (32, 64):
+            got = gpu_samples(O.SAMPLER_CDF, prec, bl, prng, 13.42, 215.0, seeds, 512, calls=2)
+            assert np.array_equal(got, G["gauss_cdf%d_%s_b%d" % (prec, pname, bl)])
+    got = gpu_samples(O.SAMPLER_CDF, 64, 0, prng, 13.42, 215.0, seeds, 512, discard=4)
+    assert np.array_equal(got, G["gauss_cdf64_%s_discard" % pname])
+    for key, smp, tail, sigma, n in (("ky64", O.SAMPLER_KNUTH_YAO, 13.42, 215.0, 128), ("ky64s", O.SAMPLER_KNUTH_YAO, 13.0, 4.5, 512),
+                                     ("ber64", O.SAMPLER_BERNOULLI, 13.42, 215.0, 128), ("ber64s", O.SAMPLER_BERNOULLI, 13.0, 4.5, 512)):
+        got = gpu_samples(smp, 64, 0, prng, tail, sigma, seeds, n)
+        assert np.array_equal(got, G["gauss_%s_%s" % (key, pname)]), key
+
+
+def test_survey_anchor_samples_on_gpu():
+    ent = np.array([[(i * 7 + 3) & 0xFF for i in range(64)]], dtype=np.uint8)
+    c = gpu_samples(O.SAMPLER_CDF, 64, 0, O.PRNG_CHACHA, 13.42, 215.0, ent, 12)[0]
+    a = gpu_samples(O.SAMPLER_CDF, 64, 0, O.PRNG_AES_CTR_DRBG, 13.42, 215.0, ent, 12)[0]
+    assert list(c) == [0, 0, -251, 248, 113, 96, -138, 17, -341, 64, -399, -212]
+    assert list(a) == [-319, 333, 125, -307, -208, 85, -140, -269, -1, 74, -120, 180]
+
+
+@pytest.mark.parametrize("sampler,precision", [(O.SAMPLER_KNUTH_YAO, 64), (O.SAMPLER_KNUTH_YAO, 32), (O.SAMPLER_BERNOULLI, 64)])
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+@pytest.mark.parametrize("tail,sigma,n", [(13.42, 215.0, 96), (13.0, 4.5, 512)])
+def test_ky_bernoulli_samples(sampler, precision, prng, tail, sigma, n):
+    seeds = seeds_for(40, salt=1)
+    got = gpu_samples(sampler, precision, 0, prng, tail, sigma, seeds, n)
+    exp = O.port().gauss_streams(sampler, precision, 0, prng, tail, sigma, seeds, n)
+    assert np.array_equal(got, exp)
+
+
+def test_sampling_statistics_at_scale():
+    """2^14 streams x 512 samples: moments of the CDF sampler, and determinism of a re-run."""
+    rng = np.random.default_rng(5)
+    seeds = rng.integers(0, 256, size=(1 << 14, 40)).astype(np.uint8)
+    for prng in (O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG):
+        x = gpu_samples(O.SAMPLER_CDF, 64, 0, prng, 13.42, 215.0, seeds, 512)
+        assert abs(x.mean()) < 0.5 and abs(x.std() - 215.0) < 0.5 and np.abs(x).max() < 4096
+        assert np.array_equal(x, gpu_samples(O.SAMPLER_CDF, 64, 0, prng, 13.42, 215.0, seeds, 512))
+        sl = slice(5000, 5016)
+        assert np.array_equal(x[sl], O.port().gauss_streams(O.SAMPLER_CDF, 64, 0, prng, 13.42, 215.0, seeds[sl], 512))
+
+
+def test_dropin_sampler_api():
+    """create_sampler / get_vector_32 / prng_* with the reference's signatures, interleaving host draws
+    (prng_32, prng_var) with device-side sampling on the same context."""
+    L = sc.lib()
+    L.prng_create.restype = ctypes.c_void_p
+    L.prng_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t]
+    L.prng_set_entropy.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+    L.prng_init.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+    L.prng_32.restype = ctypes.c_uint32
+    L.prng_32.argtypes = [ctypes.c_void_p]
+    L.prng_var.restype = ctypes.c_uint32
+    L.prng_var.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    L.prng_destroy.argtypes = [ctypes.c_void_p]
+    L.create_sampler.restype = ctypes.c_void_p
+    L.create_sampler.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int32, ctypes.c_int, ctypes.c_void_p,
+                                 ctypes.c_float, ctypes.c_float]
+    L.get_vector_32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float]
+    L.get_sample.argtypes = [ctypes.c_void_p]
+    L.get_sample.restype = ctypes.c_int32
+    L.destroy_sampler.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+    seed = bytes(((i * 7 + 3) & 0xFF) for i in range(64))
+    for prng in (O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG):
+        ctx = L.prng_create(5, prng, 0, 0x00100000)          # SC_ENTROPY_USER_PROVIDED
+        assert ctx
+        assert L.prng_set_entropy(ctx, seed, len(seed)) == 0 and L.prng_init(ctx, b"SAFEcrypto nonce", 16) == 0
+        smp = L.create_sampler(0, 64, 0, 512, 0, ctx, 13.42, 215.0)
+        assert smp
+        v1 = np.zeros(512, dtype=np.int32)
+        L.get_vector_32(smp, v1.ctypes.data, 512, 0.0)
+        words = [L.prng_32(ctx) for _ in range(3)]
+        bits = L.prng_var(ctx, 5)
+        single = L.get_sample(smp)
+        v2 = np.zeros(100, dtype=np.int32)
+        L.get_vector_32(smp, v2.ctypes.data, 100, 2.0)
+        # the same call sequence on the oracle: 512 samples = 1024 words, then 3 words, 5 bits (1 word), ...
+        script = [(64, 0)] * 512 + [(32, 0)] * 3 + [(0, 5)] + [(64, 0)] * 101
+        raw = O.port().prng_script(prng, seed, script)
+        tab = O.port().cdf_table(64, 0, 13.42, 215.0)
+
+        def cdf(hi, lo):
+            x = (int(hi) << 32) | int(lo)
+            a = 0
+            st = tab.size >> 1
+            while st:
+                if a + st < tab.size and int(tab[a + st]) < x:
+                    a += st
+                st >>= 1
+            return a if x & 1 else -a
+        exp1 = [cdf(raw[2 * i], raw[2 * i + 1]) for i in range(512)]
+        assert list(v1) == exp1
+        assert words == [int(x) for x in raw[1024:1027]] and bits == int(raw[1027])
+        rest = raw[1028:]
+        assert single == cdf(rest[0], rest[1])
+        assert list(v2) == [cdf(rest[2 + 2 * i], rest[3 + 2 * i]) + 2 for i in range(100)]
+        h = ctypes.c_void_p(smp)
+        assert L.destroy_sampler(ctypes.byref(h)) == 0
+        L.prng_destroy(ctx)

@@ -1,0 +1,370 @@
+"""Parity of the CUDA NTT path (through the C-ABI of libscgpu.so) with the CPU oracle.
+
+Every comparison is bit-exact (integer work).  The oracle is oracle/libscoracle.so (the port,
+pinned to the reference in test_oracle_vs_ref.py / test_oracle_golden.py); where the compiled
+reference itself travelled to the box (oracle/_ref/libscref.so) it is checked as well.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import libsafecrypto_b200 as sc  # noqa: E402
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+PARAMS = [(12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417, 256, 32), (8399873, 512, 32)]
+DEV = "cuda:0"
+
+
+def variants_for(q):
+    v = [O.REFERENCE, O.BARRETT, O.FP, O.AVX]
+    if q == 7681:
+        v.append(O.SOLINAS_7681)
+    if q == 8380417:
+        v.append(O.SOLINAS_8380417)
+    return v
+
+
+def checkers():
+    return [O.port()] + ([O.ref()] if O.ref_available() else [])
+
+
+_plans = {}
+
+
+def plan(q, n, tw, variant):
+    key = (q, n, tw, variant)
+    if key not in _plans:
+        w, r = O.tables(q, n, tw)
+        _plans[key] = (sc.NttPlan(n, q, variant, w, r), w, r)
+    return _plans[key]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def run_gpu(q, n, tw, variant, op, a, b=None, scalar=0, inplace=False):
+    p, _, _ = plan(q, n, tw, variant)
+    da = dev(a.reshape(-1, n) if a.dtype != np.int16 else a.reshape(-1, n))
+    db = dev(b) if b is not None else None
+    out = da if inplace else torch.full((da.shape[0], n), -7, dtype=torch.int32, device=DEV)
+    rc = torch.full((da.shape[0],), -1, dtype=torch.int32, device=DEV)
+    p.batch(op, out, da, db, scalar=scalar, rc=rc)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), rc.cpu().numpy()
+
+
+def rand_inputs(rng, kind, q, shape):
+    if kind == "uniform":
+        return rng.integers(0, q, size=shape, dtype=np.int64).astype(np.int32)
+    if kind == "small":
+        return rng.integers(-300, 301, size=shape, dtype=np.int64).astype(np.int32)
+    if kind == "lazy":
+        return rng.integers(-70000, q * 600, size=shape, dtype=np.int64).astype(np.int32)
+    if kind == "signed":
+        return rng.integers(-q + 1, q, size=shape, dtype=np.int64).astype(np.int32)
+    if kind == "extreme":
+        x = rng.integers(-2**31, 2**31, size=shape, dtype=np.int64).astype(np.int32)
+        x.flat[:8] = [2**31 - 1, -2**31, -1, 0, 1, q, -q, 2**31 - 2]
+        return x
+    raise ValueError(kind)
+
+
+UNARY = [O.OP_FWD, O.OP_INV, O.OP_FWD_LARGE, O.OP_INV_LARGE, O.OP_FFT, O.OP_FFT_LARGE, O.OP_NORMALIZE,
+         O.OP_CENTER, O.OP_FLIP, O.OP_MODN, O.OP_SQRN]
+
+
+@pytest.mark.parametrize("q,n,tw", PARAMS)
+def test_exact_unary_ops(q, n, tw):
+    rng = np.random.default_rng(q + n)
+    w, r = O.tables(q, n, tw)
+    for variant in variants_for(q):
+        for kind in ("uniform", "small", "lazy", "signed", "extreme"):
+            a = rand_inputs(rng, kind, q, (37, n))
+            for op in UNARY:
+                if kind == "extreme" and op == O.OP_CENTER and variant in (O.SOLINAS_7681, O.SOLINAS_8380417):
+                    continue
+                got, _ = run_gpu(q, n, tw, variant, op, a)
+                for chk in checkers():
+                    exp = chk.ntt_batch(variant, op, n, q, tw, a, None, w, r)
+                    assert np.array_equal(got, exp), (O.VARIANT_NAMES[variant], kind, op, chk.prefix)
+
+
+@pytest.mark.parametrize("q,n,tw", PARAMS)
+def test_exact_binary_ops(q, n, tw):
+    rng = np.random.default_rng(7 * q + n)
+    w, r = O.tables(q, n, tw)
+    for variant in variants_for(q):
+        for ka, kb in (("uniform", "uniform"), ("lazy", "uniform"), ("lazy", "lazy"), ("small", "signed"), ("extreme", "extreme")):
+            a = rand_inputs(rng, ka, q, (21, n))
+            b = rand_inputs(rng, kb, q, (21, n))
+            for op in (O.OP_PW, O.OP_MULN, O.OP_POLYMUL):
+                got, _ = run_gpu(q, n, tw, variant, op, a, b)
+                for chk in checkers():
+                    exp = chk.ntt_batch(variant, op, n, q, tw, a, b, w, r)
+                    assert np.array_equal(got, exp), (O.VARIANT_NAMES[variant], ka, kb, op, chk.prefix)
+            # shared second operand (b_stride == 0)
+            got, _ = run_gpu(q, n, tw, variant, O.OP_PW, a, b[0])
+            exp = O.port().ntt_batch(variant, O.OP_PW, n, q, tw, a, b[0], w, r)
+            assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("q,n", [(12289, 512), (12289, 1024), (7681, 256)])
+def test_exact_pointwise16_and_triple(q, n):
+    rng = np.random.default_rng(n)
+    w, r = O.tables(q, n, 16)
+    key = rng.integers(0, q, size=n).astype(np.int16)
+    keys = rng.integers(0, q, size=(9, n)).astype(np.int16)
+    for variant in variants_for(q):
+        for kind in ("uniform", "small", "lazy", "extreme"):
+            a = rand_inputs(rng, kind, q, (9, n))
+            for op in (O.OP_PW16, O.OP_TRIPLE16):
+                for b in (key, keys):
+                    got, _ = run_gpu(q, n, 16, variant, op, a, b)
+                    for chk in checkers():
+                        exp = chk.ntt_batch(variant, op, n, q, 16, a, b, w, r)
+                        assert np.array_equal(got, exp), (O.VARIANT_NAMES[variant], kind, op, chk.prefix)
+
+
+@pytest.mark.parametrize("q,n,tw", PARAMS)
+def test_invert_div_pwr(q, n, tw):
+    rng = np.random.default_rng(5)
+    for variant in variants_for(q):
+        a = rand_inputs(rng, "uniform", q, (5, n))
+        a[a == 0] = 1
+        a[2, n // 2] = 0
+        a[4, 0] = 0
+        b = rand_inputs(rng, "uniform", q, (5, n))
+        e = rng.integers(0, 2 * q, size=(5, n)).astype(np.int32)
+        for op, aa, bb in ((O.OP_INVERT, a, None), (O.OP_DIV, b, a), (O.OP_PWR, a, e)):
+            got, rc = run_gpu(q, n, tw, variant, op, aa, bb)
+            exp, erc, _ = O.port().ntt_batch(variant, op, n, q, tw, aa, bb, None, None, want_rc=True)
+            assert np.array_equal(got, exp), (O.VARIANT_NAMES[variant], op)
+            if op != O.OP_PWR:
+                assert list(rc) == list(erc) == [0, 0, 1, 0, 1]
+
+
+def test_scalar_sparse_and_inplace():
+    q, n, tw = 12289, 512, 16
+    rng = np.random.default_rng(9)
+    w, r = O.tables(q, n, tw)
+    a = rand_inputs(rng, "signed", q, (6, n))
+    for c in (1, -5, 12288, 77777):
+        got, _ = run_gpu(q, n, tw, O.REFERENCE, O.OP_SCALAR, a, scalar=c)
+        assert np.array_equal(got, O.port().ntt_batch(O.REFERENCE, O.OP_SCALAR, n, q, tw, a, scalar=c))
+    omega = 19
+    idx = np.stack([rng.choice(n, size=omega, replace=False) for _ in range(6)]).astype(np.int32)
+    got, _ = run_gpu(q, n, tw, O.REFERENCE, O.OP_SPARSE32, a, idx, scalar=omega)
+    assert np.array_equal(got, O.port().ntt_batch(O.REFERENCE, O.OP_SPARSE32, n, q, tw, a, idx, scalar=omega))
+    a16 = a.astype(np.int16)
+    got, _ = run_gpu(q, n, tw, O.REFERENCE, O.OP_SPARSE16, a16, idx, scalar=omega)
+    assert np.array_equal(got, O.port().ntt_batch(O.REFERENCE, O.OP_SPARSE16, n, q, tw, a16, idx, scalar=omega, a_dtype=np.int16))
+    # v == t aliasing, as the reference allows (ntt_template.c.in:1570-1576)
+    for op in (O.OP_FWD, O.OP_INV, O.OP_NORMALIZE, O.OP_FLIP):
+        got, _ = run_gpu(q, n, tw, O.FP, op, a, inplace=True)
+        assert np.array_equal(got, O.port().ntt_batch(O.FP, op, n, q, tw, a, None, w, r))
+
+
+@pytest.mark.parametrize("q,n,tw", [(12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417, 256, 32)])
+def test_golden_vectors_on_gpu(q, n, tw):
+    """The committed fixtures generated from the compiled reference, replayed on the GPU."""
+    tag = "ntt_%d_%d" % (q, n)
+    a, b, key = G[tag + "_a"], G[tag + "_b"], G[tag + "_key"]
+    checked = 0
+    for v in variants_for(q):
+        for op in range(22):
+            name = "%s_v%d_op%d" % (tag, v, op)
+            if name not in G:
+                continue
+            if op == O.OP_INVERT:
+                nz = a.copy()
+                nz[nz % q == 0] = 1
+                got, _ = run_gpu(q, n, tw, v, op, nz[:1])
+            elif op in (O.OP_PW16, O.OP_TRIPLE16):
+                got, _ = run_gpu(q, n, tw, v, op, a, key)
+            elif op in (O.OP_PW, O.OP_POLYMUL, O.OP_MULN):
+                got, _ = run_gpu(q, n, tw, v, op, a, b)
+            else:
+                got, _ = run_gpu(q, n, tw, v, op, a)
+            assert np.array_equal(got, G[name]), name
+            checked += 1
+    assert checked >= 40
+
+
+def test_ibe_fixture_on_gpu():
+    """unit_ntt.c:1773-1906 through the GPU: (s1 - c) f + s2 g == 0 mod 8399873."""
+    n, q, v = 512, 8399873, O.FP
+    f, g, c, s1, s2 = (G["ibe_" + k].reshape(1, n) for k in ("f", "g", "c", "s1", "s2"))
+    s1 = (s1 - c).astype(np.int32)
+    run = lambda op, x, y=None: run_gpu(q, n, 32, v, op, x, y)[0]  # noqa: E731
+    p1 = run(O.OP_INV_LARGE, run(O.OP_PW, run(O.OP_FWD_LARGE, s1), run(O.OP_FWD, f)))
+    p2 = run(O.OP_INV_LARGE, run(O.OP_PW, run(O.OP_FWD_LARGE, s2), run(O.OP_FWD, g)))
+    assert not np.any(run(O.OP_NORMALIZE, (p1 + p2).astype(np.int32)))
+
+
+# ---- fused kernels ------------------------------------------------------------------------------------
+
+FAST_PARAMS = [(12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417, 256, 32), (18433, 512, 16), (8399873, 512, 32)]
+
+
+@pytest.mark.parametrize("q,n,tw", FAST_PARAMS)
+def test_fused_polymul_matches_reference_composition(q, n, tw):
+    rng = np.random.default_rng(q * 3 + n)
+    w, r = O.tables(q, n, tw)
+    p, _, _ = plan(q, n, tw, O.REFERENCE)
+    for ka, kb, rows in (("uniform", "uniform", 1), ("uniform", "uniform", 1031), ("small", "uniform", 64),
+                         ("lazy", "lazy", 64), ("extreme", "extreme", 257), ("signed", "small", 3)):
+        a = rand_inputs(rng, ka, q, (rows, n))
+        b = rand_inputs(rng, kb, q, (rows, n))
+        out = torch.full((rows, n), -7, dtype=torch.int32, device=DEV)
+        p.polymul(out, dev(a), dev(b))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a, b, w, r)
+        assert np.array_equal(got, exp), (ka, kb, rows)
+        assert got.min() >= 0 and got.max() < q
+        if ka == "uniform" and q < (1 << 15):
+            for v in (O.FP, O.AVX):    # canonical output: every sane variant agrees (SURVEY 8a rule 1)
+                assert np.array_equal(got[:8], O.port().ntt_batch(v, O.OP_POLYMUL, n, q, tw, a[:8], b[:8], w, r))
+    # shared second operand
+    a = rand_inputs(rng, "uniform", q, (33, n))
+    b = rand_inputs(rng, "uniform", q, (n,))
+    out = torch.empty((33, n), dtype=torch.int32, device=DEV)
+    p.polymul(out, dev(a), dev(b))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a, np.tile(b, (33, 1)), w, r))
+
+
+def test_fused_polymul_is_schoolbook_product():
+    q, n = 12289, 512
+    a, b = G["ntt_12289_512_a"][:1], G["ntt_12289_512_b"][:1]
+    p, _, _ = plan(q, n, 16, O.REFERENCE)
+    out = torch.empty((1, n), dtype=torch.int32, device=DEV)
+    p.polymul(out, dev(a), dev(b))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), G["ntt_12289_512_v0_op%d" % O.OP_POLYMUL][:1])
+
+
+@pytest.mark.parametrize("q,n", [(12289, 512), (12289, 1024), (7681, 256)])
+def test_fused_key_product_matches_triple(q, n):
+    rng = np.random.default_rng(n + 1)
+    w, r = O.tables(q, n, 16)
+    p, _, _ = plan(q, n, 16, O.REFERENCE)
+    key = rng.integers(0, q, size=n).astype(np.int16)
+    keys = rng.integers(0, q, size=(65, n)).astype(np.int16)
+    for kind in ("small", "uniform", "extreme"):
+        t = rand_inputs(rng, kind, q, (65, n))
+        for k in (key, keys):
+            out = torch.empty((65, n), dtype=torch.int32, device=DEV)
+            p.mul_key(out, dev(t), dev(k))
+            torch.cuda.synchronize()
+            exp = O.port().ntt_batch(O.REFERENCE, O.OP_TRIPLE16, n, q, 16, t, k, w, r)
+            assert np.array_equal(out.cpu().numpy(), exp), kind
+            out32 = torch.empty((65, n), dtype=torch.int32, device=DEV)
+            p.mul_key(out32, dev(t), dev(k.astype(np.int32)))
+            torch.cuda.synchronize()
+            assert np.array_equal(out32.cpu().numpy(), exp)
+
+
+@pytest.mark.parametrize("q,tw,k,eta", [(7681, 16, 2, 5), (7681, 16, 3, 4), (7681, 16, 4, 3), (8380417, 32, 4, 5)])
+def test_matvec_matches_reference_composition(q, tw, k, eta):
+    """create_rand_product_32 (module_lwe.c:588-748) with A given in the NTT domain:
+    t_i = normalize(inv_ntt(sum_j A_ij o fwd_ntt(s_j)))."""
+    n, l, count = 256, k, 19
+    rng = np.random.default_rng(k)
+    w, r = O.tables(q, n, tw)
+    A = rng.integers(0, q, size=(count, k, l, n)).astype(np.int32)
+    s = rng.integers(-eta, eta + 1, size=(count, l, n)).astype(np.int32)
+    p, _, _ = plan(q, n, tw, O.REFERENCE)
+    out = torch.empty((count, k, n), dtype=torch.int32, device=DEV)
+    p.matvec(out, dev(A), dev(s), k, l)
+    torch.cuda.synchronize()
+    P = O.port()
+    sh = P.ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, s.reshape(-1, n), None, w, r).reshape(count, l, n)
+    exp = np.zeros((count, k, n), dtype=np.int32)
+    for i in range(k):
+        acc = np.zeros((count, n), dtype=np.int64)
+        for j in range(l):
+            acc += P.ntt_batch(O.REFERENCE, O.OP_PW, n, q, tw, A[:, i, j], sh[:, j])
+        t = P.ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw, acc.astype(np.int32))
+        t = P.ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, t, None, w, r)
+        exp[:, i] = P.ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw, t)
+    assert np.array_equal(out.cpu().numpy(), exp)
+
+
+def test_full_size_properties():
+    """BASELINE config C2 at full size (2^20 polynomials): size-independent properties.
+    (1) a * 1 == a mod q; (2) linearity: (a + a') * b == a*b + a'*b mod q; (3) commutativity;
+    (4) x^(n-1) * x == -1: negacyclic wrap; (5) a checksum of the whole output against per-chunk runs."""
+    q, n, B = 12289, 512, 1 << 20
+    p, _, _ = plan(q, n, 16, O.REFERENCE)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    a = torch.randint(0, q, (B, n), dtype=torch.int32, device=DEV, generator=g)
+    b = torch.randint(0, q, (B, n), dtype=torch.int32, device=DEV, generator=g)
+    one = torch.zeros(n, dtype=torch.int32, device=DEV)
+    one[0] = 1
+    out = torch.empty_like(a)
+    p.polymul(out, a, one)
+    assert torch.equal(out, a)
+    ab = torch.empty_like(a)
+    p.polymul(ab, a, b)
+    ba = torch.empty_like(a)
+    p.polymul(ba, b, a)
+    assert torch.equal(ab, ba)
+    a2 = torch.randint(0, q, (B, n), dtype=torch.int32, device=DEV, generator=g)
+    p.polymul(out, a2, b)
+    lhs = torch.empty_like(a)
+    p.polymul(lhs, a + a2, b)
+    assert torch.equal(lhs, (ab + out) % q)
+    del a2, lhs, ba
+    xn1 = torch.zeros(n, dtype=torch.int32, device=DEV)
+    xn1[n - 1] = 1
+    x1 = torch.zeros((4, n), dtype=torch.int32, device=DEV)
+    x1[:, 1] = 1
+    o4 = torch.empty_like(x1)
+    p.polymul(o4, x1, xn1)
+    assert int(o4[0, 0]) == q - 1 and int(o4[0, 1:].abs().sum()) == 0
+    # chunked re-run must give the same bits as the single launch
+    chk = torch.empty((4096, n), dtype=torch.int32, device=DEV)
+    for start in (0, 123456, B - 4096):
+        p.polymul(chk, a[start:start + 4096], b[start:start + 4096])
+        assert torch.equal(chk, ab[start:start + 4096])
+    # and a slice against the oracle
+    w, r = O.tables(q, n, 16)
+    sl = slice(777, 777 + 64)
+    exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, 16, a[sl].cpu().numpy(), b[sl].cpu().numpy(), w, r)
+    assert np.array_equal(ab[sl].cpu().numpy(), exp)
+
+
+def test_host_pipeline_and_ragged_counts():
+    q, n, tw = 12289, 512, 16
+    w, r = O.tables(q, n, tw)
+    rng = np.random.default_rng(3)
+    p, _, _ = plan(q, n, tw, O.REFERENCE)
+    for rows in (0, 1, 5, 8191, 20000):
+        a = rand_inputs(rng, "uniform", q, (rows, n))
+        b = rand_inputs(rng, "uniform", q, (rows, n))
+        out = np.full((rows, n), -7, dtype=np.int32)
+        p.polymul_host(out, a, b, count=rows)
+        if rows:
+            exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a, b, w, r)
+            assert np.array_equal(out, exp)
+    a = rand_inputs(rng, "lazy", q, (9000, n))
+    out = np.empty_like(a)
+    pf, _, _ = plan(q, n, tw, O.FP)
+    pf.batch_host(O.OP_FWD, out, a)
+    assert np.array_equal(out, O.port().ntt_batch(O.FP, O.OP_FWD, n, q, tw, a, None, w, r))
+    rcs = np.full(9000, -1, dtype=np.int32)
+    a[a % q == 0] = 1
+    a[17, 3] = 0
+    pf.batch_host(O.OP_INVERT, out, a, rc=rcs)
+    assert rcs[17] == 1 and rcs.sum() == 1
