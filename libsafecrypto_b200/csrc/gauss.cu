@@ -46,32 +46,54 @@ __device__ __forceinline__ int32_t sample_cdf(const GaussTablesDev &g, PrngStrea
     return (x & 1) ? (int32_t)a : -(int32_t)a;
 }
 
-// Knuth-Yao walk.  The reference scans row `row` of the probability matrix column by column and stops at
-// the first column where the running distance goes negative; with one-positions precomputed per row that
-// is "the (dist+1)-th one of the row, if the row has that many".  After the first hit the distance stays
-// negative, every later row contributes column 0, and only the fixed RNG consumption remains
-// (one word per 32 rows plus the trailing word).
+// Knuth-Yao walk (gaussian_knuth_yao.c:301-364).  The reference walks a byte-per-bit probability matrix
+// with a running pointer: each row doubles the 32-bit distance, adds a random bit, then subtracts matrix
+// entries until the distance goes negative (adding the number of entries scanned to the sample) or a whole
+// row's worth of entries is consumed.  It does NOT re-align the pointer after a hit, and the distance keeps
+// doubling and eventually wraps around, so later rows keep contributing.  With the sorted flat positions of
+// the one-bits this is evaluated per row in O(log) time: "ones in [ptr, ptr+len)" and "k-th one after ptr".
+__device__ __forceinline__ uint32_t ky_lower_bound(const GaussTablesDev &g, uint32_t pos)
+{
+    uint32_t lo = 0, hi = g.ky_nones;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (g.ky_flat[mid] < pos) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 __device__ __forceinline__ int32_t sample_ky(const GaussTablesDev &g, PrngStream &rng)
 {
+    const uint32_t cols = (uint32_t)g.ky_cols;
     for (;;) {
-        int32_t dist = 0, sample = 0;
-        bool hit = false;
+        uint32_t dist = 0;              // the reference's SINT32, with explicit wrap-around
+        int32_t sample = 0;
+        uint32_t ptr = 0;
         uint32_t rnd = rng.next32();
         for (int row = 0; row < g.ky_rows; row++) {
-            dist = 2 * dist + (int32_t)(rnd & 1);
+            dist = 2u * dist + (rnd & 1u);
             rnd >>= 1;
             if ((row & 0x1F) == 0x1F) rnd = rng.next32();
-            if (!hit) {
-                int32_t ones = (int32_t)(g.ky_rowoff[row + 1] - g.ky_rowoff[row]);
-                if (dist < ones) {
-                    sample = g.ky_onepos[g.ky_rowoff[row] + dist];
-                    hit = true;
-                    dist = -1;
-                } else {
-                    dist -= ones;
-                }
+            uint32_t len = cols, col0 = 0;
+            uint32_t i0 = ky_lower_bound(g, ptr);
+            if ((int32_t)dist < 0) {
+                // first entry of the scan
+                uint32_t bit = (i0 < g.ky_nones && g.ky_flat[i0] == ptr) ? 1u : 0u;
+                dist -= bit;
+                ptr += 1; i0 += bit;
+                if ((int32_t)dist < 0) continue;        // hit at column 0: sample += 0
+                len = cols - 1; col0 = 1;               // wrapped to INT_MAX: keep scanning this row
+            }
+            uint32_t i1 = ky_lower_bound(g, ptr + len);
+            uint32_t cnt = i1 - i0;                     // ones in the window
+            if (dist < cnt) {
+                uint32_t f = g.ky_flat[i0 + dist];      // the (dist+1)-th one takes the distance to -1
+                sample += (int32_t)(col0 + (f - ptr));
+                ptr = f + 1;
+                dist = 0xFFFFFFFFu;
             } else {
-                dist = -1;             // any negative value: 2*dist + bit - {0,1} stays negative
+                dist -= cnt;
+                ptr += len;
             }
         }
         rnd = rng.next32();

@@ -16,10 +16,11 @@ struct GaussTablesDev {
     const uint64_t *cdf64;
     const uint32_t *cdf32;
     uint32_t cdf_size;
-    // Knuth-Yao (gaussian_knuth_yao.c:81-189): per-row positions of the one-bits of the probability matrix
-    int ky_rows, ky_bound;
-    const uint32_t *ky_rowoff;      // [rows + 1]
-    const uint16_t *ky_onepos;
+    // Knuth-Yao (gaussian_knuth_yao.c:81-189): sorted flat indices (row * cols + col) of the one-bits of
+    // the row-major probability matrix
+    int ky_rows, ky_cols, ky_bound;
+    uint32_t ky_nones;
+    const uint32_t *ky_flat;
     // Bernoulli (gaussian_bernoulli.c:40-103): entries x 8 bytes, most significant byte first
     const uint8_t *ber_tab;
     int ber_entries, ber_maxval, ber_maxlog;

@@ -26,8 +26,7 @@ struct scgpu_gauss_plan {
     GaussTablesDev t;
     int device, sm_count;
     void *d_cdf = nullptr;
-    uint32_t *d_rowoff = nullptr;
-    uint16_t *d_onepos = nullptr;
+    uint32_t *d_flat = nullptr;
     uint8_t *d_ber = nullptr;
     std::mutex mu;
     uint32_t *d_keys = nullptr; size_t keys_cap = 0;        // DRBG round keys of the fast path
@@ -164,11 +163,10 @@ extern "C" int scgpu_gauss_plan_create(scgpu_gauss_plan_t **out, int sampler, in
         rc = upload(&d, cdf);
         p->d_cdf = d; p->t.cdf32 = d; p->t.cdf_size = (uint32_t)cdf.size();
     } else if (sampler == SCGPU_SAMPLER_KNUTH_YAO && (precision == 32 || precision == 64) && blinding != SCGPU_BLINDING_SAMPLES) {
-        // gaussian_knuth_yao.c:126-189; the matrix is stored as per-row positions of its one-bits
+        // gaussian_knuth_yao.c:126-189; the matrix is stored as the sorted flat positions of its one-bits
         const int rows = precision;
         const int bound = (int32_t)ceil(tail * sigma);
         const int cols = bound + 1;
-        if (cols > 65535) { delete p; set_error("Knuth-Yao table too wide (%d columns)", cols); return SCGPU_ERR_UNSUPPORTED; }
         long double d = 0.7978845608028653558798L / sigma;
         long double e = -0.5L / (sigma * sigma);
         std::vector<uint64_t> colbits((size_t)cols);
@@ -176,17 +174,13 @@ extern "C" int scgpu_gauss_plan_create(scgpu_gauss_plan_t **out, int sampler, in
             long double pr = (col == 0) ? d : d * expl(e * ((long double)(col * col)));
             colbits[col] = bin_expansion((double)pr, rows);
         }
-        std::vector<uint32_t> rowoff((size_t)rows + 1);
-        std::vector<uint16_t> onepos;
-        for (int row = 0; row < rows; row++) {
-            rowoff[row] = (uint32_t)onepos.size();
+        std::vector<uint32_t> flat;
+        for (int row = 0; row < rows; row++)
             for (int col = 0; col < cols; col++)
-                if ((colbits[col] >> (rows - 1 - row)) & 1) onepos.push_back((uint16_t)col);
-        }
-        rowoff[rows] = (uint32_t)onepos.size();
-        rc = upload(&p->d_rowoff, rowoff);
-        if (rc == SCGPU_OK) rc = upload(&p->d_onepos, onepos);
-        p->t.ky_rows = rows; p->t.ky_bound = bound; p->t.ky_rowoff = p->d_rowoff; p->t.ky_onepos = p->d_onepos;
+                if ((colbits[col] >> (rows - 1 - row)) & 1) flat.push_back((uint32_t)(row * cols + col));
+        rc = upload(&p->d_flat, flat);
+        p->t.ky_rows = rows; p->t.ky_cols = cols; p->t.ky_bound = bound;
+        p->t.ky_nones = (uint32_t)flat.size(); p->t.ky_flat = p->d_flat;
     } else if (sampler == SCGPU_SAMPLER_BERNOULLI && precision == 64) {
         // gaussian_bernoulli.c:40-103
         float max_gauss_val = ceil(tail * sigma);
@@ -216,7 +210,7 @@ extern "C" void scgpu_gauss_plan_destroy(scgpu_gauss_plan_t *p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
-    cudaFree(p->d_cdf); cudaFree(p->d_rowoff); cudaFree(p->d_onepos); cudaFree(p->d_ber);
+    cudaFree(p->d_cdf); cudaFree(p->d_flat); cudaFree(p->d_ber);
     cudaFree(p->d_keys); cudaFree(p->d_seeds); cudaFree(p->d_out);
     delete p;
 }

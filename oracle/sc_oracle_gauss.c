@@ -147,8 +147,11 @@ static void ky_build(ky_t *k, int bitwidth, float tail, float sigma)
 }
 
 /* gaussian_knuth_yao.c:301-364.  After the first hit the reference `break`s out of the
- * column scan without re-aligning its table pointer; from then on `dist` stays negative so
- * every later row contributes column 0.  The walk below keeps the same pointer arithmetic. */
+ * column scan without re-aligning its table pointer, and keeps doubling the (now negative)
+ * distance once per row: about 31 rows later the 32-bit distance wraps, turns positive and the
+ * walk resumes from the drifted pointer, adding further columns to the sample.  That is what
+ * the compiled reference returns, so it is restated literally, with the wrap-around made
+ * explicit (unsigned arithmetic) instead of relying on signed overflow. */
 static int32_t ky_sample(const ky_t *k, orc_prng_t *rng)
 {
     for (;;) {
@@ -156,11 +159,11 @@ static int32_t ky_sample(const ky_t *k, orc_prng_t *rng)
         const uint8_t *pm = k->pmat;
         uint32_t rnd = orc_prng_32(rng);
         for (int row = 0; row < k->rows; row++) {
-            dist = 2 * dist + (int32_t)(rnd & 1);
+            dist = (int32_t)(2u * (uint32_t)dist + (rnd & 1u));
             rnd >>= 1;
             if ((row & 0x1F) == 0x1F) rnd = orc_prng_32(rng);
             for (int col = 0; col < k->cols; col++) {
-                dist -= *pm++;
+                dist = (int32_t)((uint32_t)dist - (uint32_t)*pm++);
                 if (dist < 0) { sample += col; break; }
             }
         }
