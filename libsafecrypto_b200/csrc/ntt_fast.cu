@@ -21,39 +21,17 @@
 //  * arbitrary SINT32 inputs: the pass-through half of the first stage is range-compressed by
 //    x - (x >> ceil(log2 q)) * q, everything else is bounded by the Montgomery products.
 #include "scgpu_internal.h"
+#include "fast_common.cuh"
 #include "../../include/scgpu.h"
 
+#include <cstdlib>
 #include <vector>
 
 namespace scgpu {
 
 namespace {
 
-constexpr int kCtaThreads = 256;
-
-template <int LOGN>
-__device__ __forceinline__ int swz(int idx)
-{
-    if (LOGN == 8)  return idx ^ ((idx >> 5) & 7) ^ (((idx >> 5) & 3) << 3);
-    if (LOGN == 9)  return idx ^ ((idx >> 5) & 7) ^ (((idx >> 6) & 3) << 3);
-    return idx ^ ((idx >> 5) & 7) ^ (((idx >> 5) & 1) << 3) ^ (((idx >> 7) & 1) << 4);
-}
-
-// pass p of the schedule: stages [3p, 3p + J), slot stride D
-template <int LOGN, int PASS>
-struct PassCfg {
-    static constexpr int N = 1 << LOGN;
-    static constexpr int S0 = 3 * PASS;
-    static constexpr int J = (LOGN - S0) >= 3 ? 3 : (LOGN - S0);
-    static constexpr int D = (J == 3) ? (N >> (S0 + 3)) : 1;
-};
-template <int LOGN> struct NumPasses { static constexpr int value = (LOGN + 2) / 3; };
-
-template <int D>
-__device__ __forceinline__ int elem_index(int tau, int m)
-{
-    return (tau / D) * (8 * D) + (tau % D) + m * D;
-}
+using namespace fast;
 
 __device__ __forceinline__ MontTw ld_tw(const MontTw *p)
 {
@@ -127,19 +105,6 @@ __device__ __forceinline__ void inv_pass(int32_t (&x)[8], const PassTw &tw, int3
 #pragma unroll
         for (int m = 0; m < 4; m++) gs_bfly(x[m], x[m + 4], tw.z4, q);
     }
-}
-
-template <int LOGN, int PASS>
-__device__ __forceinline__ void tile_store(int32_t *tile, const int32_t (&x)[8], int tau)
-{
-#pragma unroll
-    for (int m = 0; m < 8; m++) tile[swz<LOGN>(elem_index<PassCfg<LOGN, PASS>::D>(tau, m))] = x[m];
-}
-template <int LOGN, int PASS>
-__device__ __forceinline__ void tile_load(const int32_t *tile, int32_t (&x)[8], int tau)
-{
-#pragma unroll
-    for (int m = 0; m < 8; m++) x[m] = tile[swz<LOGN>(elem_index<PassCfg<LOGN, PASS>::D>(tau, m))];
 }
 
 struct FastConst {
@@ -419,6 +384,20 @@ void free_fast_tables(NttPlanDev &p)
     p.zeta_fwd = p.zeta_inv = nullptr;
 }
 
+// SCGPU_FORCE_MONT=1 routes small moduli through the Montgomery kernels too (tests cover both)
+static int g_force_mont = -1;
+static bool use_sq(const NttPlanDev &p)
+{
+    if (g_force_mont < 0) g_force_mont = (getenv("SCGPU_FORCE_MONT") && atoi(getenv("SCGPU_FORCE_MONT")) != 0) ? 1 : 0;
+    return p.sq_ok && !g_force_mont;
+}
+int set_force_montgomery(int on)
+{
+    int old = g_force_mont > 0 ? 1 : 0;
+    g_force_mont = on ? 1 : 0;
+    return old;
+}
+
 #define SCGPU_REQUIRE_FAST(p)                                                                   \
     if (!(p).zeta_fwd) {                                                                        \
         set_error("fused kernels need an odd q < 2^30 and a table with w[1]^n == -1 (q=%d n=%d)", (p).rc.q, (p).n); \
@@ -429,6 +408,7 @@ int launch_polymul(const NttPlanDev &p, int32_t *out, const int32_t *a, const in
                    size_t b_stride, size_t count, cudaStream_t st)
 {
     if (count == 0) return SCGPU_OK;
+    if (use_sq(p)) return launch_polymul_sq(p, 0, out, a, b, b_stride, count, st);
     SCGPU_REQUIRE_FAST(p);
     FastConst c = make_const(p);
     const size_t G = kCtaThreads / (p.n / 8);
@@ -448,8 +428,9 @@ int launch_mul_key(const NttPlanDev &p, int32_t *out, const int32_t *t, const vo
                    int key_bits, size_t key_stride, size_t count, cudaStream_t st)
 {
     if (count == 0) return SCGPU_OK;
-    SCGPU_REQUIRE_FAST(p);
     if (key_bits != 16 && key_bits != 32) { set_error("key_bits must be 16 or 32"); return SCGPU_ERR_ARG; }
+    if (use_sq(p)) return launch_polymul_sq(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
+    SCGPU_REQUIRE_FAST(p);
     FastConst c = make_const(p);
     const size_t G = kCtaThreads / (p.n / 8);
     const unsigned grid = grid_for(p, (count + G - 1) / G);
@@ -475,6 +456,8 @@ int launch_matvec(const NttPlanDev &p, int32_t *out, const int32_t *A, const int
     SCGPU_REQUIRE_FAST(p);
     if (k < 1 || l < 1 || l > 8) { set_error("matvec supports 1 <= l <= 8 (got k=%d l=%d)", k, l); return SCGPU_ERR_ARG; }
     if (p.logn != 8) { set_error("matvec is instantiated for n = 256 (Kyber / Dilithium); got n=%d", p.n); return SCGPU_ERR_UNSUPPORTED; }
+    if (l > 4) { set_error("matvec l > 4 not instantiated"); return SCGPU_ERR_UNSUPPORTED; }
+    if (use_sq(p)) return launch_matvec_sq(p, out, A, s, k, l, count, st);
     FastConst c = make_const(p);
     const size_t G = kCtaThreads / (p.n / 8);
     // shared-memory stash limits residency to 1-2 CTAs per SM

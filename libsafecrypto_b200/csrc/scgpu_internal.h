@@ -34,6 +34,11 @@ struct NttPlanDev {
     int32_t qinv;        // q^-1 mod 2^32
     int32_t fold;        // reserved
     int sm_count;
+    // small-modulus fused kernels (32-bit Barrett, ntt_fast_sq.cu); sq_ok == 0: not applicable to (q, n)
+    int sq_ok, sq_qbits, sq_r_pw, sq_r_inv[4], sq_r_inv_mv[4];
+    int32_t *sq_zf, *sq_zi;
+    int32_t sq_ninv, sq_x0;
+    uint32_t sq_M;
 };
 
 struct ExactArgs {
@@ -60,5 +65,12 @@ int launch_matvec(const NttPlanDev &plan, int32_t *out, const int32_t *A, const 
                   int k, int l, size_t count, cudaStream_t stream);
 int build_fast_tables(NttPlanDev &plan, const int32_t *w_host);
 void free_fast_tables(NttPlanDev &plan);
+int set_force_montgomery(int on);
+int build_sq_tables(NttPlanDev &plan, const int32_t *w_host);
+void free_sq_tables(NttPlanDev &plan);
+int launch_polymul_sq(const NttPlanDev &plan, int mode, int32_t *out, const int32_t *a, const void *b,
+                      size_t b_stride, size_t count, cudaStream_t stream);
+int launch_matvec_sq(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
+                     size_t count, cudaStream_t stream);
 
 }  // namespace scgpu

@@ -50,6 +50,7 @@ struct scgpu_ntt_plan {
 
 extern "C" const char *scgpu_last_error(void) { return g_err; }
 extern "C" uint64_t scgpu_launch_count(void) { return g_launches.load(); }
+extern "C" int scgpu_force_montgomery(int on) { return set_force_montgomery(on); }
 extern "C" int scgpu_device_count(void)
 {
     int n = 0;
@@ -117,6 +118,7 @@ extern "C" int scgpu_ntt_plan_create(scgpu_ntt_plan_t **out, const void *params,
             SCGPU_CUDA_CHECK(cudaMemcpy(d.r, rh.data(), sizeof(int32_t) * d.n, cudaMemcpyHostToDevice));
         }
         int rcode = build_fast_tables(d, wh.data());
+        if (rcode == SCGPU_OK) rcode = build_sq_tables(d, wh.data());
         if (rcode != SCGPU_OK) { delete plan; return rcode; }
     }
     *out = plan;
@@ -135,6 +137,7 @@ extern "C" void scgpu_ntt_plan_destroy(scgpu_ntt_plan_t *plan)
     cudaFree(plan->dev.w);
     cudaFree(plan->dev.r);
     free_fast_tables(plan->dev);
+    free_sq_tables(plan->dev);
     delete plan;
 }
 

@@ -216,8 +216,17 @@ def test_ibe_fixture_on_gpu():
 FAST_PARAMS = [(12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417, 256, 32), (18433, 512, 16), (8399873, 512, 32)]
 
 
+@pytest.fixture(params=["auto", "montgomery"])
+def arithmetic(request):
+    """Run the fused-kernel tests with the automatic choice (32-bit Barrett for small q) and with
+    Montgomery forced for every modulus."""
+    old = sc.lib().scgpu_force_montgomery(1 if request.param == "montgomery" else 0)
+    yield request.param
+    sc.lib().scgpu_force_montgomery(old)
+
+
 @pytest.mark.parametrize("q,n,tw", FAST_PARAMS)
-def test_fused_polymul_matches_reference_composition(q, n, tw):
+def test_fused_polymul_matches_reference_composition(q, n, tw, arithmetic):
     rng = np.random.default_rng(q * 3 + n)
     w, r = O.tables(q, n, tw)
     p, _, _ = plan(q, n, tw, O.REFERENCE)
@@ -255,7 +264,7 @@ def test_fused_polymul_is_schoolbook_product():
 
 
 @pytest.mark.parametrize("q,n", [(12289, 512), (12289, 1024), (7681, 256)])
-def test_fused_key_product_matches_triple(q, n):
+def test_fused_key_product_matches_triple(q, n, arithmetic):
     rng = np.random.default_rng(n + 1)
     w, r = O.tables(q, n, 16)
     p, _, _ = plan(q, n, 16, O.REFERENCE)
@@ -276,7 +285,7 @@ def test_fused_key_product_matches_triple(q, n):
 
 
 @pytest.mark.parametrize("q,tw,k,eta", [(7681, 16, 2, 5), (7681, 16, 3, 4), (7681, 16, 4, 3), (8380417, 32, 4, 5)])
-def test_matvec_matches_reference_composition(q, tw, k, eta):
+def test_matvec_matches_reference_composition(q, tw, k, eta, arithmetic):
     """create_rand_product_32 (module_lwe.c:588-748) with A given in the NTT domain:
     t_i = normalize(inv_ntt(sum_j A_ij o fwd_ntt(s_j)))."""
     n, l, count = 256, k, 19
@@ -343,6 +352,34 @@ def test_full_size_properties():
     sl = slice(777, 777 + 64)
     exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, 16, a[sl].cpu().numpy(), b[sl].cpu().numpy(), w, r)
     assert np.array_equal(ab[sl].cpu().numpy(), exp)
+
+
+def test_small_modulus_inputs_at_the_proof_boundary(arithmetic):
+    """Inputs just inside / outside the +-4q window the 32-bit kernels are proven for, adversarial sign
+    patterns, and keys at the SINT16 extremes."""
+    q, n = 12289, 512
+    w, r = O.tables(q, n, 16)
+    p, _, _ = plan(q, n, 16, O.REFERENCE)
+    rng = np.random.default_rng(12)
+    cases = []
+    for mag in (4 * q, 4 * q + 1, 4 * q - 1, q - 1, 2**31 - 1):
+        cases.append(np.full((3, n), mag, dtype=np.int64))
+        cases.append(np.full((3, n), -mag, dtype=np.int64))
+        cases.append(mag * rng.choice([-1, 1], size=(3, n)))
+    cases.append(np.full((3, n), -2**31, dtype=np.int64))
+    for a in cases:
+        a = a.astype(np.int32)
+        for b in (a, np.ascontiguousarray(a[::-1]), rng.integers(0, q, size=a.shape).astype(np.int32)):
+            out = torch.empty((a.shape[0], n), dtype=torch.int32, device=DEV)
+            p.polymul(out, dev(a), dev(b))
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, 16, a, b, w, r))
+        for kval in (32767, -32768, q - 1, 0):
+            key = np.full(n, kval, dtype=np.int16)
+            out = torch.empty((a.shape[0], n), dtype=torch.int32, device=DEV)
+            p.mul_key(out, dev(a), dev(key))
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_TRIPLE16, n, q, 16, a, key, w, r))
 
 
 def test_host_pipeline_and_ragged_counts():

@@ -1,0 +1,43 @@
+"""Small driver for ncu captures: a few launches of each hot kernel at benchmark shape.
+Usage (on the GPU box): ncu ... python tools/profile_run.py [polymul|fwd|gauss|all] [log2_batch]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import libsafecrypto_b200 as sc  # noqa: E402
+import _oracle as O  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+lb = int(sys.argv[2]) if len(sys.argv) > 2 else 18
+n, q, B = 512, 12289, 1 << lb
+w, r = O.tables(q, n, 16)
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(1)
+a = torch.randint(0, q, (B, n), dtype=torch.int32, device=dev, generator=g)
+b = torch.randint(0, q, (B, n), dtype=torch.int32, device=dev, generator=g)
+out = torch.empty_like(a)
+if what in ("polymul", "all"):
+    plan = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    for _ in range(5):
+        plan.polymul(out, a, b)
+if what in ("fwd", "all"):
+    for v in (sc.REFERENCE, sc.FP, sc.BARRETT):
+        p = sc.NttPlan(n, q, v, w, r)
+        for _ in range(3):
+            p.batch(sc.OP_FWD, out, a)
+        p.batch(sc.OP_INV, out, a)
+        p.batch(sc.OP_NORMALIZE, out, a)
+if what in ("gauss", "all"):
+    gp = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0)
+    seeds = torch.randint(0, 256, (B // 2, 40), dtype=torch.uint8, device=dev, generator=g)
+    smp = torch.empty((B // 2, n), dtype=torch.int32, device=dev)
+    for prng in (sc.PRNG_AES_CTR_DRBG, sc.PRNG_CHACHA):
+        for _ in range(3):
+            gp.streams(prng, seeds, n, smp)
+torch.cuda.synchronize()
+print("done")
