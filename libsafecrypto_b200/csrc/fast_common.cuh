@@ -38,6 +38,20 @@ __device__ __forceinline__ int elem_index(int tau, int m)
     return (tau / D) * (8 * D) + (tau % D) + m * D;
 }
 
+// Barrier over the n/8 threads that share one polynomial's tile (not the whole CTA): a warp-level sync for
+// n = 256, a named barrier (ids 1..) for n = 512 / 1024.  Polynomials in a CTA never wait for each other.
+template <int LOGN>
+__device__ __forceinline__ void group_sync()
+{
+    constexpr int T = (1 << LOGN) / 8;
+    if (T == 32) {
+        __syncwarp();
+    } else {
+        const int id = 1 + (int)threadIdx.x / T;
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(T) : "memory");
+    }
+}
+
 template <int LOGN, int PASS>
 __device__ __forceinline__ void tile_store(int32_t *tile, const int32_t (&x)[8], int tau)
 {

@@ -125,7 +125,7 @@ __device__ __forceinline__ void fwd_all(int32_t (&xa)[8], int32_t (&xb)[8], int3
     PassTw tw;
     load_pass_tw<LOGN, PASS>(tw, c.zf, tau);
     if (PASS > 0) {
-        __syncthreads();
+        group_sync<LOGN>();
         tile_load<LOGN, PASS>(ta, xa, tau);
         if (NOPS == 2) tile_load<LOGN, PASS>(tb, xb, tau);
     }
@@ -146,7 +146,7 @@ __device__ __forceinline__ void inv_all(int32_t (&x)[8], int32_t *tile, const Fa
     PassTw tw;
     load_pass_tw<LOGN, PASS>(tw, c.zi, tau);
     if (PASS + 1 < NumPasses<LOGN>::value) {
-        __syncthreads();
+        group_sync<LOGN>();
         tile_load<LOGN, PASS>(tile, x, tau);
     }
     if constexpr (PASS == 0) {
@@ -240,7 +240,7 @@ k_polymul(int32_t *__restrict__ out, const int32_t *__restrict__ a, const void *
 #pragma unroll
             for (int m = 0; m < 8; m++) orow[tau + m * D0] = xa[m];
         }
-        __syncthreads();
+        group_sync<LOGN>();
     }
 }
 
@@ -275,7 +275,7 @@ k_matvec(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t
             fwd_all<LOGN, 0, 1>(x, dummy, tile, tile, c, tau);
 #pragma unroll
             for (int m = 0; m < 8; m++) stash[g][j][m * T + tau] = mont_mul(x[m], c.rsq, c.q);
-            __syncthreads();
+            group_sync<LOGN>();
         }
         for (int i = 0; i < k; i++) {
             int32_t acc[8];
@@ -295,7 +295,7 @@ k_matvec(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t
 #pragma unroll
                 for (int m = 0; m < 8; m++) orow[tau + m * D0] = acc[m];
             }
-            __syncthreads();
+            group_sync<LOGN>();
         }
     }
 }

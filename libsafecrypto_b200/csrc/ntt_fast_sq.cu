@@ -31,7 +31,7 @@ namespace {
 struct SqConst {
     const int32_t *zf;      // [n] psi^brv(k), centred
     const int32_t *zi;      // [n] inverses, entry 1 pre-multiplied by n^-1
-    int32_t q, M, ninv, x0; // M = floor(2^32/q); x0 = input magnitude the bounds were proven for
+    int32_t q, nq, M, ninv, x0; // nq = -q; M = floor(2^32/q); x0 = input magnitude the bounds were proven for
     int qbits;
     int r_pw;               // compress rounds before the pointwise product
     int r_inv[4];           // compress rounds at the entry of inverse pass p
@@ -41,13 +41,16 @@ struct SqConst {
 __device__ __forceinline__ int32_t bred(int32_t p, const SqConst &c)
 {
     int32_t qe = (int32_t)(((int64_t)p * (int64_t)c.M + 0x80000000ll) >> 32);
-    return p - qe * c.q;
+    return qe * c.nq + p;           // one IMAD: no separate negation
 }
 __device__ __forceinline__ int32_t bmul(int32_t x, int32_t w, const SqConst &c) { return bred(x * w, c); }
 
 __device__ __forceinline__ int32_t compress(int32_t x, int rounds, const SqConst &c)
 {
-    for (int r = 0; r < rounds; r++) x -= (x >> c.qbits) * c.q;
+    // rounds is a plan constant in 0..3 (uniform branches; a counted loop makes nvcc unroll by 8)
+    if (rounds > 0) x = (x >> c.qbits) * c.nq + x;
+    if (rounds > 1) x = (x >> c.qbits) * c.nq + x;
+    if (rounds > 2) x = (x >> c.qbits) * c.nq + x;
     return x;
 }
 
@@ -107,7 +110,7 @@ __device__ __forceinline__ void sq_fwd_all(int32_t (&xa)[8], int32_t (&xb)[8], i
     SqTw tw;
     sq_load_tw<LOGN, PASS>(tw, c.zf, tau);
     if (PASS > 0) {
-        __syncthreads();
+        group_sync<LOGN>();
         tile_load<LOGN, PASS>(ta, xa, tau);
         if (NOPS == 2) tile_load<LOGN, PASS>(tb, xb, tau);
     }
@@ -127,7 +130,7 @@ __device__ __forceinline__ void sq_inv_all(int32_t (&x)[8], int32_t *tile, const
     SqTw tw;
     sq_load_tw<LOGN, PASS>(tw, c.zi, tau);
     if (PASS + 1 < NumPasses<LOGN>::value) {
-        __syncthreads();
+        group_sync<LOGN>();
         tile_load<LOGN, PASS>(tile, x, tau);
     }
     if (c.r_inv[PASS]) {
@@ -181,7 +184,7 @@ __device__ __forceinline__ void sq_load_operand(int32_t (&x)[8], const int32_t *
 enum { SQ_POLYMUL = 0, SQ_KEY16 = 1, SQ_KEY32 = 2 };
 
 template <int LOGN, int MODE>
-__global__ void __launch_bounds__(kCtaThreads, 3)
+__global__ void __launch_bounds__(kCtaThreads, 4)
 k_polymul_sq(int32_t *__restrict__ out, const int32_t *__restrict__ a, const void *__restrict__ bsrc,
              size_t b_stride, size_t count, SqConst c)
 {
@@ -225,7 +228,7 @@ k_polymul_sq(int32_t *__restrict__ out, const int32_t *__restrict__ a, const voi
 #pragma unroll
             for (int m = 0; m < 8; m++) orow[tau + m * D0] = xa[m];
         }
-        __syncthreads();
+        group_sync<LOGN>();
     }
 }
 
@@ -256,7 +259,7 @@ k_matvec_sq(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int3
             sq_fwd_all<LOGN, 0, 1>(x, dummy, tile, tile, c, tau);
 #pragma unroll
             for (int m = 0; m < 8; m++) stash[g][j][m * T + tau] = bred(x[m], c);      // |.| < q
-            __syncthreads();
+            group_sync<LOGN>();
         }
         for (int i = 0; i < k; i++) {
             int32_t acc[8];
@@ -277,7 +280,7 @@ k_matvec_sq(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int3
 #pragma unroll
                 for (int m = 0; m < 8; m++) orow[tau + m * D0] = acc[m];
             }
-            __syncthreads();
+            group_sync<LOGN>();
         }
     }
 }
@@ -294,7 +297,7 @@ int32_t centre(int64_t v, int64_t q) { return (int32_t)(v > q / 2 ? v - q : v); 
 SqConst sq_const(const NttPlanDev &p)
 {
     SqConst c;
-    c.zf = p.sq_zf; c.zi = p.sq_zi; c.q = p.rc.q; c.M = (int32_t)p.sq_M; c.ninv = p.sq_ninv; c.x0 = p.sq_x0;
+    c.zf = p.sq_zf; c.zi = p.sq_zi; c.q = p.rc.q; c.nq = -p.rc.q; c.M = (int32_t)p.sq_M; c.ninv = p.sq_ninv; c.x0 = p.sq_x0;
     c.qbits = p.sq_qbits; c.r_pw = p.sq_r_pw;
     for (int i = 0; i < 4; i++) c.r_inv[i] = p.sq_r_inv[i];
     return c;
@@ -418,7 +421,7 @@ int launch_polymul_sq(const NttPlanDev &p, int mode, int32_t *out, const int32_t
 {
     SqConst c = sq_const(p);
     const size_t G = kCtaThreads / (p.n / 8);
-    const unsigned grid = sq_grid(p, (count + G - 1) / G, 3);
+    const unsigned grid = sq_grid(p, (count + G - 1) / G, 4);
 #define SQ_LAUNCH(L)                                                                                             \
     if (mode == SQ_POLYMUL)    k_polymul_sq<L, SQ_POLYMUL><<<grid, kCtaThreads, 0, st>>>(out, a, b, b_stride, count, c); \
     else if (mode == SQ_KEY16) k_polymul_sq<L, SQ_KEY16><<<grid, kCtaThreads, 0, st>>>(out, a, b, b_stride, count, c);   \
