@@ -75,9 +75,20 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_run(count, threads=0, variant=None, repeats=1):
-    """Time the reference's CPU polymul (fwd, fwd, pointwise, inv per pair) on `count` pairs."""
+    """Time the reference's CPU polymul (fwd, fwd, pointwise, inv per pair) on `count` pairs.
+    threads = 0 means every host thread this process may run on (explicit, so that torchrun's
+    OMP_NUM_THREADS=1 does not turn the baseline into a single-core number)."""
     import _oracle as O
+    if threads == 0:
+        threads = host_threads()
     if O.ref_available():
         chk, kind = O.ref(), "reference"
         variant = O.AVX if variant is None else variant        # what every scheme selects on an AVX2 host (bliss_b.c:273-277)
@@ -94,7 +105,7 @@ def cpu_reference_run(count, threads=0, variant=None, repeats=1):
         chk.ntt_batch(variant, O.OP_POLYMUL, N_COEF, Q, 16, a, b, w, r, threads=threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    cores = chk.num_threads() if threads == 0 else threads
+    cores = threads
     return count / best, cores, kind, O.VARIANT_NAMES[variant], best
 
 
@@ -129,7 +140,7 @@ def run_reference_arm(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -170,11 +181,13 @@ def main():
     out = torch.empty_like(a)
 
     # ---- device-resident leg ---------------------------------------------------------------------------
+    # clocks / throttle reasons are sampled from the first warm-up step to the end of the end-to-end leg
+    # (the device-resident timed region alone lasts tens of milliseconds, shorter than one nvidia-smi poll)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         plan.polymul(out, a, b)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = sc.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
@@ -190,8 +203,6 @@ def main():
     ev1.record()
     barrier()
     launches = sc.launch_count() - launches0
-    sampler.stop_flag.set()
-    sampler.join()
     elapsed_ms = ev0.elapsed_time(ev1)
     kernel_ms = [s.elapsed_time(e) for s, e in evs]
     if world > 1:
@@ -247,6 +258,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * E2E_BATCH * e2e_steps / e2e_s
+    sampler.stop_flag.set()
+    sampler.join()
     exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, N_COEF, Q, 16, ha[:8].numpy(), hb[:8].numpy(), w, r)
     assert np.array_equal(ho[:8].numpy(), exp), "host-path output differs from the oracle"
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 4 * N_COEF * E2E_BATCH,

@@ -44,9 +44,8 @@ void ref_get_params(int n, int q, int32_t *m, int32_t *k, double *inv_q_dbl, flo
 
 static int max_threads(int threads)
 {
-    int t = omp_get_max_threads();
-    if (threads > 0 && threads < t) t = threads;
-    return t;
+    /* an explicit request wins over OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1) */
+    return threads > 0 ? threads : omp_get_max_threads();
 }
 
 /* One reference call per batch row.  `a`, `b`, `out` are [count][n] SINT32 row-major

@@ -336,8 +336,7 @@ int orc_gauss_streams(int sampler, int precision, int blinding, int prng_type, f
     } else {
         return 1;
     }
-    int nt = omp_get_max_threads();
-    if (threads > 0 && threads < nt) nt = threads;
+    int nt = threads > 0 ? threads : omp_get_max_threads();
     int fail = 0;
 #pragma omp parallel for schedule(static) num_threads(nt) reduction(|:fail)
     for (size_t st = 0; st < nstreams; st++) {

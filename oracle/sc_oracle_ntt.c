@@ -452,8 +452,7 @@ int orc_ntt_batch(int variant, int op, int n, int q, int tw_bits,
 {
     orc_params_t p;
     orc_init_reduce(&p, n, q);
-    int nt = omp_get_max_threads();
-    if (threads > 0 && threads < nt) nt = threads;
+    int nt = threads > 0 ? threads : omp_get_max_threads();
     int any = 0;
 #pragma omp parallel for schedule(static) num_threads(nt) reduction(|:any)
     for (size_t i = 0; i < count; i++) {
