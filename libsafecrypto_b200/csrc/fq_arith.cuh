@@ -1,0 +1,98 @@
+// fq_arith.cuh -- "float-quotient" modular arithmetic of the fused small-modulus kernels
+// (ntt_fast_fq.cu).  Shared by device code and by a host model (tools/fq_model.cpp) that checks the
+// arithmetic and the proven bounds bit for bit without a GPU.
+//
+// Why: on B200 the fma-heavy pipe issues IMAD at 16 lanes/clk/SMSP and IMAD.HI at 8; FFMA also runs on
+// the fma-lite pipe (profiles/int_peaks_r02.txt).  A modular product whose quotient estimate comes from
+// ONE FFMA and whose remainder comes from two low-half IMADs leaves the heavy pipe at 4 clk per
+// butterfly instead of 8 (IMAD + IMAD.HI + IMAD).
+//
+// Representation: every coefficient x travels as the integer  xb = x + kBias,  kBias = 0x4B400000 = the bit
+// pattern of 1.5 * 2^23.  For |x| < 2^22 those same 32 bits, read as a float, are exactly 1.5 * 2^23 + x
+// (ulp is 1 in [2^23, 2^24)), so no int->float conversion is ever issued.
+//
+// Product by a constant w in [0, q):   k22 = round(w * 2^22 / q),  wq = k22 * 2^-22 (exact float),
+// c = 1.5 * 2^23 - 3 * k22 (an integer below 2^24, exact float).  Then
+//     fmaf(as_float(xb), wq, c)  =  RN( (1.5 * 2^23 + x) * wq + c )  =  RN( 1.5 * 2^23 + x * wq )
+// because 1.5 * 2^23 * wq = 3 * k22 cancels exactly inside the FMA: one rounding, to an integer, and the
+// bits of the result are kBias + qe with qe = rint(x * k22 / 2^22),  |qe - x w / q| <= 1/2 + |x| 2^-23.
+//     t = xb * w + K - bits * q   (mod 2^32),   K = kBias * q - kBias * w (+ kBias for a biased result)
+// is x w - qe q exactly (|t| <= q (1/2 + |x| 2^-23) < 2^31, so the wrap-around is harmless).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+
+#ifdef __CUDACC__
+#define FQ_HD __host__ __device__ __forceinline__
+#else
+#define FQ_HD inline
+#endif
+
+namespace scgpu {
+namespace fq {
+
+constexpr int32_t kBias = 0x4B400000;
+constexpr float kBiasF = 12582912.0f;
+constexpr int32_t kLimit = 1 << 22;          // |x| must stay below this wherever x is read as a float
+
+struct alignas(16) Tw {
+    int32_t w;      // multiplier in [0, q)
+    float wq;       // k22 * 2^-22
+    int32_t k;      // additive constant of the low product (includes the output bias when wanted)
+    float c;        // 1.5 * 2^23 - 3 * k22
+};
+
+FQ_HD float as_f(int32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __int_as_float(x);
+#else
+    float f; memcpy(&f, &x, 4); return f;
+#endif
+}
+FQ_HD int32_t as_i(float f)
+{
+#ifdef __CUDA_ARCH__
+    return __float_as_int(f);
+#else
+    int32_t x; memcpy(&x, &f, 4); return x;
+#endif
+}
+FQ_HD float fma_rn(float a, float b, float c)
+{
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+// wrap-around 32-bit multiply-add (signed overflow is undefined in C++, the hardware IMAD is not)
+FQ_HD int32_t mad(int32_t a, int32_t b, int32_t c)
+{
+    return (int32_t)((uint32_t)a * (uint32_t)b + (uint32_t)c);
+}
+
+// xb biased, |x| < 2^22.  Result: x * w - qe * q, plus kBias when tw.k was built with the output bias.
+FQ_HD int32_t mul(int32_t xb, const Tw &tw, int32_t nq)
+{
+    const float f = fma_rn(as_f(xb), tw.wq, tw.c);
+    const int32_t p = mad(xb, tw.w, tw.k);
+    return mad(as_i(f), nq, p);
+}
+
+// product of two UNBIASED values, |a b| / q < 2^22, |a|, |b| < 2^24.  pwk = kBias * q.
+FQ_HD int32_t mul_var(int32_t a, int32_t b, float invq, int32_t pwk, int32_t nq)
+{
+#ifdef __CUDA_ARCH__
+    const float g = __fmul_rn(__int2float_rn(a), __int2float_rn(b));
+#else
+    const float g = (float)a * (float)b;
+#endif
+    const float f = fma_rn(g, invq, kBiasF);
+    const int32_t p = mad(a, b, pwk);
+    return mad(as_i(f), nq, p);
+}
+
+}  // namespace fq
+}  // namespace scgpu

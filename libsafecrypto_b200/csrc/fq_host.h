@@ -1,0 +1,139 @@
+// fq_host.h -- host-side set-up of the float-quotient kernels: twiddle entries and the interval analysis
+// that proves every value read as a float stays below 2^22 and the final residue lies in (-q, q).
+// Plain C++ (no CUDA) so that tools/fq_model.cpp can run the same code on the CPU.
+#pragma once
+#include "fq_arith.cuh"
+
+#include <vector>
+
+namespace scgpu {
+namespace fq {
+
+struct Schedule {
+    int ok;             // 0: (q, n) cannot be served by this arithmetic
+    int r_inv[4];       // reduce all slots at the entry of inverse pass p (pass 0 holds the final stage)
+    int32_t x0;         // |input| bound of the fast path
+    double fwd_max;     // proven bounds (for the model's assertions)
+    double inv_max;
+    double final_max;
+};
+
+inline int64_t powmod(int64_t b, int64_t e, int64_t q)
+{
+    __int128 r = 1, x = ((b % q) + q) % q;
+    while (e > 0) { if (e & 1) r = (r * x) % q; x = (x * x) % q; e >>= 1; }
+    return (int64_t)r;
+}
+
+// entry for multiplication by w (any representative), result biased when out_biased
+inline Tw make_tw(int64_t w, int64_t q, bool out_biased)
+{
+    Tw t;
+    w = ((w % q) + q) % q;
+    const int64_t k22 = (w * (1ll << 23) + q) / (2 * q);             // round(w * 2^22 / q)
+    t.w = (int32_t)w;
+    t.wq = (float)((double)k22 / 4194304.0);                         // k22 <= 2^22: exact
+    t.c = (float)(12582912.0 - 3.0 * (double)k22);                   // integer in [0, 2^24): exact
+    uint32_t k = (uint32_t)kBias * (uint32_t)q - (uint32_t)kBias * (uint32_t)w;
+    if (out_biased) k += (uint32_t)kBias;
+    t.k = (int32_t)k;
+    return t;
+}
+
+// |x w - qe q| for |x| <= b  (+1 of slack for the rounding of the bound itself)
+inline double mul_bound(double b, double q) { return q * (0.5 + b / 8388608.0) + 1.0; }
+
+// Interval propagation over the kernels' dataflow; `accumulate` = number of pointwise products summed before
+// the inverse transform (1: polymul / key product, l: mat-vec).  key_max = largest |second operand| of a
+// key product (SINT16 keys: 32768).
+inline Schedule analyse(int logn, int64_t qi, int accumulate)
+{
+    Schedule s;
+    s.ok = 0;
+    for (int i = 0; i < 4; i++) s.r_inv[i] = 0;
+    const double q = (double)qi, lim = (double)kLimit - 2.0;
+    s.x0 = (int32_t)(4 * qi);
+    if (qi < 257 || qi >= (1 << 18) || (qi & 1) == 0) return s;
+    // forward: one product per stage on the difference branch, additive growth
+    double b = (double)s.x0;
+    for (int st = 0; st < logn; st++) {
+        if (b >= lim) return s;
+        b += mul_bound(b, q);
+    }
+    s.fwd_max = b;
+    if (b >= lim) return s;
+    // pointwise: |a b| / q < 2^22 with both operands at the forward bound, or one at max(q, 32768)
+    const double other = b > 32768.0 ? b : 32768.0;
+    const double quo = b * other / q;
+    if (quo >= lim) return s;
+    const double pw = q * (0.5 + 2.0 * quo / 16777216.0) + 2.0;       // roundings: g, 1/q (2^-24 relative each), the FMA (1/2)
+    // inverse passes: pass np-1 first; slots m = 0..7, stage distance 1, 2, 4 in slot units
+    const int npass = (logn + 2) / 3;
+    double bin = pw * accumulate;
+    s.inv_max = bin;
+    for (int pass = npass - 1; pass >= 0; pass--) {
+        const int J = (logn - 3 * pass) >= 3 ? 3 : (logn - 3 * pass);
+        int chosen = -1;
+        double bout = 0, seen = 0, fin = 0;
+        for (int r = 0; r <= 1 && chosen < 0; r++) {
+            double v[8];
+            if (r && bin >= lim) break;
+            for (int m = 0; m < 8; m++) v[m] = r ? mul_bound(bin, q) : bin;
+            bool ok = true;
+            seen = 0; fin = 0;
+            for (int st = 0; st < J && ok; st++) {
+                const int delta = 1 << st;
+                const bool last = (pass == 0 && st == J - 1);
+                for (int m = 0; m < 8 && ok; m++) {
+                    if (m & delta) continue;
+                    const double d = v[m] + v[m + delta];
+                    if (d >= lim) { ok = false; break; }
+                    seen = d > seen ? d : seen;
+                    v[m + delta] = mul_bound(d, q);
+                    v[m] = last ? mul_bound(d, q) : d;
+                    if (last) fin = v[m] > fin ? v[m] : fin;
+                }
+            }
+            if (ok && pass == 0 && fin >= q) ok = false;          // canonicalisation adds q at most once
+            if (ok) {
+                chosen = r;
+                for (int m = 0; m < 8; m++) bout = v[m] > bout ? v[m] : bout;
+            }
+        }
+        if (chosen < 0) return s;
+        s.r_inv[pass] = chosen;
+        s.inv_max = seen > s.inv_max ? seen : s.inv_max;
+        if (pass == 0) s.final_max = fin;
+        bin = bout;
+    }
+    s.ok = 1;
+    return s;
+}
+
+// zf[k] = psi^brv(k) (k = 2^s + b: stage s, block b); zi[k] = its inverse, zi[1] also carries n^-1.
+// Forward products and the two final-stage products are unbiased, every other inverse product is biased.
+inline bool build_tables(int logn, int64_t q, const int32_t *w_host, std::vector<Tw> &zf, std::vector<Tw> &zi,
+                         Tw &ninv, Tw &one)
+{
+    const int n = 1 << logn;
+    const int64_t psi = (((int64_t)w_host[1] % q) + q) % q;
+    if (powmod(psi, n, q) != q - 1) return false;
+    const int64_t nin = powmod(n, q - 2, q);
+    zf.assign(n, make_tw(1, q, false));
+    zi.assign(n, make_tw(1, q, true));
+    for (int k = 1; k < n; k++) {
+        int e = 0;
+        for (int b = 0; b < logn; b++) e |= ((k >> b) & 1) << (logn - 1 - b);
+        const int64_t z = (((int64_t)w_host[e] % q) + q) % q;
+        int64_t zinv = (q - (((int64_t)w_host[n - e] % q) + q) % q) % q;
+        if (k == 1) zinv = (int64_t)(((__int128)zinv * nin) % q);
+        zf[k] = make_tw(z, q, false);
+        zi[k] = make_tw(zinv, q, k != 1);
+    }
+    ninv = make_tw(nin, q, false);
+    one = make_tw(1, q, true);
+    return true;
+}
+
+}  // namespace fq
+}  // namespace scgpu

@@ -32,6 +32,22 @@ __global__ void __launch_bounds__(256) k_peak(int iters, int32_t seed, int32_t *
                 else if (KIND == 6) { x[i] = x[i] * a + b; x[i] = x[i] + a + x[(i + 1) & 7]; }  // IMAD + IADD3 pair
                 else if (KIND == 7) f[i] = fmaf(f[i], 1.0000001f, 0.5f);         // FFMA
                 else if (KIND == 8) d[i] = fma(d[i], 1.0000001, 0.5);            // DFMA
+                else if (KIND == 10) {                                           // 32-bit Barrett butterfly (ntt_fast_sq.cu)
+                    if (i < 4) {
+                        int32_t p = x[i + 4] * a;
+                        int32_t qe = __mulhi(p, 349496) ;
+                        int32_t t = qe * -12289 + p;
+                        x[i + 4] = x[i] - t; x[i] = x[i] + t;
+                    }
+                }
+                else if (KIND == 11) {                                           // float-quotient butterfly (ntt_fast_fq.cu)
+                    if (i < 4) {
+                        float fq = fmaf(__int_as_float(x[i + 4]), __int_as_float(b), __int_as_float(a));
+                        int32_t p = x[i + 4] * a + b;
+                        int32_t t = __float_as_int(fq) * -12289 + p;
+                        x[i + 4] = x[i] - t; x[i] = x[i] + t;
+                    }
+                }
                 else if (KIND == 9) {                                            // Montgomery butterfly: 3 mul-class + 2 add-class
                     int32_t hi = __mulhi(x[i], a), lo = __mulhi(x[i] * b, 12289);
                     int32_t o = x[(i + 4) & 7];
@@ -71,6 +87,8 @@ extern "C" double scgpu_int_peak_gops(int kind, int iters, int device)
         case 6: k_peak<6><<<grid, block>>>(n, 12345, sink); break;
         case 7: k_peak<7><<<grid, block>>>(n, 12345, sink); break;
         case 8: k_peak<8><<<grid, block>>>(n, 12345, sink); break;
+        case 10: k_peak<10><<<grid, block>>>(n, 12345, sink); break;
+        case 11: k_peak<11><<<grid, block>>>(n, 12345, sink); break;
         default: k_peak<9><<<grid, block>>>(n, 12345, sink); break;
         }
         count_launch();
@@ -86,7 +104,8 @@ extern "C" double scgpu_int_peak_gops(int kind, int iters, int device)
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(sink);
     // ops per inner statement: kinds 6 -> 2, 9 -> 5 (counted per butterfly: 4 per i-pair ... see bench.py)
-    double per = (kind == 6) ? 2.0 : (kind == 9 ? 5.0 : 1.0);
+    // kinds 10 / 11 report butterflies per second (4 butterflies per 8-slot round)
+    double per = (kind == 6) ? 2.0 : (kind == 9 ? 5.0 : ((kind == 10 || kind == 11) ? 0.5 : 1.0));
     double ops = (double)grid * block * (double)iters * 4.0 * 8.0 * per;
     return ops / (ms * 1e-3) / 1e9;
 }

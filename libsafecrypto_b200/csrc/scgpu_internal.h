@@ -39,6 +39,12 @@ struct NttPlanDev {
     int32_t *sq_zf, *sq_zi;
     int32_t sq_ninv, sq_x0;
     uint32_t sq_M;
+    // small-modulus fused kernels, float-quotient arithmetic (ntt_fast_fq.cu); fq_ok == 0: not applicable
+    int fq_ok, fq_r_inv[4], fq_r_inv_mv[4];
+    int32_t fq_x0;
+    void *fq_zf, *fq_zi;                 // int32 w[n] followed by float wq[n]
+    alignas(16) unsigned char fq_ninv[16], fq_one[16];
+    alignas(16) unsigned char fq_pass0[2 * 7 * 16];   // fq::Tw entries 1..7 of the forward / inverse table
 };
 
 struct ExactArgs {
@@ -66,6 +72,13 @@ int launch_matvec(const NttPlanDev &plan, int32_t *out, const int32_t *A, const 
 int build_fast_tables(NttPlanDev &plan, const int32_t *w_host);
 void free_fast_tables(NttPlanDev &plan);
 int set_force_montgomery(int on);
+int set_fast_arith(int mode);           // 0 auto, 1 Montgomery, 2 Barrett-32, 3 float-quotient
+int build_fq_tables(NttPlanDev &plan, const int32_t *w_host);
+void free_fq_tables(NttPlanDev &plan);
+int launch_polymul_fq(const NttPlanDev &plan, int mode, int32_t *out, const int32_t *a, const void *b,
+                      size_t b_stride, size_t count, cudaStream_t stream);
+int launch_matvec_fq(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
+                     size_t count, cudaStream_t stream);
 int build_sq_tables(NttPlanDev &plan, const int32_t *w_host);
 void free_sq_tables(NttPlanDev &plan);
 int launch_polymul_sq(const NttPlanDev &plan, int mode, int32_t *out, const int32_t *a, const void *b,

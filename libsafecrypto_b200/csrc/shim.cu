@@ -51,6 +51,7 @@ struct scgpu_ntt_plan {
 extern "C" const char *scgpu_last_error(void) { return g_err; }
 extern "C" uint64_t scgpu_launch_count(void) { return g_launches.load(); }
 extern "C" int scgpu_force_montgomery(int on) { return set_force_montgomery(on); }
+extern "C" int scgpu_set_fast_arith(int mode) { return set_fast_arith(mode); }
 extern "C" int scgpu_device_count(void)
 {
     int n = 0;
@@ -119,6 +120,7 @@ extern "C" int scgpu_ntt_plan_create(scgpu_ntt_plan_t **out, const void *params,
         }
         int rcode = build_fast_tables(d, wh.data());
         if (rcode == SCGPU_OK) rcode = build_sq_tables(d, wh.data());
+        if (rcode == SCGPU_OK) rcode = build_fq_tables(d, wh.data());
         if (rcode != SCGPU_OK) { delete plan; return rcode; }
     }
     *out = plan;
@@ -138,6 +140,7 @@ extern "C" void scgpu_ntt_plan_destroy(scgpu_ntt_plan_t *plan)
     cudaFree(plan->dev.r);
     free_fast_tables(plan->dev);
     free_sq_tables(plan->dev);
+    free_fq_tables(plan->dev);
     delete plan;
 }
 

@@ -216,13 +216,13 @@ def test_ibe_fixture_on_gpu():
 FAST_PARAMS = [(12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417, 256, 32), (18433, 512, 16), (8399873, 512, 32)]
 
 
-@pytest.fixture(params=["auto", "montgomery"])
+@pytest.fixture(params=["auto", "montgomery", "barrett32"])
 def arithmetic(request):
-    """Run the fused-kernel tests with the automatic choice (32-bit Barrett for small q) and with
-    Montgomery forced for every modulus."""
-    old = sc.lib().scgpu_force_montgomery(1 if request.param == "montgomery" else 0)
+    """Run the fused-kernel tests with the automatic choice (float-quotient products for small q), with 32-bit
+    Barrett where applicable, and with Montgomery forced for every modulus."""
+    old = sc.lib().scgpu_set_fast_arith({"auto": 0, "montgomery": 1, "barrett32": 2}[request.param])
     yield request.param
-    sc.lib().scgpu_force_montgomery(old)
+    sc.lib().scgpu_set_fast_arith(old)
 
 
 @pytest.mark.parametrize("q,n,tw", FAST_PARAMS)
