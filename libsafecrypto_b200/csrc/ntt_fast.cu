@@ -384,8 +384,9 @@ void free_fast_tables(NttPlanDev &p)
     p.zeta_fwd = p.zeta_inv = nullptr;
 }
 
-// Arithmetic of the fused kernels: 0 = automatic (float-quotient where its bounds are proven, else 32-bit
-// Barrett, else Montgomery), 1 = Montgomery for every modulus, 2 = Barrett-32 where applicable, 3 = same as 0.
+// Arithmetic of the fused kernels: 0 = automatic (float-quotient where its bounds are proven -- the warp-local
+// 32-coefficient schedule for polymul / key products -- else 32-bit Barrett, else Montgomery), 1 = Montgomery
+// for every modulus, 2 = Barrett-32 where applicable, 3 = float-quotient with the 8-coefficient schedule.
 // SCGPU_FAST_ARITH / SCGPU_FORCE_MONT=1 set the initial value; tests switch it to cover all three.
 static int g_arith = -1;
 static int arith_mode()
@@ -398,6 +399,7 @@ static int arith_mode()
     return g_arith;
 }
 static bool use_fq(const NttPlanDev &p) { const int m = arith_mode(); return p.fq_ok && (m == 0 || m == 3); }
+static bool use_fq32(const NttPlanDev &p) { return p.fq32_ok && arith_mode() == 0; }
 static bool use_sq(const NttPlanDev &p) { return p.sq_ok && arith_mode() != 1; }
 int set_fast_arith(int mode)
 {
@@ -422,6 +424,7 @@ int launch_polymul(const NttPlanDev &p, int32_t *out, const int32_t *a, const in
                    size_t b_stride, size_t count, cudaStream_t st)
 {
     if (count == 0) return SCGPU_OK;
+    if (use_fq32(p)) return launch_polymul_fq32(p, 0, out, a, b, b_stride, count, st);
     if (use_fq(p)) return launch_polymul_fq(p, 0, out, a, b, b_stride, count, st);
     if (use_sq(p)) return launch_polymul_sq(p, 0, out, a, b, b_stride, count, st);
     SCGPU_REQUIRE_FAST(p);
@@ -444,6 +447,7 @@ int launch_mul_key(const NttPlanDev &p, int32_t *out, const int32_t *t, const vo
 {
     if (count == 0) return SCGPU_OK;
     if (key_bits != 16 && key_bits != 32) { set_error("key_bits must be 16 or 32"); return SCGPU_ERR_ARG; }
+    if (use_fq32(p)) return launch_polymul_fq32(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
     if (use_fq(p)) return launch_polymul_fq(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
     if (use_sq(p)) return launch_polymul_sq(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
     SCGPU_REQUIRE_FAST(p);

@@ -1,0 +1,456 @@
+// ntt_fast_fq32.cu -- fused negacyclic product, float-quotient arithmetic (fq_arith.cuh), WARP-LOCAL schedule:
+// 32 coefficients per thread, n/32 threads per polynomial (8 / 16 / 32 lanes of ONE warp for n = 256 / 512 /
+// 1024), so a whole product needs one shared-memory exchange per transform and only __syncwarp():
+//
+//   pass 0   stages 0..4   thread tau holds elements tau + (n/32) m, m = 0..31.  The 31 twiddles of these
+//                          stages are the same for every thread: they live in the kernel's constant bank.
+//   pass 1   stages 5..    thread tau holds the 32 contiguous elements 32 tau .. 32 tau + 31, i.e. 32 / SUB
+//                          independent sub-chunks of SUB = n/32 elements; both operands of a sub-chunk are
+//                          transformed together (shared twiddles), multiplied pointwise and taken back through
+//                          the inverse stages before the next sub-chunk is touched.
+//
+// Against the 8-coefficient schedule of ntt_fast_fq.cu (per product, n = 512): 2 exchanges instead of 6
+// (96 instead of 192 shared-memory wavefronts), no named barriers, address arithmetic amortised over 4x more
+// butterflies, 16 independent butterflies per stage per thread.  The tile is padded (4 words per 32 elements)
+// so that both the strided 32-bit accesses of pass 0 and the 128-bit accesses of pass 1 are conflict-free and
+// every address is  thread base + compile-time offset.  Pass-1 twiddles are stored thread-major per stage
+// (fq32_slot) so that a warp's 128-bit twiddle loads are contiguous.
+#include "scgpu_internal.h"
+#include "fq_host.h"
+#include "../../include/scgpu.h"
+
+#include <vector>
+
+namespace scgpu {
+
+namespace {
+
+using fq::Tw;
+using fq::kBias;
+typedef uint32_t u32;
+
+constexpr int kThreads32 = 128;
+
+template <int LOGN>
+struct Cfg32 {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int T = N / 32;             // threads per polynomial
+    static constexpr int PW = 32 / T;            // polynomials per warp
+    static constexpr int SUB = N / 32;           // elements of one pass-1 sub-chunk
+    static constexpr int NSUB = 32 / SUB;
+    static constexpr int TS = N + N / 8 + (T & 31);   // tile stride in words (bank offset T between polynomials)
+    static constexpr int POLYS = (kThreads32 / 32) * PW;
+};
+
+struct Fq32Const {
+    const int32_t *pf_w; const float *pf_q;      // pass-1 forward table, thread-major (fq32_slot)
+    const int32_t *pi_w; const float *pi_q;      // pass-1 inverse table
+    Tw f0[31], i0[31];                           // entries 1..31: stages 0..4
+    Tw ninv, one;
+    int32_t q, nq, x0, pwk, kf, ki;
+    float invq;
+    uint32_t M;
+    int r0;                                      // reduce every coefficient at the entry of inverse pass 0
+};
+
+__device__ __forceinline__ Tw derive(int32_t w, float wq, int32_t kbase)
+{
+    Tw t;
+    t.w = w;
+    t.wq = wq;
+    t.k = fq::mad(w, -kBias, kbase);
+    t.c = __fmaf_rn(wq, -fq::kBiasF, fq::kBiasF);
+    return t;
+}
+
+__device__ __forceinline__ int32_t bred(int32_t p, const Fq32Const &c)
+{
+    const int32_t qe = (int32_t)(((int64_t)p * (int64_t)c.M + 0x80000000ll) >> 32);
+    return qe * c.nq + p;
+}
+__device__ __forceinline__ bool out_of_range(int32_t v, const Fq32Const &c)
+{
+    return ((u32)v + (u32)c.x0) > (u32)(2 * c.x0);
+}
+
+__device__ __forceinline__ void ct(u32 &lo, u32 &hi, const Tw &z, int32_t nq)
+{
+    const u32 t = (u32)fq::mul((int32_t)hi, z, nq);
+    hi = lo - t;
+    lo = lo + t;
+}
+__device__ __forceinline__ void gs(u32 &lo, u32 &hi, const Tw &z, int32_t nq)
+{
+    const u32 d = lo - hi + (u32)kBias;
+    lo = lo + hi - (u32)kBias;
+    hi = (u32)fq::mul((int32_t)d, z, nq);
+}
+
+// padded tile position of element e
+__host__ __device__ constexpr int pos32(int e) { return e + 4 * (e >> 5); }
+
+// ---- pass 0: stages 0..4 on x[m] = element tau + T m ---------------------------------------------------
+__device__ __forceinline__ void fwd_pass0(u32 (&x)[32], const Fq32Const &c)
+{
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int half = 16 >> s;
+#pragma unroll
+        for (int m = 0; m < 32; m++)
+            if ((m & half) == 0) ct(x[m], x[m + half], c.f0[(1 << s) - 1 + (m >> (5 - s))], c.nq);
+    }
+}
+
+// stages 4..1, then stage 0 with n^-1 folded into both branches; returns canonical residues
+__device__ __forceinline__ void inv_pass0(u32 (&x)[32], const Fq32Const &c)
+{
+#pragma unroll
+    for (int s = 4; s >= 1; s--) {
+        const int half = 16 >> s;
+#pragma unroll
+        for (int m = 0; m < 32; m++)
+            if ((m & half) == 0) gs(x[m], x[m + half], c.i0[(1 << s) - 1 + (m >> (5 - s))], c.nq);
+    }
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+        const u32 s = x[m] + x[m + 16] - (u32)kBias;
+        const u32 d = x[m] - x[m + 16] + (u32)kBias;
+        const u32 ys = (u32)fq::mul((int32_t)s, c.ninv, c.nq);
+        const u32 yd = (u32)fq::mul((int32_t)d, c.i0[0], c.nq);
+        x[m] = min(ys, ys + (u32)c.q);
+        x[m + 16] = min(yd, yd + (u32)c.q);
+    }
+}
+
+// ---- pass 1 -------------------------------------------------------------------------------------------
+// CNT consecutive entries r0 .. r0 + CNT - 1 of thread tau for stage S (CNT in 1, 2, 4)
+template <int LOGN, int S, int CNT>
+__device__ __forceinline__ void load_entries(Tw (&tw)[CNT], const int32_t *tw_w, const float *tw_q, int32_t kbase,
+                                             int tau, int r0)
+{
+    using C = Cfg32<LOGN>;
+    constexpr int LEN = C::N >> (S + 1);
+    constexpr int G = 16 / LEN;
+    constexpr int V = G < 4 ? G : 4;
+    const int off = (1 << S) + ((r0 / V) * C::T + tau) * V + (r0 % V);
+    if (CNT == 4) {
+        const int4 w = __ldg(reinterpret_cast<const int4 *>(tw_w + off));
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(tw_q + off));
+        tw[0] = derive(w.x, f.x, kbase);
+        tw[1 % CNT] = derive(w.y, f.y, kbase);
+        tw[2 % CNT] = derive(w.z, f.z, kbase);
+        tw[3 % CNT] = derive(w.w, f.w, kbase);
+    } else if (CNT == 2) {
+        const int2 w = __ldg(reinterpret_cast<const int2 *>(tw_w + off));
+        const float2 f = __ldg(reinterpret_cast<const float2 *>(tw_q + off));
+        tw[0] = derive(w.x, f.x, kbase);
+        tw[1 % CNT] = derive(w.y, f.y, kbase);
+    } else {
+        tw[0] = derive(__ldg(tw_w + off), __ldg(tw_q + off), kbase);
+    }
+}
+
+// one radix-2 stage S (forward: Cooley-Tukey, inverse: Gentleman-Sande) on sub-chunk h of NOPS operands
+template <int LOGN, int S, int NOPS, bool INV>
+__device__ __forceinline__ void stage1(u32 (&xa)[Cfg32<LOGN>::SUB], u32 (&xb)[Cfg32<LOGN>::SUB],
+                                       const Fq32Const &c, int tau, int h)
+{
+    using C = Cfg32<LOGN>;
+    constexpr int LEN = C::N >> (S + 1);
+    constexpr int CNT = C::SUB / (2 * LEN);          // twiddles of this sub-chunk in this stage
+    constexpr int GRP = CNT < 4 ? CNT : 4;
+    const int32_t *tw_w = INV ? c.pi_w : c.pf_w;
+    const float *tw_q = INV ? c.pi_q : c.pf_q;
+    const int32_t kb = INV ? c.ki : c.kf;
+#pragma unroll
+    for (int g0 = 0; g0 < CNT; g0 += GRP) {
+        Tw tw[GRP];
+        load_entries<LOGN, S, GRP>(tw, tw_w, tw_q, kb, tau, h * CNT + g0);
+#pragma unroll
+        for (int g = 0; g < GRP; g++) {
+#pragma unroll
+            for (int j = 0; j < LEN; j++) {
+                const int i = (g0 + g) * 2 * LEN + j;
+                if (INV) {
+                    gs(xa[i], xa[i + LEN], tw[g], c.nq);
+                } else {
+                    ct(xa[i], xa[i + LEN], tw[g], c.nq);
+                    if (NOPS == 2) ct(xb[i], xb[i + LEN], tw[g], c.nq);
+                }
+            }
+        }
+    }
+}
+
+template <int LOGN, int S, int NOPS>
+__device__ __forceinline__ void fwd_stages1(u32 (&xa)[Cfg32<LOGN>::SUB], u32 (&xb)[Cfg32<LOGN>::SUB],
+                                            const Fq32Const &c, int tau, int h)
+{
+    if constexpr (S < LOGN) {
+        stage1<LOGN, S, NOPS, false>(xa, xb, c, tau, h);
+        fwd_stages1<LOGN, S + 1, NOPS>(xa, xb, c, tau, h);
+    }
+}
+template <int LOGN, int S>
+__device__ __forceinline__ void inv_stages1(u32 (&x)[Cfg32<LOGN>::SUB], const Fq32Const &c, int tau, int h)
+{
+    if constexpr (S >= 5) {
+        stage1<LOGN, S, 1, true>(x, x, c, tau, h);
+        inv_stages1<LOGN, S - 1>(x, c, tau, h);
+    }
+}
+
+template <int LOGN>
+__device__ __forceinline__ void load_operand(u32 (&x)[32], const int32_t *row, int tau, const Fq32Const &c)
+{
+    constexpr int T = Cfg32<LOGN>::T;
+    int32_t v[32];
+    bool wide = false;
+#pragma unroll
+    for (int m = 0; m < 32; m++) {
+        v[m] = __ldg(row + tau + m * T);
+        wide |= out_of_range(v[m], c);
+    }
+    if (__any_sync(0xFFFFFFFFu, wide)) {
+#pragma unroll
+        for (int m = 0; m < 32; m++) v[m] = bred(v[m], c);
+    }
+#pragma unroll
+    for (int m = 0; m < 32; m++) x[m] = (u32)v[m] + (u32)kBias;
+}
+
+template <int LOGN>
+__device__ __forceinline__ void store_pass0(int32_t *tile, const u32 (&x)[32], int tau)
+{
+    constexpr int T = Cfg32<LOGN>::T;
+#pragma unroll
+    for (int m = 0; m < 32; m++) tile[tau + pos32(T * m)] = (int32_t)x[m];
+}
+template <int LOGN>
+__device__ __forceinline__ void load_pass0(const int32_t *tile, u32 (&x)[32], int tau)
+{
+    constexpr int T = Cfg32<LOGN>::T;
+#pragma unroll
+    for (int m = 0; m < 32; m++) x[m] = (u32)tile[tau + pos32(T * m)];
+}
+
+template <int SUB>
+__device__ __forceinline__ void load_sub(const int32_t *p, u32 (&x)[SUB])
+{
+#pragma unroll
+    for (int k = 0; k < SUB; k += 4) {
+        const int4 v = *reinterpret_cast<const int4 *>(p + k);
+        x[k] = (u32)v.x; x[k + 1] = (u32)v.y; x[k + 2] = (u32)v.z; x[k + 3] = (u32)v.w;
+    }
+}
+template <int SUB>
+__device__ __forceinline__ void store_sub(int32_t *p, const u32 (&x)[SUB])
+{
+#pragma unroll
+    for (int k = 0; k < SUB; k += 4)
+        *reinterpret_cast<int4 *>(p + k) = make_int4((int32_t)x[k], (int32_t)x[k + 1], (int32_t)x[k + 2], (int32_t)x[k + 3]);
+}
+
+enum { FQ_POLYMUL = 0, FQ_KEY16 = 1, FQ_KEY32 = 2 };
+
+template <int LOGN, int MODE>
+__global__ void __launch_bounds__(kThreads32, LOGN == 10 ? 3 : 5)
+k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const void *__restrict__ bsrc,
+               size_t b_stride, size_t count, const __grid_constant__ Fq32Const c)
+{
+    using C = Cfg32<LOGN>;
+    constexpr int N = C::N, T = C::T, SUB = C::SUB;
+    __shared__ __align__(16) int32_t tiles[2][C::POLYS][C::TS];      // slot stride TS = T (mod 32) banks
+    const int lane = threadIdx.x & 31;
+    const int tau = lane % T;
+    const int slot = (threadIdx.x / 32) * C::PW + lane / T;       // polynomial slot inside the CTA
+    int32_t *ta = tiles[0][slot];
+    int32_t *tb = tiles[1][slot];
+
+    for (size_t base = (size_t)blockIdx.x * C::POLYS; base < count; base += (size_t)gridDim.x * C::POLYS) {
+        const size_t poly = base + slot;
+        const bool live = poly < count;
+        const size_t prow = live ? poly : 0;
+        // rolled loops (operand, sub-chunk): the fully unrolled body was 60 KB of SASS and spent 2 of every
+        // 7 stall cycles waiting for instructions (profiles/polymul_r02c_*); the L1.5 I-cache holds 32 KB
+#pragma unroll 1
+        for (int op = 0; op < (MODE == FQ_POLYMUL ? 2 : 1); op++) {
+            const int32_t *row = op == 0 ? a + prow * N : static_cast<const int32_t *>(bsrc) + prow * b_stride;
+            u32 x[32];
+            load_operand<LOGN>(x, row, tau, c);
+            fwd_pass0(x, c);
+            store_pass0<LOGN>(op == 0 ? ta : tb, x, tau);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int h = 0; h < C::NSUB; h++) {
+            u32 xa[SUB], xb[SUB];
+            int32_t *pa = ta + 36 * tau + SUB * h;
+            load_sub<SUB>(pa, xa);
+            if (MODE == FQ_POLYMUL) {
+                load_sub<SUB>(tb + 36 * tau + SUB * h, xb);
+                fwd_stages1<LOGN, 5, 2>(xa, xb, c, tau, h);
+#pragma unroll
+                for (int i = 0; i < SUB; i++)
+                    xa[i] = (u32)fq::mul_var((int32_t)(xa[i] - (u32)kBias), (int32_t)(xb[i] - (u32)kBias), c.invq, c.pwk, c.nq) + (u32)kBias;
+            } else {
+                fwd_stages1<LOGN, 5, 1>(xa, xb, c, tau, h);
+                int32_t kv[SUB];
+                bool wide = false;
+#pragma unroll
+                for (int i = 0; i < SUB; i++) {
+                    const int j = (int)(__brev((unsigned)(32 * tau + SUB * h + i)) >> (32 - LOGN));
+                    if (MODE == FQ_KEY16) kv[i] = (int32_t)__ldg(static_cast<const int16_t *>(bsrc) + prow * b_stride + j);
+                    else {
+                        kv[i] = __ldg(static_cast<const int32_t *>(bsrc) + prow * b_stride + j);
+                        wide |= out_of_range(kv[i], c);
+                    }
+                }
+                if (MODE == FQ_KEY32 && __any_sync(0xFFFFFFFFu, wide)) {
+#pragma unroll
+                    for (int i = 0; i < SUB; i++) kv[i] = bred(kv[i], c);
+                }
+#pragma unroll
+                for (int i = 0; i < SUB; i++)
+                    xa[i] = (u32)fq::mul_var((int32_t)(xa[i] - (u32)kBias), kv[i], c.invq, c.pwk, c.nq) + (u32)kBias;
+            }
+            inv_stages1<LOGN, LOGN - 1>(xa, c, tau, h);
+            store_sub<SUB>(pa, xa);
+        }
+        __syncwarp();
+        {
+            u32 x[32];
+            load_pass0<LOGN>(ta, x, tau);
+            if (c.r0) {
+#pragma unroll
+                for (int m = 0; m < 32; m++) x[m] = (u32)fq::mul((int32_t)x[m], c.one, c.nq);
+            }
+            inv_pass0(x, c);
+            if (live) {
+                int32_t *orow = out + poly * N;
+#pragma unroll
+                for (int m = 0; m < 32; m++) orow[tau + m * T] = (int32_t)x[m];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+// position of entry r (0 .. 16/len - 1) of thread tau in stage s of the thread-major pass-1 table
+static int fq32_slot(int logn, int s, int tau, int r)
+{
+    const int n = 1 << logn, T = n / 32, len = n >> (s + 1), G = 16 / len, V = G < 4 ? G : 4;
+    return (1 << s) + ((r / V) * T + tau) * V + (r % V);
+}
+
+// Bounds of this schedule: forward and pointwise as in fq::analyse; inverse: sums double per stage, products
+// are bounded by mul_bound; one optional reduction of every coefficient between the two inverse passes.
+static bool fq32_analyse(int logn, int64_t qi, int *r0_out, int32_t *x0_out)
+{
+    const fq::Schedule s = fq::analyse(logn, qi, 1);        // forward + pointwise part (and q range checks)
+    if (!s.ok) return false;
+    const double q = (double)qi, lim = (double)fq::kLimit - 2.0;
+    const double other = s.fwd_max > 32768.0 ? s.fwd_max : 32768.0;
+    const double quo = s.fwd_max * other / q;
+    const double pw = q * (0.5 + 2.0 * quo / 16777216.0) + 2.0;
+    for (int r0 = 0; r0 <= 1; r0++) {
+        double b = pw;
+        bool ok = true;
+        for (int st = logn - 1; st >= 0 && ok; st--) {
+            if (st == 4 && r0) { if (b >= lim) { ok = false; break; } b = fq::mul_bound(b, q); }
+            const double d = 2.0 * b;                        // |lo + hi|, |lo - hi|
+            if (d >= lim) { ok = false; break; }
+            const double prod = fq::mul_bound(d, q);
+            if (st == 0) { if (prod >= q) ok = false; b = prod; }
+            else b = d > prod ? d : prod;
+        }
+        if (ok) { *r0_out = r0; *x0_out = s.x0; return true; }
+    }
+    return false;
+}
+
+int build_fq32_tables(NttPlanDev &p, const int32_t *w_host)
+{
+    p.fq32_ok = 0; p.fq32_tab = nullptr;
+    if (p.logn < 8 || p.logn > 10) return SCGPU_OK;
+    int r0 = 0; int32_t x0 = 0;
+    if (!fq32_analyse(p.logn, p.rc.q, &r0, &x0)) return SCGPU_OK;
+    std::vector<Tw> zf, zi;
+    Tw ninv, one;
+    if (!fq::build_tables(p.logn, p.rc.q, w_host, zf, zi, ninv, one)) return SCGPU_OK;
+    const int n = p.n, T = n / 32;
+    // [pf_w | pf_q | pi_w | pi_q], each n words, entries of stages >= 5 in thread-major order
+    std::vector<int32_t> pack(4 * n, 0);
+    for (int s = 5; s < p.logn; s++) {
+        const int len = n >> (s + 1), G = 16 / len;
+        for (int tau = 0; tau < T; tau++)
+            for (int r = 0; r < G; r++) {
+                const int nat = (1 << s) + tau * G + r, at = fq32_slot(p.logn, s, tau, r);
+                pack[at] = zf[nat].w;         memcpy(&pack[n + at], &zf[nat].wq, 4);
+                pack[2 * n + at] = zi[nat].w; memcpy(&pack[3 * n + at], &zi[nat].wq, 4);
+            }
+    }
+    SCGPU_CUDA_CHECK(cudaMalloc(&p.fq32_tab, sizeof(int32_t) * 4 * n));
+    SCGPU_CUDA_CHECK(cudaMemcpy(p.fq32_tab, pack.data(), sizeof(int32_t) * 4 * n, cudaMemcpyHostToDevice));
+    memcpy(p.fq32_pass0, &zf[1], sizeof(Tw) * 31);
+    memcpy(p.fq32_pass0 + sizeof(Tw) * 31, &zi[1], sizeof(Tw) * 31);
+    memcpy(p.fq_ninv, &ninv, sizeof(Tw));
+    memcpy(p.fq_one, &one, sizeof(Tw));
+    p.fq32_r0 = r0;
+    p.fq32_x0 = x0;
+    p.fq32_ok = 1;
+    return SCGPU_OK;
+}
+
+void free_fq32_tables(NttPlanDev &p)
+{
+    if (p.fq32_tab) cudaFree(p.fq32_tab);
+    p.fq32_tab = nullptr;
+    p.fq32_ok = 0;
+}
+
+int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32_t *a, const void *b,
+                        size_t b_stride, size_t count, cudaStream_t st)
+{
+    Fq32Const c;
+    const int n = p.n;
+    c.pf_w = static_cast<const int32_t *>(p.fq32_tab);
+    c.pf_q = reinterpret_cast<const float *>(c.pf_w + n);
+    c.pi_w = c.pf_w + 2 * n;
+    c.pi_q = reinterpret_cast<const float *>(c.pf_w + 3 * n);
+    memcpy(c.f0, p.fq32_pass0, sizeof(Tw) * 31);
+    memcpy(c.i0, p.fq32_pass0 + sizeof(Tw) * 31, sizeof(Tw) * 31);
+    memcpy(&c.ninv, p.fq_ninv, sizeof(Tw));
+    memcpy(&c.one, p.fq_one, sizeof(Tw));
+    c.q = p.rc.q; c.nq = -p.rc.q; c.x0 = p.fq32_x0;
+    c.pwk = (int32_t)((uint32_t)kBias * (uint32_t)p.rc.q);
+    c.kf = c.pwk;
+    c.ki = (int32_t)((uint32_t)c.pwk + (uint32_t)kBias);
+    c.invq = (float)(1.0 / (double)p.rc.q);
+    c.M = (uint32_t)((1ull << 32) / (uint64_t)p.rc.q);
+    c.r0 = p.fq32_r0;
+    const int sms = p.sm_count > 0 ? p.sm_count : 148;
+#define FQ32_LAUNCH(L)                                                                                     \
+    {                                                                                                      \
+        const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
+        size_t grid = (size_t)sms * (L == 10 ? 3 : 5);                                                     \
+        if (grid > groups) grid = groups;                                                                  \
+        if (mode == FQ_POLYMUL)    k_polymul_fq32<L, FQ_POLYMUL><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c); \
+        else if (mode == FQ_KEY16) k_polymul_fq32<L, FQ_KEY16><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
+        else                       k_polymul_fq32<L, FQ_KEY32><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
+    }
+    switch (p.logn) {
+    case 8:  FQ32_LAUNCH(8); break;
+    case 9:  FQ32_LAUNCH(9); break;
+    case 10: FQ32_LAUNCH(10); break;
+    default: set_error("unsupported n=%d", p.n); return SCGPU_ERR_UNSUPPORTED;
+    }
+#undef FQ32_LAUNCH
+    count_launch();
+    SCGPU_CUDA_CHECK(cudaGetLastError());
+    return SCGPU_OK;
+}
+
+}  // namespace scgpu

@@ -45,6 +45,11 @@ struct NttPlanDev {
     void *fq_zf, *fq_zi;                 // int32 w[n] followed by float wq[n]
     alignas(16) unsigned char fq_ninv[16], fq_one[16];
     alignas(16) unsigned char fq_pass0[2 * 7 * 16];   // fq::Tw entries 1..7 of the forward / inverse table
+    // warp-local 32-coefficient schedule of the same arithmetic (ntt_fast_fq32.cu)
+    int fq32_ok, fq32_r0;
+    int32_t fq32_x0;
+    void *fq32_tab;                      // [pf_w | pf_q | pi_w | pi_q], n words each
+    alignas(16) unsigned char fq32_pass0[2 * 31 * 16];
 };
 
 struct ExactArgs {
@@ -77,6 +82,10 @@ int build_fq_tables(NttPlanDev &plan, const int32_t *w_host);
 void free_fq_tables(NttPlanDev &plan);
 int launch_polymul_fq(const NttPlanDev &plan, int mode, int32_t *out, const int32_t *a, const void *b,
                       size_t b_stride, size_t count, cudaStream_t stream);
+int build_fq32_tables(NttPlanDev &plan, const int32_t *w_host);
+void free_fq32_tables(NttPlanDev &plan);
+int launch_polymul_fq32(const NttPlanDev &plan, int mode, int32_t *out, const int32_t *a, const void *b,
+                        size_t b_stride, size_t count, cudaStream_t stream);
 int launch_matvec_fq(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
                      size_t count, cudaStream_t stream);
 int build_sq_tables(NttPlanDev &plan, const int32_t *w_host);

@@ -121,6 +121,7 @@ extern "C" int scgpu_ntt_plan_create(scgpu_ntt_plan_t **out, const void *params,
         int rcode = build_fast_tables(d, wh.data());
         if (rcode == SCGPU_OK) rcode = build_sq_tables(d, wh.data());
         if (rcode == SCGPU_OK) rcode = build_fq_tables(d, wh.data());
+        if (rcode == SCGPU_OK) rcode = build_fq32_tables(d, wh.data());
         if (rcode != SCGPU_OK) { delete plan; return rcode; }
     }
     *out = plan;
@@ -141,6 +142,7 @@ extern "C" void scgpu_ntt_plan_destroy(scgpu_ntt_plan_t *plan)
     free_fast_tables(plan->dev);
     free_sq_tables(plan->dev);
     free_fq_tables(plan->dev);
+    free_fq32_tables(plan->dev);
     delete plan;
 }
 
