@@ -223,7 +223,7 @@ def main():
     alg_bytes = 12 * N_COEF * BATCH                     # read a, b (4n each) + write out (4n) per product
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "k_polymul<9,MODE_POLYMUL>",
+                "traffic": None, "peak_source": peak_src, "kernel": "k_polymul_fq32<9,POLYMUL,TMA>",
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes}
     prof = os.path.join(ROOT, "profiles", "polymul_traffic.json")
     if os.path.exists(prof):
@@ -231,14 +231,42 @@ def main():
             roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
     int_roof = None
     if rank == 0:
-        # INT-issue roofline: the kernel is bound by the integer pipes, not HBM
-        mul_g = sc.int_peak_gops(0, 2048, local_rank)
-        bfly_g = sc.int_peak_gops(9, 2048, local_rank)
-        # 3 transforms x (n/2) log2 n butterflies + 2 n pointwise/scale products, 5 INT ops per butterfly-equivalent
-        int_ops = (3 * (N_COEF // 2) * 9 + 2 * N_COEF) * 5.0
-        int_roof = {"imad_gops": mul_g, "montgomery_butterfly_mix_gops": bfly_g,
-                    "achieved_gops": int_ops * BATCH / (k_ms * 1e-3) / 1e9,
-                    "frac_of_butterfly_mix_peak": int_ops * BATCH / (k_ms * 1e-3) / 1e9 / bfly_g if bfly_g > 0 else None}
+        # INT/FP32-issue roofline: the kernel is bound by instruction issue, not HBM.  Denominator =
+        # measured rate of the kernel's own butterfly (FFMA + 2 IMAD + 2 IADD3) in isolation on this device;
+        # numerator = butterfly-equivalents per product: 3 transforms x (n/2) log2 n, n pointwise products and
+        # n/2 extra products of the last inverse stage (n^-1 folded into both branches).
+        bfly_g = sc.int_peak_gops(11, 2048, local_rank)
+        imad_g = sc.int_peak_gops(0, 2048, local_rank)
+        ffma_g = sc.int_peak_gops(7, 2048, local_rank)
+        bfly = 3 * (N_COEF // 2) * 9 + N_COEF + N_COEF // 2
+        ach = bfly * BATCH / (k_ms * 1e-3) / 1e9
+        int_roof = {"bound": "issue", "unit": "G butterflies/s", "achieved": ach, "peak": bfly_g, "frac": ach / bfly_g if bfly_g > 0 else None,
+                    "butterflies_per_product": bfly, "imad_gops": imad_g, "ffma_gops": ffma_g,
+                    "peak_source": "scgpu_int_peak_gops(11): float-quotient butterfly microbenchmark on this device"}
+    # other parameter shapes of BASELINE.json configs[1..2] (device-resident, smaller batch; parity is in tests/)
+    shapes = None
+    if rank == 0:
+        shapes = {}
+        for (qq, nn) in ((12289, 1024), (7681, 256)):
+            ww, rr = O.tables(qq, nn, 16)
+            pl = sc.NttPlan(nn, qq, sc.REFERENCE, ww, rr, device=local_rank)
+            bb = (1 << 28) // (4 * nn)
+            xa = torch.randint(0, qq, (bb, nn), dtype=torch.int32, device=dev, generator=g)
+            xb = torch.randint(0, qq, (bb, nn), dtype=torch.int32, device=dev, generator=g)
+            xo = torch.empty_like(xa)
+            for _ in range(3):
+                pl.polymul(xo, xa, xb)
+            torch.cuda.synchronize()
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(10):
+                pl.polymul(xo, xa, xb)
+            e0.record()
+            torch.cuda.synchronize()
+            ms = s0.elapsed_time(e0) / 10
+            shapes["polymul_n%d_q%d" % (nn, qq)] = {"polymul_per_s": bb / (ms * 1e-3), "pairs": bb,
+                                                    "hbm_frac": 12 * nn * bb / (ms * 1e-3) / 1e9 / peak}
+            del xa, xb, xo, pl
 
     # ---- end-to-end leg: host buffers through the C-ABI ----------------------------------------------------
     ha = torch.randint(0, Q, (E2E_BATCH, N_COEF), dtype=torch.int32).pin_memory()
@@ -306,7 +334,7 @@ def main():
                        "n": N_COEF, "q": Q, "pairs_per_gpu": BATCH, "parallelism": "shard by polynomial index, no collective",
                        "cache": "operands 4 GiB + result 2 GiB per step >> 126 MB L2 (no flush needed)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
-            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss,
+            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss, "other_shapes": shapes,
         }
         print(json.dumps(line))
     if world > 1:

@@ -19,6 +19,7 @@
 #include "fq_host.h"
 #include "../../include/scgpu.h"
 
+#include <cstdlib>
 #include <vector>
 
 namespace scgpu {
@@ -30,6 +31,9 @@ using fq::kBias;
 typedef uint32_t u32;
 
 constexpr int kThreads32 = 128;
+#ifndef FQ32_MINB
+#define FQ32_MINB 5
+#endif
 
 template <int LOGN>
 struct Cfg32 {
@@ -43,8 +47,8 @@ struct Cfg32 {
 };
 
 struct Fq32Const {
-    const int32_t *pf_w; const float *pf_q;      // pass-1 forward table, thread-major (fq32_slot)
-    const int32_t *pi_w; const float *pi_q;      // pass-1 inverse table
+    const int32_t *pf;                           // pass-1 forward table, thread-major (fq32_slot): w | wq | k | c,
+    const int32_t *pi;                           // pass-1 inverse table                      n words each
     Tw f0[31], i0[31];                           // entries 1..31: stages 0..4
     Tw ninv, one;
     int32_t q, nq, x0, pwk, kf, ki;
@@ -52,16 +56,6 @@ struct Fq32Const {
     uint32_t M;
     int r0;                                      // reduce every coefficient at the entry of inverse pass 0
 };
-
-__device__ __forceinline__ Tw derive(int32_t w, float wq, int32_t kbase)
-{
-    Tw t;
-    t.w = w;
-    t.wq = wq;
-    t.k = fq::mad(w, -kBias, kbase);
-    t.c = __fmaf_rn(wq, -fq::kBiasF, fq::kBiasF);
-    return t;
-}
 
 __device__ __forceinline__ int32_t bred(int32_t p, const Fq32Const &c)
 {
@@ -86,6 +80,15 @@ __device__ __forceinline__ void gs(u32 &lo, u32 &hi, const Tw &z, int32_t nq)
     hi = (u32)fq::mul((int32_t)d, z, nq);
 }
 
+// pass-0 entry from the constant bank: w and wq are used as constant operands, k and c come as one 64-bit load
+__device__ __forceinline__ Tw cb_entry(const Tw &e)
+{
+    const int2 kc = *reinterpret_cast<const int2 *>(&e.k);
+    Tw t;
+    t.w = e.w; t.wq = e.wq; t.k = kc.x; t.c = __int_as_float(kc.y);
+    return t;
+}
+
 // padded tile position of element e
 __host__ __device__ constexpr int pos32(int e) { return e + 4 * (e >> 5); }
 
@@ -97,7 +100,7 @@ __device__ __forceinline__ void fwd_pass0(u32 (&x)[32], const Fq32Const &c)
         const int half = 16 >> s;
 #pragma unroll
         for (int m = 0; m < 32; m++)
-            if ((m & half) == 0) ct(x[m], x[m + half], c.f0[(1 << s) - 1 + (m >> (5 - s))], c.nq);
+            if ((m & half) == 0) ct(x[m], x[m + half], cb_entry(c.f0[(1 << s) - 1 + (m >> (5 - s))]), c.nq);
     }
 }
 
@@ -109,7 +112,7 @@ __device__ __forceinline__ void inv_pass0(u32 (&x)[32], const Fq32Const &c)
         const int half = 16 >> s;
 #pragma unroll
         for (int m = 0; m < 32; m++)
-            if ((m & half) == 0) gs(x[m], x[m + half], c.i0[(1 << s) - 1 + (m >> (5 - s))], c.nq);
+            if ((m & half) == 0) gs(x[m], x[m + half], cb_entry(c.i0[(1 << s) - 1 + (m >> (5 - s))]), c.nq);
     }
 #pragma unroll
     for (int m = 0; m < 16; m++) {
@@ -125,28 +128,32 @@ __device__ __forceinline__ void inv_pass0(u32 (&x)[32], const Fq32Const &c)
 // ---- pass 1 -------------------------------------------------------------------------------------------
 // CNT consecutive entries r0 .. r0 + CNT - 1 of thread tau for stage S (CNT in 1, 2, 4)
 template <int LOGN, int S, int CNT>
-__device__ __forceinline__ void load_entries(Tw (&tw)[CNT], const int32_t *tw_w, const float *tw_q, int32_t kbase,
-                                             int tau, int r0)
+__device__ __forceinline__ void load_entries(Tw (&tw)[CNT], const int32_t *tab, int tau, int r0)
 {
     using C = Cfg32<LOGN>;
     constexpr int LEN = C::N >> (S + 1);
     constexpr int G = 16 / LEN;
     constexpr int V = G < 4 ? G : 4;
-    const int off = (1 << S) + ((r0 / V) * C::T + tau) * V + (r0 % V);
+    constexpr int N = C::N;
+    const int32_t *p = tab + (1 << S) + ((r0 / V) * C::T + tau) * V + (r0 % V);
     if (CNT == 4) {
-        const int4 w = __ldg(reinterpret_cast<const int4 *>(tw_w + off));
-        const float4 f = __ldg(reinterpret_cast<const float4 *>(tw_q + off));
-        tw[0] = derive(w.x, f.x, kbase);
-        tw[1 % CNT] = derive(w.y, f.y, kbase);
-        tw[2 % CNT] = derive(w.z, f.z, kbase);
-        tw[3 % CNT] = derive(w.w, f.w, kbase);
+        const int4 w = __ldg(reinterpret_cast<const int4 *>(p));
+        const int4 f = __ldg(reinterpret_cast<const int4 *>(p + N));
+        const int4 k = __ldg(reinterpret_cast<const int4 *>(p + 2 * N));
+        const int4 e = __ldg(reinterpret_cast<const int4 *>(p + 3 * N));
+        tw[0] = Tw{w.x, __int_as_float(f.x), k.x, __int_as_float(e.x)};
+        tw[1 % CNT] = Tw{w.y, __int_as_float(f.y), k.y, __int_as_float(e.y)};
+        tw[2 % CNT] = Tw{w.z, __int_as_float(f.z), k.z, __int_as_float(e.z)};
+        tw[3 % CNT] = Tw{w.w, __int_as_float(f.w), k.w, __int_as_float(e.w)};
     } else if (CNT == 2) {
-        const int2 w = __ldg(reinterpret_cast<const int2 *>(tw_w + off));
-        const float2 f = __ldg(reinterpret_cast<const float2 *>(tw_q + off));
-        tw[0] = derive(w.x, f.x, kbase);
-        tw[1 % CNT] = derive(w.y, f.y, kbase);
+        const int2 w = __ldg(reinterpret_cast<const int2 *>(p));
+        const int2 f = __ldg(reinterpret_cast<const int2 *>(p + N));
+        const int2 k = __ldg(reinterpret_cast<const int2 *>(p + 2 * N));
+        const int2 e = __ldg(reinterpret_cast<const int2 *>(p + 3 * N));
+        tw[0] = Tw{w.x, __int_as_float(f.x), k.x, __int_as_float(e.x)};
+        tw[1 % CNT] = Tw{w.y, __int_as_float(f.y), k.y, __int_as_float(e.y)};
     } else {
-        tw[0] = derive(__ldg(tw_w + off), __ldg(tw_q + off), kbase);
+        tw[0] = Tw{__ldg(p), __int_as_float(__ldg(p + N)), __ldg(p + 2 * N), __int_as_float(__ldg(p + 3 * N))};
     }
 }
 
@@ -159,13 +166,11 @@ __device__ __forceinline__ void stage1(u32 (&xa)[Cfg32<LOGN>::SUB], u32 (&xb)[Cf
     constexpr int LEN = C::N >> (S + 1);
     constexpr int CNT = C::SUB / (2 * LEN);          // twiddles of this sub-chunk in this stage
     constexpr int GRP = CNT < 4 ? CNT : 4;
-    const int32_t *tw_w = INV ? c.pi_w : c.pf_w;
-    const float *tw_q = INV ? c.pi_q : c.pf_q;
-    const int32_t kb = INV ? c.ki : c.kf;
+    const int32_t *tab = INV ? c.pi : c.pf;
 #pragma unroll
     for (int g0 = 0; g0 < CNT; g0 += GRP) {
         Tw tw[GRP];
-        load_entries<LOGN, S, GRP>(tw, tw_w, tw_q, kb, tau, h * CNT + g0);
+        load_entries<LOGN, S, GRP>(tw, tab, tau, h * CNT + g0);
 #pragma unroll
         for (int g = 0; g < GRP; g++) {
 #pragma unroll
@@ -219,6 +224,59 @@ __device__ __forceinline__ void load_operand(u32 (&x)[32], const int32_t *row, i
     for (int m = 0; m < 32; m++) x[m] = (u32)v[m] + (u32)kBias;
 }
 
+// same, from a raw row that a bulk copy (TMA) has staged at the start of the tile region
+template <int LOGN>
+__device__ __forceinline__ void load_operand_staged(u32 (&x)[32], const int32_t *raw, int tau, const Fq32Const &c)
+{
+    constexpr int T = Cfg32<LOGN>::T;
+    int32_t v[32];
+    bool wide = false;
+#pragma unroll
+    for (int m = 0; m < 32; m++) {
+        v[m] = raw[tau + m * T];
+        wide |= out_of_range(v[m], c);
+    }
+    if (__any_sync(0xFFFFFFFFu, wide)) {
+#pragma unroll
+        for (int m = 0; m < 32; m++) v[m] = bred(v[m], c);
+    }
+#pragma unroll
+    for (int m = 0; m < 32; m++) x[m] = (u32)v[m] + (u32)kBias;
+}
+
+// ---- TMA bulk copies (cp.async.bulk) + mbarrier: the next product's operand rows are fetched into tile
+// regions the current product no longer needs, by one lane per warp, while the warp computes ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 template <int LOGN>
 __device__ __forceinline__ void store_pass0(int32_t *tile, const u32 (&x)[32], int tau)
 {
@@ -253,8 +311,9 @@ __device__ __forceinline__ void store_sub(int32_t *p, const u32 (&x)[SUB])
 
 enum { FQ_POLYMUL = 0, FQ_KEY16 = 1, FQ_KEY32 = 2 };
 
-template <int LOGN, int MODE>
-__global__ void __launch_bounds__(kThreads32, LOGN == 10 ? 3 : 5)
+// TMA = true: operand rows arrive by bulk copy (16-byte aligned rows); false: plain LDG (any alignment)
+template <int LOGN, int MODE, bool TMA>
+__global__ void __launch_bounds__(kThreads32, LOGN == 10 ? 3 : FQ32_MINB)
 k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const void *__restrict__ bsrc,
                size_t b_stride, size_t count, const __grid_constant__ Fq32Const c)
 {
@@ -266,8 +325,38 @@ k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const v
     const int slot = (threadIdx.x / 32) * C::PW + lane / T;       // polynomial slot inside the CTA
     int32_t *ta = tiles[0][slot];
     int32_t *tb = tiles[1][slot];
+    // bulk-copy pipeline state: bars[warp][0 / 1] complete when the a / b rows of the warp's next product have
+    // landed; `other` = byte offset between a polynomial's two tile regions, whose roles swap every iteration
+    __shared__ __align__(8) uint64_t bars[kThreads32 / 32][2];
+    const int warp = threadIdx.x / 32;
+    uint32_t parity = 0;
+    constexpr uint32_t ROW_BYTES = (uint32_t)N * 4u;
+    auto fetch = [&](int op, size_t nbase, int32_t *region0) {
+        // lane 0: rows of the warp's PW polynomials of the product group starting at nbase -> region0[p]
+        mbar_expect_tx(&bars[warp][op], ROW_BYTES * C::PW);
+#pragma unroll
+        for (int p = 0; p < C::PW; p++) {
+            size_t row = nbase + (size_t)warp * C::PW + p;
+            if (row >= count) row = 0;
+            const int32_t *src = op == 0 ? a + row * N : static_cast<const int32_t *>(bsrc) + row * b_stride;
+            bulk_g2s(region0 + p * C::TS, src, ROW_BYTES, &bars[warp][op]);
+        }
+    };
+    const size_t first = (size_t)blockIdx.x * C::POLYS;
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(&bars[warp][0], 1);
+            mbar_init(&bars[warp][1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0 && first < count) {
+            fetch(0, first, tiles[0][warp * C::PW]);
+            if (MODE == FQ_POLYMUL) fetch(1, first, tiles[1][warp * C::PW]);
+        }
+    }
 
-    for (size_t base = (size_t)blockIdx.x * C::POLYS; base < count; base += (size_t)gridDim.x * C::POLYS) {
+    for (size_t base = first; base < count; base += (size_t)gridDim.x * C::POLYS) {
         const size_t poly = base + slot;
         const bool live = poly < count;
         const size_t prow = live ? poly : 0;
@@ -275,11 +364,18 @@ k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const v
         // 7 stall cycles waiting for instructions (profiles/polymul_r02c_*); the L1.5 I-cache holds 32 KB
 #pragma unroll 1
         for (int op = 0; op < (MODE == FQ_POLYMUL ? 2 : 1); op++) {
-            const int32_t *row = op == 0 ? a + prow * N : static_cast<const int32_t *>(bsrc) + prow * b_stride;
             u32 x[32];
-            load_operand<LOGN>(x, row, tau, c);
+            int32_t *tile = op == 0 ? ta : tb;
+            if (TMA) {
+                mbar_wait(&bars[warp][op], parity);
+                load_operand_staged<LOGN>(x, tile, tau, c);
+                __syncwarp();                     // the padded result overwrites the raw row in place
+            } else {
+                const int32_t *row = op == 0 ? a + prow * N : static_cast<const int32_t *>(bsrc) + prow * b_stride;
+                load_operand<LOGN>(x, row, tau, c);
+            }
             fwd_pass0(x, c);
-            store_pass0<LOGN>(op == 0 ? ta : tb, x, tau);
+            store_pass0<LOGN>(tile, x, tau);
         }
         __syncwarp();
 #pragma unroll 1
@@ -317,10 +413,20 @@ k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const v
             inv_stages1<LOGN, LOGN - 1>(xa, c, tau, h);
             store_sub<SUB>(pa, xa);
         }
+        const size_t nbase = base + (size_t)gridDim.x * C::POLYS;
+        if (TMA) fence_proxy_async();
         __syncwarp();
+        // tb is free from here on: the next product's a rows go there
+        if (TMA && lane == 0 && nbase < count) fetch(0, nbase, tb - (lane / T) * C::TS);
         {
             u32 x[32];
             load_pass0<LOGN>(ta, x, tau);
+            if (TMA && MODE == FQ_POLYMUL) {
+                fence_proxy_async();
+                __syncwarp();
+                // every coefficient is in registers: ta takes the next product's b rows
+                if (lane == 0 && nbase < count) fetch(1, nbase, ta - (lane / T) * C::TS);
+            }
             if (c.r0) {
 #pragma unroll
                 for (int m = 0; m < 32; m++) x[m] = (u32)fq::mul((int32_t)x[m], c.one, c.nq);
@@ -332,7 +438,12 @@ k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const v
                 for (int m = 0; m < 32; m++) orow[tau + m * T] = (int32_t)x[m];
             }
         }
-        __syncwarp();
+        if (TMA) {
+            int32_t *t = ta; ta = tb; tb = t;         // the regions swap roles
+            parity ^= 1u;
+        } else {
+            __syncwarp();
+        }
     }
 }
 
@@ -381,19 +492,25 @@ int build_fq32_tables(NttPlanDev &p, const int32_t *w_host)
     Tw ninv, one;
     if (!fq::build_tables(p.logn, p.rc.q, w_host, zf, zi, ninv, one)) return SCGPU_OK;
     const int n = p.n, T = n / 32;
-    // [pf_w | pf_q | pi_w | pi_q], each n words, entries of stages >= 5 in thread-major order
-    std::vector<int32_t> pack(4 * n, 0);
+    // forward [w | wq | k | c] then inverse [w | wq | k | c], n words each, entries of stages >= 5 thread-major
+    std::vector<int32_t> pack(8 * n, 0);
     for (int s = 5; s < p.logn; s++) {
         const int len = n >> (s + 1), G = 16 / len;
         for (int tau = 0; tau < T; tau++)
             for (int r = 0; r < G; r++) {
                 const int nat = (1 << s) + tau * G + r, at = fq32_slot(p.logn, s, tau, r);
-                pack[at] = zf[nat].w;         memcpy(&pack[n + at], &zf[nat].wq, 4);
-                pack[2 * n + at] = zi[nat].w; memcpy(&pack[3 * n + at], &zi[nat].wq, 4);
+                const Tw *src[2] = {&zf[nat], &zi[nat]};
+                for (int d = 0; d < 2; d++) {
+                    int32_t *dst = pack.data() + 4 * n * d + at;
+                    dst[0] = src[d]->w;
+                    memcpy(dst + n, &src[d]->wq, 4);
+                    dst[2 * n] = src[d]->k;
+                    memcpy(dst + 3 * n, &src[d]->c, 4);
+                }
             }
     }
-    SCGPU_CUDA_CHECK(cudaMalloc(&p.fq32_tab, sizeof(int32_t) * 4 * n));
-    SCGPU_CUDA_CHECK(cudaMemcpy(p.fq32_tab, pack.data(), sizeof(int32_t) * 4 * n, cudaMemcpyHostToDevice));
+    SCGPU_CUDA_CHECK(cudaMalloc(&p.fq32_tab, sizeof(int32_t) * 8 * n));
+    SCGPU_CUDA_CHECK(cudaMemcpy(p.fq32_tab, pack.data(), sizeof(int32_t) * 8 * n, cudaMemcpyHostToDevice));
     memcpy(p.fq32_pass0, &zf[1], sizeof(Tw) * 31);
     memcpy(p.fq32_pass0 + sizeof(Tw) * 31, &zi[1], sizeof(Tw) * 31);
     memcpy(p.fq_ninv, &ninv, sizeof(Tw));
@@ -416,10 +533,8 @@ int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32
 {
     Fq32Const c;
     const int n = p.n;
-    c.pf_w = static_cast<const int32_t *>(p.fq32_tab);
-    c.pf_q = reinterpret_cast<const float *>(c.pf_w + n);
-    c.pi_w = c.pf_w + 2 * n;
-    c.pi_q = reinterpret_cast<const float *>(c.pf_w + 3 * n);
+    c.pf = static_cast<const int32_t *>(p.fq32_tab);
+    c.pi = c.pf + 4 * n;
     memcpy(c.f0, p.fq32_pass0, sizeof(Tw) * 31);
     memcpy(c.i0, p.fq32_pass0 + sizeof(Tw) * 31, sizeof(Tw) * 31);
     memcpy(&c.ninv, p.fq_ninv, sizeof(Tw));
@@ -432,14 +547,24 @@ int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32
     c.M = (uint32_t)((1ull << 32) / (uint64_t)p.rc.q);
     c.r0 = p.fq32_r0;
     const int sms = p.sm_count > 0 ? p.sm_count : 148;
+    // bulk copies need 16-byte aligned rows; the polymul's second operand is only staged in FQ_POLYMUL mode
+    const char *no_tma = getenv("SCGPU_NO_TMA");
+    bool tma = ((uintptr_t)a % 16) == 0 && !(no_tma && atoi(no_tma) != 0);
+    if (mode == FQ_POLYMUL) tma = tma && ((uintptr_t)b % 16) == 0 && (b_stride % 4) == 0;
 #define FQ32_LAUNCH(L)                                                                                     \
     {                                                                                                      \
         const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
-        size_t grid = (size_t)sms * (L == 10 ? 3 : 5);                                                     \
+        size_t grid = (size_t)sms * (L == 10 ? 3 : FQ32_MINB);                                                     \
         if (grid > groups) grid = groups;                                                                  \
-        if (mode == FQ_POLYMUL)    k_polymul_fq32<L, FQ_POLYMUL><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c); \
-        else if (mode == FQ_KEY16) k_polymul_fq32<L, FQ_KEY16><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
-        else                       k_polymul_fq32<L, FQ_KEY32><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
+        if (tma) {                                                                                         \
+            if (mode == FQ_POLYMUL)    k_polymul_fq32<L, FQ_POLYMUL, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c); \
+            else if (mode == FQ_KEY16) k_polymul_fq32<L, FQ_KEY16, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
+            else                       k_polymul_fq32<L, FQ_KEY32, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
+        } else {                                                                                           \
+            if (mode == FQ_POLYMUL)    k_polymul_fq32<L, FQ_POLYMUL, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c); \
+            else if (mode == FQ_KEY16) k_polymul_fq32<L, FQ_KEY16, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
+            else                       k_polymul_fq32<L, FQ_KEY32, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
+        }                                                                                                  \
     }
     switch (p.logn) {
     case 8:  FQ32_LAUNCH(8); break;

@@ -48,7 +48,7 @@ struct NttPlanDev {
     // warp-local 32-coefficient schedule of the same arithmetic (ntt_fast_fq32.cu)
     int fq32_ok, fq32_r0;
     int32_t fq32_x0;
-    void *fq32_tab;                      // [pf_w | pf_q | pi_w | pi_q], n words each
+    void *fq32_tab;                      // forward [w | wq | k | c], inverse [w | wq | k | c], n words each
     alignas(16) unsigned char fq32_pass0[2 * 31 * 16];
 };
 

@@ -383,6 +383,29 @@ def test_small_modulus_inputs_at_the_proof_boundary(arithmetic):
             assert np.array_equal(out.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_TRIPLE16, n, q, 16, a, key, w, r))
 
 
+@pytest.mark.parametrize("q,n", [(12289, 512), (12289, 1024), (7681, 256)])
+def test_unaligned_rows_take_the_plain_load_path(q, n):
+    """The warp-local kernel stages operand rows with bulk copies (TMA), which need 16-byte aligned rows; rows
+    at any other alignment go through the LDG variant of the same kernel and must give the same bits.  Also
+    ragged counts around the polynomials-per-CTA granularity."""
+    w, r = O.tables(q, n, 16)
+    p, _, _ = plan(q, n, 16, O.REFERENCE)
+    rng = np.random.default_rng(q + n)
+    for rows in (1, 7, 33, 161):
+        a = rand_inputs(rng, "uniform", q, (rows, n))
+        b = rand_inputs(rng, "signed", q, (rows, n))
+        exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, 16, a, b, w, r)
+        for off_a, off_b in ((0, 0), (1, 0), (0, 3), (2, 1)):
+            da = torch.zeros(rows * n + 8, dtype=torch.int32, device=DEV)
+            db = torch.zeros(rows * n + 8, dtype=torch.int32, device=DEV)
+            da[off_a:off_a + rows * n] = dev(a).reshape(-1)
+            db[off_b:off_b + rows * n] = dev(b).reshape(-1)
+            out = torch.full((rows, n), -7, dtype=torch.int32, device=DEV)
+            p.polymul(out, da[off_a:off_a + rows * n].view(rows, n), db[off_b:off_b + rows * n].view(rows, n))
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), exp), (rows, off_a, off_b)
+
+
 def test_host_pipeline_and_ragged_counts():
     q, n, tw = 12289, 512, 16
     w, r = O.tables(q, n, tw)
