@@ -122,6 +122,57 @@ __device__ __forceinline__ void aes256_encrypt(const AesTables &t, const uint32_
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
+// Bank-replicated T-table for the throughput kernel: te0r[x * 32 + lane] -- every lane reads its own bank, so
+// the 16 data-dependent lookups of a round are conflict-free (the 1 KiB table costs ~3.5 wavefronts per LDS
+// with 32 random indices; profiles/gauss_r01).  The S-box of the last round is byte 2 of the same entry.
+__device__ __forceinline__ void aes_rep_init(uint32_t *te0r)
+{
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
+        uint32_t s = kAesSbox[i >> 5];
+        uint32_t s2 = ((s << 1) ^ ((s & 0x80) ? 0x1B : 0)) & 0xFF;
+        te0r[i] = (s2 << 24) | (s << 16) | (s << 8) | (s2 ^ s);
+    }
+}
+
+// rk: 60 round-key words; te0r = the replicated table, l4 = 4 * lane.  A lookup's byte offset is
+// ((s >> (8k - 7)) & 0x7F80) | l4: one shift + one 3-input LOP3, the table base rides in the LDS address.
+__device__ __forceinline__ uint32_t aes_rep_at(const uint32_t *te0r, uint32_t off)
+{
+    return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(te0r) + off);
+}
+__device__ __forceinline__ void aes256_encrypt_rep(const uint32_t *te0r, uint32_t l4, const uint32_t *rk, uint32_t s0, uint32_t s1,
+                                                   uint32_t s2, uint32_t s3, uint32_t out[4])
+{
+#define SCGPU_T(x) aes_rep_at(te0r, (x))
+#define SCGPU_B3(v) ((((v) >> 17) & 0x7F80u) | l4)
+#define SCGPU_B2(v) ((((v) >> 9) & 0x7F80u) | l4)
+#define SCGPU_B1(v) ((((v) >> 1) & 0x7F80u) | l4)
+#define SCGPU_B0(v) ((((v) << 7) & 0x7F80u) | l4)
+    s0 ^= __ldg(rk + 0); s1 ^= __ldg(rk + 1); s2 ^= __ldg(rk + 2); s3 ^= __ldg(rk + 3);
+#pragma unroll 2
+    for (int r = 1; r < 14; r++) {
+        const uint4 k = __ldg(reinterpret_cast<const uint4 *>(rk) + r);
+        uint32_t t0 = SCGPU_T(SCGPU_B3(s0)) ^ rotr8(SCGPU_T(SCGPU_B2(s1)), 1) ^ rotr8(SCGPU_T(SCGPU_B1(s2)), 2) ^ rotr8(SCGPU_T(SCGPU_B0(s3)), 3) ^ k.x;
+        uint32_t t1 = SCGPU_T(SCGPU_B3(s1)) ^ rotr8(SCGPU_T(SCGPU_B2(s2)), 1) ^ rotr8(SCGPU_T(SCGPU_B1(s3)), 2) ^ rotr8(SCGPU_T(SCGPU_B0(s0)), 3) ^ k.y;
+        uint32_t t2 = SCGPU_T(SCGPU_B3(s2)) ^ rotr8(SCGPU_T(SCGPU_B2(s3)), 1) ^ rotr8(SCGPU_T(SCGPU_B1(s0)), 2) ^ rotr8(SCGPU_T(SCGPU_B0(s1)), 3) ^ k.z;
+        uint32_t t3 = SCGPU_T(SCGPU_B3(s3)) ^ rotr8(SCGPU_T(SCGPU_B2(s0)), 1) ^ rotr8(SCGPU_T(SCGPU_B1(s1)), 2) ^ rotr8(SCGPU_T(SCGPU_B0(s2)), 3) ^ k.w;
+        s0 = t0; s1 = t1; s2 = t2; s3 = t3;
+    }
+    // last round: S-box = byte 2 of the table entry, placed into byte 3 / 2 / 1 / 0
+#define SCGPU_S(x) (SCGPU_T(x) & 0x00FF0000u)
+    const uint4 k = __ldg(reinterpret_cast<const uint4 *>(rk) + 14);
+    out[0] = ((SCGPU_S(SCGPU_B3(s0)) << 8) | SCGPU_S(SCGPU_B2(s1)) | (SCGPU_S(SCGPU_B1(s2)) >> 8) | (SCGPU_S(SCGPU_B0(s3)) >> 16)) ^ k.x;
+    out[1] = ((SCGPU_S(SCGPU_B3(s1)) << 8) | SCGPU_S(SCGPU_B2(s2)) | (SCGPU_S(SCGPU_B1(s3)) >> 8) | (SCGPU_S(SCGPU_B0(s0)) >> 16)) ^ k.y;
+    out[2] = ((SCGPU_S(SCGPU_B3(s2)) << 8) | SCGPU_S(SCGPU_B2(s3)) | (SCGPU_S(SCGPU_B1(s0)) >> 8) | (SCGPU_S(SCGPU_B0(s1)) >> 16)) ^ k.z;
+    out[3] = ((SCGPU_S(SCGPU_B3(s3)) << 8) | SCGPU_S(SCGPU_B2(s0)) | (SCGPU_S(SCGPU_B1(s1)) >> 8) | (SCGPU_S(SCGPU_B0(s2)) >> 16)) ^ k.w;
+#undef SCGPU_S
+#undef SCGPU_T
+#undef SCGPU_B3
+#undef SCGPU_B2
+#undef SCGPU_B1
+#undef SCGPU_B0
+}
+
 // CTR-DRBG block input: the 32-bit counter replicated four times in native (little-endian) byte
 // order (ctr_drbg.c:180-186); as big-endian AES columns that is bswap(counter) four times.
 // Output words in prng order for the two 64-bit values of the block: (hi0, lo0, hi1, lo1) where

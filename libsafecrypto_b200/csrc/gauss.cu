@@ -27,6 +27,14 @@ template <typename T>
 __device__ __forceinline__ uint32_t cdf_search(const T *cdf, uint32_t size, T x)
 {
     uint32_t a = 0;
+    if ((size & (size - 1)) == 0) {
+        // power-of-two table (every table the reference builds): a + st < size always holds
+        for (uint32_t st = size >> 1; st > 0; st >>= 1) {
+            const uint32_t b = a + st;
+            a = (cdf[b] < x) ? b : a;
+        }
+        return a;
+    }
     for (uint32_t st = size >> 1; st > 0; st >>= 1) {
         uint32_t b = a + st;
         a = (b < size && cdf[b] < x) ? b : a;
@@ -208,6 +216,8 @@ __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
 }
 
 // ---- fast path 1: CDF over the AES-CTR-DRBG ---------------------------------------------------------------
+constexpr int kKsCache = 8;             // ChaCha20 blocks per lane kept between the two passes of k_cdf_chacha
+
 struct FastArgs {
     GaussTablesDev g;
     const uint8_t *seeds;
@@ -215,7 +225,7 @@ struct FastArgs {
     size_t nstreams, per_stream;        // per_stream = calls * n samples
     int32_t centre;
     int32_t *out;
-    uint32_t *keys;                      // [nstreams][61]: 60 round-key words + initial counter
+    uint32_t *keys;                      // [nstreams][64]: 60 round-key words + initial counter (16-byte aligned rows)
 };
 
 // one thread per stream: DRBG instantiation (zero-key block encryptions, entropy mix, key schedule)
@@ -230,7 +240,7 @@ __global__ void __launch_bounds__(128) k_drbg_setup(FastArgs a)
     rng.aes = &aes;
     rng.seed = a.seeds + sidx * a.seed_len;
     rng.init(PRNG_AES, a.seed_len, a.seed_period);
-    uint32_t *k = a.keys + sidx * 61;
+    uint32_t *k = a.keys + sidx * 64;
     for (int i = 0; i < 60; i++) k[i] = rng.s.drbg_rk[i];
     k[60] = rng.s.drbg_counter;
 }
@@ -239,21 +249,28 @@ template <int PREC>
 __global__ void __launch_bounds__(256) k_cdf_aes(FastArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    AesTables *aes = reinterpret_cast<AesTables *>(smem_raw);
-    uint64_t *cdf64 = reinterpret_cast<uint64_t *>(smem_raw + 2048);
-    uint32_t *cdf32 = reinterpret_cast<uint32_t *>(smem_raw + 2048);
-    aes_tables_init(*aes);
+    uint32_t *te0r = reinterpret_cast<uint32_t *>(smem_raw);                 // 256 x 32 words, one copy per bank
+    uint64_t *cdf64 = reinterpret_cast<uint64_t *>(smem_raw + 32768);
+    uint32_t *cdf32 = reinterpret_cast<uint32_t *>(smem_raw + 32768);
+    aes_rep_init(te0r);
     if (PREC == 64) for (uint32_t i = threadIdx.x; i < a.g.cdf_size; i += blockDim.x) cdf64[i] = a.g.cdf64[i];
     else            for (uint32_t i = threadIdx.x; i < a.g.cdf_size; i += blockDim.x) cdf32[i] = a.g.cdf32[i];
     __syncthreads();
+    const uint32_t l4 = (threadIdx.x & 31) * 4;
     constexpr int SPB = PREC == 64 ? 2 : 4;                   // samples per 16-byte DRBG block
     const size_t blocks_per_stream = (a.per_stream + SPB - 1) / SPB;
     const size_t total = a.nstreams * blocks_per_stream;
     for (size_t item = blockIdx.x * (size_t)blockDim.x + threadIdx.x; item < total; item += (size_t)gridDim.x * blockDim.x) {
         const size_t sidx = item / blocks_per_stream, blk = item % blocks_per_stream;
-        const uint32_t *k = a.keys + sidx * 61;
+        const uint32_t *k = a.keys + sidx * 64;
         uint32_t w[4];
-        drbg_block_words(*aes, k, k[60] + (uint32_t)blk, w);
+        {
+            // drbg_block_words() with the replicated table
+            const uint32_t cnt = bswap32(__ldg(k + 60) + (uint32_t)blk);
+            uint32_t o[4];
+            aes256_encrypt_rep(te0r, l4, k, cnt, cnt, cnt, cnt, o);
+            w[0] = bswap32(o[1]); w[1] = bswap32(o[0]); w[2] = bswap32(o[3]); w[3] = bswap32(o[2]);
+        }
         int32_t res[4];
         if (PREC == 64) {
 #pragma unroll
@@ -295,6 +312,9 @@ __global__ void __launch_bounds__(256) k_cdf_chacha(FastArgs a)
     const int lane = threadIdx.x & 31;
     const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    // keystream cache: the first pass keeps each block's 16 bytes so the second pass does not run ChaCha20
+    // again (kKsCache blocks per lane, lane-interleaved uint4 -> conflict-free 128-bit accesses)
+    uint4 *kscache = reinterpret_cast<uint4 *>(smem_raw + a.g.cdf_size * (PREC == 64 ? 8 : 4)) + (threadIdx.x >> 5) * (kKsCache * 32) + lane;
     constexpr int WPS = PREC == 64 ? 2 : 1;                                   // words per sample
     const size_t words = a.per_stream * WPS;
     const size_t nblocks = words > 3 ? (words - 3 + 3) / 4 : 0;                // blocks D[0..nblocks)
@@ -316,10 +336,12 @@ __global__ void __launch_bounds__(256) k_cdf_chacha(FastArgs a)
         // pass 1: XOR of this lane's blocks
         uint32_t acc[4] = {0, 0, 0, 0};
         const size_t b0 = (size_t)lane * C, b1 = (b0 + C < nblocks) ? b0 + C : nblocks;
+        const bool cached = C <= (size_t)kKsCache;
         for (size_t b = b0; b < b1; b++) {
             uint32_t ks[4];
             chacha20_first16(key, (uint32_t)b, (uint32_t)(b >> 32), iv[0], iv[1], ks);
             acc[0] ^= ks[0]; acc[1] ^= ks[1]; acc[2] ^= ks[2]; acc[3] ^= ks[3];
+            if (cached) kscache[(b - b0) * 32] = make_uint4(ks[0], ks[1], ks[2], ks[3]);
         }
         // exclusive XOR scan over lanes
         uint32_t pre[4];
@@ -347,7 +369,12 @@ __global__ void __launch_bounds__(256) k_cdf_chacha(FastArgs a)
         if (b0 > 0 && b0 <= nblocks) carry = bswap32(pre[3]);
         for (size_t b = b0; b < b1; b++) {
             uint32_t ks[4];
-            chacha20_first16(key, (uint32_t)b, (uint32_t)(b >> 32), iv[0], iv[1], ks);
+            if (cached) {
+                const uint4 v = kscache[(b - b0) * 32];
+                ks[0] = v.x; ks[1] = v.y; ks[2] = v.z; ks[3] = v.w;
+            } else {
+                chacha20_first16(key, (uint32_t)b, (uint32_t)(b >> 32), iv[0], iv[1], ks);
+            }
             run[0] ^= ks[0]; run[1] ^= ks[1]; run[2] ^= ks[2]; run[3] ^= ks[3];
             const uint32_t w0 = bswap32(run[0]), w1 = bswap32(run[1]), w2 = bswap32(run[2]), w3 = bswap32(run[3]);
             const size_t wi = 3 + 4 * b;                                           // index of w0
@@ -418,7 +445,7 @@ int launch_gauss_fast(const GaussTablesDev &g, int prng_type, const uint8_t *see
     if (prng_type == PRNG_AES) {
         k_drbg_setup<<<(unsigned)((nstreams + 127) / 128), 128, 0, st>>>(a);
         count_launch();
-        const size_t smem = 2048 + table_bytes;
+        const size_t smem = 32768 + table_bytes;
         const int spb = g.precision == 64 ? 2 : 4;
         const size_t items = nstreams * ((per_stream + spb - 1) / spb);
         const unsigned grid = cap_grid((items + 255) / 256, sm_count, 4);
@@ -430,13 +457,14 @@ int launch_gauss_fast(const GaussTablesDev &g, int prng_type, const uint8_t *see
             k_cdf_aes<32><<<grid, 256, smem, st>>>(a);
         }
     } else {
-        const unsigned grid = cap_grid((nstreams + 7) / 8, sm_count, 4);
+        const unsigned grid = cap_grid((nstreams + 7) / 8, sm_count, 3);
+        const size_t cc_smem = table_bytes + (size_t)8 * kKsCache * 32 * 16;      // table + 8 warps of cache
         if (g.precision == 64) {
-            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_cdf_chacha<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
-            k_cdf_chacha<64><<<grid, 256, table_bytes, st>>>(a);
+            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_cdf_chacha<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc_smem));
+            k_cdf_chacha<64><<<grid, 256, cc_smem, st>>>(a);
         } else {
-            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_cdf_chacha<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
-            k_cdf_chacha<32><<<grid, 256, table_bytes, st>>>(a);
+            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_cdf_chacha<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc_smem));
+            k_cdf_chacha<32><<<grid, 256, cc_smem, st>>>(a);
         }
     }
     count_launch();

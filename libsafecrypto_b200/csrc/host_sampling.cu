@@ -223,7 +223,7 @@ static int gauss_dispatch(scgpu_gauss_plan *p, int prng_type, const uint8_t *d_s
     if (discard != 0 && discard != 2 && discard != 4 && discard != 6) { set_error("gauss_streams: discard %u", discard); return SCGPU_ERR_ARG; }
     if (fast_path_ok(p->t, prng_type, n * calls, discard)) {
         if (prng_type == PRNG_AES) {
-            int e = ensure_cap(&p->d_keys, &p->keys_cap, nstreams * 61);
+            int e = ensure_cap(&p->d_keys, &p->keys_cap, nstreams * 64);
             if (e != SCGPU_OK) return e;
         }
         return launch_gauss_fast(p->t, prng_type, d_seeds, seed_len, kDefaultSeedPeriod, nstreams, n * calls, centre,
