@@ -311,6 +311,15 @@ __device__ __forceinline__ void store_sub(int32_t *p, const u32 (&x)[SUB])
 
 enum { FQ_POLYMUL = 0, FQ_KEY16 = 1, FQ_KEY32 = 2 };
 
+// reference NTT-domain index of the thread's pass-1 element e (position 32 tau + e of the bit-reversed order):
+// brev(32 tau + e) = brev5(e) << (LOGN - 5) | brev_{LOGN-5}(tau); for fixed e the lanes of a polynomial read
+// n/32 consecutive coefficients
+template <int LOGN>
+__device__ __forceinline__ int ntt_index(int tau, int e)
+{
+    return (int)((__brev((unsigned)e) >> 27) << (LOGN - 5)) | (int)(__brev((unsigned)tau) >> (32 - (LOGN - 5)));
+}
+
 // TMA = true: operand rows arrive by bulk copy (16-byte aligned rows); false: plain LDG (any alignment)
 template <int LOGN, int MODE, bool TMA>
 __global__ void __launch_bounds__(kThreads32, LOGN == 10 ? 3 : FQ32_MINB)
@@ -395,7 +404,7 @@ k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const v
                 bool wide = false;
 #pragma unroll
                 for (int i = 0; i < SUB; i++) {
-                    const int j = (int)(__brev((unsigned)(32 * tau + SUB * h + i)) >> (32 - LOGN));
+                    const int j = ntt_index<LOGN>(tau, SUB * h + i);
                     if (MODE == FQ_KEY16) kv[i] = (int32_t)__ldg(static_cast<const int16_t *>(bsrc) + prow * b_stride + j);
                     else {
                         kv[i] = __ldg(static_cast<const int32_t *>(bsrc) + prow * b_stride + j);
@@ -447,6 +456,183 @@ k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const v
     }
 }
 
+
+// ---- module-LWE matrix-vector product  t_i = INTT(sum_j A_ij o NTT(s_j))  (module_lwe.c:588-748) -------------
+// Same warp-local schedule.  The l transformed vectors stay in shared memory (padded pass-1 layout, unbiased),
+// each output row accumulates its l pointwise products in registers.  HBM traffic is dominated by A
+// (k l rows per instance against l + k for s and t), so with TMA = true every row moves by bulk copy:
+//   * A_ij rows (contiguous n words) land in a one-row staging buffer per instance; as soon as a thread group
+//     has pulled its 32 coefficients into registers the next row (or the next instance's first row) is in
+//     flight, i.e. a row's DRAM latency is covered by one whole pointwise step;
+//   * the next instance's s rows are fetched into the stash tiles during the last inverse transform.
+// The reference's NTT-domain order is our bit-reversed one: element e of thread tau is coefficient
+// brev5(e) * (n/32) + brev(tau) of the row (ntt_index), so for a fixed e the lanes of an instance read n/32
+// consecutive words: conflict-free from the staging row (instances 8 banks apart), one full sector from HBM
+// in the LDG variant.
+template <int LOGN, bool TMA>
+__global__ void __launch_bounds__(kThreads32)
+k_matvec_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t *__restrict__ s,
+              int k, int l, size_t count, const __grid_constant__ Fq32Const c)
+{
+    using C = Cfg32<LOGN>;
+    constexpr int N = C::N, T = C::T, SUB = C::SUB, NSUB = C::NSUB;
+    constexpr int AROW = N + T;                                      // staging row stride: T banks between instances
+    constexpr uint32_t ROW_BYTES = (uint32_t)N * 4u;
+    extern __shared__ __align__(16) int32_t dyn_tiles[];             // [l + 1][POLYS][TS], then [POLYS][AROW]
+    __shared__ __align__(8) uint64_t bars[kThreads32 / 32][2];       // [warp][0: s rows, 1: A row]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x / 32;
+    const int tau = lane % T;
+    const int slot = warp * C::PW + lane / T;
+    int32_t *xt = dyn_tiles + slot * C::TS;                          // exchange tile of the inverse transform
+    int32_t *astage = dyn_tiles + (size_t)(l + 1) * C::POLYS * C::TS + slot * AROW;
+    const int taurev = (int)(__brev((unsigned)tau) >> (32 - (LOGN - 5)));
+    uint32_t par_s = 0, par_a = 0;
+
+    // lane 0: rows of the warp's PW instances (clamped to instance 0 beyond the batch)
+    auto fetch_s = [&](size_t nbase) {
+        mbar_expect_tx(&bars[warp][0], ROW_BYTES * C::PW * (uint32_t)l);
+        for (int p = 0; p < C::PW; p++) {
+            size_t row = nbase + (size_t)warp * C::PW + p;
+            if (row >= count) row = 0;
+            for (int j = 0; j < l; j++)
+                bulk_g2s(dyn_tiles + ((size_t)(j + 1) * C::POLYS + warp * C::PW + p) * C::TS, s + (row * l + j) * N, ROW_BYTES, &bars[warp][0]);
+        }
+    };
+    auto fetch_a = [&](size_t nbase, int step) {
+        mbar_expect_tx(&bars[warp][1], ROW_BYTES * C::PW);
+        for (int p = 0; p < C::PW; p++) {
+            size_t row = nbase + (size_t)warp * C::PW + p;
+            if (row >= count) row = 0;
+            bulk_g2s(dyn_tiles + (size_t)(l + 1) * C::POLYS * C::TS + (warp * C::PW + p) * AROW,
+                     A + (row * k * l + step) * N, ROW_BYTES, &bars[warp][1]);
+        }
+    };
+    const size_t first = (size_t)blockIdx.x * C::POLYS;
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(&bars[warp][0], 1);
+            mbar_init(&bars[warp][1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0 && first < count) { fetch_s(first); fetch_a(first, 0); }
+    }
+
+    for (size_t base = first; base < count; base += (size_t)gridDim.x * C::POLYS) {
+        const size_t inst = base + slot;
+        const bool live = inst < count;
+        const size_t irow = live ? inst : 0;
+        const size_t nbase = base + (size_t)gridDim.x * C::POLYS;
+        if (TMA) { mbar_wait(&bars[warp][0], par_s); par_s ^= 1u; }
+#pragma unroll 1
+        for (int j = 0; j < l; j++) {
+            u32 x[32];
+            int32_t *tile = dyn_tiles + ((size_t)(j + 1) * C::POLYS + slot) * C::TS;
+            if (TMA) {
+                load_operand_staged<LOGN>(x, tile, tau, c);
+                __syncwarp();
+            } else {
+                load_operand<LOGN>(x, s + (irow * l + j) * N, tau, c);
+            }
+            fwd_pass0(x, c);
+            store_pass0<LOGN>(tile, x, tau);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int j = 0; j < l; j++) {
+#pragma unroll 1
+            for (int h = 0; h < NSUB; h++) {
+                u32 xa[SUB], xb[SUB];
+                int32_t *p = dyn_tiles + ((size_t)(j + 1) * C::POLYS + slot) * C::TS + 36 * tau + SUB * h;
+                load_sub<SUB>(p, xa);
+                fwd_stages1<LOGN, 5, 1>(xa, xb, c, tau, h);
+#pragma unroll
+                for (int i = 0; i < SUB; i++) xa[i] -= (u32)kBias;
+                store_sub<SUB>(p, xa);                               // only this thread reads it again
+            }
+        }
+#pragma unroll 1
+        for (int i = 0; i < k; i++) {
+            u32 acc[NSUB][SUB];
+#pragma unroll
+            for (int h = 0; h < NSUB; h++)
+#pragma unroll
+                for (int e = 0; e < SUB; e++) acc[h][e] = (u32)kBias;
+#pragma unroll 1
+            for (int j = 0; j < l; j++) {
+                int32_t av[32];
+                bool wide = false;
+                if (TMA) {
+                    mbar_wait(&bars[warp][1], par_a); par_a ^= 1u;
+#pragma unroll
+                    for (int e = 0; e < 32; e++) {
+                        av[e] = astage[taurev + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5))];
+                        wide |= out_of_range(av[e], c);
+                    }
+                    // the staging row is in registers: put the next row (this instance's next step, or step 0
+                    // of the warp's next instances) in flight before the arithmetic
+                    fence_proxy_async();
+                    __syncwarp();
+                    const int step = i * l + j + 1;
+                    if (lane == 0) {
+                        if (step < k * l) fetch_a(base, step);
+                        else if (nbase < count) fetch_a(nbase, 0);
+                    }
+                } else {
+                    const int32_t *arow = A + ((irow * k + i) * l + j) * N + taurev;
+#pragma unroll
+                    for (int e = 0; e < 32; e++) {
+                        av[e] = __ldg(arow + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5)));
+                        wide |= out_of_range(av[e], c);
+                    }
+                }
+                // A is canonical in the reference (sampled in [0, q)); anything else is reduced first
+                if (__any_sync(0xFFFFFFFFu, wide)) {
+#pragma unroll
+                    for (int e = 0; e < 32; e++) av[e] = bred(av[e], c);
+                }
+                const int32_t *sp = dyn_tiles + ((size_t)(j + 1) * C::POLYS + slot) * C::TS + 36 * tau;
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const int4 sv = *reinterpret_cast<const int4 *>(sp + e);
+                    acc[e / SUB][e % SUB]           += (u32)fq::mul_var(av[e], sv.x, c.invq, c.pwk, c.nq);
+                    acc[(e + 1) / SUB][(e + 1) % SUB] += (u32)fq::mul_var(av[e + 1], sv.y, c.invq, c.pwk, c.nq);
+                    acc[(e + 2) / SUB][(e + 2) % SUB] += (u32)fq::mul_var(av[e + 2], sv.z, c.invq, c.pwk, c.nq);
+                    acc[(e + 3) / SUB][(e + 3) % SUB] += (u32)fq::mul_var(av[e + 3], sv.w, c.invq, c.pwk, c.nq);
+                }
+            }
+            if (TMA && i == k - 1) {
+                // the stash is dead: the next instances' s rows travel during the last inverse transform
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && nbase < count) fetch_s(nbase);
+            }
+#pragma unroll
+            for (int h = 0; h < NSUB; h++) {
+                inv_stages1<LOGN, LOGN - 1>(acc[h], c, tau, h);
+                store_sub<SUB>(xt + 36 * tau + SUB * h, acc[h]);
+            }
+            __syncwarp();
+            {
+                u32 x[32];
+                load_pass0<LOGN>(xt, x, tau);
+                if (c.r0) {
+#pragma unroll
+                    for (int m = 0; m < 32; m++) x[m] = (u32)fq::mul((int32_t)x[m], c.one, c.nq);
+                }
+                inv_pass0(x, c);
+                if (live) {
+                    int32_t *orow = out + (inst * k + i) * N;
+#pragma unroll
+                    for (int m = 0; m < 32; m++) orow[tau + m * T] = (int32_t)x[m];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace
 
 // position of entry r (0 .. 16/len - 1) of thread tau in stage s of the thread-major pass-1 table
@@ -458,7 +644,7 @@ static int fq32_slot(int logn, int s, int tau, int r)
 
 // Bounds of this schedule: forward and pointwise as in fq::analyse; inverse: sums double per stage, products
 // are bounded by mul_bound; one optional reduction of every coefficient between the two inverse passes.
-static bool fq32_analyse(int logn, int64_t qi, int *r0_out, int32_t *x0_out)
+static bool fq32_analyse(int logn, int64_t qi, int accumulate, int *r0_out, int32_t *x0_out)
 {
     const fq::Schedule s = fq::analyse(logn, qi, 1);        // forward + pointwise part (and q range checks)
     if (!s.ok) return false;
@@ -467,7 +653,7 @@ static bool fq32_analyse(int logn, int64_t qi, int *r0_out, int32_t *x0_out)
     const double quo = s.fwd_max * other / q;
     const double pw = q * (0.5 + 2.0 * quo / 16777216.0) + 2.0;
     for (int r0 = 0; r0 <= 1; r0++) {
-        double b = pw;
+        double b = pw * accumulate;                          // mat-vec: sum of l pointwise products
         bool ok = true;
         for (int st = logn - 1; st >= 0 && ok; st--) {
             if (st == 4 && r0) { if (b >= lim) { ok = false; break; } b = fq::mul_bound(b, q); }
@@ -487,7 +673,10 @@ int build_fq32_tables(NttPlanDev &p, const int32_t *w_host)
     p.fq32_ok = 0; p.fq32_tab = nullptr;
     if (p.logn < 8 || p.logn > 10) return SCGPU_OK;
     int r0 = 0; int32_t x0 = 0;
-    if (!fq32_analyse(p.logn, p.rc.q, &r0, &x0)) return SCGPU_OK;
+    if (!fq32_analyse(p.logn, p.rc.q, 1, &r0, &x0)) return SCGPU_OK;
+    int r0_mv = 0; int32_t x0_mv = 0;
+    p.fq32_mv_ok = fq32_analyse(p.logn, p.rc.q, 8, &r0_mv, &x0_mv) ? 1 : 0;     // up to 8 accumulated products
+    p.fq32_r0_mv = r0_mv;
     std::vector<Tw> zf, zi;
     Tw ninv, one;
     if (!fq::build_tables(p.logn, p.rc.q, w_host, zf, zi, ninv, one)) return SCGPU_OK;
@@ -528,8 +717,7 @@ void free_fq32_tables(NttPlanDev &p)
     p.fq32_ok = 0;
 }
 
-int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32_t *a, const void *b,
-                        size_t b_stride, size_t count, cudaStream_t st)
+static Fq32Const fq32_const(const NttPlanDev &p, int r0)
 {
     Fq32Const c;
     const int n = p.n;
@@ -545,7 +733,44 @@ int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32
     c.ki = (int32_t)((uint32_t)c.pwk + (uint32_t)kBias);
     c.invq = (float)(1.0 / (double)p.rc.q);
     c.M = (uint32_t)((1ull << 32) / (uint64_t)p.rc.q);
-    c.r0 = p.fq32_r0;
+    c.r0 = r0;
+    return c;
+}
+
+// n = 256 (Kyber); returns SCGPU_ERR_UNSUPPORTED when this schedule does not apply (the caller falls back)
+int launch_matvec_fq32(const NttPlanDev &p, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
+                       size_t count, cudaStream_t st)
+{
+    if (!p.fq32_ok || !p.fq32_mv_ok || p.logn != 8 || l > 8) return SCGPU_ERR_UNSUPPORTED;
+    const Fq32Const c = fq32_const(p, p.fq32_r0_mv);
+    using C = Cfg32<8>;
+    const char *no_tma = getenv("SCGPU_NO_TMA");
+    const bool tma = ((uintptr_t)A % 16) == 0 && ((uintptr_t)s % 16) == 0 && !(no_tma && atoi(no_tma) != 0);
+    const size_t smem = ((size_t)(l + 1) * C::POLYS * C::TS + (tma ? (size_t)C::POLYS * (C::N + C::T) : 0)) * sizeof(int32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_fq32<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_fq32<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const int sms = p.sm_count > 0 ? p.sm_count : 148;
+    int per_sm = (int)((227 * 1024) / (smem + 1024 + 64));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const size_t groups = (count + C::POLYS - 1) / C::POLYS;
+    size_t grid = (size_t)sms * per_sm;
+    if (grid > groups) grid = groups;
+    if (tma) k_matvec_fq32<8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, c);
+    else     k_matvec_fq32<8, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, c);
+    count_launch();
+    SCGPU_CUDA_CHECK(cudaGetLastError());
+    return SCGPU_OK;
+}
+
+int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32_t *a, const void *b,
+                        size_t b_stride, size_t count, cudaStream_t st)
+{
+    const Fq32Const c = fq32_const(p, p.fq32_r0);
     const int sms = p.sm_count > 0 ? p.sm_count : 148;
     // bulk copies need 16-byte aligned rows; the polymul's second operand is only staged in FQ_POLYMUL mode
     const char *no_tma = getenv("SCGPU_NO_TMA");

@@ -46,7 +46,7 @@ struct NttPlanDev {
     alignas(16) unsigned char fq_ninv[16], fq_one[16];
     alignas(16) unsigned char fq_pass0[2 * 7 * 16];   // fq::Tw entries 1..7 of the forward / inverse table
     // warp-local 32-coefficient schedule of the same arithmetic (ntt_fast_fq32.cu)
-    int fq32_ok, fq32_r0;
+    int fq32_ok, fq32_r0, fq32_mv_ok, fq32_r0_mv;
     int32_t fq32_x0;
     void *fq32_tab;                      // forward [w | wq | k | c], inverse [w | wq | k | c], n words each
     alignas(16) unsigned char fq32_pass0[2 * 31 * 16];
@@ -86,6 +86,8 @@ int build_fq32_tables(NttPlanDev &plan, const int32_t *w_host);
 void free_fq32_tables(NttPlanDev &plan);
 int launch_polymul_fq32(const NttPlanDev &plan, int mode, int32_t *out, const int32_t *a, const void *b,
                         size_t b_stride, size_t count, cudaStream_t stream);
+int launch_matvec_fq32(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
+                       size_t count, cudaStream_t stream);
 int launch_matvec_fq(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
                      size_t count, cudaStream_t stream);
 int build_sq_tables(NttPlanDev &plan, const int32_t *w_host);
