@@ -110,6 +110,32 @@ inline Schedule analyse(int logn, int64_t qi, int accumulate)
     return s;
 }
 
+// Bounds of the warp-local 32-coefficient schedule (ntt_fast_fq32.cu): forward and pointwise as in analyse; inverse: sums double per stage, products
+// are bounded by mul_bound; one optional reduction of every coefficient between the two inverse passes.
+inline bool analyse32(int logn, int64_t qi, int accumulate, int *r0_out, int32_t *x0_out)
+{
+    const Schedule s = analyse(logn, qi, 1);        // forward + pointwise part (and q range checks)
+    if (!s.ok) return false;
+    const double q = (double)qi, lim = (double)kLimit - 2.0;
+    const double other = s.fwd_max > 32768.0 ? s.fwd_max : 32768.0;
+    const double quo = s.fwd_max * other / q;
+    const double pw = q * (0.5 + 2.0 * quo / 16777216.0) + 2.0;
+    for (int r0 = 0; r0 <= 1; r0++) {
+        double b = pw * accumulate;                          // mat-vec: sum of l pointwise products
+        bool ok = true;
+        for (int st = logn - 1; st >= 0 && ok; st--) {
+            if (st == 4 && r0) { if (b >= lim) { ok = false; break; } b = mul_bound(b, q); }
+            const double d = 2.0 * b;                        // |lo + hi|, |lo - hi|
+            if (d >= lim) { ok = false; break; }
+            const double prod = mul_bound(d, q);
+            if (st == 0) { if (prod >= q) ok = false; b = prod; }
+            else b = d > prod ? d : prod;
+        }
+        if (ok) { *r0_out = r0; *x0_out = s.x0; return true; }
+    }
+    return false;
+}
+
 // zf[k] = psi^brv(k) (k = 2^s + b: stage s, block b); zi[k] = its inverse, zi[1] also carries n^-1.
 // Forward products and the two final-stage products are unbiased, every other inverse product is biased.
 inline bool build_tables(int logn, int64_t q, const int32_t *w_host, std::vector<Tw> &zf, std::vector<Tw> &zi,

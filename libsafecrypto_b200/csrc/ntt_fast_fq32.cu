@@ -40,8 +40,12 @@ struct Cfg32 {
     static constexpr int N = 1 << LOGN;
     static constexpr int T = N / 32;             // threads per polynomial
     static constexpr int PW = 32 / T;            // polynomials per warp
-    static constexpr int SUB = N / 32;           // elements of one pass-1 sub-chunk
+    static constexpr int SUB = N / 32 > 16 ? 16 : N / 32;   // elements of one pass-1 sub-chunk
     static constexpr int NSUB = 32 / SUB;
+    // first stage of the sub-chunk loop.  n = 1024: stage 5 couples all 32 elements of a thread; it runs as a
+    // separate step over the whole chunk (one operand at a time) so that the sub-chunk loop holds 2 x 16
+    // coefficients instead of 2 x 32 (168 -> 96 registers, 3 -> 5 CTAs per SM)
+    static constexpr int S1 = LOGN == 10 ? 6 : 5;
     static constexpr int TS = N + N / 8 + (T & 31);   // tile stride in words (bank offset T between polynomials)
     static constexpr int POLYS = (kThreads32 / 32) * PW;
 };
@@ -158,13 +162,12 @@ __device__ __forceinline__ void load_entries(Tw (&tw)[CNT], const int32_t *tab, 
 }
 
 // one radix-2 stage S (forward: Cooley-Tukey, inverse: Gentleman-Sande) on sub-chunk h of NOPS operands
-template <int LOGN, int S, int NOPS, bool INV>
-__device__ __forceinline__ void stage1(u32 (&xa)[Cfg32<LOGN>::SUB], u32 (&xb)[Cfg32<LOGN>::SUB],
-                                       const Fq32Const &c, int tau, int h)
+template <int LOGN, int S, int NOPS, bool INV, int CH>
+__device__ __forceinline__ void stage1(u32 (&xa)[CH], u32 (&xb)[CH], const Fq32Const &c, int tau, int h)
 {
     using C = Cfg32<LOGN>;
     constexpr int LEN = C::N >> (S + 1);
-    constexpr int CNT = C::SUB / (2 * LEN);          // twiddles of this sub-chunk in this stage
+    constexpr int CNT = CH / (2 * LEN);              // twiddles of this (sub-)chunk in this stage
     constexpr int GRP = CNT < 4 ? CNT : 4;
     const int32_t *tab = INV ? c.pi : c.pf;
 #pragma unroll
@@ -192,16 +195,45 @@ __device__ __forceinline__ void fwd_stages1(u32 (&xa)[Cfg32<LOGN>::SUB], u32 (&x
                                             const Fq32Const &c, int tau, int h)
 {
     if constexpr (S < LOGN) {
-        stage1<LOGN, S, NOPS, false>(xa, xb, c, tau, h);
+        stage1<LOGN, S, NOPS, false, Cfg32<LOGN>::SUB>(xa, xb, c, tau, h);
         fwd_stages1<LOGN, S + 1, NOPS>(xa, xb, c, tau, h);
     }
 }
 template <int LOGN, int S>
 __device__ __forceinline__ void inv_stages1(u32 (&x)[Cfg32<LOGN>::SUB], const Fq32Const &c, int tau, int h)
 {
-    if constexpr (S >= 5) {
-        stage1<LOGN, S, 1, true>(x, x, c, tau, h);
+    if constexpr (S >= Cfg32<LOGN>::S1) {
+        stage1<LOGN, S, 1, true, Cfg32<LOGN>::SUB>(x, x, c, tau, h);
         inv_stages1<LOGN, S - 1>(x, c, tau, h);
+    }
+}
+
+template <int SUB>
+__device__ __forceinline__ void load_sub(const int32_t *p, u32 (&x)[SUB])
+{
+#pragma unroll
+    for (int k = 0; k < SUB; k += 4) {
+        const int4 v = *reinterpret_cast<const int4 *>(p + k);
+        x[k] = (u32)v.x; x[k + 1] = (u32)v.y; x[k + 2] = (u32)v.z; x[k + 3] = (u32)v.w;
+    }
+}
+template <int SUB>
+__device__ __forceinline__ void store_sub(int32_t *p, const u32 (&x)[SUB])
+{
+#pragma unroll
+    for (int k = 0; k < SUB; k += 4)
+        *reinterpret_cast<int4 *>(p + k) = make_int4((int32_t)x[k], (int32_t)x[k + 1], (int32_t)x[k + 2], (int32_t)x[k + 3]);
+}
+
+// n = 1024 only: stage 5 (forward) / its inverse on the thread's whole 32-element chunk, in place in the tile
+template <int LOGN, bool INV>
+__device__ __forceinline__ void chunk_stage5(int32_t *p, const Fq32Const &c, int tau)
+{
+    if constexpr (Cfg32<LOGN>::S1 > 5) {
+        u32 x[32];
+        load_sub<32>(p, x);
+        stage1<LOGN, 5, 1, INV, 32>(x, x, c, tau, 0);
+        store_sub<32>(p, x);
     }
 }
 
@@ -292,23 +324,6 @@ __device__ __forceinline__ void load_pass0(const int32_t *tile, u32 (&x)[32], in
     for (int m = 0; m < 32; m++) x[m] = (u32)tile[tau + pos32(T * m)];
 }
 
-template <int SUB>
-__device__ __forceinline__ void load_sub(const int32_t *p, u32 (&x)[SUB])
-{
-#pragma unroll
-    for (int k = 0; k < SUB; k += 4) {
-        const int4 v = *reinterpret_cast<const int4 *>(p + k);
-        x[k] = (u32)v.x; x[k + 1] = (u32)v.y; x[k + 2] = (u32)v.z; x[k + 3] = (u32)v.w;
-    }
-}
-template <int SUB>
-__device__ __forceinline__ void store_sub(int32_t *p, const u32 (&x)[SUB])
-{
-#pragma unroll
-    for (int k = 0; k < SUB; k += 4)
-        *reinterpret_cast<int4 *>(p + k) = make_int4((int32_t)x[k], (int32_t)x[k + 1], (int32_t)x[k + 2], (int32_t)x[k + 3]);
-}
-
 enum { FQ_POLYMUL = 0, FQ_KEY16 = 1, FQ_KEY32 = 2 };
 
 // reference NTT-domain index of the thread's pass-1 element e (position 32 tau + e of the bit-reversed order):
@@ -322,7 +337,7 @@ __device__ __forceinline__ int ntt_index(int tau, int e)
 
 // TMA = true: operand rows arrive by bulk copy (16-byte aligned rows); false: plain LDG (any alignment)
 template <int LOGN, int MODE, bool TMA>
-__global__ void __launch_bounds__(kThreads32, LOGN == 10 ? 3 : FQ32_MINB)
+__global__ void __launch_bounds__(kThreads32, FQ32_MINB)
 k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const void *__restrict__ bsrc,
                size_t b_stride, size_t count, const __grid_constant__ Fq32Const c)
 {
@@ -387,6 +402,10 @@ k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const v
             store_pass0<LOGN>(tile, x, tau);
         }
         __syncwarp();
+        if constexpr (C::S1 > 5) {
+#pragma unroll 1
+            for (int op = 0; op < (MODE == FQ_POLYMUL ? 2 : 1); op++) chunk_stage5<LOGN, false>((op == 0 ? ta : tb) + 36 * tau, c, tau);
+        }
 #pragma unroll 1
         for (int h = 0; h < C::NSUB; h++) {
             u32 xa[SUB], xb[SUB];
@@ -394,12 +413,12 @@ k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const v
             load_sub<SUB>(pa, xa);
             if (MODE == FQ_POLYMUL) {
                 load_sub<SUB>(tb + 36 * tau + SUB * h, xb);
-                fwd_stages1<LOGN, 5, 2>(xa, xb, c, tau, h);
+                fwd_stages1<LOGN, C::S1, 2>(xa, xb, c, tau, h);
 #pragma unroll
                 for (int i = 0; i < SUB; i++)
                     xa[i] = (u32)fq::mul_var((int32_t)(xa[i] - (u32)kBias), (int32_t)(xb[i] - (u32)kBias), c.invq, c.pwk, c.nq) + (u32)kBias;
             } else {
-                fwd_stages1<LOGN, 5, 1>(xa, xb, c, tau, h);
+                fwd_stages1<LOGN, C::S1, 1>(xa, xb, c, tau, h);
                 int32_t kv[SUB];
                 bool wide = false;
 #pragma unroll
@@ -422,6 +441,7 @@ k_polymul_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const v
             inv_stages1<LOGN, LOGN - 1>(xa, c, tau, h);
             store_sub<SUB>(pa, xa);
         }
+        chunk_stage5<LOGN, true>(ta + 36 * tau, c, tau);
         const size_t nbase = base + (size_t)gridDim.x * C::POLYS;
         if (TMA) fence_proxy_async();
         __syncwarp();
@@ -546,7 +566,7 @@ k_matvec_fq32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const in
                 u32 xa[SUB], xb[SUB];
                 int32_t *p = dyn_tiles + ((size_t)(j + 1) * C::POLYS + slot) * C::TS + 36 * tau + SUB * h;
                 load_sub<SUB>(p, xa);
-                fwd_stages1<LOGN, 5, 1>(xa, xb, c, tau, h);
+                fwd_stages1<LOGN, C::S1, 1>(xa, xb, c, tau, h);
 #pragma unroll
                 for (int i = 0; i < SUB; i++) xa[i] -= (u32)kBias;
                 store_sub<SUB>(p, xa);                               // only this thread reads it again
@@ -642,40 +662,14 @@ static int fq32_slot(int logn, int s, int tau, int r)
     return (1 << s) + ((r / V) * T + tau) * V + (r % V);
 }
 
-// Bounds of this schedule: forward and pointwise as in fq::analyse; inverse: sums double per stage, products
-// are bounded by mul_bound; one optional reduction of every coefficient between the two inverse passes.
-static bool fq32_analyse(int logn, int64_t qi, int accumulate, int *r0_out, int32_t *x0_out)
-{
-    const fq::Schedule s = fq::analyse(logn, qi, 1);        // forward + pointwise part (and q range checks)
-    if (!s.ok) return false;
-    const double q = (double)qi, lim = (double)fq::kLimit - 2.0;
-    const double other = s.fwd_max > 32768.0 ? s.fwd_max : 32768.0;
-    const double quo = s.fwd_max * other / q;
-    const double pw = q * (0.5 + 2.0 * quo / 16777216.0) + 2.0;
-    for (int r0 = 0; r0 <= 1; r0++) {
-        double b = pw * accumulate;                          // mat-vec: sum of l pointwise products
-        bool ok = true;
-        for (int st = logn - 1; st >= 0 && ok; st--) {
-            if (st == 4 && r0) { if (b >= lim) { ok = false; break; } b = fq::mul_bound(b, q); }
-            const double d = 2.0 * b;                        // |lo + hi|, |lo - hi|
-            if (d >= lim) { ok = false; break; }
-            const double prod = fq::mul_bound(d, q);
-            if (st == 0) { if (prod >= q) ok = false; b = prod; }
-            else b = d > prod ? d : prod;
-        }
-        if (ok) { *r0_out = r0; *x0_out = s.x0; return true; }
-    }
-    return false;
-}
-
 int build_fq32_tables(NttPlanDev &p, const int32_t *w_host)
 {
     p.fq32_ok = 0; p.fq32_tab = nullptr;
     if (p.logn < 8 || p.logn > 10) return SCGPU_OK;
     int r0 = 0; int32_t x0 = 0;
-    if (!fq32_analyse(p.logn, p.rc.q, 1, &r0, &x0)) return SCGPU_OK;
+    if (!fq::analyse32(p.logn, p.rc.q, 1, &r0, &x0)) return SCGPU_OK;
     int r0_mv = 0; int32_t x0_mv = 0;
-    p.fq32_mv_ok = fq32_analyse(p.logn, p.rc.q, 8, &r0_mv, &x0_mv) ? 1 : 0;     // up to 8 accumulated products
+    p.fq32_mv_ok = fq::analyse32(p.logn, p.rc.q, 8, &r0_mv, &x0_mv) ? 1 : 0;     // up to 8 accumulated products
     p.fq32_r0_mv = r0_mv;
     std::vector<Tw> zf, zi;
     Tw ninv, one;
@@ -779,7 +773,7 @@ int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32
 #define FQ32_LAUNCH(L)                                                                                     \
     {                                                                                                      \
         const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
-        size_t grid = (size_t)sms * (L == 10 ? 3 : FQ32_MINB);                                                     \
+        size_t grid = (size_t)sms * FQ32_MINB;                                                     \
         if (grid > groups) grid = groups;                                                                  \
         if (tma) {                                                                                         \
             if (mode == FQ_POLYMUL)    k_polymul_fq32<L, FQ_POLYMUL, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c); \

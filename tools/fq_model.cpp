@@ -10,6 +10,7 @@ using namespace scgpu::fq;
 static double g_max_fwd, g_max_inv, g_max_fin;
 static int32_t rd(int32_t xb, double &mx) { double a = fabs((double)(xb - kBias)); if (a > mx) mx = a; return xb; }
 
+static int g_r0 = -1;      // >= 0: warp-local schedule (one optional reduction before stage 4) instead of sc.r_inv
 static void polymul(int logn, int64_t q, const std::vector<Tw> &zf, const std::vector<Tw> &zi, const Tw &ninv, const Tw &one,
                     const Schedule &sc, const int32_t *a, const int32_t *b, int32_t *out)
 {
@@ -34,10 +35,11 @@ static void polymul(int logn, int64_t q, const std::vector<Tw> &zf, const std::v
     for (int s = logn - 1; s >= 0; s--) {
         const int len = n >> (s + 1);
         // reduce at the entry of a pass (first stage the pass executes is its highest stage index)
-        for (int p = 0; p < npass; p++) {
+        for (int p = 0; p < npass && g_r0 < 0; p++) {
             const int J = (logn - 3 * p) >= 3 ? 3 : (logn - 3 * p);
             if (s == 3 * p + J - 1 && sc.r_inv[p]) for (int i = 0; i < n; i++) y[i] = mul(rd(y[i], g_max_inv), one, nq);
         }
+        if (g_r0 == 1 && s == 4) for (int i = 0; i < n; i++) y[i] = mul(rd(y[i], g_max_inv), one, nq);
         for (int blk = 0; blk < (1 << s); blk++)
             for (int j = 0; j < len; j++) {
                 int32_t &lo = y[2 * blk * len + j], &hi = y[2 * blk * len + j + len];
@@ -82,9 +84,17 @@ int main()
         printf("q=%lld n=%d ok=%d r_inv=%d%d%d%d x0=%d fwd_max=%.0f inv_max=%.0f final=%.0f\n", (long long)q, n, sc.ok, sc.r_inv[0], sc.r_inv[1], sc.r_inv[2], sc.r_inv[3], sc.x0, sc.fwd_max, sc.inv_max, sc.final_max);
         if (!sc.ok) continue;
         if (!build_tables(logn, q, w.data(), zf, zi, ninv, one)) { printf("  tables failed\n"); bad++; continue; }
-        g_max_fwd = g_max_inv = g_max_fin = 0;
         std::vector<int32_t> a(n), b(n), o(n), e(n);
         const int x0 = sc.x0;
+        for (int sched = 0; sched < 2; sched++) {
+        g_max_fwd = g_max_inv = g_max_fin = 0;
+        g_r0 = -1;
+        if (sched == 1) {
+            int r0 = 0; int32_t x032 = 0;
+            if (!analyse32(logn, q, 1, &r0, &x032)) { printf("  warp-local schedule: not applicable\n"); continue; }
+            g_r0 = r0;
+            printf("  warp-local schedule: r0=%d\n", r0);
+        }
         for (int trial = 0; trial < 60; trial++) {
             for (int i = 0; i < n; i++) {
                 switch (trial % 6) {
@@ -101,7 +111,9 @@ int main()
             for (int i = 0; i < n; i++) if (o[i] != e[i]) { if (bad < 5) printf("  MISMATCH trial %d i=%d got %d want %d\n", trial, i, o[i], e[i]); bad++; break; }
         }
         printf("  observed: fwd %.0f inv %.0f final %.0f  (limit %d)\n", g_max_fwd, g_max_inv, g_max_fin, kLimit);
-        if (g_max_fwd > sc.fwd_max || g_max_inv > sc.inv_max || g_max_fin > sc.final_max) { printf("  BOUND VIOLATED\n"); bad++; }
+        if (g_max_fwd > sc.fwd_max || g_max_inv >= (double)kLimit || g_max_fin >= (double)q) { printf("  BOUND VIOLATED\n"); bad++; }
+        if (sched == 0 && (g_max_inv > sc.inv_max || g_max_fin > sc.final_max)) { printf("  BOUND VIOLATED (8-coefficient schedule)\n"); bad++; }
+        }
     }
     printf(bad ? "FAIL %d\n" : "ALL OK\n", bad);
     return bad != 0;
