@@ -50,6 +50,7 @@ def lib():
         L.scgpu_polymul_batch_host.argtypes = [vp, vp, vp, vp, sz, sz]
         L.scgpu_ntt_mul_key_batch.argtypes = [vp, vp, vp, vp, ctypes.c_int, sz, sz, vp]
         L.scgpu_matvec_batch.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, sz, vp]
+        L.scgpu_gauss_plan_create_table.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, vp, sz, ctypes.c_int]
         L.scgpu_gauss_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_float, ctypes.c_float, ctypes.c_int]
         L.scgpu_gauss_plan_destroy.argtypes = [vp]
@@ -188,10 +189,18 @@ class NttPlan:
 class GaussPlan:
     """scgpu_gauss_plan_t: sampler tables (built on the host with the reference's formulas) on the device."""
 
-    def __init__(self, sampler, precision, blinding, tail, sigma, device=0):
+    def __init__(self, sampler, precision, blinding, tail, sigma, device=0, table=None):
         h = ctypes.c_void_p()
-        _check(lib().scgpu_gauss_plan_create(ctypes.byref(h), sampler, precision, blinding, tail, sigma, device),
-               "scgpu_gauss_plan_create")
+        if table is not None:
+            # 128 / 192 / 256-bit CDF over a caller-built table: numpy uint64 [entries, precision / 64]
+            import numpy as np
+            t = np.ascontiguousarray(table, dtype=np.uint64)
+            assert t.ndim == 2 and t.shape[1] * 64 == precision
+            _check(lib().scgpu_gauss_plan_create_table(ctypes.byref(h), precision, blinding, ctypes.c_void_p(t.ctypes.data),
+                                                       ctypes.c_size_t(t.shape[0]), device), "scgpu_gauss_plan_create_table")
+        else:
+            _check(lib().scgpu_gauss_plan_create(ctypes.byref(h), sampler, precision, blinding, tail, sigma, device),
+                   "scgpu_gauss_plan_create")
         self.handle = h
 
     def close(self):

@@ -42,8 +42,33 @@ __device__ __forceinline__ uint32_t cdf_search(const T *cdf, uint32_t size, T x)
     return a;
 }
 
+// gaussian_cdf.c:112-190, 480-532: x = precision/64 successive prng_64 draws, word 0 first; fixed halving
+// steps keep the largest a with "x >= l[a]" as compare_ge_prec evaluates it: retval = !x_lt_y | (equal & retval)
+// folded from word 0 up.  An equal word yields !x_lt_y = 1, so the fold reduces to the TOP words' >= and the
+// lower words never decide; reproduced literally.  Sign from bit 0 of word 0.
+__device__ __forceinline__ int32_t sample_cdf_high(const GaussTablesDev &g, PrngStream &rng)
+{
+    const int nw = g.precision >> 6;
+    uint64_t x[4];
+    for (int i = 0; i < nw; i++) x[i] = rng.next64();
+    uint32_t a = 0;
+    for (uint32_t st = g.cdf_size >> 1; st > 0; st >>= 1) {
+        const uint32_t b = a + st;
+        if (b >= g.cdf_size) continue;
+        const uint64_t *l = g.cdfh + (size_t)b * nw;
+        unsigned ge = 1;
+        for (int i = 0; i < nw; i++) {
+            const unsigned lt = x[i] < l[i], eq = x[i] == l[i];
+            ge = (!lt) | (eq & ge);
+        }
+        if (ge) a = b;
+    }
+    return (x[0] & 1) ? (int32_t)a : -(int32_t)a;
+}
+
 __device__ __forceinline__ int32_t sample_cdf(const GaussTablesDev &g, PrngStream &rng)
 {
+    if (g.precision > 64) return sample_cdf_high(g, rng);
     if (g.precision == 64) {
         uint64_t x = rng.next64();
         uint32_t a = cdf_search<uint64_t>(g.cdf64, g.cdf_size, x);
@@ -207,8 +232,15 @@ __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
                     bool discard = a.thresh && rng.next32() < a.thresh;
                     if (!discard) i++;
                 }
-                if (a.g.blinding == SCGPU_BLINDING_SAMPLES)      // sampling.c:170-191
+                if (a.g.blinding == SCGPU_BLINDING_SAMPLES) {    // sampling.c:170-191
                     for (size_t i = 0; i < n; i++) v[i] -= draw(a.g, rng);
+                    // :176,182-188: swap v[i] with v[i & (n - 1)], a no-op only when n is a power of two
+                    const uint32_t mask = (uint32_t)(n - 1);
+                    for (size_t i = 0; i < n; i++) {
+                        const size_t j = i & mask;
+                        const int32_t t = v[i]; v[i] = v[j]; v[j] = t;
+                    }
+                }
             }
         }
     }

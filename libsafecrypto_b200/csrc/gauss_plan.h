@@ -10,12 +10,15 @@ struct PrngState;
 
 struct GaussTablesDev {
     int sampler;            // random_sampling_e
-    int precision;          // 32 / 64
+    int precision;          // 32 / 64, or 128 / 192 / 256 with a caller-built table (cdfh)
     int blinding;           // sample_blinding_e
     // CDF (gaussian_cdf.c:555-610, 679-728)
     const uint64_t *cdf64;
     const uint32_t *cdf32;
     uint32_t cdf_size;
+    // high-precision CDF (gaussian_cdf.c:112-532): cdf_size entries of precision/64 words, word 0 least
+    // significant (the reference's u128_t / u192_t / u256_t arrays on a 64-bit-limb build)
+    const uint64_t *cdfh;
     // Knuth-Yao (gaussian_knuth_yao.c:81-189): sorted flat indices (row * cols + col) of the one-bits of
     // the row-major probability matrix
     int ky_rows, ky_cols, ky_bound;

@@ -126,6 +126,7 @@ const uint32_t kDefaultSeedPeriod = 0x00100000;     // safecrypto.c:379
 bool fast_path_ok(const GaussTablesDev &t, int prng_type, size_t per_stream, uint32_t discard)
 {
     if (t.sampler != SCGPU_SAMPLER_CDF || t.blinding != SCGPU_NORMAL_SAMPLES || discard != 0) return false;
+    if (t.precision > 64) return false;                  // high-precision tables: sequential kernel
     const size_t words = per_stream * (t.precision == 64 ? 2 : 1);
     if (prng_type == PRNG_CHACHA20) return words <= 2 * ((size_t)kDefaultSeedPeriod / 8 - 1);   // first reseed epoch
     const size_t blocks = (words + 3) / 4;
@@ -201,6 +202,39 @@ extern "C" int scgpu_gauss_plan_create(scgpu_gauss_plan_t **out, int sampler, in
         set_error("gauss_plan_create: sampler %d at %d-bit precision (blinding %d) is not on the GPU path", sampler, precision, blinding);
         return SCGPU_ERR_UNSUPPORTED;
     }
+    if (rc != SCGPU_OK) { scgpu_gauss_plan_destroy(p); return rc; }
+    *out = p;
+    return SCGPU_OK;
+}
+
+// CDF sampler over a table the CALLER built (gauss_cdf_create_high_precision, gaussian_cdf.c:192-318, needs
+// the reference's multi-precision float library; the table is host set-up, the sampling is the hot path).
+extern "C" int scgpu_gauss_plan_create_table(scgpu_gauss_plan_t **out, int precision, int blinding,
+                                             const uint64_t *table, size_t entries, int device)
+{
+    if (!out || !table) { set_error("gauss_plan_create_table: null argument"); return SCGPU_ERR_ARG; }
+    if (precision == 256) {
+        set_error("gauss_plan_create_table: the reference's 256-bit sampler reads an uninitialised word (gaussian_cdf.c:519-522): there is no behaviour to reproduce");
+        return SCGPU_ERR_UNSUPPORTED;
+    }
+    if (precision != 128 && precision != 192) { set_error("gauss_plan_create_table: precision %d (128 or 192)", precision); return SCGPU_ERR_ARG; }
+    if (blinding < 0 || blinding > 2) { set_error("gauss_plan_create_table: blinding %d", blinding); return SCGPU_ERR_ARG; }
+    if (entries < 2 || entries > (1u << 24)) { set_error("gauss_plan_create_table: %zu entries", entries); return SCGPU_ERR_ARG; }
+    int ndev = 0;
+    SCGPU_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("gauss_plan_create_table: device %d of %d", device, ndev); return SCGPU_ERR_ARG; }
+    SCGPU_CUDA_CHECK(cudaSetDevice(device));
+    scgpu_gauss_plan *p = new scgpu_gauss_plan();
+    memset(&p->t, 0, sizeof(p->t));
+    p->t.sampler = SCGPU_SAMPLER_CDF; p->t.precision = precision; p->t.blinding = blinding;
+    p->device = device;
+    cudaDeviceProp prop;
+    SCGPU_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    p->sm_count = prop.multiProcessorCount;
+    std::vector<uint64_t> words(table, table + entries * (size_t)(precision / 64));
+    uint64_t *d = nullptr;
+    const int rc = upload(&d, words);
+    p->d_cdf = d; p->t.cdfh = d; p->t.cdf_size = (uint32_t)entries;
     if (rc != SCGPU_OK) { scgpu_gauss_plan_destroy(p); return rc; }
     *out = p;
     return SCGPU_OK;

@@ -185,6 +185,7 @@ int ref_prng_script(int prng_type, const uint8_t *seed, size_t seed_len, size_t 
 SC_STRUCT_PACK_START
 typedef struct { UINT64 *cdf; SINT32 cdf_size; SINT32 k; SINT32 use_kl; prng_ctx_t *prng; } SC_STRUCT_PACKED drv_cdf64_t;
 typedef struct { UINT32 *cdf; SINT32 cdf_size; SINT32 k; SINT32 use_kl; prng_ctx_t *prng; } SC_STRUCT_PACKED drv_cdf32_t;
+typedef struct { void *cdf_256; void *cdf_192; void *cdf_128; SINT32 cdf_size; SINT32 k; SINT32 use_kl; prng_ctx_t *prng; } SC_STRUCT_PACKED drv_cdfh_t;
 typedef struct { SINT32 num_rows, num_cols; FLOAT tailcut; SINT32 bound; UINT8 *prelut; SINT32 *hamming; UINT8 *pmat; prng_ctx_t *prng; } SC_STRUCT_PACKED drv_ky_t;
 typedef struct { UINT16 max_gauss_val, max_gauss_log; FLOAT sigma; UINT16 max_ber_entries, max_ber_bytes; SINT32 bits; UINT8 **ber_table; SINT32 reject_counter; prng_ctx_t *prng; } SC_STRUCT_PACKED drv_ber_t;
 SC_STRUCT_PACK_END
@@ -206,6 +207,18 @@ int ref_cdf_table(int precision, int blinding, float tail, float sigma, void *ou
         size = c->cdf_size;
         if ((size_t)size <= cap_entries) memcpy(out, c->cdf, (size_t)size * 4);
         gaussian_cdf_destroy_32(&g);
+    } else if (precision == 128 || precision == 192 || precision == 256) {
+        /* gauss_cdf_high_t (gaussian_cdf.c:60-72): entries of precision/64 limbs, limb 0 least significant */
+        void *g = precision == 128 ? gaussian_cdf_create_128(ctx, tail, sigma, 0, (sample_blinding_e)blinding)
+                : precision == 192 ? gaussian_cdf_create_192(ctx, tail, sigma, 0, (sample_blinding_e)blinding)
+                                   : gaussian_cdf_create_256(ctx, tail, sigma, 0, (sample_blinding_e)blinding);
+        drv_cdfh_t *c = (drv_cdfh_t *)g;
+        const void *tab = precision == 128 ? c->cdf_128 : precision == 192 ? c->cdf_192 : c->cdf_256;
+        size = c->cdf_size;
+        if ((size_t)size <= cap_entries) memcpy(out, tab, (size_t)size * (size_t)(precision / 8));
+        if (precision == 128) gaussian_cdf_destroy_128(&g);
+        else if (precision == 192) gaussian_cdf_destroy_192(&g);
+        else gaussian_cdf_destroy_256(&g);
     }
     prng_destroy(ctx);
     return size;
@@ -239,6 +252,20 @@ int ref_ber_table(float tail, float sigma, uint8_t *tab, size_t cap, int32_t *en
     return (int)sz;
 }
 
+/* Optional caller-supplied 128 / 192-bit CDF table written over the one create_sampler() built: the reference's
+ * own table construction needs GMP/MPFR to be meaningful (with USE_SAFECRYPTO_FLOAT_MP every entry comes out
+ * as {2, 2, ..}), the SAMPLING over a table is what the GPU path is compared against. */
+static const uint64_t *g_high_tab[2];
+static int g_high_entries[2];
+int ref_set_high_table(int precision, const uint64_t *words, int entries)
+{
+    int k = precision == 128 ? 0 : precision == 192 ? 1 : -1;
+    if (k < 0) return 1;
+    g_high_tab[k] = words;            /* caller keeps it alive; NULL clears */
+    g_high_entries[k] = entries;
+    return 0;
+}
+
 /* One independent PRNG stream + sampler per row; row i is seeded with seeds[i*seed_len ..].
  * sampler: 0 CDF (through create_sampler/get_vector_32), 1 Knuth-Yao, 5 Bernoulli (direct
  * create/sample calls as src/unit/unit_sampling.c does: they are not reachable through
@@ -259,6 +286,14 @@ int ref_gauss_streams(int sampler, int precision, int blinding, int prng_type, f
             utils_sampling_t *smp = create_sampler(CDF_GAUSSIAN_SAMPLING, (sample_precision_e)precision,
                 (sample_blinding_e)blinding, (SINT32)n, SAMPLING_DISABLE_BOOTSTRAP, ctx, tail, sigma);
             if (!smp) { fail |= 1; prng_destroy(ctx); continue; }
+            if (precision == 128 || precision == 192) {
+                int k = precision == 128 ? 0 : 1;
+                drv_cdfh_t *c = (drv_cdfh_t *)smp->gauss;
+                if (g_high_tab[k]) {
+                    if (g_high_entries[k] != c->cdf_size) { fail |= 1; destroy_sampler(&smp); prng_destroy(ctx); continue; }
+                    memcpy(precision == 128 ? c->cdf_128 : c->cdf_192, g_high_tab[k], (size_t)c->cdf_size * (size_t)(precision / 8));
+                }
+            }
             set_discard(smp, discard);
             for (size_t c = 0; c < calls_per_stream; c++)
                 get_vector_32(smp, v + c * n, n, (FLOAT)centre);

@@ -86,6 +86,8 @@ enum { ORC_SAMPLER_CDF = 0, ORC_SAMPLER_KNUTH_YAO = 1, ORC_SAMPLER_BERNOULLI = 5
 enum { ORC_NORMAL_SAMPLES = 0, ORC_BLINDING_SAMPLES = 1, ORC_SHUFFLE_SAMPLES = 2 };
 
 int orc_cdf_table(int precision, int blinding, float tail, float sigma, void *out, size_t cap_entries);
+/* inject a reference-built 128 / 192 / 256-bit CDF table (entries x precision/64 words) for orc_gauss_streams */
+int orc_set_high_table(int precision, const uint64_t *words, int entries);
 int orc_ky_table(int bitwidth, float tail, float sigma, uint8_t *pmat, size_t cap,
                  int32_t *rows, int32_t *cols, int32_t *bound);
 int orc_ber_table(float tail, float sigma, uint8_t *tab, size_t cap,

@@ -41,7 +41,27 @@ static uint64_t bin_expansion(double x, int nbits)
 
 /* ---- CDF ------------------------------------------------------------------------------- */
 
-typedef struct { uint64_t *t64; uint32_t *t32; int size; int precision; } cdf_t;
+typedef struct { uint64_t *t64; uint32_t *t32; uint64_t *thi; int size; int precision; } cdf_t;
+
+/* 128 / 192 / 256-bit tables are built by the reference's multi-precision float code (gaussian_cdf.c:192-318);
+ * the port restates the SAMPLING over such a table, which the test harness injects here (one per precision). */
+static uint64_t *g_high_tab[2];
+static int g_high_size[2];
+int orc_set_high_table(int precision, const uint64_t *words, int entries)
+{
+    /* 256-bit: gaussian_cdf_sample_256 stores its fourth draw in w[4] and reads w[3] uninitialised
+     * (gaussian_cdf.c:519-522): no defined behaviour to restate */
+    int k = precision == 128 ? 0 : precision == 192 ? 1 : -1;
+    if (k < 0) return 1;
+    if (!words) { free(g_high_tab[k]); g_high_tab[k] = NULL; return 0; }
+    if (entries < 2) return 1;
+    free(g_high_tab[k]);
+    size_t bytes = (size_t)entries * (size_t)(precision / 8);
+    g_high_tab[k] = malloc(bytes);
+    memcpy(g_high_tab[k], words, bytes);
+    g_high_size[k] = entries;
+    return 0;
+}
 
 #define L_2_SQRTPI 1.128379167095512573896158903121545172L   /* SC_M_2_SQRTPIl */
 #define L_SQRT1_2  0.707106781186547524400844362104849039L   /* SC_M_SQRT1_2l  */
@@ -51,7 +71,16 @@ static int cdf_build(cdf_t *c, int precision, int blinding, float tail, float si
     int bits = (int)ceil_log2_sz((size_t)(tail * sigma));
     c->size = 1 << bits;
     c->precision = precision;
-    c->t64 = NULL; c->t32 = NULL;
+    c->t64 = NULL; c->t32 = NULL; c->thi = NULL;
+    if (precision == 128 || precision == 192) {
+        int k = precision == 128 ? 0 : 1;
+        if (!g_high_tab[k]) return 1;
+        size_t bytes = (size_t)g_high_size[k] * (size_t)(precision / 8);
+        c->size = g_high_size[k];
+        c->thi = malloc(bytes);
+        memcpy(c->thi, g_high_tab[k], bytes);
+        return 0;
+    }
     if (precision == 64) {
         /* gaussian_cdf.c:555-610 */
         c->t64 = malloc(sizeof(uint64_t) * (size_t)c->size);
@@ -89,12 +118,33 @@ static int cdf_build(cdf_t *c, int precision, int blinding, float tail, float si
     return 1;
 }
 
-static void cdf_free(cdf_t *c) { free(c->t64); free(c->t32); }
+static void cdf_free(cdf_t *c) { free(c->t64); free(c->t32); free(c->thi); }
 
 /* gaussian_cdf.c:536-553 / 661-677: largest index a (by fixed halving steps) with l[a] < x */
 static int32_t cdf_sample(const cdf_t *c, orc_prng_t *rng)
 {
     uint32_t a = 0;
+    if (c->precision > 64) {
+        /* gaussian_cdf.c:480-532 (sample), :112-190 (compare_ge_prec, binary_search_*): x >= l[b] */
+        int nw = c->precision / 64;
+        uint64_t x[4];
+        for (int i = 0; i < nw; i++) x[i] = orc_prng_64(rng);
+        for (uint32_t st = (uint32_t)c->size >> 1; st > 0; st >>= 1) {
+            uint32_t b = a + st;
+            if (b >= (uint32_t)c->size) continue;
+            const uint64_t *l = c->thi + (size_t)b * (size_t)nw;
+            /* compare_ge_prec, gaussian_cdf.c:112-136, literally: retval = !x_lt_y | (equal & retval).  An equal
+             * word gives !x_lt_y = 1, so the fold ends as "top word of x >= top word of l": the lower words
+             * never decide (a quirk of the reference that parity has to keep). */
+            unsigned ge = 1;
+            for (int i = 0; i < nw; i++) {
+                unsigned lt = x[i] < l[i], eq = x[i] == l[i];
+                ge = (!lt) | (eq & ge);
+            }
+            if (ge) a = b;
+        }
+        return (x[0] & 1) ? (int32_t)a : -(int32_t)a;
+    }
     if (c->precision == 64) {
         uint64_t x = orc_prng_64(rng);
         for (uint32_t st = (uint32_t)c->size >> 1; st > 0; st >>= 1) {
@@ -314,6 +364,12 @@ static void vec_blinding(smp_t *s, int32_t *v, size_t n, int32_t centre)
 {
     vec_shuffle(s, v, n, centre);
     for (size_t i = 0; i < n; i++) v[i] -= draw(s);
+    /* sampling.c:176,182-188: swap v[i] with v[i & (n - 1)] -- a no-op only when n is a power of two */
+    uint32_t mask = (uint32_t)(n - 1);
+    for (size_t i = 0; i < n; i++) {
+        size_t j = i & mask;
+        int32_t t = v[i]; v[i] = v[j]; v[j] = t;
+    }
 }
 
 int orc_gauss_streams(int sampler, int precision, int blinding, int prng_type, float tail, float sigma,

@@ -115,10 +115,34 @@ class Checker:
         f.restype = ctypes.c_int
         f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t]
         cap = 1 << 16
+        if precision > 64:
+            nw = precision // 64
+            buf = np.zeros(cap * nw, dtype=np.uint64)
+            size = f(precision, blinding, tail, sigma, _vp(buf), cap)
+            assert 0 < size <= cap
+            return buf[:size * nw].reshape(size, nw).copy()
         buf = np.zeros(cap, dtype=np.uint64 if precision == 64 else np.uint32)
         size = f(precision, blinding, tail, sigma, _vp(buf), cap)
         assert 0 < size <= cap
         return buf[:size].copy()
+
+    def set_high_table(self, precision, table):
+        """Inject a 128 / 192-bit CDF table (uint64 [entries, precision / 64]) for gauss_streams(): the port
+        needs one (it does not restate the reference's multi-precision table construction), the compiled
+        reference has the table it built overwritten.  None clears."""
+        f = self._fn("set_high_table")
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        if table is None:
+            self._high = getattr(self, "_high", {})
+            self._high.pop(precision, None)
+            assert f(precision, None, 0) == 0
+            return
+        t = np.ascontiguousarray(table, dtype=np.uint64)
+        self._high = getattr(self, "_high", {})
+        self._high[precision] = t                       # the reference driver keeps the pointer
+        assert f(precision, _vp(t), t.shape[0]) == 0
+
 
     def ky_table(self, bitwidth, tail, sigma):
         f = self._fn("ky_table")
@@ -218,3 +242,34 @@ def tables(q, n, tw_bits):
     generated ntt_tables.c in tests/test_oracle_vs_ref.py and tests/golden/tables.json)."""
     w, r, _ = port().roots_of_unity(q, n, tw_bits)
     return w, r
+
+
+def high_precision_cdf_table(precision, tail, sigma, blinding=0):
+    """What gauss_cdf_create_high_precision (gaussian_cdf.c:192-318) computes when its multi-precision floats
+    are exact: entry i = floor(s_i), s_1 = d / 2, s_{i+1} = s_i + d exp(-i^2 / (2 sigma^2)),
+    d = 2 / sqrt(2 pi) * 2^precision / sigma, entry 0 = 0, saturating to all-ones.  Returned as uint64
+    [entries, precision / 64] with word 0 least significant.  Used as a realistic table for the sampling tests."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = precision // 3 + 40
+    entries = 1 << int(np.ceil(np.log2(np.float32(tail) * np.float32(sigma))))
+    sg = Decimal(float(np.float32(sigma)))
+    if blinding == 1:
+        sg = sg * Decimal(0.5).sqrt()
+    pi = Decimal("3.14159265358979323846264338327950288419716939937510582097494459230781640628620899862803482534211706798214808651")
+    d = Decimal(2) / (2 * pi).sqrt() * (Decimal(2) ** precision) / sg
+    e = -Decimal(0.5) / (sg * sg)
+    nw = precision // 64
+    top = (1 << precision) - 1
+    tab = np.zeros((entries, nw), dtype=np.uint64)
+    s = d / 2
+    i = 1
+    while i < entries - 1:
+        v = int(s)
+        if v > top:
+            break
+        for j in range(nw):
+            tab[i, j] = (v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+        s += d * (e * i * i).exp()
+        i += 1
+    tab[i:, :] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    return tab

@@ -117,6 +117,28 @@ def main():
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
 
+    # ---- golden_v2: 128 / 192-bit CDF sampling (gaussian_cdf.c:112-509) over an injected table ------------
+    # The table construction needs the reference's multi-precision floats (degenerate under
+    # USE_SAFECRYPTO_FLOAT_MP: every entry {2, 2, ..}); the fixture pins the SAMPLING of the compiled reference
+    # over (a) the table it builds itself and (b) the exact table of _oracle.high_precision_cdf_table.
+    out2 = {"gauss_seeds": seeds}
+    for prec in (128, 192):
+        own = ref.cdf_table(prec, 0, 13.0, 4.5)
+        out2["cdf%d_own_sigma4p5" % prec] = own
+        for bl in (0, 1, 2):
+            tab = O.high_precision_cdf_table(prec, 13.0, 4.5, bl)
+            out2["cdf%d_b%d_sigma4p5" % (prec, bl)] = tab
+            ref.set_high_table(prec, tab)
+            for pname, pt in (("chacha", O.PRNG_CHACHA), ("aes", O.PRNG_AES_CTR_DRBG)):
+                out2["gauss_cdf%d_%s_b%d" % (prec, pname, bl)] = ref.gauss_streams(
+                    O.SAMPLER_CDF, prec, bl, pt, 13.0, 4.5, seeds, 256, calls=2, discard=(2 if bl == 2 else 0))
+            ref.set_high_table(prec, None)
+        for pname, pt in (("chacha", O.PRNG_CHACHA), ("aes", O.PRNG_AES_CTR_DRBG)):
+            out2["gauss_cdf%d_%s_own" % (prec, pname)] = ref.gauss_streams(O.SAMPLER_CDF, prec, 0, pt, 13.0, 4.5, seeds, 64)
+    path = os.path.join(HERE, "golden_v2.npz")
+    np.savez_compressed(path, **out2)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(out2), "arrays")
+
 
 if __name__ == "__main__":
     main()

@@ -73,6 +73,38 @@ def test_cdf_vectors(prng, precision, blinding):
         assert np.array_equal(got, exp), (discard, n, calls)
 
 
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+@pytest.mark.parametrize("precision", [128, 192])
+def test_high_precision_cdf_vectors(prng, precision):
+    """128 / 192-bit CDF sampling over a caller-built table (scgpu_gauss_plan_create_table): every vector mode,
+    discard, several calls; plus the golden samples of the compiled reference; 256-bit is refused."""
+    seeds = seeds_for(37)
+    pname = "chacha" if prng == O.PRNG_CHACHA else "aes"
+    G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz"))
+
+    def run(table, blinding, sd, n, calls=1, centre=0, discard=0):
+        plan = sc.GaussPlan(sc.SAMPLER_CDF, precision, blinding, 0.0, 0.0, table=table)
+        out = torch.full((sd.shape[0], n * calls), 123456, dtype=torch.int32, device=DEV)
+        plan.streams(prng, torch.from_numpy(sd).to(DEV), n, out, calls=calls, centre=centre, discard=discard)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    for blinding in (O.NORMAL_SAMPLES, O.BLINDING_SAMPLES, O.SHUFFLE_SAMPLES):
+        tab = O.high_precision_cdf_table(precision, 13.42, 215.0, blinding)
+        O.port().set_high_table(precision, tab)
+        for discard, n, calls, centre in ((0, 512, 2, 3), (4, 200, 1, 0), (0, 1, 3, -7)):
+            exp = O.port().gauss_streams(O.SAMPLER_CDF, precision, blinding, prng, 13.42, 215.0, seeds, n,
+                                         discard=discard, centre=centre, calls=calls)
+            assert np.array_equal(run(tab, blinding, seeds, n, calls, centre, discard), exp), (blinding, discard, n)
+        g = G2["cdf%d_b%d_sigma4p5" % (precision, blinding)]
+        got = run(g, blinding, G2["gauss_seeds"], 256, calls=2, discard=(2 if blinding == 2 else 0))
+        assert np.array_equal(got, G2["gauss_cdf%d_%s_b%d" % (precision, pname, blinding)])
+    got = run(G2["cdf%d_own_sigma4p5" % precision], 0, G2["gauss_seeds"], 64)
+    assert np.array_equal(got, G2["gauss_cdf%d_%s_own" % (precision, pname)])
+    with pytest.raises(sc.ScgpuError):
+        sc.GaussPlan(sc.SAMPLER_CDF, 256, 0, 0.0, 0.0, table=np.zeros((64, 4), dtype=np.uint64))
+
+
 @pytest.mark.parametrize("pname,prng", [("chacha", O.PRNG_CHACHA), ("aes", O.PRNG_AES_CTR_DRBG)])
 def test_golden_samples_on_gpu(pname, prng):
     seeds = G["gauss_seeds"]

@@ -257,6 +257,23 @@ def test_golden_samples(pname, pt):
         assert np.array_equal(got, G["gauss_%s_%s" % (key, pname)])
 
 
+@pytest.mark.parametrize("pname,pt", [("chacha", O.PRNG_CHACHA), ("aes", O.PRNG_AES_CTR_DRBG)])
+@pytest.mark.parametrize("precision", [128, 192])
+def test_golden_high_precision_samples(pname, pt, precision):
+    """golden_v2: samples of the compiled reference's 128 / 192-bit CDF sampler over injected tables."""
+    G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz"))
+    seeds = G2["gauss_seeds"]
+    P.set_high_table(precision, G2["cdf%d_own_sigma4p5" % precision])
+    assert np.array_equal(P.gauss_streams(O.SAMPLER_CDF, precision, 0, pt, 13.0, 4.5, seeds, 64),
+                          G2["gauss_cdf%d_%s_own" % (precision, pname)])
+    for bl in (0, 1, 2):
+        tab = G2["cdf%d_b%d_sigma4p5" % (precision, bl)]
+        assert np.array_equal(tab, O.high_precision_cdf_table(precision, 13.0, 4.5, bl))
+        P.set_high_table(precision, tab)
+        got = P.gauss_streams(O.SAMPLER_CDF, precision, bl, pt, 13.0, 4.5, seeds, 256, calls=2, discard=(2 if bl == 2 else 0))
+        assert np.array_equal(got, G2["gauss_cdf%d_%s_b%d" % (precision, pname, bl)])
+
+
 def test_sample_statistics():
     """func_samplers.c histograms 2^20 samples; here: mean ~ 0 and std ~ sigma for each sampler."""
     seeds = np.random.default_rng(1).integers(0, 256, size=(64, 64)).astype(np.uint8)

@@ -205,6 +205,38 @@ def test_cdf_vectors(prng, blinding, precision):
         exp = O.ref().gauss_streams(O.SAMPLER_CDF, precision, blinding, prng, 13.42, 215.0, seeds, 512,
                                     discard=discard, centre=3, calls=2)
         assert np.array_equal(got, exp)
+    # lengths that are not a power of two: blinding_sample_vector_32 ends with a v[i] <-> v[i & (n-1)] swap pass
+    for n in (77, 300, 1):
+        got = O.port().gauss_streams(O.SAMPLER_CDF, precision, blinding, prng, 13.42, 215.0, seeds, n, centre=-1, calls=2)
+        exp = O.ref().gauss_streams(O.SAMPLER_CDF, precision, blinding, prng, 13.42, 215.0, seeds, n, centre=-1, calls=2)
+        assert np.array_equal(got, exp), n
+
+
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+@pytest.mark.parametrize("precision", [128, 192])
+def test_high_precision_cdf_sampling(prng, precision):
+    """gaussian_cdf_sample_128/192 over (a) the table the compiled reference builds itself and (b) an exact
+    table written over it; the port restates only the sampling (compare_ge_prec as written)."""
+    seeds = np.array([list(seed_bytes(i)) for i in range(5)], dtype=np.uint8)
+    own = O.ref().cdf_table(precision, 0, 13.42, 215.0)
+    O.port().set_high_table(precision, own)
+    got = O.port().gauss_streams(O.SAMPLER_CDF, precision, 0, prng, 13.42, 215.0, seeds, 300)
+    assert np.array_equal(got, O.ref().gauss_streams(O.SAMPLER_CDF, precision, 0, prng, 13.42, 215.0, seeds, 300))
+    for blinding in (O.NORMAL_SAMPLES, O.BLINDING_SAMPLES, O.SHUFFLE_SAMPLES):
+        tab = O.high_precision_cdf_table(precision, 13.42, 215.0, blinding)
+        O.ref().set_high_table(precision, tab)
+        O.port().set_high_table(precision, tab)
+        try:
+            for discard in (0, 4):
+                got = O.port().gauss_streams(O.SAMPLER_CDF, precision, blinding, prng, 13.42, 215.0, seeds, 300,
+                                             discard=discard, centre=-2, calls=2)
+                exp = O.ref().gauss_streams(O.SAMPLER_CDF, precision, blinding, prng, 13.42, 215.0, seeds, 300,
+                                            discard=discard, centre=-2, calls=2)
+                assert np.array_equal(got, exp)
+                if blinding == O.NORMAL_SAMPLES and discard == 0:
+                    assert 190 < got.std() < 240          # a sane Gaussian, unlike the reference's own table
+        finally:
+            O.ref().set_high_table(precision, None)
 
 
 def test_survey_anchor_samples():
