@@ -400,6 +400,7 @@ static int arith_mode()
 }
 static bool use_fq(const NttPlanDev &p) { const int m = arith_mode(); return p.fq_ok && (m == 0 || m == 3); }
 static bool use_fq32(const NttPlanDev &p) { return p.fq32_ok && arith_mode() == 0; }
+static bool use_sh32(const NttPlanDev &p) { return p.sh32_ok && arith_mode() == 0; }
 static bool use_sq(const NttPlanDev &p) { return p.sq_ok && arith_mode() != 1; }
 int set_fast_arith(int mode)
 {
@@ -427,6 +428,7 @@ int launch_polymul(const NttPlanDev &p, int32_t *out, const int32_t *a, const in
     if (use_fq32(p)) return launch_polymul_fq32(p, 0, out, a, b, b_stride, count, st);
     if (use_fq(p)) return launch_polymul_fq(p, 0, out, a, b, b_stride, count, st);
     if (use_sq(p)) return launch_polymul_sq(p, 0, out, a, b, b_stride, count, st);
+    if (use_sh32(p)) return launch_polymul_sh32(p, 0, out, a, b, b_stride, count, st);
     SCGPU_REQUIRE_FAST(p);
     FastConst c = make_const(p);
     const size_t G = kCtaThreads / (p.n / 8);
@@ -450,6 +452,7 @@ int launch_mul_key(const NttPlanDev &p, int32_t *out, const int32_t *t, const vo
     if (use_fq32(p)) return launch_polymul_fq32(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
     if (use_fq(p)) return launch_polymul_fq(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
     if (use_sq(p)) return launch_polymul_sq(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
+    if (use_sh32(p)) return launch_polymul_sh32(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
     SCGPU_REQUIRE_FAST(p);
     FastConst c = make_const(p);
     const size_t G = kCtaThreads / (p.n / 8);
@@ -480,6 +483,7 @@ int launch_matvec(const NttPlanDev &p, int32_t *out, const int32_t *A, const int
     if (use_fq32(p) && p.fq32_mv_ok) return launch_matvec_fq32(p, out, A, s, k, l, count, st);
     if (use_fq(p)) return launch_matvec_fq(p, out, A, s, k, l, count, st);
     if (use_sq(p)) return launch_matvec_sq(p, out, A, s, k, l, count, st);
+    if (use_sh32(p) && p.sh32_mv_ok) return launch_matvec_sh32(p, out, A, s, k, l, count, st);
     FastConst c = make_const(p);
     const size_t G = kCtaThreads / (p.n / 8);
     // shared-memory stash limits residency to 1-2 CTAs per SM

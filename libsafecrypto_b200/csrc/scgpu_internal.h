@@ -50,6 +50,11 @@ struct NttPlanDev {
     int32_t fq32_x0;
     void *fq32_tab;                      // forward [w | wq | k | c], inverse [w | wq | k | c], n words each
     alignas(16) unsigned char fq32_pass0[2 * 31 * 16];
+    // Shoup / Montgomery arithmetic on the same schedule, for moduli up to 2^25 (ntt_fast_sh32.cu)
+    int sh32_ok, sh32_r0, sh32_mv_ok, sh32_r0_mv;
+    int32_t sh32_x0;
+    void *sh32_tab;                      // forward [w | wp], inverse [w | wp], n words each
+    alignas(16) unsigned char sh32_pass0[2 * 31 * 8], sh32_ninv[8], sh32_one[8];
 };
 
 struct ExactArgs {
@@ -86,6 +91,12 @@ int build_fq32_tables(NttPlanDev &plan, const int32_t *w_host);
 void free_fq32_tables(NttPlanDev &plan);
 int launch_polymul_fq32(const NttPlanDev &plan, int mode, int32_t *out, const int32_t *a, const void *b,
                         size_t b_stride, size_t count, cudaStream_t stream);
+int build_sh32_tables(NttPlanDev &plan, const int32_t *w_host);
+void free_sh32_tables(NttPlanDev &plan);
+int launch_polymul_sh32(const NttPlanDev &plan, int mode, int32_t *out, const int32_t *a, const void *b,
+                        size_t b_stride, size_t count, cudaStream_t stream);
+int launch_matvec_sh32(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
+                       size_t count, cudaStream_t stream);
 int launch_matvec_fq32(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
                        size_t count, cudaStream_t stream);
 int launch_matvec_fq(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,

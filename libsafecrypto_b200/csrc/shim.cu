@@ -122,6 +122,7 @@ extern "C" int scgpu_ntt_plan_create(scgpu_ntt_plan_t **out, const void *params,
         if (rcode == SCGPU_OK) rcode = build_sq_tables(d, wh.data());
         if (rcode == SCGPU_OK) rcode = build_fq_tables(d, wh.data());
         if (rcode == SCGPU_OK) rcode = build_fq32_tables(d, wh.data());
+        if (rcode == SCGPU_OK && !d.fq32_ok && d.zeta_fwd) rcode = build_sh32_tables(d, wh.data());
         if (rcode != SCGPU_OK) { delete plan; return rcode; }
     }
     *out = plan;
@@ -143,6 +144,7 @@ extern "C" void scgpu_ntt_plan_destroy(scgpu_ntt_plan_t *plan)
     free_sq_tables(plan->dev);
     free_fq_tables(plan->dev);
     free_fq32_tables(plan->dev);
+    free_sh32_tables(plan->dev);
     delete plan;
 }
 

@@ -73,7 +73,7 @@ q = 8380417
 w, r = O.tables(q, n, 32)
 pl = sc.NttPlan(n, q, sc.REFERENCE, w, r)
 a, b = rnd(q, (1 << 20, n)), rnd(q, (1 << 20, n))
-report("C4 polymul n=256 q=8380417 (Montgomery)", 1 << 20, timeit(lambda: pl.polymul(o, a, b)), 12 * n)
+report("C4 polymul n=256 q=8380417 (Shoup, warp-local)", 1 << 20, timeit(lambda: pl.polymul(o, a, b)), 12 * n)
 for v, vn in ((sc.REFERENCE, "reference"), (sc.FP, "fp")):
     pe = sc.NttPlan(n, q, v, w, r)
     report("C4 exact fwd_ntt_32_32 %s" % vn, 1 << 20, timeit(lambda: pe.batch(sc.OP_FWD, o, a)), 8 * n, "ntt")
