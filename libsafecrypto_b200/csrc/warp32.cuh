@@ -715,12 +715,9 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
     using C = Cfg32<8>;
     const bool tma = ((uintptr_t)A % 16) == 0 && ((uintptr_t)s % 16) == 0 && tma_allowed();
     const size_t smem = ((size_t)(l + 1) * C::POLYS * C::TS + (tma ? (size_t)C::POLYS * (C::N + C::T) : 0)) * sizeof(int32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    // per launch, not once: the attribute belongs to the current device's context and plans exist per device
+    if (tma) SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    else     SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (smem > 200 * 1024) { set_error("matvec: l=%d needs %zu bytes of shared memory", l, smem); return SCGPU_ERR_UNSUPPORTED; }
     const int sms = sm_count > 0 ? sm_count : 148;
     int per_sm = (int)((227 * 1024) / (smem + 1024 + 64));
