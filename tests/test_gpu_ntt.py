@@ -355,6 +355,69 @@ def test_full_size_properties():
     assert np.array_equal(ab[sl].cpu().numpy(), exp)
 
 
+@pytest.mark.parametrize("q,n,tw,logb", [(12289, 1024, 16, 19), (7681, 256, 16, 20), (8380417, 256, 32, 20)])
+def test_full_size_properties_other_shapes(q, n, tw, logb):
+    """The other BASELINE shapes (Falcon-1024, Kyber, Dilithium moduli) at full batch size: identity,
+    commutativity, linearity, negacyclic wrap, and a slice against the oracle."""
+    B = 1 << logb
+    p, _, _ = plan(q, n, tw, O.REFERENCE)
+    g = torch.Generator(device=DEV).manual_seed(q + n)
+    a = torch.randint(0, q, (B, n), dtype=torch.int32, device=DEV, generator=g)
+    b = torch.randint(0, q, (B, n), dtype=torch.int32, device=DEV, generator=g)
+    one = torch.zeros(n, dtype=torch.int32, device=DEV)
+    one[0] = 1
+    out = torch.empty_like(a)
+    p.polymul(out, a, one)
+    assert torch.equal(out, a)
+    ab = torch.empty_like(a)
+    p.polymul(ab, a, b)
+    p.polymul(out, b, a)
+    assert torch.equal(ab, out)
+    a2 = torch.randint(0, q, (B, n), dtype=torch.int32, device=DEV, generator=g)
+    p.polymul(out, a2, b)
+    lhs = torch.empty_like(a)
+    p.polymul(lhs, a + a2, b)                       # inputs up to 2q - 2: lazily reduced operands
+    assert torch.equal(lhs, ((ab.long() + out.long()) % q).int())
+    xn1 = torch.zeros(n, dtype=torch.int32, device=DEV)
+    xn1[n - 1] = 1
+    x1 = torch.zeros((4, n), dtype=torch.int32, device=DEV)
+    x1[:, 1] = 1
+    o4 = torch.empty_like(x1)
+    p.polymul(o4, x1, xn1)
+    assert int(o4[0, 0]) == q - 1 and int(o4[0, 1:].abs().sum()) == 0
+    w, r = O.tables(q, n, tw)
+    sl = slice(B - 40, B)
+    exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a[sl].cpu().numpy(), b[sl].cpu().numpy(), w, r)
+    assert np.array_equal(ab[sl].cpu().numpy(), exp)
+
+
+@pytest.mark.parametrize("q,tw,k,l", [(7681, 16, 3, 3), (8380417, 32, 5, 4)])
+def test_full_size_matvec_properties(q, tw, k, l):
+    """Module mat-vec at 2^16 instances: A = identity (the constant 1 is the all-ones vector in the NTT domain)
+    returns the normalised s; linearity in s; a slice against the oracle composition."""
+    n, B = 256, 1 << 16
+    p, _, _ = plan(q, n, tw, O.REFERENCE)
+    g = torch.Generator(device=DEV).manual_seed(q + k)
+    s1 = torch.randint(-5, 6, (B, l, n), dtype=torch.int32, device=DEV, generator=g)
+    s2 = torch.randint(0, q, (B, l, n), dtype=torch.int32, device=DEV, generator=g)
+    kk = min(k, l)
+    eye = torch.zeros((B, kk, l, n), dtype=torch.int32, device=DEV)
+    for i in range(kk):
+        eye[:, i, i, :] = 1
+    out = torch.empty((B, kk, n), dtype=torch.int32, device=DEV)
+    p.matvec(out, eye.view(B, kk * l, n), s1, kk, l)
+    assert torch.equal(out, s1[:, :kk] % q)
+    A = torch.randint(0, q, (B, k * l, n), dtype=torch.int32, device=DEV, generator=g)
+    t1 = torch.empty((B, k, n), dtype=torch.int32, device=DEV)
+    t2 = torch.empty_like(t1)
+    t12 = torch.empty_like(t1)
+    p.matvec(t1, A, s1, k, l)
+    p.matvec(t2, A, s2, k, l)
+    p.matvec(t12, A, s1 + s2, k, l)
+    assert torch.equal(t12, ((t1.long() + t2.long()) % q).int())
+    assert int(t1.min()) >= 0 and int(t1.max()) < q
+
+
 def test_small_modulus_inputs_at_the_proof_boundary(arithmetic):
     """Inputs just inside / outside the +-4q window the 32-bit kernels are proven for, adversarial sign
     patterns, and keys at the SINT16 extremes."""
