@@ -294,26 +294,32 @@ def main():
            "d2h_bytes_per_step": 4 * N_COEF * E2E_BATCH, "pairs_per_step": E2E_BATCH, "steps": e2e_steps,
            "api": "scgpu_polymul_batch_host (pinned host buffers, chunked 3-stream H2D/kernel/D2H pipeline)"}
 
-    # ---- secondary metric: Gaussian samples/s (BASELINE config 5 shape) -----------------------------------------
-    gauss = None
-    if rank == 0:
-        gp = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0, device=local_rank)
-        nstreams, n = 1 << 18, 512
-        seeds = torch.randint(0, 256, (nstreams, 40), dtype=torch.uint8, device=dev, generator=g)
-        smp = torch.empty((nstreams, n), dtype=torch.int32, device=dev)
-        gauss = {}
-        for name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
-            for _ in range(2):
-                gp.streams(prng, seeds, n, smp)
-            torch.cuda.synchronize()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for _ in range(3):
-                gp.streams(prng, seeds, n, smp)
-            e.record()
-            torch.cuda.synchronize()
-            gauss["cdf64_sigma215_%s_samples_per_s" % name] = 3 * nstreams * n / (s.elapsed_time(e) * 1e-3)
-        gauss["shape"] = "%d streams x %d samples, CDF-64, sigma 215, tail 13.42" % (nstreams, n)
+    # ---- secondary metric: Gaussian samples/s (BASELINE config 5 shape), every rank its own streams -------------
+    gp = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0, device=local_rank)
+    nstreams, n = 1 << 18, 512
+    seeds = torch.randint(0, 256, (nstreams, 40), dtype=torch.uint8, device=dev, generator=g)
+    smp = torch.empty((nstreams, n), dtype=torch.int32, device=dev)
+    gauss = {}
+    for name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
+        for _ in range(3):
+            gp.streams(prng, seeds, n, smp)
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(5):
+            gp.streams(prng, seeds, n, smp)
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        gauss["cdf64_sigma215_%s_samples_per_s" % name] = world * 5 * nstreams * n / (ms * 1e-3)
+    gauss["shape"] = "%d streams x %d samples per GPU on %d GPU(s), CDF-64, sigma 215, tail 13.42; whole-job rate, max over ranks" % (nstreams, n, world)
+    # spot check against the oracle
+    exp = O.port().gauss_streams(O.SAMPLER_CDF, 64, 0, sc.PRNG_CHACHA, 13.42, 215.0, seeds[:4].cpu().numpy(), n)
+    assert np.array_equal(smp[:4].cpu().numpy(), exp), "sampler output differs from the oracle"
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------------
     cpu = None
