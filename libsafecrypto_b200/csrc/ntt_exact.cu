@@ -21,31 +21,39 @@ __device__ __forceinline__ int brev(int i) { return (int)(__brev((unsigned)i) >>
 
 // One DIT pass over v[] (bit-reversed order in, natural order out).  ntt_template.c.in:
 // fft_32 :1144-1244, large_fft_32 :1246-1339, fft_16 :1341-1482, large_fft_16 :1484-1539.
-template <int V, int LOGN>
-__device__ __forceinline__ void dit_fft(int32_t *v, const int32_t *w, const RedConst &c, bool tw16, bool large)
+// TW16 / LARGE are compile-time and the stage loop is unrolled: the generic runtime-flag version spent a third of
+// its issue slots on branches, predicate and uniform-datapath bookkeeping (profiles/exact_fwd_r03_ncu_mix.txt).
+template <int V, int LOGN, bool TW16, bool LARGE>
+__device__ __forceinline__ void dit_fft_t(int32_t *v, const int32_t *w, const RedConst &c)
 {
     constexpr int N = 1 << LOGN;
     const int t = threadIdx.x;
-#pragma unroll 1
+#pragma unroll
     for (int s = 0; s < LOGN; s++) {
         const int half = 1 << s;
         const int j = t & (half - 1);
         const int k = j + ((t >> s) << (s + 1));
-        const int32_t y = w[j << (LOGN - s)];
         int32_t lo = v[k], hi = v[k + half], x;
         // AVX2 build: stages with half < n/8 of fft_32, large_fft_32 and fft_16 run the vector
         // lanes on every column (j = 0 included) and never re-reduce the sums.
-        const bool vec = (V == V_AVX) && (half < (N >> 3)) && !(large && tw16);
-        bool reduce_out = large;
+        const bool vec = (V == V_AVX) && (half < (N >> 3)) && !(LARGE && TW16);
+        bool reduce_out = LARGE;
         if (vec) {
+            const int32_t y = w[j << (LOGN - s)];
             int64_t prod = (int64_t)hi * (int64_t)y;
-            if (tw16) x = (c.q <= 12289) ? lane_flt((int32_t)prod, c) : lane_dbl(prod, false, c);
-            else      x = lane_dbl(prod, large, c);
+            if (TW16) x = (c.q <= 12289) ? lane_flt((int32_t)prod, c) : lane_dbl(prod, false, c);
+            else      x = lane_dbl(prod, LARGE, c);
             reduce_out = false;
-        } else if (j == 0 && !(large && !tw16)) {
-            x = (!tw16 || large) ? Exact<V>::modn(hi, c) : hi;
+        } else if (LARGE && !TW16) {
+            x = Exact<V>::muln(hi, w[j << (LOGN - s)], c);                 // every column multiplied
         } else {
-            x = Exact<V>::muln(hi, y, c);
+            // column j = 0 is not multiplied: reduced only (fft_32, large_fft_16) or passed through (fft_16)
+            const int32_t x0 = (!TW16 || LARGE) ? Exact<V>::modn(hi, c) : hi;
+            if (half == 1) x = x0;                                           // stage 0: j = 0 for every thread
+            else {
+                const int32_t xm = Exact<V>::muln(hi, w[j << (LOGN - s)], c);
+                x = (j == 0) ? x0 : xm;
+            }
         }
         int32_t d = (int32_t)((uint32_t)lo - (uint32_t)x);
         int32_t a = (int32_t)((uint32_t)lo + (uint32_t)x);
@@ -54,6 +62,13 @@ __device__ __forceinline__ void dit_fft(int32_t *v, const int32_t *w, const RedC
         v[k] = a;
         __syncthreads();
     }
+}
+
+template <int V, int LOGN, bool LARGE>
+__device__ __forceinline__ void dit_fft(int32_t *v, const int32_t *w, const RedConst &c, bool tw16)
+{
+    if (tw16) dit_fft_t<V, LOGN, true, LARGE>(v, w, c);
+    else      dit_fft_t<V, LOGN, false, LARGE>(v, w, c);
 }
 
 // global row -> shared, optional pre-twist, optional bit reversal.  Each thread moves two
@@ -128,21 +143,24 @@ k_transform(ExactArgs g)
         case SCGPU_OP_FWD_LARGE:
             load_row<V, LOGN>(va, a, sw, true, tw16, true, c);
             __syncthreads();
-            dit_fft<V, LOGN>(va, sw, c, tw16, g.op == SCGPU_OP_FWD_LARGE);
+            if (g.op == SCGPU_OP_FWD_LARGE) dit_fft<V, LOGN, true>(va, sw, c, tw16);
+            else                            dit_fft<V, LOGN, false>(va, sw, c, tw16);
             store_row<LOGN>(out, va);
             break;
         case SCGPU_OP_FFT:
         case SCGPU_OP_FFT_LARGE:
             load_row<V, LOGN>(va, a, sw, false, tw16, false, c);
             __syncthreads();
-            dit_fft<V, LOGN>(va, sw, c, tw16, g.op == SCGPU_OP_FFT_LARGE);
+            if (g.op == SCGPU_OP_FFT_LARGE) dit_fft<V, LOGN, true>(va, sw, c, tw16);
+            else                            dit_fft<V, LOGN, false>(va, sw, c, tw16);
             store_row<LOGN>(out, va);
             break;
         case SCGPU_OP_INV:
         case SCGPU_OP_INV_LARGE:
             load_row<V, LOGN>(va, a, sw, false, tw16, true, c);
             __syncthreads();
-            dit_fft<V, LOGN>(va, sw, c, tw16, g.op == SCGPU_OP_INV_LARGE);
+            if (g.op == SCGPU_OP_INV_LARGE) dit_fft<V, LOGN, true>(va, sw, c, tw16);
+            else                            dit_fft<V, LOGN, false>(va, sw, c, tw16);
             store_inverse<V, LOGN>(out, va, sr, tw16, c);
             break;
         case SCGPU_OP_POLYMUL: {
@@ -150,8 +168,8 @@ k_transform(ExactArgs g)
             load_row<V, LOGN>(va, a, sw, true, tw16, true, c);
             load_row<V, LOGN>(vb, b, sw, true, tw16, true, c);
             __syncthreads();
-            dit_fft<V, LOGN>(va, sw, c, tw16, false);
-            dit_fft<V, LOGN>(vb, sw, c, tw16, false);
+            dit_fft<V, LOGN, false>(va, sw, c, tw16);
+            dit_fft<V, LOGN, false>(vb, sw, c, tw16);
             // mul_32_pointwise, then the inverse transform's own shuffle
             int32_t p0 = Exact<V>::pw32(va[2 * t], vb[2 * t], c);
             int32_t p1 = Exact<V>::pw32(va[2 * t + 1], vb[2 * t + 1], c);
@@ -159,21 +177,21 @@ k_transform(ExactArgs g)
             va[brev<LOGN>(2 * t)] = p0;
             va[brev<LOGN>(2 * t + 1)] = p1;
             __syncthreads();
-            dit_fft<V, LOGN>(va, sw, c, tw16, false);
+            dit_fft<V, LOGN, false>(va, sw, c, tw16);
             store_inverse<V, LOGN>(out, va, sr, tw16, c);
         } break;
         case SCGPU_OP_TRIPLE16: {
             const int16_t *key = static_cast<const int16_t *>(g.b) + row * g.b_stride;
             load_row<V, LOGN>(va, a, sw, true, true, true, c);
             __syncthreads();
-            dit_fft<V, LOGN>(va, sw, c, true, false);
+            dit_fft_t<V, LOGN, true, false>(va, sw, c);
             int32_t p0 = Exact<V>::pw16(va[2 * t], key[2 * t], c);
             int32_t p1 = Exact<V>::pw16(va[2 * t + 1], key[2 * t + 1], c);
             __syncthreads();
             va[brev<LOGN>(2 * t)] = p0;
             va[brev<LOGN>(2 * t + 1)] = p1;
             __syncthreads();
-            dit_fft<V, LOGN>(va, sw, c, true, false);
+            dit_fft_t<V, LOGN, true, false>(va, sw, c);
             store_inverse<V, LOGN>(out, va, sr, true, c);
         } break;
         default: break;
