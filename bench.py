@@ -134,7 +134,37 @@ def run_reference_arm(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
+def bind_to_gpu_numa_node(index):
+    """Best effort: run this rank (and first-touch its pinned staging buffers) on the CPUs NVML reports as local
+    to the GPU, so that the host side of the end-to-end leg does not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
 
 
 def main():
@@ -151,6 +181,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # The contract is ONE JSON line on stdout.  Libraries may print banners there from C code (NCCL's version
+    # line did on an 8-GPU box), so everything else this process writes to fd 1 goes to stderr and the JSON line
+    # is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    global _JSON_FD
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference_arm(args, rank)
@@ -162,6 +199,8 @@ def main():
     import _oracle as O
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -342,7 +381,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
             "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss, "other_shapes": shapes,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

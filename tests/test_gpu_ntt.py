@@ -373,6 +373,9 @@ def test_full_size_properties_other_shapes(q, n, tw, logb):
     p.polymul(ab, a, b)
     p.polymul(out, b, a)
     assert torch.equal(ab, out)
+    out.copy_(a)
+    p.polymul(out, out, b)                          # in place at full concurrency
+    assert torch.equal(ab, out)
     a2 = torch.randint(0, q, (B, n), dtype=torch.int32, device=DEV, generator=g)
     p.polymul(out, a2, b)
     lhs = torch.empty_like(a)
@@ -467,6 +470,16 @@ def test_unaligned_rows_take_the_plain_load_path(q, n):
             p.polymul(out, da[off_a:off_a + rows * n].view(rows, n), db[off_b:off_b + rows * n].view(rows, n))
             torch.cuda.synchronize()
             assert np.array_equal(out.cpu().numpy(), exp), (rows, off_a, off_b)
+        # in place (v == t aliasing is allowed by the reference, ntt_template.c.in:1570-1576): the prefetch of
+        # the next rows must never see a row that has already been overwritten
+        ia, ib = dev(a), dev(b)
+        p.polymul(ia, ia, ib)
+        torch.cuda.synchronize()
+        assert np.array_equal(ia.cpu().numpy(), exp), ("in place", rows)
+        ia = dev(a)
+        p.polymul(ib, ia, ib)
+        torch.cuda.synchronize()
+        assert np.array_equal(ib.cpu().numpy(), exp), ("in place (second operand)", rows)
 
 
 def test_host_pipeline_and_ragged_counts():
