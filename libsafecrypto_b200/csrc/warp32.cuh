@@ -410,12 +410,16 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
                 W::template fwd_stages1<LOGN, C::S1, 1>(xa, xb, c, tau, h);
                 int32_t kv[SUB];
                 bool wide = false;
+                // ntt_index(tau, SUB h + i) = (brev5(i) + brev5(SUB h)) << (LOGN - 5) | brev(tau): the low bits
+                // of the 5-bit field come from i (compile time), the high ones from h -- one base per sub-chunk,
+                // immediate offsets per element
+                const size_t kbase = prow * b_stride + (size_t)ntt_index<LOGN>(tau, SUB * h);
 #pragma unroll
                 for (int i = 0; i < SUB; i++) {
-                    const int j = ntt_index<LOGN>(tau, SUB * h + i);
-                    if (MODE == FQ_KEY16) kv[i] = (int32_t)__ldg(static_cast<const int16_t *>(bsrc) + prow * b_stride + j);
+                    const int off = (int)((__brev((unsigned)i) >> 27) << (LOGN - 5));
+                    if (MODE == FQ_KEY16) kv[i] = (int32_t)__ldg(static_cast<const int16_t *>(bsrc) + kbase + off);
                     else {
-                        kv[i] = __ldg(static_cast<const int32_t *>(bsrc) + prow * b_stride + j);
+                        kv[i] = __ldg(static_cast<const int32_t *>(bsrc) + kbase + off);
                         wide |= W::out_of_range(kv[i], c);
                     }
                 }

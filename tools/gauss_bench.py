@@ -23,3 +23,20 @@ for prec in (64, 32):
             gp.streams(prng, seeds, n, smp)
         e.record(); torch.cuda.synchronize()
         print("cdf%d %-13s %.4g samples/s" % (prec, name, 5 * ns * n / (s.elapsed_time(e) * 1e-3)))
+
+# sequential-semantics kernel (k_stream_seq): shuffle / blinding / discard wrappers, Knuth-Yao, Bernoulli
+ns2 = 1 << 16
+seeds2 = seeds[:ns2]
+smp2 = torch.empty((ns2, n), dtype=torch.int32, device=dev)
+cases = [("cdf64 shuffle", sc.SAMPLER_CDF, 64, 2, 0), ("cdf64 blinding", sc.SAMPLER_CDF, 64, 1, 0), ("cdf64 normal discard=4", sc.SAMPLER_CDF, 64, 0, 4),
+         ("knuth-yao 64", sc.SAMPLER_KNUTH_YAO, 64, 0, 0), ("bernoulli 64", sc.SAMPLER_BERNOULLI, 64, 0, 0)]
+for label, smpl, prec, bl, disc in cases:
+    gp = sc.GaussPlan(smpl, prec, bl, 13.42, 215.0)
+    for name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
+        gp.streams(prng, seeds2, n, smp2, discard=disc)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        gp.streams(prng, seeds2, n, smp2, discard=disc)
+        e.record(); torch.cuda.synchronize()
+        print("%-24s %-13s %.4g samples/s" % (label, name, ns2 * n / (s.elapsed_time(e) * 1e-3)))
