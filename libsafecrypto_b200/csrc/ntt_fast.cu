@@ -386,7 +386,8 @@ void free_fast_tables(NttPlanDev &p)
 
 // Arithmetic of the fused kernels: 0 = automatic (float-quotient where its bounds are proven -- the warp-local
 // 32-coefficient schedule for polymul / key products -- else 32-bit Barrett, else Montgomery), 1 = Montgomery
-// for every modulus, 2 = Barrett-32 where applicable, 3 = float-quotient with the 8-coefficient schedule.
+// for every modulus, 2 = Barrett-32 where applicable, 3 = float-quotient with the 8-coefficient schedule,
+// 4 = Shoup products on the warp-local schedule for every modulus they can serve.
 // SCGPU_FAST_ARITH / SCGPU_FORCE_MONT=1 set the initial value; tests switch it to cover all three.
 static int g_arith = -1;
 static int arith_mode()
@@ -394,18 +395,19 @@ static int arith_mode()
     if (g_arith < 0) {
         g_arith = 0;
         if (getenv("SCGPU_FORCE_MONT") && atoi(getenv("SCGPU_FORCE_MONT")) != 0) g_arith = 1;
-        if (getenv("SCGPU_FAST_ARITH")) g_arith = atoi(getenv("SCGPU_FAST_ARITH")) & 3;
+        if (getenv("SCGPU_FAST_ARITH")) g_arith = atoi(getenv("SCGPU_FAST_ARITH")) & 7;
     }
     return g_arith;
 }
 static bool use_fq(const NttPlanDev &p) { const int m = arith_mode(); return p.fq_ok && (m == 0 || m == 3); }
 static bool use_fq32(const NttPlanDev &p) { return p.fq32_ok && arith_mode() == 0; }
-static bool use_sh32(const NttPlanDev &p) { return p.sh32_ok && arith_mode() == 0; }
+static bool use_sh32(const NttPlanDev &p) { return p.sh32_ok && (arith_mode() == 0 || arith_mode() == 4); }
+static bool force_sh32(const NttPlanDev &p) { return p.sh32_ok && arith_mode() == 4; }
 static bool use_sq(const NttPlanDev &p) { return p.sq_ok && arith_mode() != 1; }
 int set_fast_arith(int mode)
 {
     const int old = arith_mode();
-    g_arith = mode & 3;
+    g_arith = mode & 7;
     return old;
 }
 int set_force_montgomery(int on)
@@ -425,6 +427,7 @@ int launch_polymul(const NttPlanDev &p, int32_t *out, const int32_t *a, const in
                    size_t b_stride, size_t count, cudaStream_t st)
 {
     if (count == 0) return SCGPU_OK;
+    if (force_sh32(p)) return launch_polymul_sh32(p, 0, out, a, b, b_stride, count, st);
     if (use_fq32(p)) return launch_polymul_fq32(p, 0, out, a, b, b_stride, count, st);
     if (use_fq(p)) return launch_polymul_fq(p, 0, out, a, b, b_stride, count, st);
     if (use_sq(p)) return launch_polymul_sq(p, 0, out, a, b, b_stride, count, st);
@@ -449,6 +452,7 @@ int launch_mul_key(const NttPlanDev &p, int32_t *out, const int32_t *t, const vo
 {
     if (count == 0) return SCGPU_OK;
     if (key_bits != 16 && key_bits != 32) { set_error("key_bits must be 16 or 32"); return SCGPU_ERR_ARG; }
+    if (force_sh32(p)) return launch_polymul_sh32(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
     if (use_fq32(p)) return launch_polymul_fq32(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
     if (use_fq(p)) return launch_polymul_fq(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
     if (use_sq(p)) return launch_polymul_sq(p, key_bits == 16 ? 1 : 2, out, t, key, key_stride, count, st);
@@ -480,6 +484,7 @@ int launch_matvec(const NttPlanDev &p, int32_t *out, const int32_t *A, const int
     if (k < 1 || l < 1 || l > 8) { set_error("matvec supports 1 <= l <= 8 (got k=%d l=%d)", k, l); return SCGPU_ERR_ARG; }
     if (p.logn != 8) { set_error("matvec is instantiated for n = 256 (Kyber / Dilithium); got n=%d", p.n); return SCGPU_ERR_UNSUPPORTED; }
     if (l > 4) { set_error("matvec l > 4 not instantiated"); return SCGPU_ERR_UNSUPPORTED; }
+    if (force_sh32(p) && p.sh32_mv_ok) return launch_matvec_sh32(p, out, A, s, k, l, count, st);
     if (use_fq32(p) && p.fq32_mv_ok) return launch_matvec_fq32(p, out, A, s, k, l, count, st);
     if (use_fq(p)) return launch_matvec_fq(p, out, A, s, k, l, count, st);
     if (use_sq(p)) return launch_matvec_sq(p, out, A, s, k, l, count, st);

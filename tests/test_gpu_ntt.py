@@ -216,12 +216,13 @@ def test_ibe_fixture_on_gpu():
 FAST_PARAMS = [(12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417, 256, 32), (18433, 512, 16), (8399873, 512, 32)]
 
 
-@pytest.fixture(params=["auto", "montgomery", "barrett32", "fq8"])
+@pytest.fixture(params=["auto", "montgomery", "barrett32", "fq8", "shoup"])
 def arithmetic(request):
     """Run the fused-kernel tests with the automatic choice (float-quotient products for small q, warp-local
     32-coefficient schedule), with 32-bit Barrett where applicable, with Montgomery forced for every modulus,
-    and with the float-quotient arithmetic on the 8-coefficient schedule."""
-    old = sc.lib().scgpu_set_fast_arith({"auto": 0, "montgomery": 1, "barrett32": 2, "fq8": 3}[request.param])
+    with the float-quotient arithmetic on the 8-coefficient schedule, and with Shoup products on the warp-local
+    schedule for every modulus."""
+    old = sc.lib().scgpu_set_fast_arith({"auto": 0, "montgomery": 1, "barrett32": 2, "fq8": 3, "shoup": 4}[request.param])
     yield request.param
     sc.lib().scgpu_set_fast_arith(old)
 

@@ -16,7 +16,7 @@ a = torch.randint(0, q, (B, n), dtype=torch.int32, device=dev, generator=g)
 b = torch.randint(0, q, (B, n), dtype=torch.int32, device=dev, generator=g)
 out = torch.empty_like(a)
 plan = sc.NttPlan(n, q, sc.REFERENCE, w, r)
-for mode, name in ((0, "auto"), (3, "fq8"), (2, "barrett32")):
+for mode, name in ((0, "auto"), (4, "shoup"), (3, "fq8"), (2, "barrett32")):
     sc.lib().scgpu_set_fast_arith(mode)
     for _ in range(3):
         plan.polymul(out, a, b)
