@@ -139,8 +139,6 @@ __device__ __forceinline__ void fq_fwd_pass(u32 (&x)[8], const FqTw &tw, int32_t
     for (int m = 0; m < 8; m += 2) fq_ct(x[m], x[m + 1], tw.z1[m >> 1], nq);
 }
 
-__device__ __forceinline__ void t_store(int32_t *tile, int idx, u32 v) { tile[idx] = (int32_t)v; }
-
 template <int LOGN, int PASS>
 __device__ __forceinline__ void fq_tile_store(int32_t *tile, const u32 (&x)[8], int tau)
 {

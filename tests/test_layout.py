@@ -72,3 +72,76 @@ def test_merged_twiddle_ordering_matches_reference_domain(q, n):
         ln //= 2
     ref = O.port().ntt_batch(O.REFERENCE, O.OP_FWD, n, q, 16, a.astype(np.int32), None, w, r)[0].astype(np.int64) % q
     assert all(x[i] == ref[brv(i)] for i in range(n))
+
+
+# ---- warp-local 32-coefficient schedule (libsafecrypto_b200/csrc/warp32.cuh) ---------------------------------
+
+def pos32(e):
+    return e + 4 * (e >> 5)
+
+
+def slot32(logn, s, tau, r):
+    n = 1 << logn
+    t, ln = n // 32, n >> (s + 1)
+    g = 16 // ln
+    v = g if g < 4 else 4
+    return (1 << s) + ((r // v) * t + tau) * v + (r % v)
+
+
+@pytest.mark.parametrize("logn", [8, 9, 10])
+def test_warp32_tile_layout(logn):
+    """Padded tile: (1) injective; (2) pass-0 accesses (element tau + T m, 32-bit) of the warp's 32 / T polynomials,
+    whose tiles are TS words apart, hit 32 distinct banks; (3) pass-1 accesses (128-bit at 36 tau + 4 k) are
+    conflict-free per quarter-warp and 16-byte aligned; (4) both passes tile the polynomial."""
+    n = 1 << logn
+    t = n // 32
+    pw = 32 // t
+    ts = n + n // 8 + (t & 31)
+    assert len({pos32(e) for e in range(n)}) == n and max(pos32(e) for e in range(n)) < ts
+    for m in range(32):
+        banks = {(p * ts + tau + pos32(t * m)) % 32 for p in range(pw) for tau in range(t)}
+        assert len(banks) == 32
+        assert all(pos32(tau + t * m) == tau + pos32(t * m) for tau in range(t))       # thread base + immediate
+    for k in range(8):
+        for quarter in range(4):
+            lanes = range(8 * quarter, 8 * quarter + 8)
+            groups = set()
+            for lane in lanes:
+                p, tau = lane // t, lane % t
+                addr = p * ts + 36 * tau + 4 * k
+                assert addr % 4 == 0 and all(pos32(32 * tau + 4 * k + j) == 36 * tau + 4 * k + j for j in range(4))
+                groups.add((addr % 32) // 4)
+            assert len(groups) == 8
+    assert sorted(tau + t * m for tau in range(t) for m in range(32)) == list(range(n))
+    assert sorted(32 * tau + i for tau in range(t) for i in range(32)) == list(range(n))
+
+
+@pytest.mark.parametrize("logn", [8, 9, 10])
+def test_warp32_twiddle_table_is_a_permutation_with_contiguous_vectors(logn):
+    """Thread-major pass-1 table: a permutation inside every stage's region [2^s, 2^(s+1)), and the 4 (2, 1)
+    consecutive entries a thread loads with one 128 (64, 32)-bit access are contiguous and aligned."""
+    n = 1 << logn
+    t = n // 32
+    for s in range(5, logn):
+        g = 16 // (n >> (s + 1))
+        v = min(g, 4)
+        slots = [slot32(logn, s, tau, r) for tau in range(t) for r in range(g)]
+        assert sorted(slots) == list(range(1 << s, 2 << s))
+        for tau in range(t):
+            for r0 in range(0, g, v):
+                base = slot32(logn, s, tau, r0)
+                assert base % v == 0
+                assert [slot32(logn, s, tau, r0 + i) for i in range(v)] == list(range(base, base + v))
+        # lanes of one vector load are contiguous across the polynomial's threads
+        assert [slot32(logn, s, tau, 0) for tau in range(t)] == list(range(1 << s, (1 << s) + v * t, v))
+
+
+@pytest.mark.parametrize("logn", [8, 9, 10])
+def test_warp32_ntt_index_is_the_bit_reversal(logn):
+    """Element e of thread tau in the pass-1 layout (position 32 tau + e of the bit-reversed order) is the
+    reference's coefficient brev5(e) * (n / 32) + brev(tau): what key / matrix gathers use."""
+    n = 1 << logn
+    brv = lambda i, bits: int(format(i, "0%db" % bits)[::-1], 2)  # noqa: E731
+    for tau in range(n // 32):
+        for e in range(32):
+            assert brv(32 * tau + e, logn) == (brv(e, 5) << (logn - 5)) | brv(tau, logn - 5)
