@@ -6,6 +6,8 @@
 
 namespace scgpu {
 
+constexpr int kGuideBits = 10;
+
 struct PrngState;
 
 struct GaussTablesDev {
@@ -16,6 +18,9 @@ struct GaussTablesDev {
     const uint64_t *cdf64;
     const uint32_t *cdf32;
     uint32_t cdf_size;
+    // optional guide for the throughput kernels (32 / 64-bit, sorted tables only): entry b = lo | hi << 16, the
+    // search results of the smallest and the largest x whose top kGuideBits bits are b
+    const uint32_t *cdf_guide;
     // high-precision CDF (gaussian_cdf.c:112-532): cdf_size entries of precision/64 words, word 0 least
     // significant (the reference's u128_t / u192_t / u256_t arrays on a 64-bit-limb build)
     const uint64_t *cdfh;

@@ -28,6 +28,7 @@ struct scgpu_gauss_plan {
     void *d_cdf = nullptr;
     uint32_t *d_flat = nullptr;
     uint8_t *d_ber = nullptr;
+    uint32_t *d_guide = nullptr;
     std::mutex mu;
     uint32_t *d_keys = nullptr; size_t keys_cap = 0;        // DRBG round keys of the fast path
     uint8_t *d_seeds = nullptr; size_t seeds_cap = 0;       // staging for *_host
@@ -123,6 +124,33 @@ int ensure_cap(T **buf, size_t *cap, size_t want)
 const uint32_t kDefaultSeedPeriod = 0x00100000;     // safecrypto.c:379
 
 // Can the position-addressable kernels serve this request?  They assume no reseed inside a stream.
+// Guide of the throughput kernels (gauss.cu: cdf_search_guided).  Built only for a sorted table: then the
+// reference's fixed-step search (gaussian_cdf.c:536-553) IS the predecessor search the guided bisection performs.
+template <typename T>
+std::vector<uint32_t> build_guide(const std::vector<T> &cdf)
+{
+    std::vector<uint32_t> g;
+    const size_t size = cdf.size();
+    if (size < 2 || size > 65536) return g;
+    for (size_t i = 1; i < size; i++) if (cdf[i] < cdf[i - 1]) return g;
+    auto search = [&](T x) {
+        uint32_t a = 0;
+        for (uint32_t st = (uint32_t)size >> 1; st > 0; st >>= 1) {
+            uint32_t b = a + st;
+            if (b < size && cdf[b] < x) a = b;
+        }
+        return a;
+    };
+    const int shift = (int)sizeof(T) * 8 - kGuideBits;
+    g.resize((size_t)1 << kGuideBits);
+    for (uint32_t b = 0; b < g.size(); b++) {
+        const T xmin = (T)((T)b << shift);
+        const T xmax = (T)(xmin | (T)(((T)1 << shift) - 1));
+        g[b] = search(xmin) | (search(xmax) << 16);
+    }
+    return g;
+}
+
 bool fast_path_ok(const GaussTablesDev &t, int prng_type, size_t per_stream, uint32_t discard)
 {
     if (t.sampler != SCGPU_SAMPLER_CDF || t.blinding != SCGPU_NORMAL_SAMPLES || discard != 0) return false;
@@ -158,11 +186,15 @@ extern "C" int scgpu_gauss_plan_create(scgpu_gauss_plan_t **out, int sampler, in
         uint64_t *d = nullptr;
         rc = upload(&d, cdf);
         p->d_cdf = d; p->t.cdf64 = d; p->t.cdf_size = (uint32_t)cdf.size();
+        const std::vector<uint32_t> guide = build_guide(cdf);
+        if (rc == SCGPU_OK && !guide.empty()) { rc = upload(&p->d_guide, guide); p->t.cdf_guide = p->d_guide; }
     } else if (sampler == SCGPU_SAMPLER_CDF && precision == 32) {
         std::vector<uint32_t> cdf = build_cdf32(blinding, tail, sigma);
         uint32_t *d = nullptr;
         rc = upload(&d, cdf);
         p->d_cdf = d; p->t.cdf32 = d; p->t.cdf_size = (uint32_t)cdf.size();
+        const std::vector<uint32_t> guide = build_guide(cdf);
+        if (rc == SCGPU_OK && !guide.empty()) { rc = upload(&p->d_guide, guide); p->t.cdf_guide = p->d_guide; }
     } else if (sampler == SCGPU_SAMPLER_KNUTH_YAO && (precision == 32 || precision == 64) && blinding != SCGPU_BLINDING_SAMPLES) {
         // gaussian_knuth_yao.c:126-189; the matrix is stored as the sorted flat positions of its one-bits
         const int rows = precision;
@@ -244,7 +276,7 @@ extern "C" void scgpu_gauss_plan_destroy(scgpu_gauss_plan_t *p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
-    cudaFree(p->d_cdf); cudaFree(p->d_flat); cudaFree(p->d_ber);
+    cudaFree(p->d_cdf); cudaFree(p->d_flat); cudaFree(p->d_ber); cudaFree(p->d_guide);
     cudaFree(p->d_keys); cudaFree(p->d_seeds); cudaFree(p->d_out);
     delete p;
 }
