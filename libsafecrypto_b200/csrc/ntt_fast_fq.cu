@@ -6,10 +6,11 @@
 // fma-lite, fma-heavy and ALU pipes (measured 5.6e12 butterflies/s against 3.9e12 for the IMAD/IMAD.HI/IMAD
 // Barrett butterfly of ntt_fast_sq.cu, profiles/int_peaks_r02.txt).
 //
-// Same schedule as the other fused kernels (fast_common.cuh): n/8 threads per polynomial, 8 coefficients
+// This file: the arithmetic on the r01 schedule of fast_common.cuh (n/8 threads per polynomial, 8 coefficients
 // per thread, three radix-2 stages per register pass, shared-memory tile between passes, both operands of a
-// product share a pass's twiddle registers.  Twiddle entries are 16 bytes {w, wq, k, c} read with one
-// LDG.128 from an L1-resident table.
+// product share a pass's twiddle registers).  It is the SCGPU_FAST_ARITH=3 cross-check; production products go
+// through the warp-local 32-coefficient schedule (warp32.cuh, ntt_fast_fq32.cu).  Twiddles: two parallel arrays
+// (w, wq), k and c rebuilt per entry; pass-0 entries from the constant bank.
 //
 // Exactness: the host proves by interval propagation over this dataflow (fq_host.h: analyse) that every
 // value read as a float stays below 2^22 and that the last product lies in (-q, q); tools/fq_model.cpp runs
