@@ -122,15 +122,21 @@ __device__ __forceinline__ void aes256_encrypt(const AesTables &t, const uint32_
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
-// Bank-replicated T-table for the throughput kernel: te0r[x * 32 + lane] -- every lane reads its own bank, so
+// Bank-replicated T-tables for the throughput kernel: te_k[x * 32 + lane] -- every lane reads its own bank, so
 // the 16 data-dependent lookups of a round are conflict-free (the 1 KiB table costs ~3.5 wavefronts per LDS
 // with 32 random indices; profiles/gauss_r01).  The S-box of the last round is byte 2 of the same entry.
+// Four tables te0..te3 (te_k = te0 rotated right by k bytes), 32 KiB each, so that a round needs no rotations:
+// per column 4 x (shift + LOP3) index computations, 4 LDS and 2 three-input XORs.
 __device__ __forceinline__ void aes_rep_init(uint32_t *te0r)
 {
     for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
         uint32_t s = kAesSbox[i >> 5];
         uint32_t s2 = ((s << 1) ^ ((s & 0x80) ? 0x1B : 0)) & 0xFF;
-        te0r[i] = (s2 << 24) | (s << 16) | (s << 8) | (s2 ^ s);
+        const uint32_t t0 = (s2 << 24) | (s << 16) | (s << 8) | (s2 ^ s);
+        te0r[i] = t0;
+        te0r[i + 8192] = __funnelshift_r(t0, t0, 8);
+        te0r[i + 16384] = __funnelshift_r(t0, t0, 16);
+        te0r[i + 24576] = __funnelshift_r(t0, t0, 24);
     }
 }
 
@@ -144,6 +150,9 @@ __device__ __forceinline__ void aes256_encrypt_rep(const uint32_t *te0r, uint32_
                                                    uint32_t s2, uint32_t s3, uint32_t out[4])
 {
 #define SCGPU_T(x) aes_rep_at(te0r, (x))
+#define SCGPU_T1(x) aes_rep_at(te0r, (x) + 32768u)
+#define SCGPU_T2(x) aes_rep_at(te0r, (x) + 65536u)
+#define SCGPU_T3(x) aes_rep_at(te0r, (x) + 98304u)
 #define SCGPU_B3(v) ((((v) >> 17) & 0x7F80u) | l4)
 #define SCGPU_B2(v) ((((v) >> 9) & 0x7F80u) | l4)
 #define SCGPU_B1(v) ((((v) >> 1) & 0x7F80u) | l4)
@@ -152,10 +161,10 @@ __device__ __forceinline__ void aes256_encrypt_rep(const uint32_t *te0r, uint32_
 #pragma unroll 2
     for (int r = 1; r < 14; r++) {
         const uint4 k = __ldg(reinterpret_cast<const uint4 *>(rk) + r);
-        uint32_t t0 = SCGPU_T(SCGPU_B3(s0)) ^ rotr8(SCGPU_T(SCGPU_B2(s1)), 1) ^ rotr8(SCGPU_T(SCGPU_B1(s2)), 2) ^ rotr8(SCGPU_T(SCGPU_B0(s3)), 3) ^ k.x;
-        uint32_t t1 = SCGPU_T(SCGPU_B3(s1)) ^ rotr8(SCGPU_T(SCGPU_B2(s2)), 1) ^ rotr8(SCGPU_T(SCGPU_B1(s3)), 2) ^ rotr8(SCGPU_T(SCGPU_B0(s0)), 3) ^ k.y;
-        uint32_t t2 = SCGPU_T(SCGPU_B3(s2)) ^ rotr8(SCGPU_T(SCGPU_B2(s3)), 1) ^ rotr8(SCGPU_T(SCGPU_B1(s0)), 2) ^ rotr8(SCGPU_T(SCGPU_B0(s1)), 3) ^ k.z;
-        uint32_t t3 = SCGPU_T(SCGPU_B3(s3)) ^ rotr8(SCGPU_T(SCGPU_B2(s0)), 1) ^ rotr8(SCGPU_T(SCGPU_B1(s1)), 2) ^ rotr8(SCGPU_T(SCGPU_B0(s2)), 3) ^ k.w;
+        uint32_t t0 = SCGPU_T(SCGPU_B3(s0)) ^ SCGPU_T1(SCGPU_B2(s1)) ^ SCGPU_T2(SCGPU_B1(s2)) ^ SCGPU_T3(SCGPU_B0(s3)) ^ k.x;
+        uint32_t t1 = SCGPU_T(SCGPU_B3(s1)) ^ SCGPU_T1(SCGPU_B2(s2)) ^ SCGPU_T2(SCGPU_B1(s3)) ^ SCGPU_T3(SCGPU_B0(s0)) ^ k.y;
+        uint32_t t2 = SCGPU_T(SCGPU_B3(s2)) ^ SCGPU_T1(SCGPU_B2(s3)) ^ SCGPU_T2(SCGPU_B1(s0)) ^ SCGPU_T3(SCGPU_B0(s1)) ^ k.z;
+        uint32_t t3 = SCGPU_T(SCGPU_B3(s3)) ^ SCGPU_T1(SCGPU_B2(s0)) ^ SCGPU_T2(SCGPU_B1(s1)) ^ SCGPU_T3(SCGPU_B0(s2)) ^ k.w;
         s0 = t0; s1 = t1; s2 = t2; s3 = t3;
     }
     // last round: S-box = byte 2 of the table entry, placed into byte 3 / 2 / 1 / 0
@@ -167,6 +176,9 @@ __device__ __forceinline__ void aes256_encrypt_rep(const uint32_t *te0r, uint32_
     out[3] = ((SCGPU_S(SCGPU_B3(s3)) << 8) | SCGPU_S(SCGPU_B2(s0)) | (SCGPU_S(SCGPU_B1(s1)) >> 8) | (SCGPU_S(SCGPU_B0(s2)) >> 16)) ^ k.w;
 #undef SCGPU_S
 #undef SCGPU_T
+#undef SCGPU_T1
+#undef SCGPU_T2
+#undef SCGPU_T3
 #undef SCGPU_B3
 #undef SCGPU_B2
 #undef SCGPU_B1

@@ -293,17 +293,20 @@ __global__ void __launch_bounds__(128) k_drbg_setup(FastArgs a)
     k[60] = rng.s.drbg_counter;
 }
 
+constexpr int kAesCta = 1024;            // one CTA per SM: 128 KiB of replicated AES tables are shared by 32 warps
+constexpr size_t kAesTabBytes = 4 * 32768;
+
 template <int PREC>
-__global__ void __launch_bounds__(256) k_cdf_aes(FastArgs a)
+__global__ void __launch_bounds__(kAesCta) k_cdf_aes(FastArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *te0r = reinterpret_cast<uint32_t *>(smem_raw);                 // 256 x 32 words, one copy per bank
-    uint64_t *cdf64 = reinterpret_cast<uint64_t *>(smem_raw + 32768);
-    uint32_t *cdf32 = reinterpret_cast<uint32_t *>(smem_raw + 32768);
+    uint32_t *te0r = reinterpret_cast<uint32_t *>(smem_raw);                 // 4 tables x 256 x 32 words, one copy per bank
+    uint64_t *cdf64 = reinterpret_cast<uint64_t *>(smem_raw + kAesTabBytes);
+    uint32_t *cdf32 = reinterpret_cast<uint32_t *>(smem_raw + kAesTabBytes);
     aes_rep_init(te0r);
     if (PREC == 64) for (uint32_t i = threadIdx.x; i < a.g.cdf_size; i += blockDim.x) cdf64[i] = a.g.cdf64[i];
     else            for (uint32_t i = threadIdx.x; i < a.g.cdf_size; i += blockDim.x) cdf32[i] = a.g.cdf32[i];
-    uint32_t *guide = reinterpret_cast<uint32_t *>(smem_raw + 32768 + a.g.cdf_size * (PREC == 64 ? 8 : 4));
+    uint32_t *guide = reinterpret_cast<uint32_t *>(smem_raw + kAesTabBytes + a.g.cdf_size * (PREC == 64 ? 8 : 4));
     const bool guided = a.g.cdf_guide != nullptr;
     if (guided) for (uint32_t i = threadIdx.x; i < (1u << kGuideBits); i += blockDim.x) guide[i] = a.g.cdf_guide[i];
     __syncthreads();
@@ -499,16 +502,17 @@ int launch_gauss_fast(const GaussTablesDev &g, int prng_type, const uint8_t *see
     if (prng_type == PRNG_AES) {
         k_drbg_setup<<<(unsigned)((nstreams + 127) / 128), 128, 0, st>>>(a);
         count_launch();
-        const size_t smem = 32768 + table_bytes + (sizeof(uint32_t) << kGuideBits);
+        const size_t smem = kAesTabBytes + table_bytes + (sizeof(uint32_t) << kGuideBits);
         const int spb = g.precision == 64 ? 2 : 4;
         const size_t items = nstreams * ((per_stream + spb - 1) / spb);
-        const unsigned grid = cap_grid((items + 255) / 256, sm_count, 4);
+        if (smem > 220 * 1024) { set_error("CDF table of %zu bytes does not fit beside the AES tables", table_bytes); return SCGPU_ERR_UNSUPPORTED; }
+        const unsigned grid = cap_grid((items + kAesCta - 1) / kAesCta, sm_count, 1);
         if (g.precision == 64) {
             SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_cdf_aes<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_cdf_aes<64><<<grid, 256, smem, st>>>(a);
+            k_cdf_aes<64><<<grid, kAesCta, smem, st>>>(a);
         } else {
             SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_cdf_aes<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_cdf_aes<32><<<grid, 256, smem, st>>>(a);
+            k_cdf_aes<32><<<grid, kAesCta, smem, st>>>(a);
         }
     } else {
         const unsigned grid = cap_grid((nstreams + 7) / 8, sm_count, 3);
