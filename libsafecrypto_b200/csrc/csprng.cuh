@@ -198,8 +198,18 @@ __device__ __forceinline__ void drbg_block_words(const AesTables &t, const uint3
 }
 
 // ---- ChaCha20 ----------------------------------------------------------------------------------------
+// One of the four rotations of a quarter-round is issued on the fma pipe as  hi32(x * 2^r) + x * 2^r  (IMAD.HI +
+// IMAD): the ALU pipe (LOP3, SHF) is this kernel's bottleneck -- 8 of a quarter-round's 12 operations -- while
+// the fma-heavy pipe only carries the 4 additions.
+__device__ __forceinline__ uint32_t rotl_fma(uint32_t x, uint32_t pow2)
+{
+    uint32_t hi, r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(x), "r"(pow2));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(pow2), "r"(hi));
+    return r;
+}
 #define SCGPU_QR(a, b, c, d)                                                                  \
-    a += b; d ^= a; d = __funnelshift_l(d, d, 16); c += d; b ^= c; b = __funnelshift_l(b, b, 12); \
+    a += b; d ^= a; d = rotl_fma(d, 1u << 16); c += d; b ^= c; b = __funnelshift_l(b, b, 12); \
     a += b; d ^= a; d = __funnelshift_l(d, d, 8);  c += d; b ^= c; b = __funnelshift_l(b, b, 7);
 
 // first four keystream words of one block
