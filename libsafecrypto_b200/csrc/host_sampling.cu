@@ -155,6 +155,10 @@ bool fast_path_ok(const GaussTablesDev &t, int prng_type, size_t per_stream, uin
 {
     if (t.sampler != SCGPU_SAMPLER_CDF || t.blinding != SCGPU_NORMAL_SAMPLES || discard != 0) return false;
     if (t.precision > 64) return false;                  // high-precision tables: sequential kernel
+    // the throughput kernels keep the CDF table in shared memory beside 128 KiB of AES tables / 32 KiB of
+    // keystream cache (gauss.cu); larger tables go through the sequential kernel
+    const size_t table_bytes = (size_t)t.cdf_size * (t.precision == 64 ? 8 : 4);
+    if (table_bytes + (prng_type == PRNG_AES ? 4 * 32768 : 32768) + 4096 > 216 * 1024) return false;
     const size_t words = per_stream * (t.precision == 64 ? 2 : 1);
     if (prng_type == PRNG_CHACHA20) return words <= 2 * ((size_t)kDefaultSeedPeriod / 8 - 1);   // first reseed epoch
     const size_t blocks = (words + 3) / 4;
