@@ -262,7 +262,7 @@ def main():
     alg_bytes = 12 * N_COEF * BATCH                     # read a, b (4n each) + write out (4n) per product
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "k_polymul_fq32<9,POLYMUL,TMA>",
+                "traffic": None, "peak_source": peak_src, "kernel": "k_polymul_w32<ArFq,9,POLYMUL,TMA>",
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes}
     prof = os.path.join(ROOT, "profiles", "polymul_traffic.json")
     if os.path.exists(prof):
