@@ -34,11 +34,14 @@ struct ArSh {
         const int32_t qe = __mulhi((int32_t)x, e.wp);
         return x * (u32)e.w + (u32)qe * (u32)k.nq;
     }
+    // forward butterfly in 4 instructions: the sum rides in the IMAD addend (lo + hi w - qe q), the difference is
+    // 2 lo - sum (one IADD3)
     static __device__ __forceinline__ void ct(u32 &lo, u32 &hi, const E &z, const K &k)
     {
-        const u32 t = mul(hi, z, k);
-        hi = lo - t;
-        lo = lo + t;
+        const int32_t qe = __mulhi((int32_t)hi, z.wp);
+        const u32 sum = (u32)qe * (u32)k.nq + (hi * (u32)z.w + lo);
+        hi = lo + lo - sum;
+        lo = sum;
     }
     static __device__ __forceinline__ void gs(u32 &lo, u32 &hi, const E &z, const K &k)
     {
