@@ -59,6 +59,8 @@ def lib():
         L.scgpu_gauss_streams_host.argtypes = [vp, ctypes.c_int, vp, sz, sz, sz, sz, i32, u32, vp]
         L.scgpu_prng_words.argtypes = [ctypes.c_int, vp, sz, sz, sz, sz, vp, vp]
         L.scgpu_force_montgomery.argtypes = [ctypes.c_int]
+        L.scgpu_set_fixed_probe_search.argtypes = [ctypes.c_int]
+        L.scgpu_set_fixed_probe_search.restype = ctypes.c_int
         L.scgpu_set_fast_arith.argtypes = [ctypes.c_int]
         L.scgpu_set_fast_arith.restype = ctypes.c_int
         L.init_reduce.argtypes = [vp, sz, i32]

@@ -12,6 +12,7 @@
 //                  encrypts a contiguous run of blocks, a warp XOR-scan rebuilds the running XOR the
 //                  reference's encrypt-in-place framing creates, samples go out through shared memory.
 #include "scgpu_internal.h"
+#include <cstdlib>
 #include "csprng.cuh"
 #include "gauss_plan.h"
 #include "../../include/scgpu.h"
@@ -490,13 +491,28 @@ int launch_gauss_seq(const GaussTablesDev &g, int prng_type, const uint8_t *seed
     return SCGPU_OK;
 }
 
+// 1: the throughput kernels keep the reference's fixed probe sequence (log2(size) probes for every draw) instead
+// of the guide-bracketed bisection, whose trip count depends on the draw.  Same samples either way.
+static int g_fixed_probe_search = -1;
+int set_fixed_probe_search(int on)
+{
+    const int old = g_fixed_probe_search > 0 ? 1 : 0;
+    g_fixed_probe_search = on ? 1 : 0;
+    return old;
+}
+
 int launch_gauss_fast(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
                       uint32_t seed_period, size_t nstreams, size_t per_stream, int32_t centre, int32_t *out,
                       uint32_t *key_scratch, int sm_count, cudaStream_t st)
 {
     if (nstreams == 0 || per_stream == 0) return SCGPU_OK;
+    if (g_fixed_probe_search < 0) {
+        const char *e = getenv("SCGPU_FIXED_PROBE_SEARCH");
+        g_fixed_probe_search = (e && atoi(e) != 0) ? 1 : 0;
+    }
     FastArgs a;
-    a.g = g; a.seeds = seeds; a.seed_len = (uint32_t)seed_len; a.seed_period = seed_period;
+    a.g = g;
+    if (g_fixed_probe_search) a.g.cdf_guide = nullptr; a.seeds = seeds; a.seed_len = (uint32_t)seed_len; a.seed_period = seed_period;
     a.nstreams = nstreams; a.per_stream = per_stream; a.centre = centre; a.out = out; a.keys = key_scratch;
     const size_t table_bytes = (size_t)g.cdf_size * (g.precision == 64 ? 8 : 4);
     if (prng_type == PRNG_AES) {

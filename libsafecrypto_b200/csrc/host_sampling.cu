@@ -276,6 +276,8 @@ extern "C" int scgpu_gauss_plan_create_table(scgpu_gauss_plan_t **out, int preci
     return SCGPU_OK;
 }
 
+extern "C" int scgpu_set_fixed_probe_search(int on) { return set_fixed_probe_search(on); }
+
 extern "C" void scgpu_gauss_plan_destroy(scgpu_gauss_plan_t *p)
 {
     if (!p) return;

@@ -165,6 +165,11 @@ def test_throughput_kernels_against_the_port_in_bulk(prng, precision, tail, sigm
     exp = O.port().gauss_streams(O.SAMPLER_CDF, precision, 0, prng, tail, sigma, seeds, n)
     assert np.array_equal(got, exp)
     assert np.abs(got).max() > 3.5 * sigma            # the tails were visited
+    old = sc.lib().scgpu_set_fixed_probe_search(1)    # the reference's fixed probe sequence: same samples
+    try:
+        assert np.array_equal(gpu_samples(O.SAMPLER_CDF, precision, 0, prng, tail, sigma, seeds, n), exp)
+    finally:
+        sc.lib().scgpu_set_fixed_probe_search(old)
 
 
 def test_dropin_sampler_api():

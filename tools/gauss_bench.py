@@ -11,7 +11,12 @@ g = torch.Generator(device=dev).manual_seed(1)
 ns = 1 << lb
 seeds = torch.randint(0, 256, (ns, 40), dtype=torch.uint8, device=dev, generator=g)
 smp = torch.empty((ns, n), dtype=torch.int32, device=dev)
-for prec in (64, 32):
+for prec in (64, 32, -64):
+    fixed = prec < 0
+    prec = abs(prec)
+    sc.lib().scgpu_set_fixed_probe_search(1 if fixed else 0)
+    if fixed:
+        print("fixed probe sequence (scgpu_set_fixed_probe_search(1)):")
     gp = sc.GaussPlan(sc.SAMPLER_CDF, prec, 0, 13.42, 215.0)
     for name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
         for _ in range(2):
@@ -24,6 +29,7 @@ for prec in (64, 32):
         e.record(); torch.cuda.synchronize()
         print("cdf%d %-13s %.4g samples/s" % (prec, name, 5 * ns * n / (s.elapsed_time(e) * 1e-3)))
 
+sc.lib().scgpu_set_fixed_probe_search(0)
 # sequential-semantics kernel (k_stream_seq): shuffle / blinding / discard wrappers, Knuth-Yao, Bernoulli
 ns2 = 1 << 16
 seeds2 = seeds[:ns2]
