@@ -512,7 +512,8 @@ int launch_gauss_fast(const GaussTablesDev &g, int prng_type, const uint8_t *see
     }
     FastArgs a;
     a.g = g;
-    if (g_fixed_probe_search) a.g.cdf_guide = nullptr; a.seeds = seeds; a.seed_len = (uint32_t)seed_len; a.seed_period = seed_period;
+    if (g_fixed_probe_search) a.g.cdf_guide = nullptr;
+    a.seeds = seeds; a.seed_len = (uint32_t)seed_len; a.seed_period = seed_period;
     a.nstreams = nstreams; a.per_stream = per_stream; a.centre = centre; a.out = out; a.keys = key_scratch;
     const size_t table_bytes = (size_t)g.cdf_size * (g.precision == 64 ? 8 : 4);
     if (prng_type == PRNG_AES) {
