@@ -119,9 +119,19 @@ inline bool analyse32(int logn, int64_t qi, int accumulate, int *r0_out, int32_t
     const double q = (double)qi, lim = (double)kLimit - 2.0;
     const double other = s.fwd_max > 32768.0 ? s.fwd_max : 32768.0;
     const double quo = s.fwd_max * other / q;
-    const double pw = q * (0.5 + 2.0 * quo / 16777216.0) + 2.0;
+    double pw = q * (0.5 + 2.0 * quo / 16777216.0) + 2.0;
+    if (accumulate > 1) {
+        // mat-vec (ArFq::Acc): the products of an output coefficient, |a| <= x0 times |s| <= fwd_max each, share
+        // one quotient: the summed quotient must stay in the magic-number range, and the float sum adds
+        // accumulate roundings of half an ulp of the largest partial sum
+        const double sum = accumulate * (double)s.x0 * s.fwd_max;
+        if (sum / q >= lim) return false;
+        const double ulp = std::ldexp(1.0, std::ilogb(sum) - 23);
+        pw = q * (0.5 + 2.0 * (sum / q) / 16777216.0) + accumulate * ulp + 2.0;
+        accumulate = 1;
+    }
     for (int r0 = 0; r0 <= 1; r0++) {
-        double b = pw * accumulate;                          // mat-vec: sum of l pointwise products
+        double b = pw * accumulate;
         bool ok = true;
         for (int st = logn - 1; st >= 0 && ok; st--) {
             if (st == 4 && r0) { if (b >= lim) { ok = false; break; } b = mul_bound(b, q); }

@@ -81,9 +81,20 @@ struct ArFq {
     {
         return (u32)fq::mul_var(dec(a), kv, k.invq, k.pwk, k.nq) + (u32)kBias;
     }
-    static __device__ __forceinline__ u32 prod(int32_t av, int32_t sv, const K &k)
+    // mat-vec accumulator: the l products of an output coefficient share ONE quotient.  p = sum of the low
+    // products (wrap-around), f = the same sum in floats (each product below 2^32, l <= 8: the float error is a
+    // few thousand, i.e. a fraction of q in the quotient); acc_fin = p - rint(f / q) q, biased.
+    struct Acc { u32 p; float f; };
+    static __device__ __forceinline__ Acc acc_zero() { return Acc{0u, 0.0f}; }
+    static __device__ __forceinline__ void acc_add(Acc &a, int32_t av, int32_t sv, const K &)
     {
-        return (u32)fq::mul_var(av, sv, k.invq, k.pwk, k.nq);
+        a.p = (u32)fq::mad(av, sv, (int32_t)a.p);
+        a.f = __fmaf_rn(__int2float_rn(av), __int2float_rn(sv), a.f);
+    }
+    static __device__ __forceinline__ u32 acc_fin(const Acc &a, const K &k)
+    {
+        const float f = __fmaf_rn(a.f, k.invq, fq::kBiasF);
+        return (u32)fq::mad(fq::as_i(f), k.nq, (int32_t)(a.p + (u32)k.pwk)) + (u32)kBias;
     }
 };
 
@@ -117,7 +128,7 @@ int build_fq32_tables(NttPlanDev &p, const int32_t *w_host)
     int r0 = 0; int32_t x0 = 0;
     if (!fq::analyse32(p.logn, p.rc.q, 1, &r0, &x0)) return SCGPU_OK;
     int r0_mv = 0; int32_t x0_mv = 0;
-    p.fq32_mv_ok = fq::analyse32(p.logn, p.rc.q, 8, &r0_mv, &x0_mv) ? 1 : 0;     // up to 8 accumulated products
+    p.fq32_mv_ok = fq::analyse32(p.logn, p.rc.q, 4, &r0_mv, &x0_mv) ? 1 : 0;     // up to 4 accumulated products
     p.fq32_r0_mv = r0_mv;
     std::vector<Tw> zf, zi;
     Tw ninv, one;
@@ -153,7 +164,7 @@ void free_fq32_tables(NttPlanDev &p)
 int launch_matvec_fq32(const NttPlanDev &p, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
                        size_t count, cudaStream_t st)
 {
-    if (!p.fq32_ok || !p.fq32_mv_ok || p.logn != 8 || l > 8) return SCGPU_ERR_UNSUPPORTED;
+    if (!p.fq32_ok || !p.fq32_mv_ok || p.logn != 8 || l > 4) return SCGPU_ERR_UNSUPPORTED;
     return w32::launch_matvec_w32<ArFq>(fq32_const(p, p.fq32_r0_mv), p.sm_count, out, A, s, k, l, count, st);
 }
 

@@ -71,7 +71,11 @@ struct ArSh {
     }
     static __device__ __forceinline__ u32 pw(u32 a, u32 b, const K &k) { return mont((int32_t)a, (int32_t)b, k); }
     static __device__ __forceinline__ u32 pwraw(u32 a, int32_t kv, const K &k) { return mont((int32_t)a, kv, k); }
-    static __device__ __forceinline__ u32 prod(int32_t av, int32_t sv, const K &k) { return mont(av, sv, k); }
+    // mat-vec accumulator: Montgomery products, each in (-q, q), summed
+    struct Acc { u32 v; };
+    static __device__ __forceinline__ Acc acc_zero() { return Acc{0u}; }
+    static __device__ __forceinline__ void acc_add(Acc &a, int32_t av, int32_t sv, const K &k) { a.v += mont(av, sv, k); }
+    static __device__ __forceinline__ u32 acc_fin(const Acc &a, const K &) { return a.v; }
 };
 
 typedef w32::W32Const<ArSh> ShConst32;

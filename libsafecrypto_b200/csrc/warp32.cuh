@@ -13,7 +13,9 @@
 //   red(x, one, k)              x * 1 mod q (range reduction), internal in / out
 //   pw(a, b, k)                 pointwise product of two internal values, internal out
 //   pwraw(a, kv, k)             internal a times raw kv, internal out
-//   prod(av, sv, k)             raw av times decoded sv, additive term for an accumulator started at zero()
+//   Acc, acc_zero / acc_add(acc, av, sv, k) / acc_fin(acc, k)
+//                               accumulator of raw av times decoded sv over the mat-vec's inner index; acc_fin
+//                               returns the internal representation of the sum
 #pragma once
 #include "scgpu_internal.h"
 #include "../../include/scgpu.h"
@@ -568,11 +570,9 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
         }
 #pragma unroll 1
         for (int i = 0; i < k; i++) {
-            u32 acc[NSUB][SUB];
+            typename AR::Acc part[32];
 #pragma unroll
-            for (int h = 0; h < NSUB; h++)
-#pragma unroll
-                for (int e = 0; e < SUB; e++) acc[h][e] = AR::zero();
+            for (int e = 0; e < 32; e++) part[e] = AR::acc_zero();
 #pragma unroll 1
             for (int j = 0; j < l; j++) {
                 int32_t av[32];
@@ -610,12 +610,15 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
                     const int4 sv = *reinterpret_cast<const int4 *>(sp + e);
-                    acc[e / SUB][e % SUB]           += AR::prod(av[e], sv.x, c.k);
-                    acc[(e + 1) / SUB][(e + 1) % SUB] += AR::prod(av[e + 1], sv.y, c.k);
-                    acc[(e + 2) / SUB][(e + 2) % SUB] += AR::prod(av[e + 2], sv.z, c.k);
-                    acc[(e + 3) / SUB][(e + 3) % SUB] += AR::prod(av[e + 3], sv.w, c.k);
+                    AR::acc_add(part[e], av[e], sv.x, c.k);
+                    AR::acc_add(part[e + 1], av[e + 1], sv.y, c.k);
+                    AR::acc_add(part[e + 2], av[e + 2], sv.z, c.k);
+                    AR::acc_add(part[e + 3], av[e + 3], sv.w, c.k);
                 }
             }
+            u32 acc[NSUB][SUB];
+#pragma unroll
+            for (int e = 0; e < 32; e++) acc[e / SUB][e % SUB] = AR::acc_fin(part[e], c.k);
             if (TMA && i == k - 1) {
                 // the stash is dead: the next instances' s rows travel during the last inverse transform
                 fence_proxy_async();
