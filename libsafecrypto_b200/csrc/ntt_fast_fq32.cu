@@ -34,6 +34,7 @@ using w32::u32;
 struct ArFq {
     typedef Tw E;
     struct K { int32_t nq, q, pwk; float invq; };
+    static constexpr bool STASH16 = true;          // mat-vec may keep the transformed vectors as int16
     static constexpr int WORDS = 4;
     static __device__ __forceinline__ u32 enc(int32_t x) { return (u32)x + (u32)kBias; }
     static __device__ __forceinline__ int32_t dec(u32 x) { return (int32_t)(x - (u32)kBias); }

@@ -23,6 +23,7 @@ using w32::u32;
 struct ArSh {
     struct E { int32_t w, wp; };
     struct K { int32_t q, nq, qinv; };
+    static constexpr bool STASH16 = false;          // mat-vec may keep the transformed vectors as int16
     static constexpr int WORDS = 2;
     static __device__ __forceinline__ u32 enc(int32_t x) { return (u32)x; }
     static __device__ __forceinline__ int32_t dec(u32 x) { return (int32_t)x; }

@@ -651,6 +651,177 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
 }
 
 
+// ---- mat-vec with a 16-bit stash (moduli below 2^15.8, policies with AR::STASH16) --------------------------------
+// The kernel above is limited to 8-9 warps per SM by the l full tiles it keeps per instance.  Here the transformed
+// vectors are reduced to |x| <= q/2 + and kept as int16 (20 words per thread: conflict-free 128-bit reads), the
+// forward transforms run through the one exchange tile, and EVERY row of the instance -- s_0 .. s_{l-1}, then
+// A_00 .. A_{k-1,l-1} -- travels through ONE staging row and ONE mbarrier: as soon as a row is in registers the
+// next row of the sequence (or s_0 of the warp's next instances) is put in flight.  13-15 warps per SM.
+template <class AR, int LOGN, bool TMA>
+__global__ void __launch_bounds__(kThreads32)
+k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t *__restrict__ s,
+               int k, int l, size_t count, const __grid_constant__ W32Const<AR> c)
+{
+    using C = Cfg32<LOGN>;
+    using W = W32<AR>;
+    constexpr int N = C::N, T = C::T, SUB = C::SUB, NSUB = C::NSUB;
+    constexpr int AROW = N + T;                      // staging row stride: T banks between instances
+    constexpr int SROW = 20 * T + T;                 // 16-bit stash row of one vector, in words (20 per thread)
+    constexpr uint32_t ROW_BYTES = (uint32_t)N * 4u;
+    extern __shared__ __align__(16) int32_t dyn_tiles[];             // [POLYS][TS] | [POLYS][AROW] | [l][POLYS][SROW]
+    __shared__ __align__(8) uint64_t bars[kThreads32 / 32];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x / 32;
+    const int tau = lane % T;
+    const int slot = warp * C::PW + lane / T;
+    int32_t *xt = dyn_tiles + slot * C::TS;
+    int32_t *stage = dyn_tiles + C::POLYS * C::TS + slot * AROW;
+    int32_t *stash0 = dyn_tiles + C::POLYS * (C::TS + AROW) + slot * SROW + 20 * tau;
+    const int stash_stride = C::POLYS * SROW;                        // between vectors j
+    const int taurev = (int)(__brev((unsigned)tau) >> (32 - (LOGN - 5)));
+    const int rows_per_inst = l + k * l;
+    uint32_t parity = 0;
+
+    // lane 0: row r of the sequence for the warp's PW instances starting at nbase
+    auto fetch = [&](size_t nbase, int r) {
+        mbar_expect_tx(&bars[warp], ROW_BYTES * C::PW);
+        for (int p = 0; p < C::PW; p++) {
+            size_t inst = nbase + (size_t)warp * C::PW + p;
+            if (inst >= count) inst = 0;
+            const int32_t *src = r < l ? s + (inst * l + r) * N : A + (inst * k * l + (r - l)) * N;
+            bulk_g2s(dyn_tiles + C::POLYS * C::TS + (warp * C::PW + p) * AROW, src, ROW_BYTES, &bars[warp]);
+        }
+    };
+    const size_t first = (size_t)blockIdx.x * C::POLYS;
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(&bars[warp], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0 && first < count) fetch(first, 0);
+    }
+
+    for (size_t base = first; base < count; base += (size_t)gridDim.x * C::POLYS) {
+        const size_t inst = base + slot;
+        const bool live = inst < count;
+        const size_t irow = live ? inst : 0;
+        const size_t nbase = base + (size_t)gridDim.x * C::POLYS;
+        int r = 0;                                                   // row of the sequence being consumed
+        // after the staging row has been read into registers: next row of this instance, or row 0 of the next
+        auto advance = [&]() {
+            if (TMA) {
+                fence_proxy_async();
+                __syncwarp();
+                r++;
+                if (lane == 0) {
+                    if (r < rows_per_inst) fetch(base, r);
+                    else if (nbase < count) fetch(nbase, 0);
+                }
+            }
+        };
+#pragma unroll 1
+        for (int j = 0; j < l; j++) {
+            u32 x[32];
+            if (TMA) {
+                mbar_wait(&bars[warp], parity); parity ^= 1u;
+                W::template load_operand_staged<LOGN>(x, stage, tau, c);
+                advance();
+            } else {
+                W::template load_operand<LOGN>(x, s + (irow * l + j) * N, tau, c);
+            }
+            W::fwd_pass0(x, c);
+            store_pass0<LOGN>(xt, x, tau);
+            __syncwarp();
+#pragma unroll 1
+            for (int h = 0; h < NSUB; h++) {
+                u32 xa[SUB], xb[SUB];
+                load_sub<SUB>(xt + 36 * tau + SUB * h, xa);
+                W::template fwd_stages1<LOGN, C::S1, 1>(xa, xb, c, tau, h);
+                // reduce, decode, pack two coefficients per word
+                uint32_t pk[SUB / 2];
+#pragma unroll
+                for (int i = 0; i < SUB; i += 2) {
+                    const int32_t v0 = AR::dec(AR::red(xa[i], c.one, c.k));
+                    const int32_t v1 = AR::dec(AR::red(xa[i + 1], c.one, c.k));
+                    pk[i / 2] = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
+                }
+                int32_t *dst = stash0 + j * stash_stride + (SUB / 2) * h;
+#pragma unroll
+                for (int i = 0; i < SUB / 2; i += 4)
+                    *reinterpret_cast<uint4 *>(dst + i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+            }
+            __syncwarp();                                            // the exchange tile is reused by the next vector
+        }
+#pragma unroll 1
+        for (int i = 0; i < k; i++) {
+            typename AR::Acc part[32];
+#pragma unroll
+            for (int e = 0; e < 32; e++) part[e] = AR::acc_zero();
+#pragma unroll 1
+            for (int j = 0; j < l; j++) {
+                int32_t av[32];
+                bool wide = false;
+                if (TMA) {
+                    mbar_wait(&bars[warp], parity); parity ^= 1u;
+#pragma unroll
+                    for (int e = 0; e < 32; e++) {
+                        av[e] = stage[taurev + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5))];
+                        wide |= W::out_of_range(av[e], c);
+                    }
+                    advance();
+                } else {
+                    const int32_t *arow = A + ((irow * k + i) * l + j) * N + taurev;
+#pragma unroll
+                    for (int e = 0; e < 32; e++) {
+                        av[e] = __ldg(arow + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5)));
+                        wide |= W::out_of_range(av[e], c);
+                    }
+                }
+                if (__any_sync(0xFFFFFFFFu, wide)) {
+#pragma unroll
+                    for (int e = 0; e < 32; e++) av[e] = W::bred(av[e], c);
+                }
+                const int32_t *sp = stash0 + j * stash_stride;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                    const uint4 sv = *reinterpret_cast<const uint4 *>(sp + e / 2);
+                    const uint32_t wds[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        AR::acc_add(part[e + 2 * u], av[e + 2 * u], (int32_t)(int16_t)(wds[u] & 0xFFFFu), c.k);
+                        AR::acc_add(part[e + 2 * u + 1], av[e + 2 * u + 1], (int32_t)wds[u] >> 16, c.k);
+                    }
+                }
+            }
+            u32 acc[NSUB][SUB];
+#pragma unroll
+            for (int e = 0; e < 32; e++) acc[e / SUB][e % SUB] = AR::acc_fin(part[e], c.k);
+#pragma unroll
+            for (int h = 0; h < NSUB; h++) {
+                W::template inv_stages1<LOGN, LOGN - 1>(acc[h], c, tau, h);
+                store_sub<SUB>(xt + 36 * tau + SUB * h, acc[h]);
+            }
+            __syncwarp();
+            {
+                u32 x[32];
+                load_pass0<LOGN>(xt, x, tau);
+                if (c.r0) {
+#pragma unroll
+                    for (int m = 0; m < 32; m++) x[m] = AR::red(x[m], c.one, c.k);
+                }
+                W::inv_pass0(x, c);
+                if (live) {
+                    int32_t *orow = out + (inst * k + i) * N;
+#pragma unroll
+                    for (int m = 0; m < 32; m++) orow[tau + m * T] = (int32_t)x[m];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ---- host side, shared by the arithmetic policies -------------------------------------------------------------
 // position of entry r (0 .. 16/len - 1) of thread tau in stage s of the thread-major pass-1 table
 inline int slot32(int logn, int s, int tau, int r)
@@ -726,16 +897,34 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
 {
     using C = Cfg32<8>;
     const bool tma = ((uintptr_t)A % 16) == 0 && ((uintptr_t)s % 16) == 0 && tma_allowed();
+    const int sms = sm_count > 0 ? sm_count : 148;
+    const size_t groups = (count + C::POLYS - 1) / C::POLYS;
+    // 16-bit stash: the reduced transform values must fit an int16 (|x| <= 0.55 q + 2)
+    const char *no16 = getenv("SCGPU_MATVEC_STASH32");
+    // measured (Kyber, q = 7681): k = l = 3 / 4 gain 16 % / 3 % from the higher occupancy; k = l = 2 loses 19 %
+    // (half of its rows are s rows, whose long forward transforms serialise behind the single staging row), and
+    // without bulk copies the rows are not prefetched at all: those shapes keep the 32-bit stash
+    if (AR::STASH16 && c.q < 59000 && l >= 3 && tma && !(no16 && atoi(no16) != 0)) {
+        const size_t smem = ((size_t)C::POLYS * (C::TS + (C::N + C::T)) + (size_t)l * C::POLYS * (20 * C::T + C::T)) * sizeof(int32_t);
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int per_sm = (int)((227 * 1024) / (smem + 1024 + 64));
+        if (per_sm > 16) per_sm = 16;
+        if (per_sm < 1) per_sm = 1;
+        size_t grid = (size_t)sms * per_sm;
+        if (grid > groups) grid = groups;
+        k_matvec16_w32<AR, 8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, c);
+        count_launch();
+        SCGPU_CUDA_CHECK(cudaGetLastError());
+        return SCGPU_OK;
+    }
     const size_t smem = ((size_t)(l + 1) * C::POLYS * C::TS + (tma ? (size_t)C::POLYS * (C::N + C::T) : 0)) * sizeof(int32_t);
     // per launch, not once: the attribute belongs to the current device's context and plans exist per device
     if (tma) SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     else     SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (smem > 200 * 1024) { set_error("matvec: l=%d needs %zu bytes of shared memory", l, smem); return SCGPU_ERR_UNSUPPORTED; }
-    const int sms = sm_count > 0 ? sm_count : 148;
     int per_sm = (int)((227 * 1024) / (smem + 1024 + 64));
     if (per_sm > 16) per_sm = 16;
     if (per_sm < 1) per_sm = 1;
-    const size_t groups = (count + C::POLYS - 1) / C::POLYS;
     size_t grid = (size_t)sms * per_sm;
     if (grid > groups) grid = groups;
     if (tma) k_matvec_w32<AR, 8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, c);
