@@ -658,7 +658,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
 // A_00 .. A_{k-1,l-1} -- travels through ONE staging row and ONE mbarrier: as soon as a row is in registers the
 // next row of the sequence (or s_0 of the warp's next instances) is put in flight.  13-15 warps per SM.
 template <class AR, int LOGN, bool TMA>
-__global__ void __launch_bounds__(kThreads32)
+__global__ void __launch_bounds__(kThreads32, 16)        // 128 registers: 4 warps per scheduler fit (140 allowed 3)
 k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t *__restrict__ s,
                int k, int l, size_t count, const __grid_constant__ W32Const<AR> c)
 {
