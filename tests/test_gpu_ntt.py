@@ -286,6 +286,27 @@ def test_fused_key_product_matches_triple(q, n, arithmetic):
             assert np.array_equal(out32.cpu().numpy(), exp)
 
 
+@pytest.mark.parametrize("q,n,tw", [(12289, 512, 16), (7681, 256, 16), (8380417, 256, 32)])
+def test_fused_key_product_with_arbitrary_32bit_keys(q, n, tw, arithmetic):
+    """SINT32 keys far outside [0, q) (the out-of-range path of the key load): against the reference composition
+    fwd_ntt, mul_32_pointwise, inv_ntt evaluated by the port."""
+    rng = np.random.default_rng(q + n + 7)
+    w, r = O.tables(q, n, tw)
+    p, _, _ = plan(q, n, tw, O.REFERENCE)
+    P = O.port()
+    t = rand_inputs(rng, "uniform", q, (40, n))
+    for key in (rng.integers(-2**31, 2**31, size=(40, n)).astype(np.int32),
+                np.full((40, n), 2**31 - 1, dtype=np.int32), np.full((40, n), -2**31, dtype=np.int32),
+                (rng.integers(-4 * q, 4 * q + 1, size=(40, n))).astype(np.int32)):
+        out = torch.empty((40, n), dtype=torch.int32, device=DEV)
+        p.mul_key(out, dev(t), dev(key))
+        torch.cuda.synchronize()
+        sh = P.ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, t, None, w, r)
+        pr = P.ntt_batch(O.REFERENCE, O.OP_PW, n, q, tw, sh, key, w, r)
+        exp = P.ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, pr, None, w, r)
+        assert np.array_equal(out.cpu().numpy(), exp)
+
+
 @pytest.mark.parametrize("q,tw,k,eta", [(7681, 16, 2, 5), (7681, 16, 3, 4), (7681, 16, 4, 3), (8380417, 32, 4, 5)])
 def test_matvec_matches_reference_composition(q, tw, k, eta, arithmetic):
     """create_rand_product_32 (module_lwe.c:588-748) with A given in the NTT domain:
