@@ -306,6 +306,19 @@ def main():
             shapes["polymul_n%d_q%d" % (nn, qq)] = {"polymul_per_s": bb / (ms * 1e-3), "pairs": bb,
                                                     "hbm_frac": 12 * nn * bb / (ms * 1e-3) / 1e9 / peak}
             del xa, xb, xo, pl
+        # single transforms with canonical output (normalize_32 o fwd_ntt, inv_ntt), n = 512: 8 n bytes each
+        for inverse, name in ((False, "fwd_ntt_canonical_n512_q12289"), (True, "inv_ntt_canonical_n512_q12289")):
+            for _ in range(3):
+                plan.ntt_canonical(out, a, inverse=inverse)
+            torch.cuda.synchronize()
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(10):
+                plan.ntt_canonical(out, a, inverse=inverse)
+            e0.record()
+            torch.cuda.synchronize()
+            ms = s0.elapsed_time(e0) / 10
+            shapes[name] = {"ntt_per_s": BATCH / (ms * 1e-3), "polys": BATCH, "hbm_frac": 8 * N_COEF * BATCH / (ms * 1e-3) / 1e9 / peak}
 
     # ---- end-to-end leg: host buffers through the C-ABI ----------------------------------------------------
     ha = torch.randint(0, Q, (E2E_BATCH, N_COEF), dtype=torch.int32).pin_memory()

@@ -59,6 +59,7 @@ def lib():
         L.scgpu_gauss_streams_host.argtypes = [vp, ctypes.c_int, vp, sz, sz, sz, sz, i32, u32, vp]
         L.scgpu_prng_words.argtypes = [ctypes.c_int, vp, sz, sz, sz, sz, vp, vp]
         L.scgpu_force_montgomery.argtypes = [ctypes.c_int]
+        L.scgpu_ntt_canonical_batch.argtypes = [vp, ctypes.c_int, vp, vp, sz, vp]
         L.scgpu_set_fixed_probe_search.argtypes = [ctypes.c_int]
         L.scgpu_set_fixed_probe_search.restype = ctypes.c_int
         L.scgpu_set_fast_arith.argtypes = [ctypes.c_int]
@@ -156,6 +157,12 @@ class NttPlan:
         b_stride = 0 if b.dim() == 1 else b.shape[-1]
         return _check(lib().scgpu_polymul_batch(self.handle, _ptr(out), _ptr(a), _ptr(b), b_stride, count,
                                                 _stream_handle(stream)), "scgpu_polymul_batch")
+
+    def ntt_canonical(self, out, a, inverse=False, count=None, stream=None):
+        if count is None:
+            count = a.shape[0]
+        return _check(lib().scgpu_ntt_canonical_batch(self.handle, 1 if inverse else 0, _ptr(out), _ptr(a), count,
+                                                      _stream_handle(stream)), "scgpu_ntt_canonical_batch")
 
     def mul_key(self, out, t, key, count=None, stream=None):
         if count is None:

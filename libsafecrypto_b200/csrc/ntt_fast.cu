@@ -447,6 +447,17 @@ int launch_polymul(const NttPlanDev &p, int32_t *out, const int32_t *a, const in
     return SCGPU_OK;
 }
 
+// normalize_32(fwd_ntt(a)) / inv_ntt(a) through the warp-local kernels; SCGPU_ERR_UNSUPPORTED when neither
+// arithmetic policy serves the modulus (the caller then composes the variant-exact kernels)
+int launch_ntt_canonical(const NttPlanDev &p, int inverse, int32_t *out, const int32_t *a, size_t count, cudaStream_t st)
+{
+    if (count == 0) return SCGPU_OK;
+    const int m = arith_mode();
+    if (p.sh32_ok && (m == 4 || !p.fq32_ok)) return launch_ntt_sh32(p, inverse, out, a, count, st);
+    if (p.fq32_ok) return launch_ntt_fq32(p, inverse, out, a, count, st);
+    return SCGPU_ERR_UNSUPPORTED;
+}
+
 int launch_mul_key(const NttPlanDev &p, int32_t *out, const int32_t *t, const void *key,
                    int key_bits, size_t key_stride, size_t count, cudaStream_t st)
 {

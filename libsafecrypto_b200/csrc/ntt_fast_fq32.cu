@@ -175,4 +175,9 @@ int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32
     return w32::launch_polymul_w32<ArFq>(fq32_const(p, p.fq32_r0), p.logn, p.sm_count, mode, out, a, b, b_stride, count, st);
 }
 
+int launch_ntt_fq32(const NttPlanDev &p, int inverse, int32_t *out, const int32_t *a, size_t count, cudaStream_t st)
+{
+    return w32::launch_ntt_w32<ArFq>(fq32_const(p, p.fq32_r0), p.logn, p.sm_count, inverse, out, a, count, st);
+}
+
 }  // namespace scgpu

@@ -179,6 +179,15 @@ int build_sh32_tables(NttPlanDev &p, const int32_t *w_host)
         zi[k] = make_entry(zinv, q);
     }
     const ArSh::E ninv = make_entry(ninvR, q), one = make_entry(1, q);
+    {
+        // a stand-alone inverse transform has no Montgomery product to compensate: plain n^-1 and n^-1 psi^-(n/2)
+        const int64_t nin = powmod(n, q - 2, q);
+        const int e1 = 1 << (p.logn - 1);                                    // brv(1)
+        const int64_t zinv1 = (q - (((int64_t)w_host[n - e1] % q) + q) % q) % q;
+        const ArSh::E np = make_entry(nin, q), zp = make_entry((int64_t)(((__int128)zinv1 * nin) % q), q);
+        memcpy(p.sh32_ninv_plain, &np, sizeof(np));
+        memcpy(p.sh32_zi1_plain, &zp, sizeof(zp));
+    }
     std::vector<int32_t> pack(4 * n, 0);
     w32::pack_pass1<ArSh>(p.logn, zf, zi, [](const ArSh::E &e, int k) { return k == 0 ? e.w : e.wp; }, pack.data());
     SCGPU_CUDA_CHECK(cudaMalloc(&p.sh32_tab, sizeof(int32_t) * 4 * n));
@@ -211,6 +220,16 @@ int launch_polymul_sh32(const NttPlanDev &p, int mode, int32_t *out, const int32
                         size_t b_stride, size_t count, cudaStream_t st)
 {
     return w32::launch_polymul_w32<ArSh>(sh32_const(p, p.sh32_r0), p.logn, p.sm_count, mode, out, a, b, b_stride, count, st);
+}
+
+int launch_ntt_sh32(const NttPlanDev &p, int inverse, int32_t *out, const int32_t *a, size_t count, cudaStream_t st)
+{
+    ShConst32 c = sh32_const(p, p.sh32_r0);
+    if (inverse) {
+        memcpy(&c.ninv, p.sh32_ninv_plain, sizeof(ArSh::E));
+        memcpy(&c.i0[0], p.sh32_zi1_plain, sizeof(ArSh::E));
+    }
+    return w32::launch_ntt_w32<ArSh>(c, p.logn, p.sm_count, inverse, out, a, count, st);
 }
 
 }  // namespace scgpu

@@ -55,6 +55,7 @@ struct NttPlanDev {
     int32_t sh32_x0;
     void *sh32_tab;                      // forward [w | wp], inverse [w | wp], n words each
     alignas(16) unsigned char sh32_pass0[2 * 31 * 8], sh32_ninv[8], sh32_one[8];
+    alignas(16) unsigned char sh32_ninv_plain[8], sh32_zi1_plain[8];   // last-stage multipliers without the factor R
 };
 
 struct ExactArgs {
@@ -97,6 +98,9 @@ int launch_polymul_sh32(const NttPlanDev &plan, int mode, int32_t *out, const in
                         size_t b_stride, size_t count, cudaStream_t stream);
 int launch_matvec_sh32(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
                        size_t count, cudaStream_t stream);
+int launch_ntt_fq32(const NttPlanDev &plan, int inverse, int32_t *out, const int32_t *a, size_t count, cudaStream_t stream);
+int launch_ntt_sh32(const NttPlanDev &plan, int inverse, int32_t *out, const int32_t *a, size_t count, cudaStream_t stream);
+int launch_ntt_canonical(const NttPlanDev &plan, int inverse, int32_t *out, const int32_t *a, size_t count, cudaStream_t stream);
 int launch_matvec_fq32(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
                        size_t count, cudaStream_t stream);
 int launch_matvec_fq(const NttPlanDev &plan, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,

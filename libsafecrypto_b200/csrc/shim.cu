@@ -200,6 +200,22 @@ extern "C" int scgpu_polymul_batch(const scgpu_ntt_plan_t *plan, int32_t *out, c
     return launch_polymul(plan->dev, out, a, b, b_stride, count, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int scgpu_ntt_canonical_batch(const scgpu_ntt_plan_t *plan, int inverse, int32_t *out, const int32_t *a,
+                                         size_t count, void *stream)
+{
+    if (!plan || !out || !a) { set_error("ntt_canonical_batch: null argument"); return SCGPU_ERR_ARG; }
+    if (!plan->dev.w || (inverse && !plan->dev.r)) { set_error("ntt_canonical_batch: the plan has no twiddle tables"); return SCGPU_ERR_ARG; }
+    SCGPU_CUDA_CHECK(cudaSetDevice(plan->dev.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int e = launch_ntt_canonical(plan->dev, inverse, out, a, count, st);
+    if (e != SCGPU_ERR_UNSUPPORTED) return e;
+    // moduli outside both fused arithmetics: the variant-exact kernels compose the same result
+    if (inverse) return scgpu_ntt_batch(plan, SCGPU_OP_INV, out, a, nullptr, 0, count, 0, nullptr, stream);
+    const int e2 = scgpu_ntt_batch(plan, SCGPU_OP_FWD, out, a, nullptr, 0, count, 0, nullptr, stream);
+    if (e2 != SCGPU_OK) return e2;
+    return scgpu_ntt_batch(plan, SCGPU_OP_NORMALIZE, out, out, nullptr, 0, count, 0, nullptr, stream);
+}
+
 extern "C" int scgpu_ntt_mul_key_batch(const scgpu_ntt_plan_t *plan, int32_t *out, const int32_t *t,
                                        const void *key, int key_bits, size_t key_stride, size_t count,
                                        void *stream)

@@ -472,6 +472,94 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
 }
 
 
+// ---- single transforms with CANONICAL output ---------------------------------------------------------------------
+//   INV = false:  out = normalize_32(fwd_ntt_32_16/32(a))   residues in [0, q), the reference's NTT-domain order
+//   INV = true :  out = inv_ntt_32_16/32(a)                 a in the reference's NTT-domain order, any SINT32
+// Both results are canonical in the reference, so the arithmetic inside is free (as for the fused products); the
+// variant-exact kernels of ntt_exact.cu remain the way to get fwd_ntt's lazily reduced representative itself.
+template <class AR, int LOGN, bool INV>
+__global__ void __launch_bounds__(kThreads32, FQ32_MINB)
+k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count, const __grid_constant__ W32Const<AR> c)
+{
+    using C = Cfg32<LOGN>;
+    using W = W32<AR>;
+    constexpr int N = C::N, T = C::T, SUB = C::SUB;
+    __shared__ __align__(16) int32_t tiles[C::POLYS][C::TS];
+    const int lane = threadIdx.x & 31;
+    const int tau = lane % T;
+    const int slot = (threadIdx.x / 32) * C::PW + lane / T;
+    int32_t *tile = tiles[slot];
+
+    for (size_t base = (size_t)blockIdx.x * C::POLYS; base < count; base += (size_t)gridDim.x * C::POLYS) {
+        const size_t poly = base + slot;
+        const bool live = poly < count;
+        const size_t prow = live ? poly : 0;
+        if (!INV) {
+            {
+                u32 x[32];
+                W::template load_operand<LOGN>(x, a + prow * N, tau, c);
+                W::fwd_pass0(x, c);
+                store_pass0<LOGN>(tile, x, tau);
+            }
+            __syncwarp();
+            W::template chunk_stage5<LOGN, false>(tile + 36 * tau, c, tau);
+#pragma unroll 1
+            for (int h = 0; h < C::NSUB; h++) {
+                u32 xa[SUB], xb[SUB];
+                load_sub<SUB>(tile + 36 * tau + SUB * h, xa);
+                W::template fwd_stages1<LOGN, C::S1, 1>(xa, xb, c, tau, h);
+                int32_t *orow = out + poly * N + ntt_index<LOGN>(tau, SUB * h);
+#pragma unroll
+                for (int i = 0; i < SUB; i++) {
+                    u32 v = (u32)AR::dec(AR::red(xa[i], c.one, c.k));           // in (-q, q + q/16)
+                    v = min(v, v + (u32)c.q);
+                    v = min(v, v - (u32)c.q);
+                    if (live) orow[(int)((__brev((unsigned)i) >> 27) << (LOGN - 5))] = (int32_t)v;
+                }
+            }
+            __syncwarp();
+        } else {
+#pragma unroll 1
+            for (int h = 0; h < C::NSUB; h++) {
+                const int32_t *irow = a + prow * N + ntt_index<LOGN>(tau, SUB * h);
+                int32_t v[SUB];
+                bool wide = false;
+#pragma unroll
+                for (int i = 0; i < SUB; i++) {
+                    v[i] = __ldg(irow + (int)((__brev((unsigned)i) >> 27) << (LOGN - 5)));
+                    wide |= W::out_of_range(v[i], c);
+                }
+                if (__any_sync(0xFFFFFFFFu, wide)) {
+#pragma unroll
+                    for (int i = 0; i < SUB; i++) v[i] = W::bred(v[i], c);
+                }
+                u32 x[SUB];
+#pragma unroll
+                for (int i = 0; i < SUB; i++) x[i] = AR::red(AR::enc(v[i]), c.one, c.k);   // the bounds assume reduced input
+                W::template inv_stages1<LOGN, LOGN - 1>(x, c, tau, h);
+                store_sub<SUB>(tile + 36 * tau + SUB * h, x);
+            }
+            W::template chunk_stage5<LOGN, true>(tile + 36 * tau, c, tau);
+            __syncwarp();
+            {
+                u32 x[32];
+                load_pass0<LOGN>(tile, x, tau);
+                if (c.r0) {
+#pragma unroll
+                    for (int m = 0; m < 32; m++) x[m] = AR::red(x[m], c.one, c.k);
+                }
+                W::inv_pass0(x, c);
+                if (live) {
+                    int32_t *orow = out + poly * N;
+#pragma unroll
+                    for (int m = 0; m < 32; m++) orow[tau + m * T] = (int32_t)x[m];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ---- module-LWE matrix-vector product  t_i = INTT(sum_j A_ij o NTT(s_j))  (module_lwe.c:588-748) -------------
 // Same warp-local schedule.  The l transformed vectors stay in shared memory (padded pass-1 layout, unbiased),
 // each output row accumulates its l pointwise products in registers.  HBM traffic is dominated by A
@@ -885,6 +973,31 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
     default: set_error("unsupported n=%d", 1 << logn); return SCGPU_ERR_UNSUPPORTED;
     }
 #undef W32_LAUNCH
+    count_launch();
+    SCGPU_CUDA_CHECK(cudaGetLastError());
+    return SCGPU_OK;
+}
+
+template <class AR>
+int launch_ntt_w32(const W32Const<AR> &c, int logn, int sm_count, int inverse, int32_t *out, const int32_t *a, size_t count,
+                   cudaStream_t st)
+{
+    const int sms = sm_count > 0 ? sm_count : 148;
+#define W32_NTT(L)                                                                                         \
+    {                                                                                                      \
+        const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
+        size_t grid = (size_t)sms * FQ32_MINB;                                                             \
+        if (grid > groups) grid = groups;                                                                  \
+        if (inverse) k_ntt_w32<AR, L, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c);      \
+        else         k_ntt_w32<AR, L, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c);     \
+    }
+    switch (logn) {
+    case 8:  W32_NTT(8); break;
+    case 9:  W32_NTT(9); break;
+    case 10: W32_NTT(10); break;
+    default: set_error("unsupported n=%d", 1 << logn); return SCGPU_ERR_UNSUPPORTED;
+    }
+#undef W32_NTT
     count_launch();
     SCGPU_CUDA_CHECK(cudaGetLastError());
     return SCGPU_OK;

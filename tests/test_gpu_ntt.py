@@ -286,6 +286,34 @@ def test_fused_key_product_matches_triple(q, n, arithmetic):
             assert np.array_equal(out32.cpu().numpy(), exp)
 
 
+@pytest.mark.parametrize("q,n,tw", FAST_PARAMS)
+def test_canonical_single_transforms(q, n, tw, arithmetic):
+    """scgpu_ntt_canonical_batch: forward = normalize_32(fwd_ntt(a)) for every SINT32 input, inverse = inv_ntt(a)
+    for inputs the reference itself handles without overflow; and inverse(forward(a)) == a mod q."""
+    rng = np.random.default_rng(q + 5 * n)
+    w, r = O.tables(q, n, tw)
+    p, _, _ = plan(q, n, tw, O.REFERENCE)
+    P = O.port()
+    for kind, rows in (("uniform", 1), ("uniform", 517), ("small", 33), ("lazy", 64), ("extreme", 65), ("signed", 7)):
+        a = rand_inputs(rng, kind, q, (rows, n))
+        out = torch.full((rows, n), -7, dtype=torch.int32, device=DEV)
+        p.ntt_canonical(out, dev(a))
+        torch.cuda.synchronize()
+        exp = P.ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw, P.ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, a, None, w, r))
+        assert np.array_equal(out.cpu().numpy(), exp), ("fwd", kind, rows)
+        back = torch.empty_like(out)
+        p.ntt_canonical(back, out, inverse=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(back.cpu().numpy(), np.mod(a.astype(np.int64), q).astype(np.int32)), ("round trip", kind)
+    for x in (rng.integers(0, q, size=(129, n)), rng.integers(-q + 1, q, size=(33, n)),
+              rng.integers(-(2**31 // n) + 1, 2**31 // n, size=(65, n))):
+        x = x.astype(np.int32)
+        out = torch.empty((x.shape[0], n), dtype=torch.int32, device=DEV)
+        p.ntt_canonical(out, dev(x), inverse=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), P.ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, x, None, w, r)), "inv"
+
+
 @pytest.mark.parametrize("q,n,tw", [(12289, 512, 16), (7681, 256, 16), (8380417, 256, 32)])
 def test_fused_key_product_with_arbitrary_32bit_keys(q, n, tw, arithmetic):
     """SINT32 keys far outside [0, q) (the out-of-range path of the key load): against the reference composition

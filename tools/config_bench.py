@@ -48,6 +48,8 @@ for n in (512, 1024):
     report("C2 polymul n=%d q=12289" % n, B, timeit(lambda: pl.polymul(o, a, b)), 12 * n)
     key = rnd(q, (n,)).to(torch.int16)
     report("C2 key product n=%d (shared SINT16 key)" % n, B, timeit(lambda: pl.mul_key(o, a, key)), 8 * n)
+    report("C2 canonical fwd NTT n=%d (normalize o fwd_ntt)" % n, B, timeit(lambda: pl.ntt_canonical(o, a)), 8 * n, "ntt")
+    report("C2 canonical inv NTT n=%d" % n, B, timeit(lambda: pl.ntt_canonical(o, a, inverse=True)), 8 * n, "ntt")
     for v, vn in ((sc.REFERENCE, "reference"), (sc.BARRETT, "barrett")):
         pe = sc.NttPlan(n, q, v, w, r)
         report("exact fwd_ntt_32_16 n=%d %s" % (n, vn), B, timeit(lambda: pe.batch(sc.OP_FWD, o, a)), 8 * n, "ntt")
@@ -74,6 +76,8 @@ w, r = O.tables(q, n, 32)
 pl = sc.NttPlan(n, q, sc.REFERENCE, w, r)
 a, b = rnd(q, (1 << 20, n)), rnd(q, (1 << 20, n))
 report("C4 polymul n=256 q=8380417 (Shoup, warp-local)", 1 << 20, timeit(lambda: pl.polymul(o, a, b)), 12 * n)
+report("C4 canonical fwd NTT n=256 q=8380417", 1 << 20, timeit(lambda: pl.ntt_canonical(o, a)), 8 * n, "ntt")
+report("C4 canonical inv NTT n=256 q=8380417", 1 << 20, timeit(lambda: pl.ntt_canonical(o, a, inverse=True)), 8 * n, "ntt")
 for v, vn in ((sc.REFERENCE, "reference"), (sc.FP, "fp")):
     pe = sc.NttPlan(n, q, v, w, r)
     report("C4 exact fwd_ntt_32_32 %s" % vn, 1 << 20, timeit(lambda: pe.batch(sc.OP_FWD, o, a)), 8 * n, "ntt")
