@@ -60,6 +60,7 @@ def lib():
         L.scgpu_prng_words.argtypes = [ctypes.c_int, vp, sz, sz, sz, sz, vp, vp]
         L.scgpu_force_montgomery.argtypes = [ctypes.c_int]
         L.scgpu_ntt_canonical_batch.argtypes = [vp, ctypes.c_int, vp, vp, sz, vp]
+        L.scgpu_ntt_canonical_batch_host.argtypes = [vp, ctypes.c_int, vp, vp, sz]
         L.scgpu_set_fixed_probe_search.argtypes = [ctypes.c_int]
         L.scgpu_set_fixed_probe_search.restype = ctypes.c_int
         L.scgpu_set_fast_arith.argtypes = [ctypes.c_int]
@@ -186,6 +187,12 @@ class NttPlan:
             b_stride = 0 if (b is None or len(b.shape) == 1) else b.shape[-1]
         return _check(lib().scgpu_ntt_batch_host(self.handle, op, _ptr(out), _ptr(a), _ptr(b), b_stride, count,
                                                  int(scalar), _ptr(rc)), "scgpu_ntt_batch_host")
+
+    def ntt_canonical_host(self, out, a, inverse=False, count=None):
+        if count is None:
+            count = a.shape[0]
+        return _check(lib().scgpu_ntt_canonical_batch_host(self.handle, 1 if inverse else 0, _ptr(out), _ptr(a), count),
+                      "scgpu_ntt_canonical_batch_host")
 
     def polymul_host(self, out, a, b, count=None):
         if count is None:

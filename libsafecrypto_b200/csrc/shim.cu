@@ -271,7 +271,7 @@ static int ensure_shared(scgpu_ntt_plan *plan, const void *host, size_t bytes)
     return SCGPU_OK;
 }
 
-// kind: 0 exact op, 1 fused polymul, 2 fused key product (key_bits in `op`)
+// kind: 0 exact op, 1 fused polymul, 2 fused key product (key_bits in `op`), 3 canonical transform (inverse in `op`)
 static int run_host_pipeline(scgpu_ntt_plan *plan, int kind, int op, int32_t *out, const void *a, const void *b,
                              size_t b_stride, size_t count, int32_t scalar, int32_t *rc)
 {
@@ -281,7 +281,7 @@ static int run_host_pipeline(scgpu_ntt_plan *plan, int kind, int op, int32_t *ou
     const size_t n = (size_t)plan->dev.n;
     const size_t ra = n * (kind == 0 ? a_elem_size(op) : 4);
     const size_t belem = kind == 0 ? b_elem_size(op) : (kind == 2 ? (size_t)op / 8 : 4);
-    const bool has_b = kind != 0 || op_needs_b(op);
+    const bool has_b = kind == 3 ? false : (kind != 0 || op_needs_b(op));
     const size_t rb = has_b ? (b_stride ? b_stride : n) * belem : 0;
     int e = ensure_staging(plan, ra, b_stride ? rb : 0, n * 4, count);
     if (e != SCGPU_OK) return e;
@@ -312,6 +312,8 @@ static int run_host_pipeline(scgpu_ntt_plan *plan, int kind, int op, int32_t *ou
             status = launch_exact(plan->dev, g, st);
         } else if (kind == 1) {
             status = launch_polymul(plan->dev, plan->d_o[s], plan->d_a[s], static_cast<const int32_t *>(db), b_stride, cnt, st);
+        } else if (kind == 3) {
+            status = scgpu_ntt_canonical_batch(plan, op, plan->d_o[s], plan->d_a[s], cnt, st);
         } else {
             status = launch_mul_key(plan->dev, plan->d_o[s], plan->d_a[s], db, op, b_stride, cnt, st);
         }
@@ -336,6 +338,13 @@ extern "C" int scgpu_polymul_batch_host(const scgpu_ntt_plan_t *plan, int32_t *o
 {
     if (!plan || !out || !a || !b) { set_error("polymul_batch_host: null argument"); return SCGPU_ERR_ARG; }
     return run_host_pipeline(const_cast<scgpu_ntt_plan *>(plan), 1, 0, out, a, b, b_stride, count, 0, nullptr);
+}
+
+extern "C" int scgpu_ntt_canonical_batch_host(const scgpu_ntt_plan_t *plan, int inverse, int32_t *out, const int32_t *a,
+                                              size_t count)
+{
+    if (!plan || !out || !a) { set_error("ntt_canonical_batch_host: null argument"); return SCGPU_ERR_ARG; }
+    return run_host_pipeline(const_cast<scgpu_ntt_plan *>(plan), 3, inverse ? 1 : 0, out, a, nullptr, 0, count, 0, nullptr);
 }
 
 // =======================================================================================================

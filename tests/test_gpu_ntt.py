@@ -545,6 +545,13 @@ def test_host_pipeline_and_ragged_counts():
         if rows:
             exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a, b, w, r)
             assert np.array_equal(out, exp)
+    a = rand_inputs(rng, "uniform", q, (20000, n))
+    fwd, back = np.empty_like(a), np.empty_like(a)
+    p.ntt_canonical_host(fwd, a)
+    p.ntt_canonical_host(back, fwd, inverse=True)
+    assert np.array_equal(back, a)
+    assert np.array_equal(fwd[:16], O.port().ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw,
+                                                      O.port().ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, a[:16], None, w, r)))
     a = rand_inputs(rng, "lazy", q, (9000, n))
     out = np.empty_like(a)
     pf, _, _ = plan(q, n, tw, O.FP)
