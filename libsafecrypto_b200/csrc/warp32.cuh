@@ -477,27 +477,63 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
 //   INV = true :  out = inv_ntt_32_16/32(a)                 a in the reference's NTT-domain order, any SINT32
 // Both results are canonical in the reference, so the arithmetic inside is free (as for the fused products); the
 // variant-exact kernels of ntt_exact.cu remain the way to get fwd_ntt's lazily reduced representative itself.
-template <class AR, int LOGN, bool INV>
+// TMA = true: the next polynomial's row is bulk-copied into a staging row while the current one is transformed
+// (16-byte aligned rows); false: plain loads.
+template <class AR, int LOGN, bool INV, bool TMA>
 __global__ void __launch_bounds__(kThreads32, FQ32_MINB)
 k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count, const __grid_constant__ W32Const<AR> c)
 {
     using C = Cfg32<LOGN>;
     using W = W32<AR>;
     constexpr int N = C::N, T = C::T, SUB = C::SUB;
+    constexpr int AROW = N + T;                                      // staging row stride: T banks between polynomials
+    constexpr uint32_t ROW_BYTES = (uint32_t)N * 4u;
     __shared__ __align__(16) int32_t tiles[C::POLYS][C::TS];
+    __shared__ __align__(16) int32_t stage_rows[TMA ? C::POLYS : 1][AROW];
+    __shared__ __align__(8) uint64_t bars[kThreads32 / 32];
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x / 32;
     const int tau = lane % T;
-    const int slot = (threadIdx.x / 32) * C::PW + lane / T;
+    const int slot = warp * C::PW + lane / T;
     int32_t *tile = tiles[slot];
+    const int32_t *stage = stage_rows[TMA ? slot : 0];
+    const int taurev = (int)(__brev((unsigned)tau) >> (32 - (LOGN - 5)));
+    uint32_t parity = 0;
+    auto fetch = [&](size_t nbase) {                                 // lane 0: rows of the warp's PW polynomials
+        mbar_expect_tx(&bars[warp], ROW_BYTES * C::PW);
+        for (int p = 0; p < C::PW; p++) {
+            size_t row = nbase + (size_t)warp * C::PW + p;
+            if (row >= count) row = 0;
+            bulk_g2s(stage_rows[TMA ? warp * C::PW + p : 0], a + row * N, ROW_BYTES, &bars[warp]);
+        }
+    };
+    const size_t first = (size_t)blockIdx.x * C::POLYS;
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(&bars[warp], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0 && first < count) fetch(first);
+    }
 
-    for (size_t base = (size_t)blockIdx.x * C::POLYS; base < count; base += (size_t)gridDim.x * C::POLYS) {
+    for (size_t base = first; base < count; base += (size_t)gridDim.x * C::POLYS) {
         const size_t poly = base + slot;
         const bool live = poly < count;
         const size_t prow = live ? poly : 0;
+        const size_t nbase = base + (size_t)gridDim.x * C::POLYS;
         if (!INV) {
             {
                 u32 x[32];
-                W::template load_operand<LOGN>(x, a + prow * N, tau, c);
+                if (TMA) {
+                    mbar_wait(&bars[warp], parity); parity ^= 1u;
+                    W::template load_operand_staged<LOGN>(x, stage, tau, c);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && nbase < count) fetch(nbase);    // the staging row is in registers
+                } else {
+                    W::template load_operand<LOGN>(x, a + prow * N, tau, c);
+                }
                 W::fwd_pass0(x, c);
                 store_pass0<LOGN>(tile, x, tau);
             }
@@ -519,15 +555,25 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
             }
             __syncwarp();
         } else {
+            if (TMA) { mbar_wait(&bars[warp], parity); parity ^= 1u; }
 #pragma unroll 1
             for (int h = 0; h < C::NSUB; h++) {
-                const int32_t *irow = a + prow * N + ntt_index<LOGN>(tau, SUB * h);
                 int32_t v[SUB];
                 bool wide = false;
+                if (TMA) {
+                    const int32_t *irow = stage + ntt_index<LOGN>(tau, SUB * h);
 #pragma unroll
-                for (int i = 0; i < SUB; i++) {
-                    v[i] = __ldg(irow + (int)((__brev((unsigned)i) >> 27) << (LOGN - 5)));
-                    wide |= W::out_of_range(v[i], c);
+                    for (int i = 0; i < SUB; i++) {
+                        v[i] = irow[(int)((__brev((unsigned)i) >> 27) << (LOGN - 5))];
+                        wide |= W::out_of_range(v[i], c);
+                    }
+                } else {
+                    const int32_t *irow = a + prow * N + ntt_index<LOGN>(tau, SUB * h);
+#pragma unroll
+                    for (int i = 0; i < SUB; i++) {
+                        v[i] = __ldg(irow + (int)((__brev((unsigned)i) >> 27) << (LOGN - 5)));
+                        wide |= W::out_of_range(v[i], c);
+                    }
                 }
                 if (__any_sync(0xFFFFFFFFu, wide)) {
 #pragma unroll
@@ -538,6 +584,11 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
                 for (int i = 0; i < SUB; i++) x[i] = AR::red(AR::enc(v[i]), c.one, c.k);   // the bounds assume reduced input
                 W::template inv_stages1<LOGN, LOGN - 1>(x, c, tau, h);
                 store_sub<SUB>(tile + 36 * tau + SUB * h, x);
+            }
+            if (TMA) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && nbase < count) fetch(nbase);        // every sub-chunk has been read
             }
             W::template chunk_stage5<LOGN, true>(tile + 36 * tau, c, tau);
             __syncwarp();
@@ -558,6 +609,7 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
             __syncwarp();
         }
     }
+    (void)taurev;
 }
 
 // ---- module-LWE matrix-vector product  t_i = INTT(sum_j A_ij o NTT(s_j))  (module_lwe.c:588-748) -------------
@@ -983,13 +1035,19 @@ int launch_ntt_w32(const W32Const<AR> &c, int logn, int sm_count, int inverse, i
                    cudaStream_t st)
 {
     const int sms = sm_count > 0 ? sm_count : 148;
+    const bool tma = ((uintptr_t)a % 16) == 0 && tma_allowed();
 #define W32_NTT(L)                                                                                         \
     {                                                                                                      \
         const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
         size_t grid = (size_t)sms * FQ32_MINB;                                                             \
         if (grid > groups) grid = groups;                                                                  \
-        if (inverse) k_ntt_w32<AR, L, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c);      \
-        else         k_ntt_w32<AR, L, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c);     \
+        if (tma) {                                                                                         \
+            if (inverse) k_ntt_w32<AR, L, true, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c);   \
+            else         k_ntt_w32<AR, L, false, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c);  \
+        } else {                                                                                           \
+            if (inverse) k_ntt_w32<AR, L, true, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c);  \
+            else         k_ntt_w32<AR, L, false, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c); \
+        }                                                                                                  \
     }
     switch (logn) {
     case 8:  W32_NTT(8); break;
