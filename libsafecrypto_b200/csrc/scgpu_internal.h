@@ -10,6 +10,7 @@ namespace scgpu {
 
 void set_error(const char *fmt, ...);
 void count_launch();
+int next_work_counter(cudaStream_t stream, unsigned long long **ctr);   // nullptr: static stride
 
 #define SCGPU_CUDA_CHECK(expr)                                                              \
     do {                                                                                    \

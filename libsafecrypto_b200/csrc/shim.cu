@@ -29,6 +29,33 @@ void set_error(const char *fmt, ...)
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// Work counters of the persistent warp-local kernels (warp32.cuh: claim_next).  A ring of slots per device; a launch
+// takes the next slot and zeroes it on its own stream, so launches in flight on different streams never share one
+// (the ring is far longer than any queue of launches).  *ctr stays nullptr with SCGPU_STATIC_SCHED=1.
+int next_work_counter(cudaStream_t st, unsigned long long **ctr)
+{
+    constexpr int kMaxDev = 64;
+    constexpr unsigned kSlots = 8192;
+    static std::mutex mu;
+    static unsigned long long *pool[kMaxDev] = {};
+    static unsigned next[kMaxDev] = {};
+    *ctr = nullptr;
+    const char *env = getenv("SCGPU_STATIC_SCHED");
+    if (env && atoi(env) != 0) return SCGPU_OK;
+    int dev = 0;
+    SCGPU_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDev) return SCGPU_OK;
+    unsigned long long *slot;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pool[dev]) SCGPU_CUDA_CHECK(cudaMalloc(&pool[dev], sizeof(unsigned long long) * kSlots));
+        slot = pool[dev] + (next[dev]++ % kSlots);
+    }
+    SCGPU_CUDA_CHECK(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), st));
+    *ctr = slot;
+    return SCGPU_OK;
+}
+
 }  // namespace scgpu
 
 using namespace scgpu;

@@ -108,6 +108,30 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- dynamic work distribution -------------------------------------------------------------------------------
+// The grids are persistent (one-warp CTAs, FQ32_MINB per SM).  With a static stride every warp owns the same number
+// of groups, but the warps of a scheduler do not advance at the same rate: ncu showed 3.9 of 5 resident warps alive
+// on average (profiles/polymul_r04_ncu.json), i.e. the favoured warps retire early and the last ones run alone.
+// So the groups after the first grid-full are claimed from a global counter (zeroed by the launcher): lane 0 claims
+// the NEXT group at the top of an iteration, which is when its rows are put in flight; the other lanes learn the
+// index at the end of the iteration.  ctr == nullptr keeps the static stride (SCGPU_STATIC_SCHED=1).
+static_assert(kThreads32 == 32, "the work counter is claimed per CTA: one warp per CTA");
+template <int POLYS>
+__device__ __forceinline__ size_t claim_next(unsigned long long *ctr, size_t base, int lane)
+{
+    if (ctr == nullptr) return base + (size_t)gridDim.x * POLYS;
+    unsigned long long g = 0;
+    if (lane == 0) g = atomicAdd(ctr, 1ull) + gridDim.x;
+    return (size_t)g * POLYS;                               // meaningful on lane 0 only
+}
+__device__ __forceinline__ size_t share_next(unsigned long long *ctr, size_t nbase)
+{
+    if (ctr == nullptr) return nbase;
+    const unsigned lo = __shfl_sync(0xFFFFFFFFu, (unsigned)nbase, 0);
+    const unsigned hi = __shfl_sync(0xFFFFFFFFu, (unsigned)((unsigned long long)nbase >> 32), 0);
+    return (size_t)(((unsigned long long)hi << 32) | lo);
+}
+
 template <int LOGN>
 __device__ __forceinline__ void store_pass0(int32_t *tile, const u32 (&x)[32], int tau)
 {
@@ -329,7 +353,7 @@ static __device__ __forceinline__ void load_operand_staged(u32 (&x)[32], const i
 template <class AR, int LOGN, int MODE, bool TMA>
 __global__ void __launch_bounds__(kThreads32, FQ32_MINB)
 k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const void *__restrict__ bsrc,
-               size_t b_stride, size_t count, const __grid_constant__ W32Const<AR> c)
+               size_t b_stride, size_t count, unsigned long long *ctr, const __grid_constant__ W32Const<AR> c)
 {
     using C = Cfg32<LOGN>;
     using W = W32<AR>;
@@ -371,10 +395,11 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
         }
     }
 
-    for (size_t base = first; base < count; base += (size_t)gridDim.x * C::POLYS) {
+    for (size_t base = first; base < count;) {
         const size_t poly = base + slot;
         const bool live = poly < count;
         const size_t prow = live ? poly : 0;
+        const size_t nbase = claim_next<C::POLYS>(ctr, base, lane);
         // rolled loops (operand, sub-chunk): the fully unrolled body was 60 KB of SASS and spent 2 of every
         // 7 stall cycles waiting for instructions (profiles/polymul_r02c_*); the L1.5 I-cache holds 32 KB
 #pragma unroll 1
@@ -437,7 +462,6 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
             store_sub<SUB>(pa, xa);
         }
         W::template chunk_stage5<LOGN, true>(ta + 36 * tau, c, tau);
-        const size_t nbase = base + (size_t)gridDim.x * C::POLYS;
         if (TMA) fence_proxy_async();
         __syncwarp();
         // tb is free from here on: the next product's a rows go there
@@ -468,6 +492,7 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
         } else {
             __syncwarp();
         }
+        base = share_next(ctr, nbase);
     }
 }
 
@@ -481,7 +506,8 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
 // (16-byte aligned rows); false: plain loads.
 template <class AR, int LOGN, bool INV, bool TMA>
 __global__ void __launch_bounds__(kThreads32, FQ32_MINB)
-k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count, const __grid_constant__ W32Const<AR> c)
+k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count, unsigned long long *ctr,
+          const __grid_constant__ W32Const<AR> c)
 {
     using C = Cfg32<LOGN>;
     using W = W32<AR>;
@@ -517,11 +543,11 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
         if (lane == 0 && first < count) fetch(first);
     }
 
-    for (size_t base = first; base < count; base += (size_t)gridDim.x * C::POLYS) {
+    for (size_t base = first; base < count;) {
         const size_t poly = base + slot;
         const bool live = poly < count;
         const size_t prow = live ? poly : 0;
-        const size_t nbase = base + (size_t)gridDim.x * C::POLYS;
+        const size_t nbase = claim_next<C::POLYS>(ctr, base, lane);
         if (!INV) {
             {
                 u32 x[32];
@@ -608,6 +634,7 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
             }
             __syncwarp();
         }
+        base = share_next(ctr, nbase);
     }
     (void)taurev;
 }
@@ -627,7 +654,7 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
 template <class AR, int LOGN, bool TMA>
 __global__ void __launch_bounds__(kThreads32)
 k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t *__restrict__ s,
-              int k, int l, size_t count, const __grid_constant__ W32Const<AR> c)
+              int k, int l, size_t count, unsigned long long *ctr, const __grid_constant__ W32Const<AR> c)
 {
     using C = Cfg32<LOGN>;
     using W = W32<AR>;
@@ -675,11 +702,11 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
         if (lane == 0 && first < count) { fetch_s(first); fetch_a(first, 0); }
     }
 
-    for (size_t base = first; base < count; base += (size_t)gridDim.x * C::POLYS) {
+    for (size_t base = first; base < count;) {
         const size_t inst = base + slot;
         const bool live = inst < count;
         const size_t irow = live ? inst : 0;
-        const size_t nbase = base + (size_t)gridDim.x * C::POLYS;
+        const size_t nbase = claim_next<C::POLYS>(ctr, base, lane);
         if (TMA) { mbar_wait(&bars[warp][0], par_s); par_s ^= 1u; }
 #pragma unroll 1
         for (int j = 0; j < l; j++) {
@@ -787,6 +814,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
             }
             __syncwarp();
         }
+        base = share_next(ctr, nbase);
     }
 }
 
@@ -800,7 +828,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
 template <class AR, int LOGN, bool TMA>
 __global__ void __launch_bounds__(kThreads32, 16)        // 128 registers: 4 warps per scheduler fit (140 allowed 3)
 k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t *__restrict__ s,
-               int k, int l, size_t count, const __grid_constant__ W32Const<AR> c)
+               int k, int l, size_t count, unsigned long long *ctr, const __grid_constant__ W32Const<AR> c)
 {
     using C = Cfg32<LOGN>;
     using W = W32<AR>;
@@ -842,11 +870,11 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
         if (lane == 0 && first < count) fetch(first, 0);
     }
 
-    for (size_t base = first; base < count; base += (size_t)gridDim.x * C::POLYS) {
+    for (size_t base = first; base < count;) {
         const size_t inst = base + slot;
         const bool live = inst < count;
         const size_t irow = live ? inst : 0;
-        const size_t nbase = base + (size_t)gridDim.x * C::POLYS;
+        const size_t nbase = claim_next<C::POLYS>(ctr, base, lane);
         int r = 0;                                                   // row of the sequence being consumed
         // after the staging row has been read into registers: next row of this instance, or row 0 of the next
         auto advance = [&]() {
@@ -959,6 +987,7 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
             }
             __syncwarp();
         }
+        base = share_next(ctr, nbase);
     }
 }
 
@@ -1003,19 +1032,21 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
     // bulk copies need 16-byte aligned rows; the second operand is only staged in FQ_POLYMUL mode
     bool tma = ((uintptr_t)a % 16) == 0 && tma_allowed();
     if (mode == FQ_POLYMUL) tma = tma && ((uintptr_t)b % 16) == 0 && (b_stride % 4) == 0;
+    unsigned long long *ctr = nullptr;               // work counter, only when the batch exceeds one grid-full
 #define W32_LAUNCH(L)                                                                                      \
     {                                                                                                      \
         const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
         size_t grid = (size_t)sms * FQ32_MINB;                                                             \
         if (grid > groups) grid = groups;                                                                  \
+        if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }     \
         if (tma) {                                                                                         \
-            if (mode == FQ_POLYMUL)    k_polymul_w32<AR, L, FQ_POLYMUL, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c); \
-            else if (mode == FQ_KEY16) k_polymul_w32<AR, L, FQ_KEY16, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
-            else                       k_polymul_w32<AR, L, FQ_KEY32, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
+            if (mode == FQ_POLYMUL)    k_polymul_w32<AR, L, FQ_POLYMUL, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c); \
+            else if (mode == FQ_KEY16) k_polymul_w32<AR, L, FQ_KEY16, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c);   \
+            else                       k_polymul_w32<AR, L, FQ_KEY32, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c);   \
         } else {                                                                                           \
-            if (mode == FQ_POLYMUL)    k_polymul_w32<AR, L, FQ_POLYMUL, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c); \
-            else if (mode == FQ_KEY16) k_polymul_w32<AR, L, FQ_KEY16, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
-            else                       k_polymul_w32<AR, L, FQ_KEY32, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, c);   \
+            if (mode == FQ_POLYMUL)    k_polymul_w32<AR, L, FQ_POLYMUL, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c); \
+            else if (mode == FQ_KEY16) k_polymul_w32<AR, L, FQ_KEY16, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c);   \
+            else                       k_polymul_w32<AR, L, FQ_KEY32, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c);   \
         }                                                                                                  \
     }
     switch (logn) {
@@ -1036,17 +1067,19 @@ int launch_ntt_w32(const W32Const<AR> &c, int logn, int sm_count, int inverse, i
 {
     const int sms = sm_count > 0 ? sm_count : 148;
     const bool tma = ((uintptr_t)a % 16) == 0 && tma_allowed();
+    unsigned long long *ctr = nullptr;
 #define W32_NTT(L)                                                                                         \
     {                                                                                                      \
         const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
         size_t grid = (size_t)sms * FQ32_MINB;                                                             \
         if (grid > groups) grid = groups;                                                                  \
+        if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }     \
         if (tma) {                                                                                         \
-            if (inverse) k_ntt_w32<AR, L, true, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c);   \
-            else         k_ntt_w32<AR, L, false, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c);  \
+            if (inverse) k_ntt_w32<AR, L, true, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);   \
+            else         k_ntt_w32<AR, L, false, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);  \
         } else {                                                                                           \
-            if (inverse) k_ntt_w32<AR, L, true, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c);  \
-            else         k_ntt_w32<AR, L, false, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, c); \
+            if (inverse) k_ntt_w32<AR, L, true, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);  \
+            else         k_ntt_w32<AR, L, false, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c); \
         }                                                                                                  \
     }
     switch (logn) {
@@ -1070,6 +1103,7 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
     const bool tma = ((uintptr_t)A % 16) == 0 && ((uintptr_t)s % 16) == 0 && tma_allowed();
     const int sms = sm_count > 0 ? sm_count : 148;
     const size_t groups = (count + C::POLYS - 1) / C::POLYS;
+    unsigned long long *ctr = nullptr;
     // 16-bit stash: the reduced transform values must fit an int16 (|x| <= 0.55 q + 2)
     const char *no16 = getenv("SCGPU_MATVEC_STASH32");
     // measured (Kyber, q = 7681): k = l = 3 / 4 gain 16 % / 3 % from the higher occupancy; k = l = 2 loses 19 %
@@ -1083,7 +1117,8 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
         if (per_sm < 1) per_sm = 1;
         size_t grid = (size_t)sms * per_sm;
         if (grid > groups) grid = groups;
-        k_matvec16_w32<AR, 8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, c);
+        if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }
+        k_matvec16_w32<AR, 8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
         count_launch();
         SCGPU_CUDA_CHECK(cudaGetLastError());
         return SCGPU_OK;
@@ -1098,8 +1133,9 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
     if (per_sm < 1) per_sm = 1;
     size_t grid = (size_t)sms * per_sm;
     if (grid > groups) grid = groups;
-    if (tma) k_matvec_w32<AR, 8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, c);
-    else     k_matvec_w32<AR, 8, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, c);
+    if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }
+    if (tma) k_matvec_w32<AR, 8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+    else     k_matvec_w32<AR, 8, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
     count_launch();
     SCGPU_CUDA_CHECK(cudaGetLastError());
     return SCGPU_OK;
