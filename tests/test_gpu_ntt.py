@@ -562,3 +562,72 @@ def test_host_pipeline_and_ragged_counts():
     a[17, 3] = 0
     pf.batch_host(O.OP_INVERT, out, a, rc=rcs)
     assert rcs[17] == 1 and rcs.sum() == 1
+
+
+@pytest.mark.parametrize("q,n,tw", [(12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417, 256, 32)])
+def test_work_counter_batches_beyond_one_grid(q, n, tw):
+    """Batches larger than one grid-full take their groups from the global work counter (warp32.cuh: claim_next):
+    whole output against the oracle, against the static stride (SCGPU_STATIC_SCHED=1), ragged count, and two
+    launches in flight on different streams (different counter slots)."""
+    rng = np.random.default_rng(n + q)
+    rows = 30011
+    w, r = O.tables(q, n, tw)
+    p, _, _ = plan(q, n, tw, O.REFERENCE)
+    P = O.port()
+    a, b = rand_inputs(rng, "uniform", q, (rows, n)), rand_inputs(rng, "signed", q, (rows, n))
+    da, db = dev(a), dev(b)
+    out = torch.full((rows, n), -7, dtype=torch.int32, device=DEV)
+    p.polymul(out, da, db)
+    torch.cuda.synchronize()
+    exp = P.ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a, b, w, r)
+    assert np.array_equal(out.cpu().numpy(), exp)
+    fwd = torch.full((rows, n), -7, dtype=torch.int32, device=DEV)
+    p.ntt_canonical(fwd, da)
+    inv = torch.full((rows, n), -7, dtype=torch.int32, device=DEV)
+    p.ntt_canonical(inv, fwd, inverse=True)
+    torch.cuda.synchronize()
+    assert torch.equal(inv, da)
+    exact = torch.full((rows, n), -7, dtype=torch.int32, device=DEV)
+    p.batch(O.OP_FWD, exact, da)
+    os.environ["SCGPU_STATIC_SCHED"] = "1"
+    try:
+        out_s, fwd_s, exact_s = torch.empty_like(out), torch.empty_like(out), torch.empty_like(out)
+        p.polymul(out_s, da, db)
+        p.ntt_canonical(fwd_s, da)
+        p.batch(O.OP_FWD, exact_s, da)
+        torch.cuda.synchronize()
+    finally:
+        os.environ["SCGPU_STATIC_SCHED"] = "0"
+    assert torch.equal(out_s, out) and torch.equal(fwd_s, fwd) and torch.equal(exact_s, exact)
+    # two launches in flight at once
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    o1, o2 = torch.full_like(out, -7), torch.full_like(out, -7)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        p.polymul(o1, da, db, stream=s1)
+        p.polymul(o2, db, da, stream=s2)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, out) and torch.equal(o2, out)
+    if n == 256:
+        k, l = 3, 2
+        inst = 9001
+        A = rand_inputs(rng, "uniform", q, (inst, k * l, n))
+        s = rng.integers(-4, 5, size=(inst, l, n)).astype(np.int32)
+        om = torch.full((inst, k, n), -7, dtype=torch.int32, device=DEV)
+        p.matvec(om, dev(A), dev(s), k, l)
+        os.environ["SCGPU_STATIC_SCHED"] = "1"
+        try:
+            om_s = torch.empty_like(om)
+            p.matvec(om_s, dev(A), dev(s), k, l)
+            torch.cuda.synchronize()
+        finally:
+            os.environ["SCGPU_STATIC_SCHED"] = "0"
+        assert torch.equal(om, om_s)
+        sh = P.ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, s[:64].reshape(-1, n), None, w, r).reshape(64, l, n)
+        for i in range(k):
+            acc = np.zeros((64, n), dtype=np.int64)
+            for j in range(l):
+                acc += P.ntt_batch(O.REFERENCE, O.OP_PW, n, q, tw, A[:64, i * l + j], sh[:, j])
+            t = P.ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw, np.mod(acc, q).astype(np.int32))
+            t = P.ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, t, None, w, r)
+            assert np.array_equal(om[:64, i].cpu().numpy(), P.ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw, t))
