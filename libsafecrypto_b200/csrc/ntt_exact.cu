@@ -135,13 +135,7 @@ k_transform(ExactArgs g)
     if (g.r) { sr[2 * t] = g.r[2 * t]; sr[2 * t + 1] = g.r[2 * t + 1]; }
     __syncthreads();
 
-    // rows beyond the first grid-full come from a global work counter (see warp32.cuh: claim_next): thread 0 claims the
-    // next row while the current one is transformed; two slots, so that a thread still reading the last claim never
-    // races with the next one
-    __shared__ unsigned long long s_next[2];
-    int it = 0;
-    for (size_t row = blockIdx.x; row < g.count; it ^= 1) {
-        if (g.ctr != nullptr && t == 0) s_next[it] = atomicAdd(g.ctr, 1ull) + gridDim.x;
+    for (size_t row = blockIdx.x; row < g.count; row += gridDim.x) {
         const int32_t *a = static_cast<const int32_t *>(g.a) + row * N;
         int32_t *out = g.out + row * N;
         switch (g.op) {
@@ -203,7 +197,6 @@ k_transform(ExactArgs g)
         default: break;
         }
         __syncthreads();
-        row = g.ctr != nullptr ? (size_t)s_next[it] : row + gridDim.x;
     }
 }
 
@@ -339,10 +332,8 @@ k_rowop(ExactArgs g, int n)
 }
 
 template <int V>
-int launch_v(const NttPlanDev &plan, const ExactArgs &g_in, cudaStream_t st)
+int launch_v(const NttPlanDev &plan, const ExactArgs &g, cudaStream_t st)
 {
-    ExactArgs g = g_in;
-    g.ctr = nullptr;
     const int n = plan.n;
     const int sms = plan.sm_count > 0 ? plan.sm_count : 148;
     switch (g.op) {
@@ -352,7 +343,6 @@ int launch_v(const NttPlanDev &plan, const ExactArgs &g_in, cudaStream_t st)
         const int per_sm = 2048 / (n / 2);
         size_t grid = (size_t)sms * per_sm;
         if (grid > g.count) grid = g.count;
-        if (g.count > grid) { const int e = next_work_counter(st, &g.ctr); if (e != SCGPU_OK) return e; }
         if (plan.logn == 8)       k_transform<V, 8><<<(unsigned)grid, 128, 0, st>>>(g);
         else if (plan.logn == 9)  k_transform<V, 9><<<(unsigned)grid, 256, 0, st>>>(g);
         else if (plan.logn == 10) k_transform<V, 10><<<(unsigned)grid, 512, 0, st>>>(g);

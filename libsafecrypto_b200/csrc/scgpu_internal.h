@@ -72,7 +72,6 @@ struct ExactArgs {
     int op;
     int tw_bits;
     int32_t scalar;
-    unsigned long long *ctr;     // work counter of the persistent transform kernel (set by the launcher)
 };
 
 int launch_exact(const NttPlanDev &plan, const ExactArgs &args, cudaStream_t stream);

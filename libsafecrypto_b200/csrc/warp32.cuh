@@ -116,20 +116,17 @@ __device__ __forceinline__ void fence_proxy_async()
 // the NEXT group at the top of an iteration, which is when its rows are put in flight; the other lanes learn the
 // index at the end of the iteration.  ctr == nullptr keeps the static stride (SCGPU_STATIC_SCHED=1).
 static_assert(kThreads32 == 32, "the work counter is claimed per CTA: one warp per CTA");
-template <int POLYS>
-__device__ __forceinline__ size_t claim_next(unsigned long long *ctr, size_t base, int lane)
+// Group indices are 32-bit (one register across the iteration; the launchers refuse batches beyond 2^32 groups).
+__device__ __forceinline__ unsigned claim_next(unsigned long long *ctr, unsigned g, int lane)
 {
-    if (ctr == nullptr) return base + (size_t)gridDim.x * POLYS;
-    unsigned long long g = 0;
-    if (lane == 0) g = atomicAdd(ctr, 1ull) + gridDim.x;
-    return (size_t)g * POLYS;                               // meaningful on lane 0 only
+    if (ctr == nullptr) return g + gridDim.x;
+    unsigned nxt = 0;
+    if (lane == 0) nxt = atomicAdd(reinterpret_cast<unsigned *>(ctr), 1u) + gridDim.x;
+    return nxt;                                             // meaningful on lane 0 only
 }
-__device__ __forceinline__ size_t share_next(unsigned long long *ctr, size_t nbase)
+__device__ __forceinline__ unsigned share_next(unsigned long long *ctr, unsigned gnext)
 {
-    if (ctr == nullptr) return nbase;
-    const unsigned lo = __shfl_sync(0xFFFFFFFFu, (unsigned)nbase, 0);
-    const unsigned hi = __shfl_sync(0xFFFFFFFFu, (unsigned)((unsigned long long)nbase >> 32), 0);
-    return (size_t)(((unsigned long long)hi << 32) | lo);
+    return ctr == nullptr ? gnext : __shfl_sync(0xFFFFFFFFu, gnext, 0);
 }
 
 template <int LOGN>
@@ -395,11 +392,13 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
         }
     }
 
-    for (size_t base = first; base < count;) {
+    for (unsigned g = blockIdx.x; (size_t)g * C::POLYS < count;) {
+        const size_t base = (size_t)g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;
         const size_t prow = live ? poly : 0;
-        const size_t nbase = claim_next<C::POLYS>(ctr, base, lane);
+        const unsigned gnext = claim_next(ctr, g, lane);
+        const size_t nbase = (size_t)gnext * C::POLYS;
         // rolled loops (operand, sub-chunk): the fully unrolled body was 60 KB of SASS and spent 2 of every
         // 7 stall cycles waiting for instructions (profiles/polymul_r02c_*); the L1.5 I-cache holds 32 KB
 #pragma unroll 1
@@ -492,7 +491,7 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
         } else {
             __syncwarp();
         }
-        base = share_next(ctr, nbase);
+        g = share_next(ctr, gnext);
     }
 }
 
@@ -543,11 +542,13 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
         if (lane == 0 && first < count) fetch(first);
     }
 
-    for (size_t base = first; base < count;) {
+    for (unsigned g = blockIdx.x; (size_t)g * C::POLYS < count;) {
+        const size_t base = (size_t)g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;
         const size_t prow = live ? poly : 0;
-        const size_t nbase = claim_next<C::POLYS>(ctr, base, lane);
+        const unsigned gnext = claim_next(ctr, g, lane);
+        const size_t nbase = (size_t)gnext * C::POLYS;
         if (!INV) {
             {
                 u32 x[32];
@@ -634,7 +635,7 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
             }
             __syncwarp();
         }
-        base = share_next(ctr, nbase);
+        g = share_next(ctr, gnext);
     }
     (void)taurev;
 }
@@ -702,11 +703,13 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
         if (lane == 0 && first < count) { fetch_s(first); fetch_a(first, 0); }
     }
 
-    for (size_t base = first; base < count;) {
+    for (unsigned g = blockIdx.x; (size_t)g * C::POLYS < count;) {
+        const size_t base = (size_t)g * C::POLYS;
         const size_t inst = base + slot;
         const bool live = inst < count;
         const size_t irow = live ? inst : 0;
-        const size_t nbase = claim_next<C::POLYS>(ctr, base, lane);
+        const unsigned gnext = claim_next(ctr, g, lane);
+        const size_t nbase = (size_t)gnext * C::POLYS;
         if (TMA) { mbar_wait(&bars[warp][0], par_s); par_s ^= 1u; }
 #pragma unroll 1
         for (int j = 0; j < l; j++) {
@@ -814,7 +817,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
             }
             __syncwarp();
         }
-        base = share_next(ctr, nbase);
+        g = share_next(ctr, gnext);
     }
 }
 
@@ -838,6 +841,10 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
     constexpr uint32_t ROW_BYTES = (uint32_t)N * 4u;
     extern __shared__ __align__(16) int32_t dyn_tiles[];             // [POLYS][TS] | [POLYS][AROW] | [l][POLYS][SROW]
     __shared__ __align__(8) uint64_t bars[kThreads32 / 32];
+    // this kernel sits at its register cap (128): the claimed group index lives in shared memory, and the claim is
+    // made where it is first needed (when the last row of an instance has been consumed) instead of a whole
+    // iteration ahead -- one exposed atomic per instance group (~1 % of its time)
+    __shared__ unsigned s_gnext[kThreads32 / 32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x / 32;
     const int tau = lane % T;
@@ -870,11 +877,11 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
         if (lane == 0 && first < count) fetch(first, 0);
     }
 
-    for (size_t base = first; base < count;) {
+    for (unsigned g = blockIdx.x; (size_t)g * C::POLYS < count;) {
+        const size_t base = (size_t)g * C::POLYS;
         const size_t inst = base + slot;
         const bool live = inst < count;
         const size_t irow = live ? inst : 0;
-        const size_t nbase = claim_next<C::POLYS>(ctr, base, lane);
         int r = 0;                                                   // row of the sequence being consumed
         // after the staging row has been read into registers: next row of this instance, or row 0 of the next
         auto advance = [&]() {
@@ -884,7 +891,12 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
                 r++;
                 if (lane == 0) {
                     if (r < rows_per_inst) fetch(base, r);
-                    else if (nbase < count) fetch(nbase, 0);
+                    else {
+                        const unsigned gnext = claim_next(ctr, g, 0);
+                        s_gnext[warp] = gnext;
+                        const size_t nbase = (size_t)gnext * C::POLYS;
+                        if (nbase < count) fetch(nbase, 0);
+                    }
                 }
             }
         };
@@ -987,7 +999,9 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
             }
             __syncwarp();
         }
-        base = share_next(ctr, nbase);
+        if (!TMA && lane == 0) s_gnext[warp] = claim_next(ctr, g, 0);
+        __syncwarp();
+        g = *reinterpret_cast<volatile unsigned *>(&s_gnext[warp]);
     }
 }
 
@@ -1018,6 +1032,9 @@ inline void pack_pass1(int logn, const Vec &zf, const Vec &zi, Get get, int32_t 
     }
 }
 
+// group indices are 32-bit in the kernels (claim_next)
+inline bool groups_fit(size_t groups, size_t grid) { return groups + grid < 0xFFFFFFFFull; }
+
 inline bool tma_allowed()
 {
     const char *no_tma = getenv("SCGPU_NO_TMA");
@@ -1038,6 +1055,7 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
         const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
         size_t grid = (size_t)sms * FQ32_MINB;                                                             \
         if (grid > groups) grid = groups;                                                                  \
+        if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; } \
         if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }     \
         if (tma) {                                                                                         \
             if (mode == FQ_POLYMUL)    k_polymul_w32<AR, L, FQ_POLYMUL, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c); \
@@ -1073,6 +1091,7 @@ int launch_ntt_w32(const W32Const<AR> &c, int logn, int sm_count, int inverse, i
         const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
         size_t grid = (size_t)sms * FQ32_MINB;                                                             \
         if (grid > groups) grid = groups;                                                                  \
+        if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; } \
         if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }     \
         if (tma) {                                                                                         \
             if (inverse) k_ntt_w32<AR, L, true, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);   \
@@ -1117,6 +1136,7 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
         if (per_sm < 1) per_sm = 1;
         size_t grid = (size_t)sms * per_sm;
         if (grid > groups) grid = groups;
+        if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; }
         if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }
         k_matvec16_w32<AR, 8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
         count_launch();
@@ -1133,6 +1153,7 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
     if (per_sm < 1) per_sm = 1;
     size_t grid = (size_t)sms * per_sm;
     if (grid > groups) grid = groups;
+    if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; }
     if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }
     if (tma) k_matvec_w32<AR, 8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
     else     k_matvec_w32<AR, 8, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);

@@ -62,10 +62,6 @@ for n, q, tw in ((512, 12289, 16), (1024, 12289, 16), (256, 7681, 16), (256, 838
             om = torch.empty((Bm, k, n), dtype=torch.int32, device=dev)
             ok &= ab("mat-vec q=%d k=%d l=%d" % (q, k, l), Bm, lambda: pl.matvec(om, A, s, k, l), om)
             del A, s, om
-    if n in (512, 256):
-        pe = sc.NttPlan(n, q, sc.REFERENCE, w, r)
-        ok &= ab("exact fwd_ntt n=%d q=%d reference" % (n, q), B, lambda: pe.batch(sc.OP_FWD, o, a), o)
-        ok &= ab("exact inv_ntt n=%d q=%d reference" % (n, q), B, lambda: pe.batch(sc.OP_INV, o, a), o)
     del a, b, o
 ns = 1 << 18
 seeds = torch.randint(0, 256, (ns, 40), dtype=torch.uint8, device=dev, generator=g)
