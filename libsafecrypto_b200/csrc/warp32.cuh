@@ -1125,10 +1125,12 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
     unsigned long long *ctr = nullptr;
     // 16-bit stash: the reduced transform values must fit an int16 (|x| <= 0.55 q + 2)
     const char *no16 = getenv("SCGPU_MATVEC_STASH32");
-    // measured (Kyber, q = 7681): k = l = 3 / 4 gain 16 % / 3 % from the higher occupancy; k = l = 2 loses 19 %
-    // (half of its rows are s rows, whose long forward transforms serialise behind the single staging row), and
-    // without bulk copies the rows are not prefetched at all: those shapes keep the 32-bit stash
-    if (AR::STASH16 && c.q < 59000 && l >= 3 && tma && !(no16 && atoi(no16) != 0)) {
+    // measured (Kyber, q = 7681, tools/matvec_stash_ab.py): with the spill-free kernel the 16-bit stash wins for every l
+    // (k = l = 2: 4.87 against 4.40e8 instances/s, k = 3, l = 2: 3.70 against 3.33e8, l = 3: equal); without bulk copies
+    // the rows are not prefetched at all and the 32-bit stash kernel is used.  SCGPU_MATVEC16_MINL raises the threshold.
+    const char *minl_env = getenv("SCGPU_MATVEC16_MINL");
+    const int minl = minl_env ? atoi(minl_env) : 1;
+    if (AR::STASH16 && c.q < 59000 && l >= minl && tma && !(no16 && atoi(no16) != 0)) {
         const size_t smem = ((size_t)C::POLYS * (C::TS + (C::N + C::T)) + (size_t)l * C::POLYS * (20 * C::T + C::T)) * sizeof(int32_t);
         SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         int per_sm = (int)((227 * 1024) / (smem + 1024 + 64));
