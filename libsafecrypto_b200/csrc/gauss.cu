@@ -153,29 +153,34 @@ __device__ __forceinline__ int32_t sample_ky(const GaussTablesDev &g, PrngStream
     }
 }
 
+// One candidate of the Bernoulli sampler (gaussian_bernoulli.c:161-246 for the candidate, :248-280 for zero / sign):
+// false = rejected, draw again.  Kept as a single attempt so that the vector loop of k_stream_seq can let every lane
+// move on to its next sample as soon as its own candidate is accepted (a warp that loops per sample until all 32
+// lanes have accepted runs for the slowest lane of every sample: ~4x the mean number of candidates at sigma = 215).
+__device__ __forceinline__ bool ber_try(const GaussTablesDev &g, PrngStream &rng, int32_t &out)
+{
+    const uint32_t val = rng.var(g.ber_maxlog);
+    if (val >= (uint32_t)g.ber_maxval) return false;
+    uint32_t accept_mask = 0, x = val * val;
+    for (int j = 0; j < 8; j++) {
+        for (int i = g.ber_entries; i--;) {
+            uint32_t r = rng.var(8) & 0xFF;
+            uint32_t tv = g.ber_tab[i * 8 + j];
+            if (r < tv && ((accept_mask >> i) & 1) == 0) accept_mask |= (1u << i);
+            if (r > tv && ((x >> i) & 1) == 1 && ((accept_mask >> i) & 1) == 0) return false;
+        }
+    }
+    const uint32_t rnd = rng.var(2);
+    if (val == 0) { if (rnd < 2) return false; out = 0; return true; }
+    out = (rnd & 1) ? -(int32_t)val : (int32_t)val;
+    return true;
+}
+
 __device__ __forceinline__ int32_t sample_ber(const GaussTablesDev &g, PrngStream &rng)
 {
-    for (;;) {
-        uint32_t val;
-        for (;;) {                                               // gaussian_bernoulli.c:161-246
-            val = rng.var(g.ber_maxlog);
-            if (val >= (uint32_t)g.ber_maxval) continue;
-            uint32_t accept_mask = 0, x = val * val;
-            bool reject = false;
-            for (int j = 0; j < 8 && !reject; j++) {
-                for (int i = g.ber_entries; i--;) {
-                    uint32_t r = rng.var(8) & 0xFF;
-                    uint32_t tv = g.ber_tab[i * 8 + j];
-                    if (r < tv && ((accept_mask >> i) & 1) == 0) accept_mask |= (1u << i);
-                    if (r > tv && ((x >> i) & 1) == 1 && ((accept_mask >> i) & 1) == 0) { reject = true; break; }
-                }
-            }
-            if (!reject) break;
-        }
-        uint32_t rnd = rng.var(2);                               // :248-280
-        if (val == 0) { if (rnd < 2) continue; return 0; }
-        return (rnd & 1) ? -(int32_t)val : (int32_t)val;
-    }
+    int32_t s;
+    while (!ber_try(g, rng, s)) { }
+    return s;
 }
 
 __device__ __forceinline__ int32_t draw(const GaussTablesDev &g, PrngStream &rng)
@@ -234,6 +239,16 @@ __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
             const size_t n = a.n;
             if (a.g.sampler != SCGPU_SAMPLER_CDF || a.g.blinding == SCGPU_NORMAL_SAMPLES) {
                 // sampling.c:211-228 (KY / Bernoulli are driven the same way: sample() + centre)
+                if (a.g.sampler == SCGPU_SAMPLER_BERNOULLI) {
+                    // one candidate per trip; the lanes of a warp sit at different samples i
+                    for (size_t i = 0; i < n;) {
+                        int32_t smp;
+                        if (!ber_try(a.g, rng, smp)) continue;
+                        v[i] = smp + a.centre;
+                        bool discard = a.thresh && rng.next32() < a.thresh;
+                        if (!discard) i++;
+                    }
+                } else
                 for (size_t i = 0; i < n;) {
                     v[i] = draw(a.g, rng) + a.centre;
                     bool discard = a.thresh && rng.next32() < a.thresh;

@@ -1,4 +1,4 @@
-"""Device-resident Gaussian sampling throughput: python tools/gauss_bench.py [log2_streams] [n]"""
+"""Device-resident Gaussian sampling throughput: python tools/gauss_bench.py [log2_streams] [n] [log2_streams_sequential]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -31,8 +31,8 @@ for prec in (64, 32, -64):
 
 sc.lib().scgpu_set_fixed_probe_search(0)
 # sequential-semantics kernel (k_stream_seq): shuffle / blinding / discard wrappers, Knuth-Yao, Bernoulli
-ns2 = 1 << 16
-seeds2 = seeds[:ns2]
+ns2 = 1 << (int(sys.argv[3]) if len(sys.argv) > 3 else 16)
+seeds2 = seeds[:ns2] if ns2 <= ns else torch.randint(0, 256, (ns2, 40), dtype=torch.uint8, device=dev, generator=g)
 smp2 = torch.empty((ns2, n), dtype=torch.int32, device=dev)
 cases = [("cdf64 shuffle", sc.SAMPLER_CDF, 64, 2, 0), ("cdf64 blinding", sc.SAMPLER_CDF, 64, 1, 0), ("cdf64 normal discard=4", sc.SAMPLER_CDF, 64, 0, 4),
          ("knuth-yao 64", sc.SAMPLER_KNUTH_YAO, 64, 0, 0), ("bernoulli 64", sc.SAMPLER_BERNOULLI, 64, 0, 0)]
