@@ -11,7 +11,7 @@ ok = True
 for q, n, tw in ((12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417, 256, 32)):
     w, r = O.tables(q, n, tw)
     pl = sc.NttPlan(n, q, sc.REFERENCE, w, r)
-    rows = 700
+    rows = 13000                      # more than one grid-full for every n: the work-counter path
     a = rng.integers(0, q, (rows, n)).astype(np.int32); b = rng.integers(-q, q, (rows, n)).astype(np.int32)
     out = torch.empty((rows, n), dtype=torch.int32, device=dev)
     pl.polymul(out, torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))
@@ -19,14 +19,14 @@ for q, n, tw in ((12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417,
     ok &= np.array_equal(out.cpu().numpy()[:64], O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a[:64], b[:64], w, r))
     if n == 256:
         k = 3
-        A = rng.integers(0, q, (200, k * k, n)).astype(np.int32); s = rng.integers(-4, 5, (200, k, n)).astype(np.int32)
-        o = torch.empty((200, k, n), dtype=torch.int32, device=dev)
+        A = rng.integers(0, q, (9000, k * k, n)).astype(np.int32); s = rng.integers(-4, 5, (9000, k, n)).astype(np.int32)
+        o = torch.empty((9000, k, n), dtype=torch.int32, device=dev)
         pl.matvec(o, torch.from_numpy(A).to(dev), torch.from_numpy(s).to(dev), k, k)
         torch.cuda.synchronize()
 gp = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0)
-seeds = torch.from_numpy(rng.integers(0, 256, (300, 40)).astype(np.uint8)).to(dev)
-smp = torch.empty((300, 512), dtype=torch.int32, device=dev)
+seeds = torch.from_numpy(rng.integers(0, 256, (4000, 40)).astype(np.uint8)).to(dev)
+smp = torch.empty((4000, 64), dtype=torch.int32, device=dev)
 for prng in (sc.PRNG_CHACHA, sc.PRNG_AES_CTR_DRBG):
-    gp.streams(prng, seeds, 512, smp)
+    gp.streams(prng, seeds, 64, smp)
 torch.cuda.synchronize()
 print("sanitize run done, parity", ok)
