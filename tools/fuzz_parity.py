@@ -51,7 +51,7 @@ while time.time() - t0 < budget:
     mode = int(rng.choice([0, 0, 0, 1, 2, 3, 4]))
     sc.lib().scgpu_set_fast_arith(mode)
     what = int(rng.integers(5))
-    rows = int(rng.choice([1, 2, 3, 5, 8, 31, 64, 257, 1000, 4099]))
+    rows = int(rng.choice([1, 2, 3, 5, 8, 31, 64, 257, 1000, 4099, 4099, 13001]))      # 13001: beyond one grid-full for every n (work counter)
     offa, offb = int(rng.choice([0, 0, 0, 1, 2, 4])), int(rng.choice([0, 0, 1, 4]))
     name = ""
     try:
