@@ -184,6 +184,7 @@ extern "C" int scgpu_gauss_plan_create(scgpu_gauss_plan_t **out, int sampler, in
     cudaDeviceProp prop;
     SCGPU_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     p->sm_count = prop.multiProcessorCount;
+    { const int e = init_work_counters(); if (e != SCGPU_OK) return e; }
     int rc = SCGPU_OK;
     if (sampler == SCGPU_SAMPLER_CDF && precision == 64) {
         std::vector<uint64_t> cdf = build_cdf64(blinding, tail, sigma);
@@ -267,6 +268,7 @@ extern "C" int scgpu_gauss_plan_create_table(scgpu_gauss_plan_t **out, int preci
     cudaDeviceProp prop;
     SCGPU_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     p->sm_count = prop.multiProcessorCount;
+    { const int e = init_work_counters(); if (e != SCGPU_OK) return e; }
     std::vector<uint64_t> words(table, table + entries * (size_t)(precision / 64));
     uint64_t *d = nullptr;
     const int rc = upload(&d, words);

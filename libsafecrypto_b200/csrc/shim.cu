@@ -32,24 +32,39 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // Work counters of the persistent warp-local kernels (warp32.cuh: claim_next).  A ring of slots per device; a launch
 // takes the next slot and zeroes it on its own stream, so launches in flight on different streams never share one
 // (the ring is far longer than any queue of launches).  *ctr stays nullptr with SCGPU_STATIC_SCHED=1.
+namespace {
+constexpr int kCtrMaxDev = 64;
+constexpr unsigned kCtrSlots = 8192;
+std::mutex g_ctr_mu;
+unsigned long long *g_ctr_pool[kCtrMaxDev] = {};
+unsigned g_ctr_next[kCtrMaxDev] = {};
+}  // namespace
+
+// Allocates the current device's ring (called at plan creation, so that no launch ever allocates -- launches may be
+// inside a stream capture).
+int init_work_counters()
+{
+    int dev = 0;
+    SCGPU_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kCtrMaxDev) return SCGPU_OK;
+    std::lock_guard<std::mutex> lk(g_ctr_mu);
+    if (!g_ctr_pool[dev]) SCGPU_CUDA_CHECK(cudaMalloc(&g_ctr_pool[dev], sizeof(unsigned long long) * kCtrSlots));
+    return SCGPU_OK;
+}
+
 int next_work_counter(cudaStream_t st, unsigned long long **ctr)
 {
-    constexpr int kMaxDev = 64;
-    constexpr unsigned kSlots = 8192;
-    static std::mutex mu;
-    static unsigned long long *pool[kMaxDev] = {};
-    static unsigned next[kMaxDev] = {};
     *ctr = nullptr;
     const char *env = getenv("SCGPU_STATIC_SCHED");
     if (env && atoi(env) != 0) return SCGPU_OK;
     int dev = 0;
     SCGPU_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= kMaxDev) return SCGPU_OK;
+    if (dev < 0 || dev >= kCtrMaxDev) return SCGPU_OK;
     unsigned long long *slot;
     {
-        std::lock_guard<std::mutex> lk(mu);
-        if (!pool[dev]) SCGPU_CUDA_CHECK(cudaMalloc(&pool[dev], sizeof(unsigned long long) * kSlots));
-        slot = pool[dev] + (next[dev]++ % kSlots);
+        std::lock_guard<std::mutex> lk(g_ctr_mu);
+        if (!g_ctr_pool[dev]) return SCGPU_OK;             // no plan was created on this device: static stride
+        slot = g_ctr_pool[dev] + (g_ctr_next[dev]++ % kCtrSlots);
     }
     SCGPU_CUDA_CHECK(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), st));
     *ctr = slot;
@@ -128,6 +143,7 @@ extern "C" int scgpu_ntt_plan_create(scgpu_ntt_plan_t **out, const void *params,
     cudaDeviceProp prop;
     SCGPU_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     d.sm_count = prop.multiProcessorCount;
+    { const int e = init_work_counters(); if (e != SCGPU_OK) return e; }
     if (w) {
         if (d.logn < 8 || d.logn > 10) {
             set_error("plan_create: transforms support n = 256, 512, 1024 (got %zu)", p->n);
