@@ -282,14 +282,14 @@ def main():
         int_roof = {"bound": "issue", "unit": "G butterflies/s", "achieved": ach, "peak": bfly_g, "frac": ach / bfly_g if bfly_g > 0 else None,
                     "butterflies_per_product": bfly, "imad_gops": imad_g, "ffma_gops": ffma_g,
                     "peak_source": "scgpu_int_peak_gops(11): float-quotient butterfly microbenchmark on this device"}
-    # other parameter shapes of BASELINE.json configs[1..2] (device-resident, smaller batch; parity is in tests/)
+    # other parameter shapes of BASELINE.json configs[1..2] (device-resident, 1 GiB per operand; parity is in tests/)
     shapes = None
     if rank == 0:
         shapes = {}
         for (qq, nn) in ((12289, 1024), (7681, 256)):
             ww, rr = O.tables(qq, nn, 16)
             pl = sc.NttPlan(nn, qq, sc.REFERENCE, ww, rr, device=local_rank)
-            bb = (1 << 28) // (4 * nn)
+            bb = (1 << 30) // (4 * nn)
             xa = torch.randint(0, qq, (bb, nn), dtype=torch.int32, device=dev, generator=g)
             xb = torch.randint(0, qq, (bb, nn), dtype=torch.int32, device=dev, generator=g)
             xo = torch.empty_like(xa)
