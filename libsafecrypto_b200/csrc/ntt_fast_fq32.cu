@@ -57,6 +57,22 @@ struct ArFq {
         hi = lo - t;
         lo = lo + t;
     }
+    static __device__ __forceinline__ void ct0(u32 &lo, u32 &hi, const E &z, const K &k)
+    {
+        const u32 t = (u32)fq::mul((int32_t)hi, z, k.nq);
+#ifdef __CUDA_ARCH__
+        // two opaque copies of kBias: written with the literal, the compiler shares (lo + kBias) between the two
+        // results (3 adds per pair); with distinct values each result is one 3-input IADD3
+        u32 kb1, kb2;
+        asm("mov.u32 %0, 0x4B400000;" : "=r"(kb1));
+        asm("mov.u32 %0, 1262485504;" : "=r"(kb2));
+        hi = lo - t + kb1;
+        lo = lo + t + kb2;
+#else
+        hi = lo - t + (u32)kBias;
+        lo = lo + t + (u32)kBias;
+#endif
+    }
     static __device__ __forceinline__ void gs(u32 &lo, u32 &hi, const E &z, const K &k)
     {
         const u32 d = lo - hi + (u32)kBias;

@@ -44,6 +44,7 @@ struct ArSh {
         hi = lo + lo - sum;
         lo = sum;
     }
+    static __device__ __forceinline__ void ct0(u32 &lo, u32 &hi, const E &z, const K &k) { ct(lo, hi, z, k); }   // enc is the identity
     static __device__ __forceinline__ void gs(u32 &lo, u32 &hi, const E &z, const K &k)
     {
         const u32 d = lo - hi;

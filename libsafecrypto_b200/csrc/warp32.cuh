@@ -9,6 +9,7 @@
 //   cb(e)                       entry read from the kernel's constant bank
 //   mk(words)                   entry from WORDS table words
 //   ct / gs                     forward / inverse butterfly on internal values
+//   ct0                         ct whose lo operand is still RAW (stage 0 encodes it for free in its 3-input adds)
 //   fin(lo, hi, ninv, z, k)     last inverse stage: both branches scaled, canonical residues out
 //   red(x, one, k)              x * 1 mod q (range reduction), internal in / out
 //   pw(a, b, k)                 pointwise product of two internal values, internal out
@@ -192,7 +193,10 @@ static __device__ __forceinline__ void fwd_pass0(u32 (&x)[32], const Const &c)
         const int half = 16 >> s;
 #pragma unroll
         for (int m = 0; m < 32; m++)
-            if ((m & half) == 0) AR::ct(x[m], x[m + half], AR::cb(c.f0[(1 << s) - 1 + (m >> (5 - s))]), c.k);
+            if ((m & half) == 0) {
+                if (s == 0) AR::ct0(x[m], x[m + half], AR::cb(c.f0[0]), c.k);      // x[0..15] arrive raw (load_operand)
+                else        AR::ct(x[m], x[m + half], AR::cb(c.f0[(1 << s) - 1 + (m >> (5 - s))]), c.k);
+            }
     }
 }
 
@@ -320,8 +324,9 @@ static __device__ __forceinline__ void load_operand(u32 (&x)[32], const int32_t 
 #pragma unroll
         for (int m = 0; m < 32; m++) v[m] = bred(v[m], c);
     }
+    // the low half stays raw: stage 0 of fwd_pass0 (AR::ct0) encodes it inside its own adds
 #pragma unroll
-    for (int m = 0; m < 32; m++) x[m] = AR::enc(v[m]);
+    for (int m = 0; m < 32; m++) x[m] = m < 16 ? (u32)v[m] : AR::enc(v[m]);
 }
 
 // same, from a raw row that a bulk copy (TMA) has staged at the start of the tile region
@@ -340,8 +345,9 @@ static __device__ __forceinline__ void load_operand_staged(u32 (&x)[32], const i
 #pragma unroll
         for (int m = 0; m < 32; m++) v[m] = bred(v[m], c);
     }
+    // the low half stays raw: stage 0 of fwd_pass0 (AR::ct0) encodes it inside its own adds
 #pragma unroll
-    for (int m = 0; m < 32; m++) x[m] = AR::enc(v[m]);
+    for (int m = 0; m < 32; m++) x[m] = m < 16 ? (u32)v[m] : AR::enc(v[m]);
 }
 
 };  // struct W32
