@@ -178,6 +178,7 @@ SINT32 prng_set_entropy_callback(prng_entropy_callback cb);
 SINT32 prng_init(prng_ctx_t *ctx, const UINT8 *nonce, size_t len_nonce);
 safecrypto_prng_e prng_get_type(prng_ctx_t *ctx);
 SINT32 prng_destroy(prng_ctx_t *ctx);
+void prng_reset(prng_ctx_t *ctx);                              /* prng.c:861-932 */
 UINT64 prng_get_csprng_bytes(prng_ctx_t *ctx);
 UINT64 prng_get_out_bytes(prng_ctx_t *ctx);
 SINT32 prng_bit(prng_ctx_t *ctx);
@@ -186,6 +187,12 @@ UINT32 prng_32(prng_ctx_t *ctx);
 UINT16 prng_16(prng_ctx_t *ctx);
 UINT8  prng_8(prng_ctx_t *ctx);
 UINT32 prng_var(prng_ctx_t *ctx, size_t n);
+#ifdef __SIZEOF_INT128__
+unsigned __int128 prng_128(prng_ctx_t *ctx);                   /* prng.c:950-960 (HAVE_128BIT, x86-64) */
+#endif
+FLOAT  prng_float(prng_ctx_t *ctx);                            /* prng.c:1005-1008 */
+DOUBLE prng_double(prng_ctx_t *ctx);                           /* prng.c:1010-1015 */
+SINT32 prng_mem(prng_ctx_t *ctx, UINT8 *mem, SINT32 length);   /* prng.c:1050-1105 */
 
 /* ---- samplers: src/utils/sampling/sampling.h:37-110, safecrypto_private.h:154-181 ---------- */
 typedef enum sample_precision {

@@ -42,10 +42,21 @@ struct PrngState {
     uint32_t have_lo;          // second half of a 64-bit draw pending
     uint32_t lo_word;
     uint32_t var_buf, var_bits;
-    uint32_t error;            // 1: a DRBG reseed would be needed (unsupported on device)
-    uint32_t pad;
-    uint64_t words_out;        // 32-bit words handed out so far
+    uint32_t error;            // 2: the fresh-entropy ring ran dry inside a launch (never re-use entropy)
+    // pooled mode = the drop-in prng_ctx_t: prng_32 & co. are served from the 4096-word bit pool that prng.c:95-132
+    // refills with 2048 generator draws at a time, prng_mem draws from the generator BEHIND that pool, and the DRBG
+    // keeps its 1 KiB transfer buffer (prng_get_func.c:174-193) so that prng_reset's stale reads are reproduced
+    uint32_t pooled;
+    uint32_t pool_rd, pool_fill;
+    uint32_t rng_cnt;          // next u64 of the DRBG transfer buffer, 128 = empty
+    uint32_t ent_fresh;        // 1: the ring holds fresh (callback / OS) entropy and must never wrap onto used bytes
+    uint32_t ent_avail;        // fresh bytes left ahead of ent_idx
+    uint32_t instantiated;     // 0: init() has not run yet (the host creates the header, the device the generator)
+    uint64_t words_out;        // 32-bit words handed out so far (stats_out_bytes / 4)
+    uint64_t draws64;          // generator draws so far (stats_csprng_bytes / 8)
 };
+constexpr uint32_t kPoolWords = 4096;      // RANDOM_POOL_SIZE, prng.h:31
+constexpr uint32_t kDrbgBufWords = 256;    // CSPRNG_BUFFER_SIZE / 4, prng_types.h:52
 
 __device__ __constant__ uint8_t kAesSbox[256] = {
     0x63,0x7c,0x77,0x7b,0xf2,0x6b,0x6f,0xc5,0x30,0x01,0x67,0x2b,0xfe,0xd7,0xab,0x76,0xca,0x82,0xc9,0x7d,0xfa,0x59,0x47,0xf0,
@@ -232,9 +243,15 @@ struct PrngStream {
     PrngState s;
     const uint8_t *seed;
     const AesTables *aes;
+    uint32_t *pool = nullptr;      // pooled mode: kPoolWords words of device memory
+    uint32_t *buf1k = nullptr;     // pooled mode, DRBG: kDrbgBufWords words in prng output order (hi, lo per u64)
 
     __device__ __forceinline__ uint8_t ent_byte()
     {
+        if (s.ent_fresh) {
+            if (s.ent_avail == 0) { s.error = 2; return 0; }
+            s.ent_avail--;
+        }
         uint8_t b = seed[s.ent_idx++];
         if (s.ent_idx == s.seed_len) s.ent_idx = 0;
         return b;
@@ -276,11 +293,13 @@ struct PrngStream {
         s.drbg_counter ^= ctr_le;
         aes256_expand(*aes, key, s.drbg_rk);
     }
+    // `pooled`, `ent_fresh` and `ent_avail` are set by the caller beforehand
     __device__ void init(uint32_t type, uint32_t seed_len, uint32_t seed_period)
     {
         s.type = type; s.seed_len = seed_len; s.ent_idx = 0;
         s.cc_count = 0; s.have_lo = 0; s.lo_word = 0; s.var_buf = 0; s.var_bits = 0; s.error = 0; s.words_out = 0;
-        s.drbg_pos = 4; s.drbg_blocks = 0; s.pad = 0;
+        s.drbg_pos = 4; s.drbg_blocks = 0; s.instantiated = 1;
+        s.pool_rd = 0; s.pool_fill = 0; s.rng_cnt = kDrbgBufWords / 2; s.draws64 = 0;
         if (type == PRNG_CHACHA20) {
             s.seed_period = seed_period;
             chacha_reseed();
@@ -309,14 +328,41 @@ struct PrngStream {
         }
         return bswap32(s.cc_data[s.cc_count]);
     }
+    // ctr_drbg_reset, ctr_drbg.c:84-101, as prng_reset drives it (prng.c:861-932): the transfer buffer position
+    // rng_cnt is left alone, so later draws first drain the blocks the OLD key left in the buffer
+    // ChaCha20: the reference's reset_chacha20 frees the generator (chacha20_csprng.c:58-67); what is done here is
+    // the swapped destroy_chacha20 body (:49-56): data_count = 0 and a reseed.
+    __device__ void reset_pooled()
+    {
+        s.pool_rd = 0; s.pool_fill = 0; s.var_bits = 0; s.words_out = 0; s.draws64 = 0;
+        if (s.type == PRNG_CHACHA20) { s.cc_count = 0; chacha_reseed(); return; }
+        uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        s.drbg_counter = 0;
+        aes256_expand(*aes, zero, s.drbg_rk);
+        drbg_reseed();
+    }
     // one 64-bit generator draw, split high word first (prng.c:108-127)
     __device__ __forceinline__ void draw64(uint32_t &hi, uint32_t &lo)
     {
+        s.draws64++;
         if (s.type == PRNG_CHACHA20) {
             s.cc_reseed_ctr += 8;                                   // chacha20_csprng.c:99-106
             if (s.seed_period <= s.cc_reseed_ctr) chacha_reseed();
             hi = chacha_next32();
             lo = chacha_next32();
+        } else if (s.pooled) {
+            // get_random_64_aes + ctr_drbg_update literally: 64 blocks per refill, reseed bookkeeping right after
+            if (s.rng_cnt == kDrbgBufWords / 2) {
+                s.rng_cnt = 0;
+                for (uint32_t blk = 0; blk < kDrbgBufWords / 4; blk++) {
+                    uint32_t w[4];
+                    drbg_block_words(*aes, s.drbg_rk, s.drbg_counter++, w);
+                    buf1k[4 * blk] = w[0]; buf1k[4 * blk + 1] = w[1]; buf1k[4 * blk + 2] = w[2]; buf1k[4 * blk + 3] = w[3];
+                }
+                if (++s.drbg_reseed_ctr >= s.seed_period) drbg_reseed();
+            }
+            hi = buf1k[2 * s.rng_cnt]; lo = buf1k[2 * s.rng_cnt + 1];
+            s.rng_cnt++;
         } else {
             if (s.drbg_pos >= 4) {
                 if (s.drbg_blocks == 64) {                          // a 1 KiB update completed (ctr_drbg.c:190-196)
@@ -331,9 +377,23 @@ struct PrngStream {
             s.drbg_pos += 2;
         }
     }
+    // update_pool, prng.c:95-132: the whole pool at once, 2048 draws, high word first
+    __device__ void pool_refill()
+    {
+        for (uint32_t i = 0; i < kPoolWords; i += 2) {
+            uint32_t hi, lo;
+            draw64(hi, lo);
+            pool[i] = hi; pool[i + 1] = lo;
+        }
+        s.pool_rd = 0; s.pool_fill = kPoolWords;
+    }
     __device__ __forceinline__ uint32_t next32()
     {
         s.words_out++;
+        if (s.pooled) {
+            if (s.pool_rd >= s.pool_fill) pool_refill();
+            return pool[s.pool_rd++];
+        }
         if (s.have_lo) { s.have_lo = 0; return s.lo_word; }
         uint32_t hi, lo;
         draw64(hi, lo);
@@ -353,9 +413,11 @@ struct PrngStream {
         uint32_t ret = s.var_buf;
         if (s.var_bits < n) {
             uint32_t need = n - s.var_bits;
+            // need == 32 shifts by the type width (undefined in C): the reference as compiled for a BMI2 host (shlx / bzhi)
+            // returns stale var_buf | fresh word; var_buf is zero whenever var_bits is, except right after prng_reset
             ret = need >= 32 ? ret : ret << need;
             s.var_buf = next32();
-            ret |= s.var_buf & (need >= 32 ? 0u : ((1u << need) - 1u));
+            ret |= s.var_buf & (need >= 32 ? 0xFFFFFFFFu : ((1u << need) - 1u));
             s.var_buf = need >= 32 ? s.var_buf : s.var_buf >> need;
             s.var_bits = 32 - need;
         } else {

@@ -12,6 +12,7 @@
 //                  encrypts a contiguous run of blocks, a warp XOR-scan rebuilds the running XOR the
 //                  reference's encrypt-in-place framing creates, samples go out through shared memory.
 #include "scgpu_internal.h"
+#include <atomic>
 #include <cstdlib>
 #include "csprng.cuh"
 #include "gauss_plan.h"
@@ -211,7 +212,9 @@ struct SeqArgs {
     int32_t centre;
     uint32_t thresh;
     int32_t *out;
-    int mode;                   // 0 sampler vector calls, 1 raw words, 2 single get_sample, 3 instantiate only
+    int mode;                   // 0 sampler vector calls, 1 raw words, 2 single get_sample, 3 instantiate only,
+                                // 4 prng_mem (n = 64-byte blocks), 5 prng_reset, 6 refill the bit pool
+    uint32_t *pool_mem;         // pooled states (drop-in prng_ctx_t): kPoolWords + kDrbgBufWords words per stream
 };
 
 __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
@@ -224,8 +227,13 @@ __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
     PrngStream rng;
     rng.aes = &aes;
     rng.seed = a.seeds + sidx * a.seed_len;
-    if (a.states && a.states[sidx].seed_len != 0) rng.s = a.states[sidx];
-    else rng.init(a.prng_type, a.seed_len, a.seed_period);
+    if (a.pool_mem) {
+        rng.pool = a.pool_mem + sidx * (size_t)(kPoolWords + kDrbgBufWords);
+        rng.buf1k = rng.pool + kPoolWords;
+    }
+    if (a.states) rng.s = a.states[sidx];
+    else { rng.s.pooled = 0; rng.s.ent_fresh = 0; rng.s.ent_avail = 0; }
+    if (!a.states || !rng.s.instantiated) rng.init(a.prng_type, a.seed_len, a.seed_period);
 
     int32_t *v = a.out + sidx * a.n * a.calls;
     if (a.mode == 1) {
@@ -234,6 +242,18 @@ __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
         v[0] = draw(a.g, rng);
     } else if (a.mode == 3) {
         // instantiate only: the state is written back below
+    } else if (a.mode == 4) {
+        // prng_mem, prng.c:1050-1105: eight generator draws per 64-byte block, each stored as a little-endian u64;
+        // the bit pool is bypassed
+        for (size_t i = 0; i < a.n * 8; i++) {
+            uint32_t hi, lo;
+            rng.draw64(hi, lo);
+            v[2 * i] = (int32_t)lo; v[2 * i + 1] = (int32_t)hi;
+        }
+    } else if (a.mode == 5) {
+        rng.reset_pooled();
+    } else if (a.mode == 6) {
+        rng.pool_refill();
     } else {
         for (size_t call = 0; call < a.calls; call++, v += a.n) {
             const size_t n = a.n;
@@ -304,6 +324,7 @@ __global__ void __launch_bounds__(128) k_drbg_setup(FastArgs a)
     PrngStream rng;
     rng.aes = &aes;
     rng.seed = a.seeds + sidx * a.seed_len;
+    rng.s.pooled = 0; rng.s.ent_fresh = 0; rng.s.ent_avail = 0;
     rng.init(PRNG_AES, a.seed_len, a.seed_period);
     uint32_t *k = a.keys + sidx * 64;
     for (int i = 0; i < 60; i++) k[i] = rng.s.drbg_rk[i];
@@ -503,14 +524,14 @@ unsigned cap_grid(size_t want, int sms, int per_sm)
 
 int launch_gauss_seq(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
                      uint32_t seed_period, PrngState *states, size_t nstreams, size_t n, size_t calls,
-                     int32_t centre, uint32_t discard, int32_t *out, int mode, cudaStream_t st)
+                     int32_t centre, uint32_t discard, int32_t *out, int mode, cudaStream_t st, uint32_t *pool_mem)
 {
-    if (nstreams == 0 || (n * calls == 0 && mode != 2)) return SCGPU_OK;
+    if (nstreams == 0 || (n * calls == 0 && mode != 2 && mode != 3 && mode != 5 && mode != 6)) return SCGPU_OK;
     SeqArgs a;
     a.g = g; a.seeds = seeds; a.states = states; a.seed_len = (uint32_t)seed_len; a.seed_period = seed_period;
     a.prng_type = (uint32_t)prng_type; a.nstreams = nstreams; a.n = n; a.calls = calls; a.centre = centre;
     a.thresh = discard == 2 ? 1u << 28 : discard == 4 ? 1u << 30 : discard == 6 ? 1u << 31 : 0;   // sampling.c:85-92
-    a.out = out; a.mode = mode;
+    a.out = out; a.mode = mode; a.pool_mem = pool_mem;
     const unsigned grid = (unsigned)((nstreams + 127) / 128);
     k_stream_seq<<<grid, 128, 0, st>>>(a);
     count_launch();
@@ -518,13 +539,28 @@ int launch_gauss_seq(const GaussTablesDev &g, int prng_type, const uint8_t *seed
     return SCGPU_OK;
 }
 
-// 1: the throughput kernels keep the reference's fixed probe sequence (log2(size) probes for every draw) instead
-// of the guide-bracketed bisection, whose trip count depends on the draw.  Same samples either way.
-static int g_fixed_probe_search = -1;
+// 1 (the default): the throughput kernels run the reference's fixed probe sequence (log2(size) probes for every
+// draw, gaussian_cdf.c:536-553) -- the number and order of table lookups does not depend on the draw.  0
+// (scgpu_set_fixed_probe_search(0) or SCGPU_GUIDED_SEARCH=1): guide-bracketed bisection, ~3 probes per draw but a
+// data-dependent trip count.  Same samples either way.
+static std::atomic<int> g_fixed_probe_search{-1};
+static int fixed_probe_search()
+{
+    int m = g_fixed_probe_search.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char *e = getenv("SCGPU_GUIDED_SEARCH");
+        m = (e && atoi(e) != 0) ? 0 : 1;
+        const char *f = getenv("SCGPU_FIXED_PROBE_SEARCH");
+        if (f) m = atoi(f) != 0 ? 1 : 0;
+        int expect = -1;
+        if (!g_fixed_probe_search.compare_exchange_strong(expect, m)) m = expect;
+    }
+    return m;
+}
 int set_fixed_probe_search(int on)
 {
-    const int old = g_fixed_probe_search > 0 ? 1 : 0;
-    g_fixed_probe_search = on ? 1 : 0;
+    const int old = fixed_probe_search();
+    g_fixed_probe_search.store(on ? 1 : 0);
     return old;
 }
 
@@ -533,13 +569,9 @@ int launch_gauss_fast(const GaussTablesDev &g, int prng_type, const uint8_t *see
                       uint32_t *key_scratch, int sm_count, cudaStream_t st)
 {
     if (nstreams == 0 || per_stream == 0) return SCGPU_OK;
-    if (g_fixed_probe_search < 0) {
-        const char *e = getenv("SCGPU_FIXED_PROBE_SEARCH");
-        g_fixed_probe_search = (e && atoi(e) != 0) ? 1 : 0;
-    }
     FastArgs a;
     a.g = g;
-    if (g_fixed_probe_search) a.g.cdf_guide = nullptr;
+    if (fixed_probe_search()) a.g.cdf_guide = nullptr;
     a.seeds = seeds; a.seed_len = (uint32_t)seed_len; a.seed_period = seed_period;
     a.nstreams = nstreams; a.per_stream = per_stream; a.centre = centre; a.out = out; a.keys = key_scratch;
     a.ctr = nullptr;

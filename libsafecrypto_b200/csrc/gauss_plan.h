@@ -36,7 +36,8 @@ struct GaussTablesDev {
 
 int launch_gauss_seq(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
                      uint32_t seed_period, PrngState *states, size_t nstreams, size_t n, size_t calls,
-                     int32_t centre, uint32_t discard, int32_t *out, int mode, cudaStream_t st);
+                     int32_t centre, uint32_t discard, int32_t *out, int mode, cudaStream_t st,
+                     uint32_t *pool_mem = nullptr);
 int set_fixed_probe_search(int on);
 int launch_gauss_fast(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
                       uint32_t seed_period, size_t nstreams, size_t per_stream, int32_t centre, int32_t *out,

@@ -30,7 +30,6 @@ struct scgpu_gauss_plan {
     uint8_t *d_ber = nullptr;
     uint32_t *d_guide = nullptr;
     std::mutex mu;
-    uint32_t *d_keys = nullptr; size_t keys_cap = 0;        // DRBG round keys of the fast path
     uint8_t *d_seeds = nullptr; size_t seeds_cap = 0;       // staging for *_host
     int32_t *d_out = nullptr; size_t out_cap = 0;
 };
@@ -285,7 +284,7 @@ extern "C" void scgpu_gauss_plan_destroy(scgpu_gauss_plan_t *p)
     if (!p) return;
     cudaSetDevice(p->device);
     cudaFree(p->d_cdf); cudaFree(p->d_flat); cudaFree(p->d_ber); cudaFree(p->d_guide);
-    cudaFree(p->d_keys); cudaFree(p->d_seeds); cudaFree(p->d_out);
+    cudaFree(p->d_seeds); cudaFree(p->d_out);
     delete p;
 }
 
@@ -296,12 +295,14 @@ static int gauss_dispatch(scgpu_gauss_plan *p, int prng_type, const uint8_t *d_s
     if (seed_len == 0 || !d_seeds || !d_out) { set_error("gauss_streams: null/empty argument"); return SCGPU_ERR_ARG; }
     if (discard != 0 && discard != 2 && discard != 4 && discard != 6) { set_error("gauss_streams: discard %u", discard); return SCGPU_ERR_ARG; }
     if (fast_path_ok(p->t, prng_type, n * calls, discard)) {
-        if (prng_type == PRNG_AES) {
-            int e = ensure_cap(&p->d_keys, &p->keys_cap, nstreams * 64);
-            if (e != SCGPU_OK) return e;
-        }
-        return launch_gauss_fast(p->t, prng_type, d_seeds, seed_len, kDefaultSeedPeriod, nstreams, n * calls, centre,
-                                 d_out, p->d_keys, p->sm_count, st);
+        // DRBG round keys of this call: stream-ordered scratch, so calls on different streams (or a second call while
+        // the first is still running) never share it and nothing here synchronises the device
+        uint32_t *keys = nullptr;
+        if (prng_type == PRNG_AES) SCGPU_CUDA_CHECK(cudaMallocAsync(&keys, nstreams * 64 * sizeof(uint32_t), st));
+        const int e = launch_gauss_fast(p->t, prng_type, d_seeds, seed_len, kDefaultSeedPeriod, nstreams, n * calls, centre,
+                                        d_out, keys, p->sm_count, st);
+        if (keys) SCGPU_CUDA_CHECK(cudaFreeAsync(keys, st));
+        return e;
     }
     return launch_gauss_seq(p->t, prng_type, d_seeds, seed_len, kDefaultSeedPeriod, nullptr, nstreams, n, calls, centre,
                             discard, d_out, 0, st);
@@ -313,7 +314,6 @@ extern "C" int scgpu_gauss_streams(const scgpu_gauss_plan_t *plan, int prng_type
 {
     if (!plan) { set_error("gauss_streams: null plan"); return SCGPU_ERR_ARG; }
     scgpu_gauss_plan *p = const_cast<scgpu_gauss_plan *>(plan);
-    std::lock_guard<std::mutex> lock(p->mu);
     SCGPU_CUDA_CHECK(cudaSetDevice(p->device));
     return gauss_dispatch(p, prng_type, seeds, seed_len, nstreams, n, calls, centre, discard, out, static_cast<cudaStream_t>(stream));
 }
@@ -353,32 +353,36 @@ extern "C" int scgpu_prng_words(int prng_type, const uint8_t *seeds, size_t seed
 // Drop-in PRNG front end and sampler objects
 // =======================================================================================================
 //
-// prng_ctx_t here is libscgpu's own context: the generator state lives on the DEVICE (PrngState) and every
-// random word -- whether handed to host callers through prng_32()/prng_var() or consumed by a sampler
-// kernel -- is produced by the kernels in gauss.cu from that state.  Host callers are served from a
-// read-ahead pool of device-generated words; before a sampler kernel runs, the device state is advanced
-// by exactly the number of pool words the host has consumed, so host and device draws interleave in the
-// reference's order.  INTEGRATION.md describes how a build inside the reference tree maps its own
-// prng_ctx_t (prng_types.h:121-232) onto this.
+// prng_ctx_t here is libscgpu's own context (the reference's is opaque to its callers, prng.h:38-100).  The
+// generator state, the 4096-word bit pool of prng.c:95-132 and the DRBG's 1 KiB transfer buffer live on the DEVICE
+// (PrngState in pooled mode, csprng.cuh); every random word -- handed to host callers through prng_32()/prng_var()/
+// prng_mem() or consumed by a sampler kernel -- is produced by the kernels in gauss.cu from that state.  The host
+// keeps a mirror of the state header and of the pool: it serves prng_32 & co. from the mirrored pool (exactly the
+// reference's pool, refilled 4096 words at a time) and pushes the header back before the next launch, so host and
+// device draws interleave in the reference's order, prng_mem draws behind the pool as the reference's does, and
+// prng_reset leaves the DRBG's stale buffer in place as the reference's does.
+//
+// Entropy: SC_ENTROPY_USER_PROVIDED is the caller's ring buffer, wrapping as prng_get_func.c:108-119 does.  Callback
+// and OS entropy is FRESH for every reseed, as in chacha20_csprng.c:21-29 / ctr_drbg.c:128-147: the device reads a
+// ring of unused seeds that the host tops up before every launch with as many seeds as the launch could possibly
+// consume; the device never wraps onto used bytes (PrngState::ent_avail) and a launch that runs the ring dry aborts.
 
 struct prng_ctx_t {
     safecrypto_prng_e type;
     safecrypto_entropy_e entropy;
     size_t seed_period;
-    std::vector<uint8_t> seed;          // entropy ring buffer handed to the device
+    std::vector<uint8_t> ring;          // host mirror of the device entropy ring
+    bool ring_dirty = false;
     const UINT8 *user_entropy = nullptr; size_t user_len = 0;
     bool inited = false;
     int device = 0;
     cudaStream_t st = nullptr;
-    uint8_t *d_seed = nullptr;
-    PrngState *d_state = nullptr;       // state at the START of the host pool
-    uint32_t *d_pool = nullptr;
+    uint8_t *d_ring = nullptr; size_t d_ring_cap = 0;
+    PrngState *d_state = nullptr;
+    PrngState hs;                       // host mirror, authoritative between launches
+    uint32_t *d_poolmem = nullptr;      // kPoolWords of pool + kDrbgBufWords of DRBG transfer buffer
+    uint32_t pool[kPoolWords];
     int32_t *d_out = nullptr; size_t out_cap = 0;
-    static constexpr size_t kPool = 4096;
-    uint32_t pool[kPool];
-    size_t pool_fill = 0, pool_rd = 0;  // words valid / consumed
-    uint32_t var_buf = 0; size_t var_bits = 0;
-    UINT64 csprng_bytes = 0, out_bytes = 0;
     std::mutex mu;
 };
 
@@ -401,58 +405,134 @@ GaussTablesDev no_tables()
     return t;
 }
 
-// advance the device state past the pool words the host already consumed and drop the pool
-void sync_device_position(prng_ctx_t *c)
+size_t per_seed_bytes(const prng_ctx_t *c) { return c->type == SC_PRNG_CHACHA ? 40 : 36; }
+
+// one seed's worth of fresh entropy, requested the way the generator's reseed requests it
+// (chacha20_csprng.c:25: 40 bytes at once; ctr_drbg.c:128-129: 4 bytes, then 32)
+bool fresh_seed(const prng_ctx_t *c, uint8_t *dst)
 {
-    PRNG_CUDA(cudaSetDevice(c->device));
-    if (c->pool_rd > 0) {
-        if (launch_gauss_seq(no_tables(), c->type, c->d_seed, c->seed.size(), (uint32_t)c->seed_period, c->d_state, 1,
-                             c->pool_rd, 1, 0, 0, reinterpret_cast<int32_t *>(c->d_pool), 1, c->st) != SCGPU_OK)
-            prng_fatal("prng advance");
+    if (c->entropy == SC_ENTROPY_CALLBACK) {
+        if (!g_entropy_cb) return false;
+        if (c->type == SC_PRNG_AES_CTR_DRBG) { g_entropy_cb(4, dst); g_entropy_cb(32, dst + 4); }
+        else g_entropy_cb(40, dst);
+        return true;
     }
-    c->pool_fill = c->pool_rd = 0;
-    // the prng_var bit buffer travels with the state
-    PrngState hs;
-    PRNG_CUDA(cudaMemcpyAsync(&hs, c->d_state, sizeof(hs), cudaMemcpyDeviceToHost, c->st));
-    PRNG_CUDA(cudaStreamSynchronize(c->st));
-    hs.var_buf = c->var_buf; hs.var_bits = (uint32_t)c->var_bits;
-    PRNG_CUDA(cudaMemcpyAsync(c->d_state, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->st));
-    PRNG_CUDA(cudaStreamSynchronize(c->st));
+    // SC_ENTROPY_RANDOM / DEV_RANDOM / DEV_URANDOM: the kernel's CSPRNG (the reference's random()-based source is
+    // seeded from the clock, prng.c:145-160; there is nothing to reproduce bit for bit)
+    FILE *fp = fopen("/dev/urandom", "rb");
+    const size_t want = per_seed_bytes(c);
+    const bool ok = fp && fread(dst, 1, want, fp) == want;
+    if (fp) fclose(fp);
+    return ok;
 }
 
-void pull_var_state(prng_ctx_t *c)
+// upper bound on the reseeds one launch that hands out `words` 32-bit words can trigger
+size_t reseeds_for(const prng_ctx_t *c, size_t words)
 {
-    PrngState hs;
-    PRNG_CUDA(cudaMemcpyAsync(&hs, c->d_state, sizeof(hs), cudaMemcpyDeviceToHost, c->st));
-    PRNG_CUDA(cudaStreamSynchronize(c->st));
-    c->var_buf = hs.var_buf; c->var_bits = hs.var_bits;
+    const size_t bytes = words * 4 + 4 * kPoolWords + 4 * kDrbgBufWords;     // + one pool refill, one DRBG update
+    if (c->type == SC_PRNG_CHACHA) return bytes / (c->seed_period ? c->seed_period : 1) + 2;
+    size_t period = c->seed_period >> 4;                                     // ctr_drbg.c:46-53, in 1 KiB updates
+    if (period < 0x1000) period = 0x1000;
+    return bytes / 1024 / period + 2;
 }
 
-void refill_pool(prng_ctx_t *c)
+// fresh-entropy mode: make sure `reseeds` unused seeds lie ahead of the device's read position
+void top_up_entropy(prng_ctx_t *c, size_t reseeds)
+{
+    if (!c->hs.ent_fresh) return;
+    const size_t ps = per_seed_bytes(c);
+    size_t L = c->ring.size();
+    if (reseeds * ps > L) {
+        // grow: keep the unused seeds in order, the rest is filled below
+        std::vector<uint8_t> nr(reseeds * ps, 0);
+        for (size_t i = 0; i < c->hs.ent_avail; i++) nr[i] = c->ring[(c->hs.ent_idx + i) % L];
+        memset(c->ring.data(), 0, c->ring.size());
+        c->ring.swap(nr);
+        c->hs.ent_idx = 0;
+        L = c->ring.size();
+        c->hs.seed_len = (uint32_t)L;
+    }
+    if (c->hs.ent_avail == L) return;
+    // used region: [ent_idx + ent_avail, ent_idx + L) mod L, a whole number of seeds starting on a seed boundary
+    for (size_t off = c->hs.ent_avail; off < L; off += ps) {
+        uint8_t seed[40];
+        if (!fresh_seed(c, seed)) { set_error("entropy source failed"); prng_fatal("prng reseed entropy"); }
+        for (size_t i = 0; i < ps; i++) c->ring[(c->hs.ent_idx + off + i) % L] = seed[i];
+        memset(seed, 0, sizeof(seed));
+    }
+    c->hs.ent_avail = (uint32_t)L;
+    c->ring_dirty = true;
+}
+
+// One kernel on the context's state: push the header (and the ring if the host refreshed it), run, pull the header
+// and -- when the kernel refilled it -- the pool.  `words` bounds the 32-bit words the launch may hand out.
+void run_state_kernel(prng_ctx_t *c, const GaussTablesDev &t, size_t n, size_t calls, int32_t centre, uint32_t discard,
+                      int mode, int32_t *d_out, size_t words)
 {
     PRNG_CUDA(cudaSetDevice(c->device));
-    // state := state advanced by the consumed words, then generate a fresh pool WITHOUT committing it:
-    // the committed state stays at the pool start, so run the generator on a scratch copy.
-    sync_device_position(c);
-    PrngState *scratch = nullptr;
-    PRNG_CUDA(cudaMalloc(&scratch, sizeof(PrngState)));
-    PRNG_CUDA(cudaMemcpyAsync(scratch, c->d_state, sizeof(PrngState), cudaMemcpyDeviceToDevice, c->st));
-    if (launch_gauss_seq(no_tables(), c->type, c->d_seed, c->seed.size(), (uint32_t)c->seed_period, scratch, 1,
-                         prng_ctx_t::kPool, 1, 0, 0, reinterpret_cast<int32_t *>(c->d_pool), 1, c->st) != SCGPU_OK)
-        prng_fatal("prng refill");
-    PRNG_CUDA(cudaMemcpyAsync(c->pool, c->d_pool, sizeof(c->pool), cudaMemcpyDeviceToHost, c->st));
+    top_up_entropy(c, reseeds_for(c, words));
+    if (c->ring_dirty || c->d_ring_cap < c->ring.size()) {
+        if (c->d_ring_cap < c->ring.size()) {
+            if (c->d_ring) { PRNG_CUDA(cudaMemsetAsync(c->d_ring, 0, c->d_ring_cap, c->st)); PRNG_CUDA(cudaStreamSynchronize(c->st)); cudaFree(c->d_ring); }
+            PRNG_CUDA(cudaMalloc(&c->d_ring, c->ring.size()));
+            c->d_ring_cap = c->ring.size();
+        }
+        PRNG_CUDA(cudaMemcpyAsync(c->d_ring, c->ring.data(), c->ring.size(), cudaMemcpyHostToDevice, c->st));
+        c->ring_dirty = false;
+    }
+    const uint64_t draws_before = c->hs.draws64;
+    PRNG_CUDA(cudaMemcpyAsync(c->d_state, &c->hs, sizeof(PrngState), cudaMemcpyHostToDevice, c->st));
+    if (launch_gauss_seq(t, c->type, c->d_ring, c->ring.size(), (uint32_t)c->seed_period, c->d_state, 1, n, calls, centre,
+                         discard, d_out, mode, c->st, c->d_poolmem) != SCGPU_OK)
+        prng_fatal("prng kernel");
+    PRNG_CUDA(cudaMemcpyAsync(&c->hs, c->d_state, sizeof(PrngState), cudaMemcpyDeviceToHost, c->st));
     PRNG_CUDA(cudaStreamSynchronize(c->st));
-    cudaFree(scratch);
-    c->pool_fill = prng_ctx_t::kPool;
-    c->pool_rd = 0;
-    c->csprng_bytes += 4 * prng_ctx_t::kPool;
+    if (c->hs.error) {
+        set_error("the device ran out of fresh entropy inside one launch (%zu words requested); entropy is never re-used", words);
+        prng_fatal("prng entropy");
+    }
+    if (mode != 4 && c->hs.draws64 != draws_before && c->hs.pool_fill) {
+        PRNG_CUDA(cudaMemcpyAsync(c->pool, c->d_poolmem, sizeof(c->pool), cudaMemcpyDeviceToHost, c->st));
+        PRNG_CUDA(cudaStreamSynchronize(c->st));
+    }
+}
+
+int32_t *ensure_out(prng_ctx_t *c, size_t words)
+{
+    if (c->out_cap < words) {
+        cudaFree(c->d_out);
+        c->d_out = nullptr;
+        PRNG_CUDA(cudaMalloc(&c->d_out, sizeof(int32_t) * words));
+        c->out_cap = words;
+    }
+    return c->d_out;
 }
 
 uint32_t host_next32(prng_ctx_t *c)
 {
-    if (c->pool_rd >= c->pool_fill) refill_pool(c);
-    c->out_bytes += 4;
-    return c->pool[c->pool_rd++];
+    if (c->hs.pool_rd >= c->hs.pool_fill) run_state_kernel(c, no_tables(), 0, 0, 0, 0, 6, nullptr, kPoolWords);
+    c->hs.words_out++;
+    return c->pool[c->hs.pool_rd++];
+}
+
+// prng.c:1017-1048 on the mirrored bit buffer
+uint32_t host_var(prng_ctx_t *c, size_t n)
+{
+    UINT32 mask = n >= 32 ? 0xFFFFFFFFu : (1u << n) - 1u;
+    if (n > 32) n = 32;
+    UINT32 ret = c->hs.var_buf;
+    if (c->hs.var_bits < n) {
+        size_t need = n - c->hs.var_bits;
+        ret = need >= 32 ? ret : ret << need;
+        c->hs.var_buf = host_next32(c);
+        ret |= c->hs.var_buf & (need >= 32 ? 0xFFFFFFFFu : ((1u << need) - 1u));     // need == 32: see csprng.cuh var()
+        c->hs.var_buf = need >= 32 ? c->hs.var_buf : c->hs.var_buf >> need;
+        c->hs.var_bits = (uint32_t)(32 - need);
+    } else {
+        c->hs.var_buf >>= n;
+        c->hs.var_bits -= (uint32_t)n;
+    }
+    return ret & mask;
 }
 
 }  // namespace
@@ -463,12 +543,15 @@ prng_ctx_t *prng_create(safecrypto_entropy_e entropy, safecrypto_prng_e type, sa
                         size_t seed_period)
 {
     (void)mt;
-    // prng.c:560-626: unknown types and a zero period are rejected; only the two generators whose byte
-    // stream is reproduced on the device are available here
+    // prng.c:564-626: unknown entropy sources, unknown types and a zero period are rejected; only the two generators
+    // whose byte stream is reproduced on the device are available here
+    if (entropy != SC_ENTROPY_RANDOM && entropy != SC_ENTROPY_DEV_RANDOM && entropy != SC_ENTROPY_DEV_URANDOM &&
+        entropy != SC_ENTROPY_DEV_HWRNG && entropy != SC_ENTROPY_CALLBACK && entropy != SC_ENTROPY_USER_PROVIDED) return NULL;
     if (type != SC_PRNG_AES_CTR_DRBG && type != SC_PRNG_CHACHA) return NULL;
     if (seed_period == 0) return NULL;
     prng_ctx_t *c = new prng_ctx_t();
     c->type = type; c->entropy = entropy; c->seed_period = seed_period;
+    memset(&c->hs, 0, sizeof(c->hs));
     const char *env = getenv("SCGPU_DEVICE");
     c->device = env ? atoi(env) : 0;
     return c;
@@ -490,45 +573,34 @@ SINT32 prng_set_entropy_callback(prng_entropy_callback cb)
 SINT32 prng_init(prng_ctx_t *ctx, const UINT8 *nonce, size_t len_nonce)
 {
     (void)nonce; (void)len_nonce;       // unused by these two generators (prng.c:219-262)
-    if (!ctx) return SC_FUNC_FAILURE;
-    // Entropy that the reference pulls lazily at every (re)seed is gathered up front into the ring the
-    // device reads: 64 reseeds' worth for callback / OS sources, the user's buffer as-is otherwise.
-    const size_t per_seed = ctx->type == SC_PRNG_CHACHA ? 40 : 36;
+    if (!ctx || ctx->inited) return SC_FUNC_FAILURE;
+    memset(&ctx->hs, 0, sizeof(ctx->hs));
+    ctx->hs.pooled = 1;
     switch (ctx->entropy) {
     case SC_ENTROPY_USER_PROVIDED:
         if (!ctx->user_entropy || ctx->user_len == 0) return SC_FUNC_FAILURE;
-        ctx->seed.assign(ctx->user_entropy, ctx->user_entropy + ctx->user_len);
+        ctx->ring.assign(ctx->user_entropy, ctx->user_entropy + ctx->user_len);
+        ctx->ring_dirty = true;
         break;
     case SC_ENTROPY_CALLBACK:
         if (!g_entropy_cb) return SC_FUNC_FAILURE;
-        ctx->seed.resize(64 * per_seed);
-        for (size_t off = 0; off < ctx->seed.size(); off += per_seed) {
-            if (ctx->type == SC_PRNG_AES_CTR_DRBG) { g_entropy_cb(4, ctx->seed.data() + off); g_entropy_cb(32, ctx->seed.data() + off + 4); }
-            else g_entropy_cb(40, ctx->seed.data() + off);
-        }
+        ctx->hs.ent_fresh = 1;
         break;
-    case SC_ENTROPY_RANDOM: case SC_ENTROPY_DEV_RANDOM: case SC_ENTROPY_DEV_URANDOM: {
-        ctx->seed.resize(64 * per_seed);
-        FILE *fp = fopen("/dev/urandom", "rb");
-        if (!fp || fread(ctx->seed.data(), 1, ctx->seed.size(), fp) != ctx->seed.size()) { if (fp) fclose(fp); return SC_FUNC_FAILURE; }
-        fclose(fp);
-    } break;
+    case SC_ENTROPY_RANDOM: case SC_ENTROPY_DEV_RANDOM: case SC_ENTROPY_DEV_URANDOM: case SC_ENTROPY_DEV_HWRNG:
+        ctx->hs.ent_fresh = 1;
+        break;
     default:
         return SC_FUNC_FAILURE;
     }
     if (cudaSetDevice(ctx->device) != cudaSuccess) return SC_FUNC_FAILURE;
     PRNG_CUDA(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
-    PRNG_CUDA(cudaMalloc(&ctx->d_seed, ctx->seed.size()));
     PRNG_CUDA(cudaMalloc(&ctx->d_state, sizeof(PrngState)));
-    PRNG_CUDA(cudaMalloc(&ctx->d_pool, sizeof(uint32_t) * prng_ctx_t::kPool));
-    PRNG_CUDA(cudaMemcpyAsync(ctx->d_seed, ctx->seed.data(), ctx->seed.size(), cudaMemcpyHostToDevice, ctx->st));
-    PRNG_CUDA(cudaMemsetAsync(ctx->d_state, 0, sizeof(PrngState), ctx->st));      // seed_len == 0: "fresh stream"
-    // instantiate the generator on the device (zero words requested, state written back)
-    if (launch_gauss_seq(no_tables(), ctx->type, ctx->d_seed, ctx->seed.size(), (uint32_t)ctx->seed_period, ctx->d_state,
-                         1, 1, 1, 0, 0, reinterpret_cast<int32_t *>(ctx->d_pool), 3, ctx->st) != SCGPU_OK)
-        return SC_FUNC_FAILURE;
-    PRNG_CUDA(cudaStreamSynchronize(ctx->st));
+    PRNG_CUDA(cudaMalloc(&ctx->d_poolmem, sizeof(uint32_t) * (kPoolWords + kDrbgBufWords)));
+    PRNG_CUDA(cudaMemsetAsync(ctx->d_poolmem, 0, sizeof(uint32_t) * (kPoolWords + kDrbgBufWords), ctx->st));
     ctx->inited = true;
+    // instantiate the generator on the device (hs.instantiated == 0); in fresh mode the ring is first filled by
+    // top_up_entropy
+    run_state_kernel(ctx, no_tables(), 0, 0, 0, 0, 3, nullptr, 0);
     return SC_FUNC_SUCCESS;
 }
 
@@ -539,16 +611,36 @@ SINT32 prng_destroy(prng_ctx_t *ctx)
     if (!ctx) return SC_FUNC_FAILURE;
     if (ctx->inited) {
         cudaSetDevice(ctx->device);
+        // zeroise what held key material before releasing it
+        if (ctx->d_ring) cudaMemsetAsync(ctx->d_ring, 0, ctx->d_ring_cap, ctx->st);
+        cudaMemsetAsync(ctx->d_state, 0, sizeof(PrngState), ctx->st);
+        cudaMemsetAsync(ctx->d_poolmem, 0, sizeof(uint32_t) * (kPoolWords + kDrbgBufWords), ctx->st);
+        if (ctx->d_out) cudaMemsetAsync(ctx->d_out, 0, sizeof(int32_t) * ctx->out_cap, ctx->st);
         cudaStreamSynchronize(ctx->st);
-        cudaFree(ctx->d_seed); cudaFree(ctx->d_state); cudaFree(ctx->d_pool); cudaFree(ctx->d_out);
+        cudaFree(ctx->d_ring); cudaFree(ctx->d_state); cudaFree(ctx->d_poolmem); cudaFree(ctx->d_out);
         cudaStreamDestroy(ctx->st);
     }
+    if (!ctx->ring.empty()) memset(ctx->ring.data(), 0, ctx->ring.size());
+    memset(&ctx->hs, 0, sizeof(ctx->hs));
+    memset(ctx->pool, 0, sizeof(ctx->pool));
     delete ctx;
     return SC_FUNC_SUCCESS;
 }
 
-UINT64 prng_get_csprng_bytes(prng_ctx_t *ctx) { return ctx->csprng_bytes; }
-UINT64 prng_get_out_bytes(prng_ctx_t *ctx) { return ctx->out_bytes; }
+// prng.c:861-932.  CTR-DRBG: ctr_drbg_reset (zero key and counter, reseed); the transfer buffer keeps its position,
+// so the next draws drain what the old key left there, as in the reference.  ChaCha20: the reference calls
+// reset_chacha20, which FREES the generator (chacha20_csprng.c:58-67, the bodies of reset/destroy are swapped) and
+// every later draw is a use after free; here the front end is reset and the generator reseeded, which is what the
+// swapped function (destroy_chacha20, :49-56) does.
+void prng_reset(prng_ctx_t *ctx)
+{
+    if (!ctx || !ctx->inited) return;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    run_state_kernel(ctx, no_tables(), 0, 0, 0, 0, 5, nullptr, 0);
+}
+
+UINT64 prng_get_csprng_bytes(prng_ctx_t *ctx) { return ctx->hs.draws64 * 8; }
+UINT64 prng_get_out_bytes(prng_ctx_t *ctx) { return ctx->hs.words_out * 4; }
 
 UINT32 prng_32(prng_ctx_t *ctx)
 {
@@ -563,30 +655,51 @@ UINT64 prng_64(prng_ctx_t *ctx)
     return (hi << 32) | host_next32(ctx);
 }
 
-// prng.c:1017-1048: bit-buffer bookkeeping on words that came from the device
+#ifdef __SIZEOF_INT128__
+// prng.c:950-960
+unsigned __int128 prng_128(prng_ctx_t *ctx)
+{
+    unsigned __int128 v = prng_64(ctx);
+    v <<= 64;
+    v |= prng_64(ctx);
+    return v;
+}
+#endif
+
 UINT32 prng_var(prng_ctx_t *ctx, size_t n)
 {
     std::lock_guard<std::mutex> lock(ctx->mu);
-    UINT32 mask = n >= 32 ? 0xFFFFFFFFu : (1u << n) - 1u;
-    if (n > 32) n = 32;
-    UINT32 ret = ctx->var_buf;
-    if (ctx->var_bits < n) {
-        size_t need = n - ctx->var_bits;
-        ret = need >= 32 ? ret : ret << need;
-        ctx->var_buf = host_next32(ctx);
-        ret |= ctx->var_buf & (need >= 32 ? 0u : ((1u << need) - 1u));
-        ctx->var_buf = need >= 32 ? ctx->var_buf : ctx->var_buf >> need;
-        ctx->var_bits = 32 - need;
-    } else {
-        ctx->var_buf >>= n;
-        ctx->var_bits -= n;
-    }
-    return ret & mask;
+    return host_var(ctx, n);
 }
 
 SINT32 prng_bit(prng_ctx_t *ctx) { return (SINT32)prng_var(ctx, 1); }
 UINT16 prng_16(prng_ctx_t *ctx) { return (UINT16)prng_var(ctx, 16); }
 UINT8 prng_8(prng_ctx_t *ctx) { return (UINT8)prng_var(ctx, 8); }
+
+// prng.c:1005-1015
+FLOAT prng_float(prng_ctx_t *ctx) { return ((FLOAT)prng_32(ctx)) / UINT32_MAX; }
+DOUBLE prng_double(prng_ctx_t *ctx)
+{
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    UINT32 a = host_var(ctx, 27);
+    UINT32 b = host_var(ctx, 26);
+    return (a * 67108864.0 + b) * 1.11022302462516e-16;
+}
+
+// prng.c:1050-1105: ceil(length / 64) blocks of eight generator draws, copied out as little-endian u64; the draws
+// come from the generator itself, behind whatever the bit pool already holds
+SINT32 prng_mem(prng_ctx_t *ctx, UINT8 *mem, SINT32 length)
+{
+    if (!ctx || !ctx->inited) return SC_FUNC_FAILURE;
+    if (length <= 0) return SC_FUNC_SUCCESS;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const size_t blocks = ((size_t)length + 63) >> 6;
+    int32_t *d = ensure_out(ctx, blocks * 16);
+    run_state_kernel(ctx, no_tables(), blocks, 1, 0, 0, 4, d, blocks * 16);
+    PRNG_CUDA(cudaMemcpyAsync(mem, d, (size_t)length, cudaMemcpyDeviceToHost, ctx->st));
+    PRNG_CUDA(cudaStreamSynchronize(ctx->st));
+    return SC_FUNC_SUCCESS;
+}
 
 }  // extern "C"
 
@@ -618,18 +731,18 @@ void run_on_ctx(GaussObj *o, int32_t *host_out, size_t n, int32_t centre, uint32
 {
     prng_ctx_t *c = o->prng;
     std::lock_guard<std::mutex> lock(c->mu);
-    sync_device_position(c);
-    if (c->out_cap < n) {
-        cudaFree(c->d_out);
-        PRNG_CUDA(cudaMalloc(&c->d_out, sizeof(int32_t) * n));
-        c->out_cap = n;
-    }
-    if (launch_gauss_seq(o->plan->t, c->type, c->d_seed, c->seed.size(), (uint32_t)c->seed_period, c->d_state, 1, n, 1,
-                         centre, discard, c->d_out, mode, c->st) != SCGPU_OK)
-        prng_fatal("sampler kernel");
-    PRNG_CUDA(cudaMemcpyAsync(host_out, c->d_out, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->st));
+    int32_t *d = ensure_out(c, n);
+    // words one launch may draw: the CDF samplers are bounded by the mode; Knuth-Yao and Bernoulli restart
+    // data-dependently, so they get a generous bound (a launch that still runs the fresh-entropy ring dry aborts)
+    const GaussTablesDev &t = o->plan->t;
+    size_t per = (size_t)(t.precision > 32 ? t.precision / 32 : 1);
+    if (t.sampler == SCGPU_SAMPLER_KNUTH_YAO) per = 64;
+    if (t.sampler == SCGPU_SAMPLER_BERNOULLI) per = 4096;
+    if (t.blinding != SCGPU_NORMAL_SAMPLES) per = 2 * per + 8;
+    if (discard) per *= 4;
+    run_state_kernel(c, t, n, 1, centre, discard, mode, d, n * per + 65536);
+    PRNG_CUDA(cudaMemcpyAsync(host_out, d, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->st));
     PRNG_CUDA(cudaStreamSynchronize(c->st));
-    pull_var_state(c);
 }
 
 SINT32 gauss_sample(void *g)

@@ -24,6 +24,7 @@
 #include "fast_common.cuh"
 #include "../../include/scgpu.h"
 
+#include <atomic>
 #include <cstdlib>
 #include <vector>
 
@@ -389,15 +390,18 @@ void free_fast_tables(NttPlanDev &p)
 // for every modulus, 2 = Barrett-32 where applicable, 3 = float-quotient with the 8-coefficient schedule,
 // 4 = Shoup products on the warp-local schedule for every modulus they can serve.
 // SCGPU_FAST_ARITH / SCGPU_FORCE_MONT=1 set the initial value; tests switch it to cover all three.
-static int g_arith = -1;
+static std::atomic<int> g_arith{-1};       // read by every launch path, written by the setters: atomic, not locked
 static int arith_mode()
 {
-    if (g_arith < 0) {
-        g_arith = 0;
-        if (getenv("SCGPU_FORCE_MONT") && atoi(getenv("SCGPU_FORCE_MONT")) != 0) g_arith = 1;
-        if (getenv("SCGPU_FAST_ARITH")) g_arith = atoi(getenv("SCGPU_FAST_ARITH")) & 7;
+    int m = g_arith.load(std::memory_order_relaxed);
+    if (m < 0) {
+        m = 0;
+        if (getenv("SCGPU_FORCE_MONT") && atoi(getenv("SCGPU_FORCE_MONT")) != 0) m = 1;
+        if (getenv("SCGPU_FAST_ARITH")) m = atoi(getenv("SCGPU_FAST_ARITH")) & 7;
+        int expect = -1;
+        if (!g_arith.compare_exchange_strong(expect, m)) m = expect;
     }
-    return g_arith;
+    return m;
 }
 static bool use_fq(const NttPlanDev &p) { const int m = arith_mode(); return p.fq_ok && (m == 0 || m == 3); }
 static bool use_fq32(const NttPlanDev &p) { return p.fq32_ok && arith_mode() == 0; }
@@ -407,13 +411,13 @@ static bool use_sq(const NttPlanDev &p) { return p.sq_ok && arith_mode() != 1; }
 int set_fast_arith(int mode)
 {
     const int old = arith_mode();
-    g_arith = mode & 7;
+    g_arith.store(mode & 7);
     return old;
 }
 int set_force_montgomery(int on)
 {
     const int old = arith_mode() == 1 ? 1 : 0;
-    g_arith = on ? 1 : 0;
+    g_arith.store(on ? 1 : 0);
     return old;
 }
 

@@ -57,6 +57,10 @@ int next_work_counter(cudaStream_t st, unsigned long long **ctr)
     *ctr = nullptr;
     const char *env = getenv("SCGPU_STATIC_SCHED");
     if (env && atoi(env) != 0) return SCGPU_OK;
+    // A captured graph would bake its slot into every replay, long after the ring has handed the slot to other
+    // launches: captured launches keep the static stride.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return SCGPU_OK; }
     int dev = 0;
     SCGPU_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= kCtrMaxDev) return SCGPU_OK;
@@ -87,7 +91,8 @@ struct scgpu_ntt_plan {
     int32_t *d_rc[kStreams] = {nullptr, nullptr, nullptr};
     void *d_shared = nullptr;      // a shared (b_stride == 0) second operand
     size_t shared_cap = 0;
-    size_t chunk_rows = 0;
+    size_t staging_bytes = 0;      // capacity of each of d_a / d_b / d_o
+    size_t staging_rc = 0;         // capacity of d_rc in rows
 };
 
 extern "C" const char *scgpu_last_error(void) { return g_err; }
@@ -125,7 +130,11 @@ extern "C" int scgpu_ntt_plan_create(scgpu_ntt_plan_t **out, const void *params,
     if (device < 0 || device >= ndev) { set_error("plan_create: device %d of %d", device, ndev); return SCGPU_ERR_ARG; }
     SCGPU_CUDA_CHECK(cudaSetDevice(device));
 
-    scgpu_ntt_plan *plan = new scgpu_ntt_plan();
+    struct Guard {                       // frees the plan on every early return below
+        scgpu_ntt_plan *p;
+        ~Guard() { if (p) scgpu_ntt_plan_destroy(p); }
+    } guard{new scgpu_ntt_plan()};
+    scgpu_ntt_plan *plan = guard.p;
     NttPlanDev &d = plan->dev;
     memset(&d, 0, sizeof(d));
     d.n = (int)p->n;
@@ -147,7 +156,6 @@ extern "C" int scgpu_ntt_plan_create(scgpu_ntt_plan_t **out, const void *params,
     if (w) {
         if (d.logn < 8 || d.logn > 10) {
             set_error("plan_create: transforms support n = 256, 512, 1024 (got %zu)", p->n);
-            delete plan;
             return SCGPU_ERR_UNSUPPORTED;
         }
         std::vector<int32_t> wh(d.n), rh(d.n);
@@ -168,8 +176,9 @@ extern "C" int scgpu_ntt_plan_create(scgpu_ntt_plan_t **out, const void *params,
         // needed where the float-quotient arithmetic does not apply; built for every modulus it can serve so that
         // scgpu_set_fast_arith(4) can cross-check it against the other arithmetics
         if (rcode == SCGPU_OK && d.zeta_fwd) rcode = build_sh32_tables(d, wh.data());
-        if (rcode != SCGPU_OK) { delete plan; return rcode; }
+        if (rcode != SCGPU_OK) return rcode;
     }
+    guard.p = nullptr;
     *out = plan;
     return SCGPU_OK;
 }
@@ -278,27 +287,49 @@ extern "C" int scgpu_matvec_batch(const scgpu_ntt_plan_t *plan, int32_t *out, co
 
 // ---- host-buffer entry points: chunked three-stream pipeline -----------------------------------------
 
-static int ensure_staging(scgpu_ntt_plan *plan, size_t row_bytes_a, size_t row_bytes_b, size_t row_bytes_o, size_t count)
+// Sizes the three staging buffers for THIS call and returns its chunk length in rows.  A chunk is a whole number of
+// waves of the persistent fused kernels (sm_count x 20 one-warp CTAs x 1024/n rows per warp) so that no chunk ends on a
+// partly filled wave, about 24 MiB of the widest operand: large enough to amortise the launch, small enough that H2D,
+// kernel and D2H of neighbouring chunks overlap.
+static int ensure_staging(scgpu_ntt_plan *plan, size_t row_bytes_a, size_t row_bytes_b, size_t row_bytes_o, size_t count,
+                          size_t *chunk_rows)
 {
-    // ~16 MiB of the widest operand per chunk keeps H2D, kernel and D2H of neighbouring chunks overlapped
     size_t widest = row_bytes_a > row_bytes_o ? row_bytes_a : row_bytes_o;
     if (row_bytes_b > widest) widest = row_bytes_b;
-    size_t rows = (16u << 20) / widest;
+    if (widest == 0) widest = 4;
+    size_t rows = (24u << 20) / widest;
+    const size_t n = (size_t)plan->dev.n;
+    const size_t wave = (size_t)(plan->dev.sm_count > 0 ? plan->dev.sm_count : 148) * 20 * (n && n <= 1024 ? 1024 / n : 1);
+    if (rows > wave) rows -= rows % wave;
     if (rows < 1) rows = 1;
     if (rows > count) rows = count;
-    if (plan->chunk_rows >= rows && plan->streams[0]) return SCGPU_OK;
-    for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) {
+    const size_t need = rows * widest;
+    for (int i = 0; i < scgpu_ntt_plan::kStreams; i++)
         if (!plan->streams[i]) SCGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->streams[i], cudaStreamNonBlocking));
-        cudaFree(plan->d_a[i]); cudaFree(plan->d_b[i]); cudaFree(plan->d_o[i]); cudaFree(plan->d_rc[i]);
-        // sized for the largest row any op uses: n SINT32
-        size_t rb = (size_t)plan->dev.n * 4;
-        if (rb < widest) rb = widest;
-        SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_a[i], rows * rb));
-        SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_b[i], rows * rb));
-        SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_o[i], rows * rb));
-        SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_rc[i], rows * sizeof(int32_t)));
+    if (plan->staging_bytes < need) {
+        for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) {
+            SCGPU_CUDA_CHECK(cudaStreamSynchronize(plan->streams[i]));
+            cudaFree(plan->d_a[i]); cudaFree(plan->d_b[i]); cudaFree(plan->d_o[i]);
+            plan->d_a[i] = plan->d_b[i] = plan->d_o[i] = nullptr;
+        }
+        plan->staging_bytes = 0;
+        for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) {
+            SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_a[i], need));
+            SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_b[i], need));
+            SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_o[i], need));
+        }
+        plan->staging_bytes = need;
     }
-    plan->chunk_rows = rows;
+    if (plan->staging_rc < rows) {
+        for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) {
+            cudaFree(plan->d_rc[i]);
+            plan->d_rc[i] = nullptr;
+        }
+        plan->staging_rc = 0;
+        for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) SCGPU_CUDA_CHECK(cudaMalloc(&plan->d_rc[i], rows * sizeof(int32_t)));
+        plan->staging_rc = rows;
+    }
+    *chunk_rows = rows;
     return SCGPU_OK;
 }
 
@@ -326,7 +357,8 @@ static int run_host_pipeline(scgpu_ntt_plan *plan, int kind, int op, int32_t *ou
     const size_t belem = kind == 0 ? b_elem_size(op) : (kind == 2 ? (size_t)op / 8 : 4);
     const bool has_b = kind == 3 ? false : (kind != 0 || op_needs_b(op));
     const size_t rb = has_b ? (b_stride ? b_stride : n) * belem : 0;
-    int e = ensure_staging(plan, ra, b_stride ? rb : 0, n * 4, count);
+    size_t rows = 0;
+    int e = ensure_staging(plan, ra, b_stride ? rb : 0, n * 4, count, &rows);
     if (e != SCGPU_OK) return e;
     const void *d_bshared = nullptr;
     if (has_b && b_stride == 0) {
@@ -335,7 +367,6 @@ static int run_host_pipeline(scgpu_ntt_plan *plan, int kind, int op, int32_t *ou
         if (e != SCGPU_OK) return e;
         d_bshared = plan->d_shared;
     }
-    const size_t rows = plan->chunk_rows;
     int status = SCGPU_OK;
     for (size_t off = 0, ci = 0; off < count; off += rows, ci++) {
         const int s = (int)(ci % scgpu_ntt_plan::kStreams);
@@ -468,53 +499,155 @@ uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603u
     return h;
 }
 
+// Plans of the drop-in calls.  A call is matched by its parameter VALUES and the ADDRESSES of its tables (a handful
+// of words compared, no table is read); only an address that was not seen before has its table contents hashed, so
+// that tables malloc'ed at run time (USE_RUNTIME_NTT_TABLES, bliss_b.c:365-374) and freed / re-created elsewhere
+// find the plan that already holds the same contents.  Every hit also compares four sentinel twiddles kept with the
+// entry, which catches an address re-used for different contents, and compares the full key, so neither a hash
+// collision nor padding bytes can select a plan of another modulus.
+struct PlanKey {
+    const void *w, *r;
+    uint64_t n;
+    double inv;
+    int32_t q, m, k;
+    int variant, tw_bits, device;
+    bool operator==(const PlanKey &o) const
+    {
+        return w == o.w && r == o.r && n == o.n && memcmp(&inv, &o.inv, sizeof(inv)) == 0 && q == o.q && m == o.m &&
+               k == o.k && variant == o.variant && tw_bits == o.tw_bits && device == o.device;
+    }
+};
+struct PlanKeyHash {
+    size_t operator()(const PlanKey &k) const
+    {
+        uint64_t h = fnv1a(&k.w, sizeof(k.w));
+        h = fnv1a(&k.r, sizeof(k.r), h); h = fnv1a(&k.n, sizeof(k.n), h); h = fnv1a(&k.inv, sizeof(k.inv), h);
+        h = fnv1a(&k.q, sizeof(k.q), h); h = fnv1a(&k.m, sizeof(k.m), h); h = fnv1a(&k.k, sizeof(k.k), h);
+        h = fnv1a(&k.variant, sizeof(k.variant), h); h = fnv1a(&k.tw_bits, sizeof(k.tw_bits), h);
+        return (size_t)fnv1a(&k.device, sizeof(k.device), h);
+    }
+};
+struct PlanEntry {
+    scgpu_ntt_plan *plan = nullptr;
+    int32_t sentinel[4] = {0, 0, 0, 0};        // w[1], w[n-1], r[1], r[n-1]
+};
+
+static void read_sentinels(const PlanKey &k, int32_t out[4])
+{
+    auto at = [&](const void *t, size_t i) -> int32_t {
+        if (!t || i >= k.n) return 0;
+        return k.tw_bits == 16 ? (int32_t)static_cast<const int16_t *>(t)[i] : static_cast<const int32_t *>(t)[i];
+    };
+    out[0] = at(k.w, 1); out[1] = at(k.w, (size_t)k.n - 1); out[2] = at(k.r, 1); out[3] = at(k.r, (size_t)k.n - 1);
+}
+
 struct PlanCache {
     std::mutex mu;
-    std::unordered_map<uint64_t, scgpu_ntt_plan *> map;
-    scgpu_ntt_plan *get(int variant, const ntt_params_t *p, size_t n, const void *w, const void *r, int tw_bits)
+    std::unordered_map<PlanKey, PlanEntry, PlanKeyHash> by_addr;
+    struct Content { PlanKey key; std::vector<unsigned char> w, r; scgpu_ntt_plan *plan; };
+    std::unordered_multimap<uint64_t, Content> by_content;      // hash -> candidates, compared in full
+    ~PlanCache()
     {
-        // Keyed by the parameter values and the table CONTENTS (tables may be malloc'ed at run time and
-        // their address reused, bliss_b.c:365-374).
-        struct { int variant, tw_bits; int32_t q, m, k; uint64_t n; double inv; } key = {
-            variant, tw_bits, p->u.ntt32.q, p->u.ntt32.m, p->u.ntt32.k, (uint64_t)n, p->inv_q_dbl };
-        uint64_t h = fnv1a(&key, sizeof(key));
-        const size_t tb = (size_t)(tw_bits / 8) * n;
-        if (w) h = fnv1a(w, tb, h);
-        if (r) h = fnv1a(r, tb, h ^ 0x9E3779B97F4A7C15ull);
+        // process exit: the CUDA context may already be gone; the driver reclaims device memory
+    }
+    scgpu_ntt_plan *get(const PlanKey &key)
+    {
+        int32_t sent[4];
+        read_sentinels(key, sent);
         std::lock_guard<std::mutex> lock(mu);
-        auto it = map.find(h);
-        if (it != map.end()) return it->second;
-        ntt_params_t q = *p;
-        q.n = n;
+        auto it = by_addr.find(key);
+        if (it != by_addr.end() && memcmp(it->second.sentinel, sent, sizeof(sent)) == 0) return it->second.plan;
+        // unknown address (or an address re-used for other contents): identify the tables by value
+        const size_t tb = (size_t)(key.tw_bits / 8) * (size_t)key.n;
+        PlanKey vkey = key;
+        vkey.w = vkey.r = nullptr;
+        uint64_t h = PlanKeyHash()(vkey);
+        if (key.w) h = fnv1a(key.w, tb, h);
+        if (key.r) h = fnv1a(key.r, tb, h ^ 0x9E3779B97F4A7C15ull);
         scgpu_ntt_plan *plan = nullptr;
-        int dev = 0;
-        const char *env = getenv("SCGPU_DEVICE");
-        if (env) dev = atoi(env);
-        if (scgpu_ntt_plan_create(&plan, &q, variant, w, r, w ? tw_bits : 0, dev) != SCGPU_OK) dropin_fatal("plan creation failed");
-        map[h] = plan;
+        auto range = by_content.equal_range(h);
+        for (auto c = range.first; c != range.second; ++c) {
+            const Content &e = c->second;
+            if (e.key == vkey && e.w.size() == (key.w ? tb : 0) && e.r.size() == (key.r ? tb : 0) &&
+                (!key.w || memcmp(e.w.data(), key.w, tb) == 0) && (!key.r || memcmp(e.r.data(), key.r, tb) == 0)) {
+                plan = e.plan;
+                break;
+            }
+        }
+        if (!plan) {
+            ntt_params_t q;
+            memset(&q, 0, sizeof(q));
+            q.n = (size_t)key.n;
+            q.u.ntt32.q = key.q; q.u.ntt32.m = key.m; q.u.ntt32.k = key.k;
+            q.inv_q_dbl = key.inv; q.q_dbl = (double)key.q; q.inv_q_flt = (float)key.inv;
+            if (scgpu_ntt_plan_create(&plan, &q, key.variant, key.w, key.r, key.w ? key.tw_bits : 0, key.device) != SCGPU_OK)
+                dropin_fatal("plan creation failed");
+            Content e;
+            e.key = vkey; e.plan = plan;
+            if (key.w) e.w.assign(static_cast<const unsigned char *>(key.w), static_cast<const unsigned char *>(key.w) + tb);
+            if (key.r) e.r.assign(static_cast<const unsigned char *>(key.r), static_cast<const unsigned char *>(key.r) + tb);
+            by_content.emplace(h, std::move(e));
+        }
+        PlanEntry pe;
+        pe.plan = plan;
+        memcpy(pe.sentinel, sent, sizeof(sent));
+        by_addr[key] = pe;
         return plan;
     }
 };
 PlanCache g_cache;
 
-// Per-thread stream and scratch: the reference's functions are re-entrant and BLISS-B calls them from
-// worker threads (bliss_b.c:74-175).
+int dropin_device()
+{
+    static const int dev = [] { const char *env = getenv("SCGPU_DEVICE"); return env ? atoi(env) : 0; }();
+    return dev;
+}
+
+// Per-thread stream, scratch and last plan: the reference's functions are re-entrant and BLISS-B calls them from
+// worker threads (bliss_b.c:74-175).  Released when the thread exits.
 struct ThreadCtx {
     cudaStream_t st = nullptr;
     char *d[3] = {nullptr, nullptr, nullptr};
     size_t cap[3] = {0, 0, 0};
     int32_t *d_rc = nullptr;
+    int device = -1;
+    PlanKey last_key;
+    int32_t last_sent[4] = {0, 0, 0, 0};
+    scgpu_ntt_plan *last_plan = nullptr;
     void *ensure(int i, size_t bytes)
     {
         if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) dropin_fatal("stream");
         if (!d_rc && cudaMalloc(&d_rc, sizeof(int32_t)) != cudaSuccess) dropin_fatal("cudaMalloc");
         if (cap[i] < bytes) {
-            cudaFree(d[i]);
+            if (d[i]) { cudaStreamSynchronize(st); cudaFree(d[i]); }
             size_t want = bytes < 8192 ? 8192 : bytes;
             if (cudaMalloc(&d[i], want) != cudaSuccess) dropin_fatal("cudaMalloc");
             cap[i] = want;
         }
         return d[i];
+    }
+    ~ThreadCtx()
+    {
+        // errors are ignored: at process exit the context may already have been torn down
+        if (device >= 0 && cudaSetDevice(device) == cudaSuccess) {
+            if (st) cudaStreamSynchronize(st);
+            for (int i = 0; i < 3; i++) cudaFree(d[i]);
+            cudaFree(d_rc);
+            if (st) cudaStreamDestroy(st);
+        }
+        cudaGetLastError();
+    }
+    scgpu_ntt_plan *plan_for(const PlanKey &key)
+    {
+        if (last_plan && key == last_key) {
+            int32_t sent[4];
+            read_sentinels(key, sent);
+            if (memcmp(sent, last_sent, sizeof(sent)) == 0) return last_plan;
+        }
+        last_plan = g_cache.get(key);
+        last_key = key;
+        read_sentinels(key, last_sent);
+        return last_plan;
     }
 };
 thread_local ThreadCtx t_ctx;
@@ -523,9 +656,14 @@ thread_local ThreadCtx t_ctx;
 SINT32 run_one(int variant, int op, const ntt_params_t *p, size_t n, SINT32 *out, const void *a, const void *b,
                size_t b_elems, const void *w, const void *r, int tw_bits, int32_t scalar)
 {
-    scgpu_ntt_plan *plan = g_cache.get(variant, p, n, w, r, tw_bits);
-    if (cudaSetDevice(plan->dev.device) != cudaSuccess) dropin_fatal("cudaSetDevice");
     ThreadCtx &c = t_ctx;
+    PlanKey key;
+    key.w = w; key.r = r; key.n = (uint64_t)n; key.inv = p->inv_q_dbl;
+    key.q = p->u.ntt32.q; key.m = p->u.ntt32.m; key.k = p->u.ntt32.k;
+    key.variant = variant; key.tw_bits = w ? tw_bits : 0; key.device = dropin_device();
+    scgpu_ntt_plan *plan = c.plan_for(key);
+    if (cudaSetDevice(plan->dev.device) != cudaSuccess) dropin_fatal("cudaSetDevice");
+    c.device = plan->dev.device;
     const size_t abytes = n * a_elem_size(op), obytes = n * 4, bbytes = b_elems * b_elem_size(op);
     void *da = c.ensure(0, abytes);
     void *dout = c.ensure(1, obytes);

@@ -172,6 +172,25 @@ int ref_prng_script(int prng_type, const uint8_t *seed, size_t seed_len, size_t 
         else if (kind == 64) { UINT64 x = prng_64(ctx); out[o++] = (uint32_t)(x >> 32); out[o++] = (uint32_t)x; }
         else if (kind == 8) out[o++] = prng_8(ctx);
         else if (kind == 1) out[o++] = (uint32_t)prng_bit(ctx);
+        else if (kind == 16) out[o++] = prng_16(ctx);
+        else if (kind == 128) {
+            UINT128 x = prng_128(ctx);
+            out[o++] = (uint32_t)(x >> 96); out[o++] = (uint32_t)(x >> 64); out[o++] = (uint32_t)(x >> 32); out[o++] = (uint32_t)x;
+        }
+        else if (kind == 2) { FLOAT f = prng_float(ctx); memcpy(&out[o++], &f, 4); }
+        else if (kind == 3) { DOUBLE d = prng_double(ctx); memcpy(&out[o], &d, 8); o += 2; }
+        else if (kind == 4) {
+            size_t nw = ((size_t)arg + 3) / 4;
+            memset(out + o, 0, nw * 4);
+            prng_mem(ctx, (UINT8 *)(out + o), arg);
+            o += nw;
+        }
+        else if (kind == 5) {
+            /* reset_chacha20 frees the generator (chacha20_csprng.c:58-67): only the DRBG has a defined reset */
+            if (prng_type != SC_PRNG_AES_CTR_DRBG) { prng_destroy(ctx); return -2; }
+            prng_reset(ctx);
+        }
+        else if (kind == 6) { out[o++] = (uint32_t)prng_get_csprng_bytes(ctx); out[o++] = (uint32_t)prng_get_out_bytes(ctx); }
         else out[o++] = prng_var(ctx, (size_t)arg);
     }
     prng_destroy(ctx);

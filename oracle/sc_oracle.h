@@ -77,6 +77,16 @@ uint64_t orc_prng_64(orc_prng_t *ctx);
 uint32_t orc_prng_var(orc_prng_t *ctx, size_t n);
 uint32_t orc_prng_8(orc_prng_t *ctx);
 int32_t  orc_prng_bit(orc_prng_t *ctx);
+float    orc_prng_float(orc_prng_t *ctx);
+double   orc_prng_double(orc_prng_t *ctx);
+int32_t  orc_prng_mem(orc_prng_t *ctx, uint8_t *mem, int32_t length);
+int      orc_prng_reset(orc_prng_t *ctx);                 /* AES-CTR-DRBG only, see sc_oracle_prng.c */
+uint64_t orc_prng_csprng_bytes(orc_prng_t *ctx);
+uint64_t orc_prng_out_bytes(orc_prng_t *ctx);
+/* script = (kind, arg) pairs: 32 prng_32, 64 prng_64 (hi, lo), 8 prng_8, 1 prng_bit, 16 prng_16, 0 prng_var(arg),
+ * 128 prng_128 (4 words, most significant first), 2 prng_float (bits), 3 prng_double (bits, low word first),
+ * 4 prng_mem(arg bytes; ceil(arg/4) words, zero padded), 5 prng_reset (no output), 6 statistics (csprng bytes,
+ * out bytes; low 32 bits each) */
 int orc_prng_script(int prng_type, const uint8_t *seed, size_t seed_len, size_t seed_period,
                     const int32_t *script, size_t ndraws, uint32_t *out);
 void orc_aes256_encrypt_block(const uint8_t key[32], const uint8_t in[16], uint8_t out[16]);

@@ -143,6 +143,8 @@ struct orc_prng {
     uint32_t counter, drbg_reseed_ctr, drbg_period;
     uint8_t buf[DRBG_BUF_BYTES];
     int rng_cnt;
+    /* statistics (prng.c: stats_csprng_bytes / stats_out_bytes) */
+    uint64_t csprng_bytes, out_bytes;
 };
 
 static void entropy(orc_prng_t *c, size_t n, uint8_t *dst)
@@ -191,6 +193,7 @@ static uint32_t chacha_next32(orc_prng_t *c)
 /* chacha20_csprng.c:99-106 */
 static uint64_t chacha_random64(orc_prng_t *c)
 {
+    c->csprng_bytes += 8;                                /* get_random_64_chacha, prng_get_func.c:242-261 */
     c->cc_reseed_ctr += 8;
     if ((uint32_t)c->seed_period <= c->cc_reseed_ctr) chacha_reseed(c);
     uint64_t hi = chacha_next32(c);
@@ -231,6 +234,7 @@ static void drbg_fill(orc_prng_t *c)
 static uint64_t drbg_random64(orc_prng_t *c)
 {
     if (c->rng_cnt == DRBG_BUF_BYTES / 8) { c->rng_cnt = 0; drbg_fill(c); }
+    c->csprng_bytes += 8;
     const uint8_t *b = c->buf + 8 * c->rng_cnt++;
     return (uint64_t)le32(b) | ((uint64_t)le32(b + 4) << 32);
 }
@@ -267,6 +271,8 @@ void orc_prng_destroy(orc_prng_t *c)
     free(c);
 }
 
+uint32_t orc_prng_var(orc_prng_t *c, size_t n);
+
 /* prng.c:95-132: refill the whole pool with 2048 64-bit draws, high word first */
 static void pool_refill(orc_prng_t *c)
 {
@@ -286,6 +292,7 @@ uint32_t orc_prng_32(orc_prng_t *c)
     uint32_t v = c->pool[c->rd_idx];
     c->bits -= 32;
     if (++c->rd_idx >= POOL_WORDS) c->rd_idx = 0;
+    c->out_bytes += 4;
     return v;
 }
 
@@ -295,6 +302,49 @@ uint64_t orc_prng_64(orc_prng_t *c)
     return (hi << 32) | orc_prng_32(c);
 }
 
+/* prng.c:1005-1015 */
+float orc_prng_float(orc_prng_t *c) { return ((float)orc_prng_32(c)) / UINT32_MAX; }
+double orc_prng_double(orc_prng_t *c)
+{
+    uint32_t a = orc_prng_var(c, 27);
+    uint32_t b = orc_prng_var(c, 26);
+    return (a * 67108864.0 + b) * 1.11022302462516e-16;
+}
+
+/* prng.c:1050-1105: whole 64-byte blocks of eight generator draws each, taken from the generator
+ * directly -- the words already sitting in the bit pool are NOT consumed and stay ahead of them */
+int32_t orc_prng_mem(orc_prng_t *c, uint8_t *mem, int32_t length)
+{
+    int32_t num_blocks = (length + 63) >> 6;
+    uint8_t *p = mem;
+    while (num_blocks--) {
+        uint64_t d[8];
+        for (int i = 0; i < 8; i++) d[i] = (c->type == ORC_PRNG_CHACHA) ? chacha_random64(c) : drbg_random64(c);
+        memcpy(p, d, (size_t)(length >= 64 ? 64 : length));      /* little-endian host, as the reference's union */
+        length -= 64;
+        p += 64;
+    }
+    return 0;
+}
+
+/* prng.c:861-932 with ctr_drbg_reset (ctr_drbg.c:84-101).  The 1 KiB transfer buffer position rng_cnt is NOT reset,
+ * so the draws that follow first drain what the old key left in it.  For ChaCha20 the reference calls
+ * reset_chacha20, which frees the generator (chacha20_csprng.c:58-67): anything after that is a use after free,
+ * there is no behaviour to restate and this function refuses. */
+int orc_prng_reset(orc_prng_t *c)
+{
+    if (c->type != ORC_PRNG_AES_CTR_DRBG) return 1;
+    c->bits = 0; c->rd_idx = 0; c->var_bits = 0;
+    c->csprng_bytes = 0; c->out_bytes = 0;
+    c->counter = 0;
+    memset(c->key, 0, 32);
+    aes256_expand(&c->ks, c->key);
+    drbg_reseed(c);
+    return 0;
+}
+uint64_t orc_prng_csprng_bytes(orc_prng_t *c) { return c->csprng_bytes; }
+uint64_t orc_prng_out_bytes(orc_prng_t *c) { return c->out_bytes; }
+
 /* prng.c:1017-1048: LSB-first bit buffer refilled from prng_32 */
 uint32_t orc_prng_var(orc_prng_t *c, size_t n)
 {
@@ -303,9 +353,13 @@ uint32_t orc_prng_var(orc_prng_t *c, size_t n)
     uint32_t ret = c->var_buf;
     if (c->var_bits < n) {
         size_t need = n - c->var_bits;
-        ret = need >= 32 ? ret : ret << need;             /* x86 shift-count masking for need == 32 */
+        /* need == 32 (n = 32 on an empty buffer) shifts by the type width, undefined in C.  As compiled with the
+         * reference's flags on a BMI2 host (shlx / bzhi, oracle/Makefile) the shift leaves the value alone and the
+         * mask keeps all 32 bits: the result is stale_var_buf | fresh word.  var_buf is zero whenever var_bits is,
+         * except right after prng_reset, so this is only observable there. */
+        ret = need >= 32 ? ret : ret << need;
         c->var_buf = orc_prng_32(c);
-        ret |= c->var_buf & (need >= 32 ? 0u : ((1u << need) - 1u));
+        ret |= c->var_buf & (need >= 32 ? 0xFFFFFFFFu : ((1u << need) - 1u));
         c->var_buf = need >= 32 ? c->var_buf : c->var_buf >> need;
         c->var_bits = 32 - need;
     } else {
@@ -330,6 +384,20 @@ int orc_prng_script(int prng_type, const uint8_t *seed, size_t seed_len, size_t 
         else if (kind == 64) { uint64_t x = orc_prng_64(c); out[o++] = (uint32_t)(x >> 32); out[o++] = (uint32_t)x; }
         else if (kind == 8) out[o++] = orc_prng_8(c);
         else if (kind == 1) out[o++] = (uint32_t)orc_prng_bit(c);
+        else if (kind == 16) out[o++] = orc_prng_var(c, 16);
+        else if (kind == 128) {                                          /* prng_128: prng_64 << 64 | prng_64 */
+            for (int h = 0; h < 2; h++) { uint64_t x = orc_prng_64(c); out[o++] = (uint32_t)(x >> 32); out[o++] = (uint32_t)x; }
+        }
+        else if (kind == 2) { float f = orc_prng_float(c); memcpy(&out[o++], &f, 4); }
+        else if (kind == 3) { double d = orc_prng_double(c); memcpy(&out[o], &d, 8); o += 2; }
+        else if (kind == 4) {                                            /* prng_mem(arg bytes), zero padded to words */
+            size_t nw = ((size_t)arg + 3) / 4;
+            memset(out + o, 0, nw * 4);
+            orc_prng_mem(c, (uint8_t *)(out + o), arg);
+            o += nw;
+        }
+        else if (kind == 5) { if (orc_prng_reset(c)) { orc_prng_destroy(c); return -2; } }
+        else if (kind == 6) { out[o++] = (uint32_t)orc_prng_csprng_bytes(c); out[o++] = (uint32_t)orc_prng_out_bytes(c); }
         else out[o++] = orc_prng_var(c, (size_t)arg);
     }
     orc_prng_destroy(c);

@@ -51,6 +51,12 @@ def aligned(a, dtype=None, align=64):
     return out
 
 
+def script_words(kind, arg):
+    """Output words of one prng_script entry (oracle/sc_oracle.h)."""
+    kind, arg = int(kind), int(arg)
+    return {64: 2, 128: 4, 3: 2, 6: 2, 5: 0}.get(kind, (arg + 3) // 4 if kind == 4 else 1)
+
+
 class Checker:
     def __init__(self, path, prefix):
         self.lib = ctypes.CDLL(path)
@@ -100,7 +106,7 @@ class Checker:
     def prng_script(self, prng_type, seed, script, seed_period=0):
         seed = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
         script = np.ascontiguousarray(script, dtype=np.int32).reshape(-1, 2)
-        nout = int(sum(2 if k == 64 else 1 for k in script[:, 0]))
+        nout = int(sum(script_words(k, a) for k, a in script))
         out = np.zeros(nout, dtype=np.uint32)
         got = self._fn("prng_script")(prng_type, _vp(seed), seed.size, seed_period, _vp(script),
                                       script.shape[0], _vp(out))

@@ -154,9 +154,10 @@ def test_sampling_statistics_at_scale():
 @pytest.mark.parametrize("precision,tail,sigma", [(64, 13.42, 215.0), (32, 13.42, 215.0), (64, 13.0, 4.5), (32, 9.0, 1000.0),
                                                   (64, 9.0, 1000.0)])     # 128 KiB table: beside the AES tables it no longer fits
 def test_throughput_kernels_against_the_port_in_bulk(prng, precision, tail, sigma):
-    """The throughput kernels bracket the CDF search with a guide table (cdf_search_guided): several million
-    samples per (generator, precision, table) against the port's fixed-step search, every sample compared.
-    sigma = 4.5: a 64-entry table (most guide buckets empty or shared); sigma = 1000: the bracket is wide."""
+    """The throughput kernels, first with the default fixed probe sequence, then with the optional guide table
+    (cdf_search_guided): several million samples per (generator, precision, table) against the port's fixed-step
+    search, every sample compared.  sigma = 4.5: a 64-entry table (most guide buckets empty or shared);
+    sigma = 1000: the bracket is wide."""
     rng = np.random.default_rng(int(sigma * 10) + precision)
     big = sigma > 500 and precision == 64
     seeds = rng.integers(0, 256, size=(300 if big else 3000, 40)).astype(np.uint8)
@@ -165,7 +166,8 @@ def test_throughput_kernels_against_the_port_in_bulk(prng, precision, tail, sigm
     exp = O.port().gauss_streams(O.SAMPLER_CDF, precision, 0, prng, tail, sigma, seeds, n)
     assert np.array_equal(got, exp)
     assert np.abs(got).max() > 3.5 * sigma            # the tails were visited
-    old = sc.lib().scgpu_set_fixed_probe_search(1)    # the reference's fixed probe sequence: same samples
+    old = sc.lib().scgpu_set_fixed_probe_search(0)    # guide-bracketed bisection: same samples
+    assert old == 1                                   # constant-time lookups are the default
     try:
         assert np.array_equal(gpu_samples(O.SAMPLER_CDF, precision, 0, prng, tail, sigma, seeds, n), exp)
     finally:

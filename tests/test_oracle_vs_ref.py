@@ -172,6 +172,25 @@ def test_prng_mixed_draws(prng):
     assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+def test_prng_full_front_end(prng):
+    """prng_128 / prng_16 / prng_float / prng_double / prng_mem / prng_reset (DRBG only: reset_chacha20 frees the
+    generator, chacha20_csprng.c:58-67) and the byte counters, randomly interleaved with the word and bit draws:
+    prng_mem bypasses the 4096-word pool (prng.c:1050-1105), prng_reset keeps the DRBG's stale 1 KiB buffer."""
+    rng = np.random.default_rng(5 + prng)
+    for trial in range(12):
+        seed = rng.integers(0, 256, size=int(rng.integers(36, 80))).astype(np.uint8)
+        script = []
+        for _ in range(400):
+            k = int(rng.choice([32, 64, 8, 1, 16, 0, 128, 2, 3, 4, 4, 6] + ([5] if prng == O.PRNG_AES_CTR_DRBG else [])))
+            arg = int(rng.integers(1, 33)) if k == 0 else int(rng.choice([1, 7, 64, 65, 512, 1000, 4096])) if k == 4 else 0
+            script.append((k, arg))
+        period = int(rng.choice([0, 64, 4096, 0x10000]))
+        got = O.port().prng_script(prng, seed, script, period)
+        exp = O.ref().prng_script(prng, seed, script, period)
+        assert np.array_equal(got, exp), trial
+
+
 @pytest.mark.parametrize("precision", [32, 64])
 @pytest.mark.parametrize("tail,sigma", [(13.42, 215.0), (13.0, 4.5), (13.42, 19.53), (10.0, 107.0)])
 def test_cdf_tables(precision, tail, sigma):
