@@ -96,7 +96,8 @@ def polymul_via_table(lib, variant, n, q, a, b, w, r):
 def test_config_c1_single_pair_through_the_count_1_shim():
     """BASELINE config #1 / SURVEY 8d C1: one pair, a[i], b[i] ~ U[0, q) from default_rng(20261017), n = 512,
     q = 12289, through the count = 1 drop-in members and through libscref's same members: identical, for every
-    variant; and equal to the schoolbook negacyclic product."""
+    variant; and equal to the schoolbook negacyclic product (congruent to it for Barrett, whose reference
+    output is itself not canonical on this composition)."""
     q, n = 12289, 512
     rng = np.random.default_rng(20261017)
     a = rng.integers(0, q, size=n).astype(np.int32)
@@ -109,7 +110,12 @@ def test_config_c1_single_pair_through_the_count_1_shim():
     school %= q
     for variant in (O.REFERENCE, O.BARRETT, O.FP, O.AVX):
         fwd_g, out_g = polymul_via_table(sc.lib(), variant, n, q, a, b, w, r)
-        assert np.array_equal(out_g, school), variant
+        if variant == O.BARRETT:
+            # unnormalised x unnormalised pointwise products leave Barrett (k = 30) only congruent: the
+            # reference's own output is not canonical here, and it is matched word for word below
+            assert np.array_equal(out_g.astype(np.int64) % q, school), variant
+        else:
+            assert np.array_equal(out_g, school), variant
         assert np.array_equal(fwd_g, O.port().ntt_batch(variant, O.OP_FWD, n, q, 16, a, None, w, r)[0])
         if O.ref_available():
             fwd_r, out_r = polymul_via_table(O.ref().lib, variant, n, q, a, b, w, r)
@@ -224,8 +230,10 @@ def counting_callback():
 
     def cb(n, data):
         for i in range(n):
-            k = state["pos"] + i
-            data[i] = (k * 167 + (k >> 8) * 13 + 5) & 0xFF
+            z = (state["pos"] + i + 1) * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF       # splitmix64 of the byte index
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+            data[i] = (z ^ (z >> 31)) & 0xFF
         state["pos"] += n
         state["calls"].append(n)
     return ENTROPY_CB(cb), state
