@@ -46,6 +46,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def instr_counts():
+    """warp-instructions per unit of the hot kernels, from the committed ncu captures (profiles/instr_counts_r2.json,
+    written by tools/instr_counts.py from `ncu --set full` reports; instruction counts do not depend on clocks)."""
+    path = os.path.join(ROOT, "profiles", "instr_counts_r2.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+def issue_peak(sm_count, sm_mhz):
+    """Hardware warp-instruction issue rate: SMs x 4 schedulers x 1 warp-instruction per clock."""
+    return sm_count * 4 * sm_mhz * 1e6
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -251,10 +266,21 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = world * BATCH / (ms_per_step * 1e-3)
 
-    # spot-check the timed output against the oracle (parity is the gate, tests/ hold the full suite)
-    sl = slice(4321, 4321 + 16)
-    exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, N_COEF, Q, 16, a[sl].cpu().numpy(), b[sl].cpu().numpy(), w, r)
-    assert np.array_equal(out[sl].cpu().numpy(), exp), "polymul output differs from the oracle"
+    # the WHOLE timed output against the checker (rank 0): the compiled reference's own fwd, fwd, pointwise, inv on
+    # all host threads when oracle/_ref is present (about 2 s for 2^20 pairs), else the port; other ranks spot-check
+    parity = None
+    if rank == 0:
+        chk, kind = (O.ref(), "reference") if O.ref_available() else (O.port(), "port")
+        t0 = time.perf_counter()
+        exp = chk.ntt_batch(O.REFERENCE, O.OP_POLYMUL, N_COEF, Q, 16, a.cpu().numpy(), b.cpu().numpy(), w, r, threads=host_threads())
+        got = out.cpu().numpy()
+        assert np.array_equal(got, exp), "polymul output differs from the oracle"
+        parity = {"rows_compared": int(BATCH), "checker": kind, "seconds": time.perf_counter() - t0, "equal": True}
+        del exp, got
+    else:
+        sl = slice(4321, 4321 + 16)
+        exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, N_COEF, Q, 16, a[sl].cpu().numpy(), b[sl].cpu().numpy(), w, r)
+        assert np.array_equal(out[sl].cpu().numpy(), exp), "polymul output differs from the oracle"
 
     # ---- roofline of the dominant (only) kernel ------------------------------------------------------------
     peak, peak_src = measured_peaks()
@@ -269,23 +295,48 @@ def main():
         with open(prof) as f:
             roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
     int_roof = None
+    props = torch.cuda.get_device_properties(dev)
+    sm_count = props.multi_processor_count
+    counts = instr_counts()
     if rank == 0:
-        # INT/FP32-issue roofline: the kernel is bound by instruction issue, not HBM.  Denominator =
-        # measured rate of the kernel's own butterfly (FFMA + 2 IMAD + 2 IADD3) in isolation on this device;
-        # numerator = butterfly-equivalents per product: 3 transforms x (n/2) log2 n, n pointwise products and
-        # n/2 extra products of the last inverse stage (n^-1 folded into both branches).
-        bfly_g = sc.int_peak_gops(11, 2048, local_rank)
-        imad_g = sc.int_peak_gops(0, 2048, local_rank)
-        ffma_g = sc.int_peak_gops(7, 2048, local_rank)
+        # Issue roofline: the kernel is bound by instruction issue, not HBM.  Denominator = the
+        # hardware's issue rate, SMs x 4 schedulers x SM clock (the maximum clock: what the part can do); numerator =
+        # warp-instructions per product (ncu count of the committed capture of this kernel) x products / s.  A better
+        # butterfly therefore shows up as fewer instructions per product at the same fraction, i.e. as throughput.
+        smi = sampler.summary() if sampler.rows else {}
+        sm_mhz = smi.get("sm_max_mhz") or props.clock_rate / 1e3
+        peak_issue = issue_peak(sm_count, sm_mhz)
+        wipp = counts.get("k_polymul_w32_n512", {}).get("per_unit")
         bfly = 3 * (N_COEF // 2) * 9 + N_COEF + N_COEF // 2
-        ach = bfly * BATCH / (k_ms * 1e-3) / 1e9
-        int_roof = {"bound": "issue", "unit": "G butterflies/s", "achieved": ach, "peak": bfly_g, "frac": ach / bfly_g if bfly_g > 0 else None,
-                    "butterflies_per_product": bfly, "imad_gops": imad_g, "ffma_gops": ffma_g,
-                    "peak_source": "scgpu_int_peak_gops(11): float-quotient butterfly microbenchmark on this device"}
-    # other parameter shapes of BASELINE.json configs[1..2] (device-resident, 1 GiB per operand; parity is in tests/)
+        int_roof = {"bound": "issue", "unit": "warp-instructions/s", "peak": peak_issue, "sm_count": sm_count, "sm_mhz": sm_mhz,
+                    "warp_instr_per_product": wipp, "butterfly_equivalents_per_product": bfly,
+                    "source": counts.get("k_polymul_w32_n512", {}).get("source"),
+                    "peak_source": "SMs x 4 schedulers x max SM clock"}
+        if wipp:
+            ach = wipp * BATCH / (k_ms * 1e-3)
+            int_roof.update({"achieved": ach, "frac": ach / peak_issue,
+                             "butterfly_instr_frac": 5.0 * bfly / 32.0 / wipp})
+    # other parameter shapes of BASELINE.json configs[1..3] (device-resident, 1 GiB per operand; parity is in tests/)
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            fn()
+        e0.record()
+        torch.cuda.synchronize()
+        return s0.elapsed_time(e0) / reps * 1e-3
+
     shapes = None
     if rank == 0:
         shapes = {}
+
+        def put(name, units, secs, bytes_per_unit, unit):
+            shapes[name] = {"per_s": units / secs, "unit": unit + "/s", "units": units,
+                            "hbm_frac": bytes_per_unit * units / secs / 1e9 / peak}
+
         for (qq, nn) in ((12289, 1024), (7681, 256)):
             ww, rr = O.tables(qq, nn, 16)
             pl = sc.NttPlan(nn, qq, sc.REFERENCE, ww, rr, device=local_rank)
@@ -293,32 +344,45 @@ def main():
             xa = torch.randint(0, qq, (bb, nn), dtype=torch.int32, device=dev, generator=g)
             xb = torch.randint(0, qq, (bb, nn), dtype=torch.int32, device=dev, generator=g)
             xo = torch.empty_like(xa)
-            for _ in range(3):
-                pl.polymul(xo, xa, xb)
-            torch.cuda.synchronize()
-            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(10):
-                pl.polymul(xo, xa, xb)
-            e0.record()
-            torch.cuda.synchronize()
-            ms = s0.elapsed_time(e0) / 10
-            shapes["polymul_n%d_q%d" % (nn, qq)] = {"polymul_per_s": bb / (ms * 1e-3), "pairs": bb,
-                                                    "hbm_frac": 12 * nn * bb / (ms * 1e-3) / 1e9 / peak}
+            put("polymul_n%d_q%d" % (nn, qq), bb, timed(lambda: pl.polymul(xo, xa, xb)), 12 * nn, "polymul")
+            if nn == 256:
+                # Kyber module product t = A s, k = l = 3 (module_lwe.c:669-748), A in the NTT domain: 4 n (k^2 + 2 k) bytes
+                k = 3
+                inst = 1 << 17
+                A = torch.randint(0, qq, (inst, k * k, nn), dtype=torch.int32, device=dev, generator=g)
+                sv = torch.randint(-4, 5, (inst, k, nn), dtype=torch.int32, device=dev, generator=g)
+                to = torch.empty((inst, k, nn), dtype=torch.int32, device=dev)
+                put("kyber_matvec_k3_n256_q7681", inst, timed(lambda: pl.matvec(to, A, sv, k, k)), 4 * nn * (k * k + 2 * k), "instance")
+                del A, sv, to
             del xa, xb, xo, pl
+        # BLISS sign / verify core: v = INTT(NTT(t) o key), one shared SINT16 key (bliss_b.c:1378-1384): 8 n bytes
+        key = torch.randint(0, Q, (N_COEF,), dtype=torch.int32, device=dev, generator=g).to(torch.int16)
+        put("bliss_key_product_n512_q12289", BATCH, timed(lambda: plan.mul_key(out, a, key)), 8 * N_COEF, "product")
         # single transforms with canonical output (normalize_32 o fwd_ntt, inv_ntt), n = 512: 8 n bytes each
-        for inverse, name in ((False, "fwd_ntt_canonical_n512_q12289"), (True, "inv_ntt_canonical_n512_q12289")):
-            for _ in range(3):
-                plan.ntt_canonical(out, a, inverse=inverse)
-            torch.cuda.synchronize()
-            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(10):
-                plan.ntt_canonical(out, a, inverse=inverse)
-            e0.record()
-            torch.cuda.synchronize()
-            ms = s0.elapsed_time(e0) / 10
-            shapes[name] = {"ntt_per_s": BATCH / (ms * 1e-3), "polys": BATCH, "hbm_frac": 8 * N_COEF * BATCH / (ms * 1e-3) / 1e9 / peak}
+        put("fwd_ntt_canonical_n512_q12289", BATCH, timed(lambda: plan.ntt_canonical(out, a)), 8 * N_COEF, "ntt")
+        put("inv_ntt_canonical_n512_q12289", BATCH, timed(lambda: plan.ntt_canonical(out, a, inverse=True)), 8 * N_COEF, "ntt")
+        # the members the drop-in table calls: the variant's own lazily reduced representative, bit for bit
+        for vv, vname in ((sc.REFERENCE, "reference"), (sc.BARRETT, "barrett"), (sc.AVX, "avx")):
+            pe = sc.NttPlan(N_COEF, Q, vv, w, r, device=local_rank)
+            put("exact_fwd_ntt_32_16_n512_%s" % vname, BATCH, timed(lambda: pe.batch(sc.OP_FWD, out, a)), 8 * N_COEF, "ntt")
+            put("exact_inv_ntt_32_16_n512_%s" % vname, BATCH, timed(lambda: pe.batch(sc.OP_INV, out, a)), 8 * N_COEF, "ntt")
+            del pe
+        # Dilithium q = 8380417, n = 256 (32-bit tables): polymul and the k = 5, l = 4 module product
+        qq, nn = 8380417, 256
+        ww, rr = O.tables(qq, nn, 32)
+        pl = sc.NttPlan(nn, qq, sc.REFERENCE, ww, rr, device=local_rank)
+        bb = 1 << 20
+        xa = torch.randint(0, qq, (bb, nn), dtype=torch.int32, device=dev, generator=g)
+        xb = torch.randint(0, qq, (bb, nn), dtype=torch.int32, device=dev, generator=g)
+        xo = torch.empty_like(xa)
+        put("polymul_n256_q8380417", bb, timed(lambda: pl.polymul(xo, xa, xb)), 12 * nn, "polymul")
+        del xa, xb, xo
+        inst = 1 << 15
+        A = torch.randint(0, qq, (inst, 20, nn), dtype=torch.int32, device=dev, generator=g)
+        sv = torch.randint(-2, 3, (inst, 4, nn), dtype=torch.int32, device=dev, generator=g)
+        to = torch.empty((inst, 5, nn), dtype=torch.int32, device=dev)
+        put("dilithium_matvec_k5_l4_n256", inst, timed(lambda: pl.matvec(to, A, sv, 5, 4)), 4 * nn * (20 + 4 + 5), "instance")
+        del A, sv, to, pl
 
     # ---- end-to-end leg: host buffers through the C-ABI ----------------------------------------------------
     ha = torch.randint(0, Q, (E2E_BATCH, N_COEF), dtype=torch.int32).pin_memory()
@@ -347,31 +411,71 @@ def main():
            "api": "scgpu_polymul_batch_host (pinned host buffers, chunked 3-stream H2D/kernel/D2H pipeline)"}
 
     # ---- secondary metric: Gaussian samples/s (BASELINE config 5 shape), every rank its own streams -------------
+    # CDF-64, sigma 215, both generators; "fixed_probe" = the default constant-time table search (the reference's
+    # log2(size) probes for every draw), "guided" = the optional guide-bracketed bisection (data-dependent trip count)
     gp = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0, device=local_rank)
     nstreams, n = 1 << 18, 512
     seeds = torch.randint(0, 256, (nstreams, 40), dtype=torch.uint8, device=dev, generator=g)
     smp = torch.empty((nstreams, n), dtype=torch.int32, device=dev)
     gauss = {}
-    for name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
-        for _ in range(3):
-            gp.streams(prng, seeds, n, smp)
-        barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(5):
-            gp.streams(prng, seeds, n, smp)
-        e.record()
-        barrier()
-        ms = s.elapsed_time(e)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        gauss["cdf64_sigma215_%s_samples_per_s" % name] = world * 5 * nstreams * n / (ms * 1e-3)
-    gauss["shape"] = "%d streams x %d samples per GPU on %d GPU(s), CDF-64, sigma 215, tail 13.42; whole-job rate, max over ranks" % (nstreams, n, world)
+    smi = sampler.summary() if sampler.rows else {}
+    peak_issue = issue_peak(sm_count, smi.get("sm_max_mhz") or props.clock_rate / 1e3)
+    for mode, fixed in (("fixed_probe", 1), ("guided", 0)):
+        old = sc.lib().scgpu_set_fixed_probe_search(fixed)
+        for name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
+            for _ in range(3):
+                gp.streams(prng, seeds, n, smp)
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(5):
+                gp.streams(prng, seeds, n, smp)
+            e.record()
+            barrier()
+            ms = s.elapsed_time(e)
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            rate = world * 5 * nstreams * n / (ms * 1e-3)
+            entry = {"samples_per_s": rate, "hbm_frac": 4 * rate / world / 1e9 / peak}
+            key = "k_cdf_%s_%s" % ("aes" if prng == sc.PRNG_AES_CTR_DRBG else "chacha", mode)
+            wips = counts.get(key, {}).get("per_unit")
+            if wips:
+                # issue roofline of the sampler: warp-instructions per sample (ncu, committed capture) x samples/s per GPU
+                entry["roofline"] = {"bound": "issue", "warp_instr_per_sample": wips, "achieved": wips * rate / world,
+                                     "peak": peak_issue, "frac": wips * rate / world / peak_issue,
+                                     "alu_pipe_pct": counts[key].get("alu_pipe_pct"), "source": counts[key].get("source")}
+            gauss["cdf64_sigma215_%s_%s" % (name, mode)] = entry
+        sc.lib().scgpu_set_fixed_probe_search(old)
+    gauss["cdf64_sigma215_aes_ctr_drbg_samples_per_s"] = gauss["cdf64_sigma215_aes_ctr_drbg_fixed_probe"]["samples_per_s"]
+    gauss["cdf64_sigma215_chacha20_samples_per_s"] = gauss["cdf64_sigma215_chacha20_fixed_probe"]["samples_per_s"]
+    gauss["shape"] = "%d streams x %d samples per GPU on %d GPU(s), CDF-64, sigma 215, tail 13.42; whole-job rate, max over ranks; 4 B of HBM per sample (the roof is instruction issue)" % (nstreams, n, world)
     # spot check against the oracle
     exp = O.port().gauss_streams(O.SAMPLER_CDF, 64, 0, sc.PRNG_CHACHA, 13.42, 215.0, seeds[:4].cpu().numpy(), n)
     assert np.array_equal(smp[:4].cpu().numpy(), exp), "sampler output differs from the oracle"
+    # Knuth-Yao-64 and Bernoulli-64 (the other two samplers north_star names), sigma 215, smaller batches
+    if rank == 0:
+        for sname, sid, ns in (("knuth_yao64", sc.SAMPLER_KNUTH_YAO, 1 << 15), ("bernoulli64", sc.SAMPLER_BERNOULLI, 1 << 15)):
+            gpx = sc.GaussPlan(sid, 64, 0, 13.42, 215.0, device=local_rank)
+            sx = torch.empty((ns, n), dtype=torch.int32, device=dev)
+            for prng_name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
+                secs = timed(lambda: gpx.streams(prng, seeds[:ns], n, sx), reps=3)
+                gauss["%s_sigma215_%s_samples_per_s" % (sname, prng_name)] = ns * n / secs
+            del gpx, sx
+    # the reference's own get_vector_32 (CDF-64 through create_sampler) on the host cores, both generators
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        chk, kind = (O.ref(), "reference") if O.ref_available() else (O.port(), "port")
+        hseeds = seeds[:1 << 15].cpu().numpy()
+        cpu_g = {"kind": kind, "cores": host_threads()}
+        for name, prng in (("aes_ctr_drbg", O.PRNG_AES_CTR_DRBG), ("chacha20", O.PRNG_CHACHA)):
+            chk.gauss_streams(O.SAMPLER_CDF, 64, 0, prng, 13.42, 215.0, hseeds[:1 << 12], n, threads=host_threads())
+            t0 = time.perf_counter()
+            chk.gauss_streams(O.SAMPLER_CDF, 64, 0, prng, 13.42, 215.0, hseeds, n, threads=host_threads())
+            dt = time.perf_counter() - t0
+            cpu_g["cdf64_sigma215_%s_samples_per_s" % name] = hseeds.shape[0] * n / dt
+        cpu_g["sample"] = "%d streams x %d samples, create_sampler(CDF, 64-bit) + get_vector_32 per stream, OpenMP over %d host threads" % (hseeds.shape[0], n, host_threads())
+        gauss["cpu_baseline"] = cpu_g
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------------
     cpu = None
@@ -392,7 +496,7 @@ def main():
                        "n": N_COEF, "q": Q, "pairs_per_gpu": BATCH, "parallelism": "shard by polynomial index, no collective",
                        "cache": "operands 4 GiB + result 2 GiB per step >> 126 MB L2 (no flush needed)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
-            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss, "other_shapes": shapes,
+            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss, "other_shapes": shapes, "parity": parity,
         }
         emit(line)
     if world > 1:

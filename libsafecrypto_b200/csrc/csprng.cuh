@@ -263,7 +263,7 @@ struct PrngStream {
         return v;
     }
     // chacha20_csprng.c:21-29
-    __device__ void chacha_reseed()
+    __device__ __noinline__ void chacha_reseed()
     {
         s.cc_reseed_ctr = 0;
         for (int i = 0; i < 8; i++) s.cc_key[i] = ent_le32();
@@ -272,7 +272,7 @@ struct PrngStream {
         s.cc_data[0] = s.cc_data[1] = s.cc_data[2] = s.cc_data[3] = 0;
     }
     // ctr_drbg.c:100-147
-    __device__ void drbg_reseed()
+    __device__ __noinline__ void drbg_reseed()
     {
         uint32_t bytes_be[12];                         // three ciphertext blocks as big-endian words
         s.drbg_reseed_ctr = 0;
@@ -294,7 +294,7 @@ struct PrngStream {
         aes256_expand(*aes, key, s.drbg_rk);
     }
     // `pooled`, `ent_fresh` and `ent_avail` are set by the caller beforehand
-    __device__ void init(uint32_t type, uint32_t seed_len, uint32_t seed_period)
+    __device__ __noinline__ void init(uint32_t type, uint32_t seed_len, uint32_t seed_period)
     {
         s.type = type; s.seed_len = seed_len; s.ent_idx = 0;
         s.cc_count = 0; s.have_lo = 0; s.lo_word = 0; s.var_buf = 0; s.var_bits = 0; s.error = 0; s.words_out = 0;
@@ -332,7 +332,7 @@ struct PrngStream {
     // rng_cnt is left alone, so later draws first drain the blocks the OLD key left in the buffer
     // ChaCha20: the reference's reset_chacha20 frees the generator (chacha20_csprng.c:58-67); what is done here is
     // the swapped destroy_chacha20 body (:49-56): data_count = 0 and a reseed.
-    __device__ void reset_pooled()
+    __device__ __noinline__ void reset_pooled()
     {
         s.pool_rd = 0; s.pool_fill = 0; s.var_bits = 0; s.words_out = 0; s.draws64 = 0;
         if (s.type == PRNG_CHACHA20) { s.cc_count = 0; chacha_reseed(); return; }
@@ -342,7 +342,9 @@ struct PrngStream {
         drbg_reseed();
     }
     // one 64-bit generator draw, split high word first (prng.c:108-127)
-    __device__ __forceinline__ void draw64(uint32_t &hi, uint32_t &lo)
+    // not inlined: every sampler of k_stream_seq draws through next32() in several places, and an inlined copy of the
+    // ChaCha20 / AES block per call site made the kernel take a quarter of an hour to assemble
+    __device__ __noinline__ void draw64(uint32_t &hi, uint32_t &lo)
     {
         s.draws64++;
         if (s.type == PRNG_CHACHA20) {
@@ -378,7 +380,7 @@ struct PrngStream {
         }
     }
     // update_pool, prng.c:95-132: the whole pool at once, 2048 draws, high word first
-    __device__ void pool_refill()
+    __device__ __noinline__ void pool_refill()
     {
         for (uint32_t i = 0; i < kPoolWords; i += 2) {
             uint32_t hi, lo;

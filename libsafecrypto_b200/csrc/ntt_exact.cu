@@ -376,6 +376,11 @@ int launch_v(const NttPlanDev &plan, const ExactArgs &g, cudaStream_t st)
 int launch_exact(const NttPlanDev &plan, const ExactArgs &g, cudaStream_t st)
 {
     if (g.count == 0) return SCGPU_OK;
+    if ((g.op == SCGPU_OP_FWD || g.op == SCGPU_OP_INV) && g.w == plan.w && g.r == plan.r) {
+        // the warp-local schedule (ntt_exact_w32.cu); not applicable (unusual tables, unaligned rows): this file's kernel
+        const int e = launch_exact_w32(plan, g.op, g.out, static_cast<const int32_t *>(g.a), g.count, st);
+        if (e != SCGPU_ERR_UNSUPPORTED) return e;
+    }
     switch (plan.variant) {
     case V_REFERENCE:  return launch_v<V_REFERENCE>(plan, g, st);
     case V_BARRETT:    return launch_v<V_BARRETT>(plan, g, st);

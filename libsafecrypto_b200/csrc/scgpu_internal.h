@@ -58,6 +58,10 @@ struct NttPlanDev {
     void *sh32_tab;                      // forward [w | wp], inverse [w | wp], n words each
     alignas(16) unsigned char sh32_pass0[2 * 31 * 8], sh32_ninv[8], sh32_one[8];
     alignas(16) unsigned char sh32_ninv_plain[8], sh32_zi1_plain[8];   // last-stage multipliers without the factor R
+    // variant-exact transforms on the warp-local schedule (ntt_exact_w32.cu): 0 not applicable, 1 forward only (no r), 2 both
+    int xw32_ok;
+    void *xw32_tab;                      // [pass-1 w | aux | fwd twist w | aux | inv twist w | aux], n words each
+    int32_t xw32_f0[62];                 // stages 0..4: 31 x w, 31 x aux
 };
 
 struct ExactArgs {
@@ -76,6 +80,9 @@ struct ExactArgs {
 };
 
 int launch_exact(const NttPlanDev &plan, const ExactArgs &args, cudaStream_t stream);
+int build_xw32_tables(NttPlanDev &plan, const int32_t *w_host, const int32_t *r_host);
+void free_xw32_tables(NttPlanDev &plan);
+int launch_exact_w32(const NttPlanDev &plan, int op, int32_t *out, const int32_t *a, size_t count, cudaStream_t stream);
 int launch_polymul(const NttPlanDev &plan, int32_t *out, const int32_t *a, const int32_t *b,
                    size_t b_stride, size_t count, cudaStream_t stream);
 int launch_mul_key(const NttPlanDev &plan, int32_t *out, const int32_t *t, const void *key,

@@ -50,7 +50,7 @@ for n in (512, 1024):
     report("C2 key product n=%d (shared SINT16 key)" % n, B, timeit(lambda: pl.mul_key(o, a, key)), 8 * n)
     report("C2 canonical fwd NTT n=%d (normalize o fwd_ntt)" % n, B, timeit(lambda: pl.ntt_canonical(o, a)), 8 * n, "ntt")
     report("C2 canonical inv NTT n=%d" % n, B, timeit(lambda: pl.ntt_canonical(o, a, inverse=True)), 8 * n, "ntt")
-    for v, vn in ((sc.REFERENCE, "reference"), (sc.BARRETT, "barrett")):
+    for v, vn in ((sc.REFERENCE, "reference"), (sc.BARRETT, "barrett"), (sc.FP, "fp"), (sc.AVX, "avx")):
         pe = sc.NttPlan(n, q, v, w, r)
         report("exact fwd_ntt_32_16 n=%d %s" % (n, vn), B, timeit(lambda: pe.batch(sc.OP_FWD, o, a)), 8 * n, "ntt")
         report("exact inv_ntt_32_16 n=%d %s" % (n, vn), B, timeit(lambda: pe.batch(sc.OP_INV, o, a)), 8 * n, "ntt")
