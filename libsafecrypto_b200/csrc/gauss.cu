@@ -102,15 +102,12 @@ __device__ __forceinline__ int32_t sample_cdf(const GaussTablesDev &g, PrngStrea
 // entries until the distance goes negative (adding the number of entries scanned to the sample) or a whole
 // row's worth of entries is consumed.  It does NOT re-align the pointer after a hit, and the distance keeps
 // doubling and eventually wraps around, so later rows keep contributing.  With the sorted flat positions of
-// the one-bits this is evaluated per row in O(log) time: "ones in [ptr, ptr+len)" and "k-th one after ptr".
-__device__ __forceinline__ uint32_t ky_lower_bound(const GaussTablesDev &g, uint32_t pos)
+// the one-bits and a bitmap with prefix counts this is evaluated per row in O(1): "ones in [ptr, ptr+len)" is a
+// difference of two ranks, "k-th one after ptr" one read of the flat table.
+__device__ __forceinline__ uint32_t ky_rank(const GaussTablesDev &g, uint32_t pos)         // one-bits before position pos
 {
-    uint32_t lo = 0, hi = g.ky_nones;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (g.ky_flat[mid] < pos) lo = mid + 1; else hi = mid;
-    }
-    return lo;
+    const uint32_t wd = pos >> 5;
+    return __ldg(g.ky_rank + wd) + (uint32_t)__popc(__ldg(g.ky_bits + wd) & ((1u << (pos & 31)) - 1u));
 }
 
 __device__ __forceinline__ int32_t sample_ky(const GaussTablesDev &g, PrngStream &rng)
@@ -126,19 +123,18 @@ __device__ __forceinline__ int32_t sample_ky(const GaussTablesDev &g, PrngStream
             rnd >>= 1;
             if ((row & 0x1F) == 0x1F) rnd = rng.next32();
             uint32_t len = cols, col0 = 0;
-            uint32_t i0 = ky_lower_bound(g, ptr);
+            uint32_t i0 = ky_rank(g, ptr);
             if ((int32_t)dist < 0) {
                 // first entry of the scan
-                uint32_t bit = (i0 < g.ky_nones && g.ky_flat[i0] == ptr) ? 1u : 0u;
+                const uint32_t bit = (__ldg(g.ky_bits + (ptr >> 5)) >> (ptr & 31)) & 1u;
                 dist -= bit;
                 ptr += 1; i0 += bit;
                 if ((int32_t)dist < 0) continue;        // hit at column 0: sample += 0
                 len = cols - 1; col0 = 1;               // wrapped to INT_MAX: keep scanning this row
             }
-            uint32_t i1 = ky_lower_bound(g, ptr + len);
-            uint32_t cnt = i1 - i0;                     // ones in the window
+            const uint32_t cnt = ky_rank(g, ptr + len) - i0;      // ones in the window
             if (dist < cnt) {
-                uint32_t f = g.ky_flat[i0 + dist];      // the (dist+1)-th one takes the distance to -1
+                const uint32_t f = __ldg(g.ky_flat + i0 + dist);  // the (dist+1)-th one takes the distance to -1
                 sample += (int32_t)(col0 + (f - ptr));
                 ptr = f + 1;
                 dist = 0xFFFFFFFFu;
@@ -257,8 +253,8 @@ __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
     } else {
         for (size_t call = 0; call < a.calls; call++, v += a.n) {
             const size_t n = a.n;
-            if (a.g.sampler != SCGPU_SAMPLER_CDF || a.g.blinding == SCGPU_NORMAL_SAMPLES) {
-                // sampling.c:211-228 (KY / Bernoulli are driven the same way: sample() + centre)
+            if (a.g.blinding == SCGPU_NORMAL_SAMPLES) {
+                // sampling.c:211-228 (every sampler is driven the same way: sample() + centre)
                 if (a.g.sampler == SCGPU_SAMPLER_BERNOULLI) {
                     // one candidate per trip; the lanes of a warp sit at different samples i
                     for (size_t i = 0; i < n;) {
@@ -297,6 +293,89 @@ __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
         }
     }
     if (a.states) a.states[sidx] = rng.s;
+}
+
+// ---- Bernoulli sampler: one lane per stream, ONE random draw per trip ---------------------------------------------
+// bernoulli_sample_64 (gaussian_bernoulli.c:161-280) draws a 12-bit candidate, then compares up to 8 x 23 random
+// bytes with its table and rejects at the first byte that decides against the candidate.  An accepted candidate costs
+// 184 byte draws, a rejected one a handful, and ~15 candidates are rejected per accepted one (sigma = 215): with one
+// sample() call per lane per trip a warp always waits for its one lane that is inside an accepted candidate
+// (3.4e7 samples/s in round 1).  Here every lane advances its own state machine by one draw per trip -- candidate,
+// byte (j, i), zero / sign, discard -- so all lanes make progress all the time, and the generator is stepped for the
+// whole warp at once: each lane keeps a four-word FIFO, and when any lane runs dry every lane with room draws its next
+// 64 bits, so the ChaCha20 / AES blocks of the 32 streams are computed side by side instead of one lane at a time.
+// Fresh streams, NORMAL_SAMPLES (any discard setting); everything else stays on k_stream_seq.
+__global__ void __launch_bounds__(128) k_ber_lanes(SeqArgs a)
+{
+    __shared__ AesTables aes;
+    aes_tables_init(aes);
+    __syncthreads();
+    const size_t sidx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t total = a.n * a.calls;
+    bool done = sidx >= a.nstreams || total == 0;
+    PrngStream rng;
+    rng.aes = &aes;
+    rng.seed = a.seeds + (done ? 0 : sidx) * a.seed_len;
+    rng.s.pooled = 0; rng.s.ent_fresh = 0; rng.s.ent_avail = 0;
+    if (!done) rng.init(a.prng_type, a.seed_len, a.seed_period);
+    int32_t *v = a.out + (done ? 0 : sidx) * total;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    int cnt = 0;                                        // words in the FIFO
+    uint32_t var_buf = 0, var_bits = 0;                 // prng_var's bit buffer (prng.c:1017-1048)
+    auto pop = [&]() { const uint32_t x = w0; w0 = w1; w1 = w2; w2 = w3; cnt--; return x; };
+    auto var = [&](uint32_t n) {                         // n < 32 here
+        uint32_t ret = var_buf;
+        if (var_bits < n) {
+            const uint32_t need = n - var_bits;
+            ret <<= need;
+            var_buf = pop();
+            ret |= var_buf & ((1u << need) - 1u);
+            var_buf >>= need;
+            var_bits = 32 - need;
+        } else {
+            var_buf >>= n;
+            var_bits -= n;
+        }
+        return ret & ((1u << n) - 1u);
+    };
+    const int entries = a.g.ber_entries;
+    int phase = 0, i = 0, j = 0;
+    uint32_t val = 0, x = 0, accept_mask = 0;
+    size_t idx = 0;
+    while (__any_sync(0xFFFFFFFFu, !done)) {
+        if (__any_sync(0xFFFFFFFFu, !done && cnt == 0)) {
+            if (!done && cnt <= 2) {
+                uint32_t hi, lo;
+                rng.draw64(hi, lo);
+                if (cnt == 0) { w0 = hi; w1 = lo; } else if (cnt == 1) { w1 = hi; w2 = lo; } else { w2 = hi; w3 = lo; }
+                cnt += 2;
+            }
+        }
+        if (done) continue;
+        if (phase == 0) {                               // candidate (gaussian_bernoulli.c:167-175)
+            val = var((uint32_t)a.g.ber_maxlog);
+            if (val < (uint32_t)a.g.ber_maxval) { x = val * val; accept_mask = 0; j = 0; i = entries - 1; phase = 1; }
+        } else if (phase == 1) {                        // one table byte (:177-243)
+            const uint32_t r = var(8);
+            const uint32_t tv = __ldg(a.g.ber_tab + i * 8 + j);
+            const uint32_t undecided = ((accept_mask >> i) & 1u) ^ 1u;
+            if (r < tv && undecided) accept_mask |= 1u << i;
+            if (r > tv && ((x >> i) & 1u) && undecided) phase = 0;                 // rejected: next candidate
+            else if (i-- == 0) { i = entries - 1; if (++j == 8) phase = 2; }
+        } else if (phase == 2) {                        // zero with probability 1/2, sign (:248-280)
+            const uint32_t rnd = var(2);
+            if (val == 0 && rnd < 2) phase = 0;
+            else {
+                const int32_t smp = val == 0 ? 0 : ((rnd & 1) ? -(int32_t)val : (int32_t)val);
+                v[idx] = smp + a.centre;
+                if (a.thresh) phase = 3;
+                else { phase = 0; done = ++idx >= total; }
+            }
+        } else {                                        // discard_sample (sampling.c:95-105): a whole prng_32 word
+            if (!(pop() < a.thresh)) done = ++idx >= total;
+            phase = 0;
+        }
+    }
 }
 
 // ---- fast path 1: CDF over the AES-CTR-DRBG ---------------------------------------------------------------
@@ -533,7 +612,10 @@ int launch_gauss_seq(const GaussTablesDev &g, int prng_type, const uint8_t *seed
     a.thresh = discard == 2 ? 1u << 28 : discard == 4 ? 1u << 30 : discard == 6 ? 1u << 31 : 0;   // sampling.c:85-92
     a.out = out; a.mode = mode; a.pool_mem = pool_mem;
     const unsigned grid = (unsigned)((nstreams + 127) / 128);
-    k_stream_seq<<<grid, 128, 0, st>>>(a);
+    if (mode == 0 && states == nullptr && g.sampler == SCGPU_SAMPLER_BERNOULLI && g.blinding == SCGPU_NORMAL_SAMPLES && g.ber_maxlog < 32)
+        k_ber_lanes<<<grid, 128, 0, st>>>(a);
+    else
+        k_stream_seq<<<grid, 128, 0, st>>>(a);
     count_launch();
     SCGPU_CUDA_CHECK(cudaGetLastError());
     return SCGPU_OK;

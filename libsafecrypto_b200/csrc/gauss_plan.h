@@ -29,6 +29,9 @@ struct GaussTablesDev {
     int ky_rows, ky_cols, ky_bound;
     uint32_t ky_nones;
     const uint32_t *ky_flat;
+    // the same matrix as a bitmap (bit p of word p / 32 = entry p) with the number of one-bits before each word:
+    // rank(p) = ky_rank[p / 32] + popc(low bits), so a whole row of the walk costs two table reads instead of a scan
+    const uint32_t *ky_bits, *ky_rank;
     // Bernoulli (gaussian_bernoulli.c:40-103): entries x 8 bytes, most significant byte first
     const uint8_t *ber_tab;
     int ber_entries, ber_maxval, ber_maxlog;

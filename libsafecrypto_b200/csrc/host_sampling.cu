@@ -26,7 +26,7 @@ struct scgpu_gauss_plan {
     GaussTablesDev t;
     int device, sm_count;
     void *d_cdf = nullptr;
-    uint32_t *d_flat = nullptr;
+    uint32_t *d_flat = nullptr, *d_kybits = nullptr, *d_kyrank = nullptr;
     uint8_t *d_ber = nullptr;
     uint32_t *d_guide = nullptr;
     std::mutex mu;
@@ -50,6 +50,19 @@ uint64_t bin_expansion(double x, int nbits)
 {
     double val = 0, step = 0.5f;
     uint64_t res = 0;
+    for (int i = 0; i < nbits; i++) {
+        res <<= 1;
+        if ((val + step) < x) { val += step; res |= 1; }
+        step = step / 2;
+    }
+    return res;
+}
+
+// the same loop with up to 128 result bits (get_binary_expansion_fraction_32/64/128, sc_math.c:1047-1100)
+unsigned __int128 bin_expansion128(double x, int nbits)
+{
+    double val = 0, step = 0.5f;
+    unsigned __int128 res = 0;
     for (int i = 0; i < nbits; i++) {
         res <<= 1;
         if ((val + step) < x) { val += step; res |= 1; }
@@ -199,25 +212,38 @@ extern "C" int scgpu_gauss_plan_create(scgpu_gauss_plan_t **out, int sampler, in
         p->d_cdf = d; p->t.cdf32 = d; p->t.cdf_size = (uint32_t)cdf.size();
         const std::vector<uint32_t> guide = build_guide(cdf);
         if (rc == SCGPU_OK && !guide.empty()) { rc = upload(&p->d_guide, guide); p->t.cdf_guide = p->d_guide; }
-    } else if (sampler == SCGPU_SAMPLER_KNUTH_YAO && (precision == 32 || precision == 64) && blinding != SCGPU_BLINDING_SAMPLES) {
-        // gaussian_knuth_yao.c:126-189; the matrix is stored as the sorted flat positions of its one-bits
+    } else if (sampler == SCGPU_SAMPLER_KNUTH_YAO && (precision == 32 || precision == 64 || precision == 128)) {
+        // gaussian_knuth_yao.c:126-189 (create), :50-124 (the 128 / 64 / 32-row tables); blinding scales sigma (:144-146).
+        // The byte-per-bit matrix is kept as (a) the sorted flat positions of its one-bits, (b) a bitmap with
+        // per-word prefix counts.
         const int rows = precision;
+        if (blinding == SCGPU_BLINDING_SAMPLES) sigma *= 0.7071067811865475244008443621L;
         const int bound = (int32_t)ceil(tail * sigma);
         const int cols = bound + 1;
         long double d = 0.7978845608028653558798L / sigma;
         long double e = -0.5L / (sigma * sigma);
-        std::vector<uint64_t> colbits((size_t)cols);
+        std::vector<unsigned __int128> colbits((size_t)cols);
         for (int col = 0; col < cols; col++) {
             long double pr = (col == 0) ? d : d * expl(e * ((long double)(col * col)));
-            colbits[col] = bin_expansion((double)pr, rows);
+            colbits[col] = bin_expansion128((double)pr, rows);
         }
-        std::vector<uint32_t> flat;
+        const size_t total = (size_t)rows * (size_t)cols;
+        std::vector<uint32_t> flat, bits(total / 32 + 2, 0), rank(total / 32 + 2, 0);
         for (int row = 0; row < rows; row++)
             for (int col = 0; col < cols; col++)
-                if ((colbits[col] >> (rows - 1 - row)) & 1) flat.push_back((uint32_t)(row * cols + col));
+                if ((colbits[col] >> (rows - 1 - row)) & 1) {
+                    const size_t pos = (size_t)row * cols + col;
+                    flat.push_back((uint32_t)pos);
+                    bits[pos >> 5] |= 1u << (pos & 31);
+                }
+        for (size_t wd = 1; wd < rank.size(); wd++) rank[wd] = rank[wd - 1] + (uint32_t)__builtin_popcount(bits[wd - 1]);
+        flat.push_back(0xFFFFFFFFu);                    // sentinel: reads one past the last one-bit stay in bounds
         rc = upload(&p->d_flat, flat);
+        if (rc == SCGPU_OK) rc = upload(&p->d_kybits, bits);
+        if (rc == SCGPU_OK) rc = upload(&p->d_kyrank, rank);
         p->t.ky_rows = rows; p->t.ky_cols = cols; p->t.ky_bound = bound;
-        p->t.ky_nones = (uint32_t)flat.size(); p->t.ky_flat = p->d_flat;
+        p->t.ky_nones = (uint32_t)flat.size() - 1; p->t.ky_flat = p->d_flat;
+        p->t.ky_bits = p->d_kybits; p->t.ky_rank = p->d_kyrank;
     } else if (sampler == SCGPU_SAMPLER_BERNOULLI && precision == 64) {
         // gaussian_bernoulli.c:40-103
         float max_gauss_val = ceil(tail * sigma);
@@ -283,7 +309,7 @@ extern "C" void scgpu_gauss_plan_destroy(scgpu_gauss_plan_t *p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
-    cudaFree(p->d_cdf); cudaFree(p->d_flat); cudaFree(p->d_ber); cudaFree(p->d_guide);
+    cudaFree(p->d_cdf); cudaFree(p->d_flat); cudaFree(p->d_kybits); cudaFree(p->d_kyrank); cudaFree(p->d_ber); cudaFree(p->d_guide);
     cudaFree(p->d_seeds); cudaFree(p->d_out);
     delete p;
 }

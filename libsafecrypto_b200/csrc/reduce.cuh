@@ -37,11 +37,14 @@ __device__ __forceinline__ uint32_t ct_lt_u32(uint32_t a, uint32_t b)
 }
 
 // x += q if negative, x -= q if x >= q, in the reference's branch-free form (ntt.c:594-595).
+// ct_lt_u32(q, u + 1) is the unsigned comparison q < u + 1 (including the wrap of u + 1 at u = 2^32 - 1); written as
+// a comparison it compiles to ISETP + select instead of the eight bit operations of the reference's branch-free C
+// (a GPU select does not branch either).
 __device__ __forceinline__ int32_t cond_fix(int32_t x, int32_t q)
 {
     uint32_t u = (uint32_t)x;
-    u += (uint32_t)q * (u >> 31);
-    u -= (uint32_t)q * ct_lt_u32((uint32_t)q, u + 1u);
+    u += (uint32_t)q & (uint32_t)(x >> 31);
+    u -= ((uint32_t)q < u + 1u) ? (uint32_t)q : 0u;
     return (int32_t)u;
 }
 
@@ -140,7 +143,9 @@ __device__ __forceinline__ int32_t lane_dbl(int64_t prod, bool full_range, const
 __device__ __forceinline__ int32_t lane_flt(int32_t p32, const RedConst &c)
 {
     float quo_f = __fmul_rn(__int2float_rn(p32), c.qs_inv);
-    int32_t quo = __float2int_rn(quo_f);
+    // cvtps_epi32 = round to nearest even.  |quo_f| <= 2^31 / q < 2^22 for every q > 512, so adding 1.5 * 2^23 performs
+    // exactly that rounding in the mantissa (one FADD + one IADD instead of a conversion on the XU pipe)
+    int32_t quo = c.q > 512 ? __float_as_int(__fadd_rn(quo_f, 12582912.0f)) - 0x4B400000 : __float2int_rn(quo_f);
     int32_t res = (int32_t)((uint32_t)p32 - (uint32_t)quo * (uint32_t)c.q);
     if (res < 0) res = (int32_t)((uint32_t)res + (uint32_t)c.q);
     return res;

@@ -247,8 +247,11 @@ int ref_ky_table(int bitwidth, float tail, float sigma, uint8_t *pmat, size_t ca
 {
     static const uint8_t z[64] = {0};
     prng_ctx_t *ctx = make_prng(SC_PRNG_CHACHA, z, 64, 0);
-    void *g = (bitwidth == 32) ? gaussian_knuth_yao_create_32(ctx, tail, sigma, 0, NORMAL_SAMPLES)
-                               : gaussian_knuth_yao_create_64(ctx, tail, sigma, 0, NORMAL_SAMPLES);
+    const sample_blinding_e bl = (sample_blinding_e)((bitwidth >> 12) & 3);     /* blinding rides in bits 12-13 */
+    bitwidth &= 0xFFF;
+    void *g = (bitwidth == 32) ? gaussian_knuth_yao_create_32(ctx, tail, sigma, 0, bl)
+            : (bitwidth == 128) ? gaussian_knuth_yao_create_128(ctx, tail, sigma, 0, bl)
+                                : gaussian_knuth_yao_create_64(ctx, tail, sigma, 0, bl);
     drv_ky_t *k = (drv_ky_t *)g;
     *rows = k->num_rows; *cols = k->num_cols; *bound = k->bound;
     size_t sz = (size_t)k->num_rows * (size_t)k->num_cols;
@@ -318,8 +321,11 @@ int ref_gauss_streams(int sampler, int precision, int blinding, int prng_type, f
                 get_vector_32(smp, v + c * n, n, (FLOAT)centre);
             destroy_sampler(&smp);
         } else if (sampler == KNUTH_YAO_GAUSSIAN_SAMPLING) {
-            void *g = (precision == 32) ? gaussian_knuth_yao_create_32(ctx, tail, sigma, 0, NORMAL_SAMPLES)
-                                        : gaussian_knuth_yao_create_64(ctx, tail, sigma, 0, NORMAL_SAMPLES);
+            /* blinding only scales the table here (gaussian_knuth_yao.c:144-146); the loop is sample_vector_32's */
+            if (blinding == SHUFFLE_SAMPLES) { fail |= 1; prng_destroy(ctx); continue; }
+            void *g = (precision == 32) ? gaussian_knuth_yao_create_32(ctx, tail, sigma, 0, (sample_blinding_e)blinding)
+                    : (precision == 128) ? gaussian_knuth_yao_create_128(ctx, tail, sigma, 0, (sample_blinding_e)blinding)
+                                         : gaussian_knuth_yao_create_64(ctx, tail, sigma, 0, (sample_blinding_e)blinding);
             for (size_t j = 0; j < n * calls_per_stream; j++) v[j] = gaussian_knuth_yao_sample(g) + centre;
         } else if (sampler == BERNOULLI_GAUSSIAN_SAMPLING) {
             void *g = bernoulli_create_64(ctx, tail, sigma, 0, NORMAL_SAMPLES);

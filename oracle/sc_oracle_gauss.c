@@ -179,9 +179,23 @@ int orc_cdf_table(int precision, int blinding, float tail, float sigma, void *ou
 
 typedef struct { int rows, cols, bound; uint8_t *pmat; } ky_t;
 
-static void ky_build(ky_t *k, int bitwidth, float tail, float sigma)
+/* sc_math.c:1047-1062: 128 binary digits of a DOUBLE (the value itself carries 53) */
+static unsigned __int128 bin_expansion_128(double x)
 {
-    /* gaussian_knuth_yao.c:126-189 with the 64- or 32-row table of :81-124 */
+    double val = 0, step = 0.5f;
+    unsigned __int128 res = 0;
+    for (int i = 1; i < 129; i++) {
+        res <<= 1;
+        if ((val + step) < x) { val += step; res |= 1; }
+        step = step / 2;
+    }
+    return res;
+}
+
+static void ky_build(ky_t *k, int bitwidth, int blinding, float tail, float sigma)
+{
+    /* gaussian_knuth_yao.c:126-189 with the 128-, 64- or 32-row table of :50-124; blinding scales sigma first (:144-146) */
+    if (blinding == ORC_BLINDING_SAMPLES) sigma *= 0.7071067811865475244008443621L;
     k->bound = (int32_t)ceil(tail * sigma);
     k->rows = bitwidth;
     k->cols = k->bound + 1;
@@ -190,6 +204,12 @@ static void ky_build(ky_t *k, int bitwidth, float tail, float sigma)
     long double e = -0.5L / (sigma * sigma);
     for (int col = 0; col < k->cols; col++) {
         long double pr = (col == 0) ? d : d * expl(e * ((long double)(col * col)));
+        if (bitwidth == 128) {
+            unsigned __int128 b128 = bin_expansion_128((double)pr);
+            for (int row = 0; row < k->rows; row++)
+                k->pmat[(size_t)row * (size_t)k->cols + (size_t)col] = (uint8_t)((b128 >> (127 - row)) & 1);
+            continue;
+        }
         uint64_t bitsv = bin_expansion((double)pr, bitwidth);
         for (int row = 0; row < k->rows; row++)
             k->pmat[(size_t)row * (size_t)k->cols + (size_t)col] = (uint8_t)((bitsv >> (bitwidth - 1 - row)) & 1);
@@ -228,7 +248,7 @@ int orc_ky_table(int bitwidth, float tail, float sigma, uint8_t *pmat, size_t ca
                  int32_t *rows, int32_t *cols, int32_t *bound)
 {
     ky_t k;
-    ky_build(&k, bitwidth, tail, sigma);
+    ky_build(&k, bitwidth & 0xFFF, (bitwidth >> 12) & 3, tail, sigma);        /* blinding rides in bits 12-13 */
     *rows = k.rows; *cols = k.cols; *bound = k.bound;
     size_t sz = (size_t)k.rows * (size_t)k.cols;
     if (sz <= cap) memcpy(pmat, k.pmat, sz);
@@ -384,11 +404,10 @@ int orc_gauss_streams(int sampler, int precision, int blinding, int prng_type, f
     if (sampler == ORC_SAMPLER_CDF) {
         if (cdf_build(&proto.cdf, precision, blinding, tail, sigma)) return 1;
     } else if (sampler == ORC_SAMPLER_KNUTH_YAO) {
-        if (blinding != ORC_NORMAL_SAMPLES) return 1;
-        ky_build(&proto.ky, precision == 32 ? 32 : 64, tail, sigma);
+        if (precision != 32 && precision != 64 && precision != 128) return 1;
+        ky_build(&proto.ky, precision, blinding, tail, sigma);
     } else if (sampler == ORC_SAMPLER_BERNOULLI) {
-        if (blinding != ORC_NORMAL_SAMPLES) return 1;
-        ber_build(&proto.ber, tail, sigma);
+        ber_build(&proto.ber, tail, sigma);            /* blinding leaves these tables alone (gaussian_bernoulli.c:122-125) */
     } else {
         return 1;
     }
@@ -401,11 +420,10 @@ int orc_gauss_streams(int sampler, int precision, int blinding, int prng_type, f
         if (!s.rng) { fail |= 1; continue; }
         for (size_t c = 0; c < calls_per_stream; c++) {
             int32_t *v = out + (st * calls_per_stream + c) * n;
-            if (sampler != ORC_SAMPLER_CDF) {
-                /* ref_driver.c calls sample() directly for KY / Bernoulli (identical when discard == 0);
-                 * here they go through sample_vector_32 as a CONSTRAINED_SYSTEM build would */
-                vec_normal(&s, v, n, centre);
-            } else if (blinding == ORC_SHUFFLE_SAMPLES) vec_shuffle(&s, v, n, centre);
+            /* ref_driver.c calls sample() directly for KY / Bernoulli (identical to sample_vector_32 when discard == 0);
+             * here every sampler goes through the vector wrapper its blinding mode selects, as configure_sampler
+             * wires them (sampling.c:395-413) in a build that has the sampler compiled in */
+            if (blinding == ORC_SHUFFLE_SAMPLES) vec_shuffle(&s, v, n, centre);
             else if (blinding == ORC_BLINDING_SAMPLES)  vec_blinding(&s, v, n, centre);
             else                                         vec_normal(&s, v, n, centre);
         }

@@ -150,12 +150,13 @@ class Checker:
         assert f(precision, _vp(t), t.shape[0]) == 0
 
 
-    def ky_table(self, bitwidth, tail, sigma):
+    def ky_table(self, bitwidth, tail, sigma, blinding=0):
+        bitwidth |= blinding << 12
         f = self._fn("ky_table")
         f.restype = ctypes.c_int
         f.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t,
                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-        cap = 1 << 22
+        cap = 1 << 23
         buf = np.zeros(cap, dtype=np.uint8)
         dims = np.zeros(3, dtype=np.int32)
         sz = f(bitwidth, tail, sigma, _vp(buf), cap, dims[0:].ctypes.data, dims[1:].ctypes.data, dims[2:].ctypes.data)

@@ -128,7 +128,8 @@ def test_survey_anchor_samples_on_gpu():
     assert list(a) == [-319, 333, 125, -307, -208, 85, -140, -269, -1, 74, -120, 180]
 
 
-@pytest.mark.parametrize("sampler,precision", [(O.SAMPLER_KNUTH_YAO, 64), (O.SAMPLER_KNUTH_YAO, 32), (O.SAMPLER_BERNOULLI, 64)])
+@pytest.mark.parametrize("sampler,precision", [(O.SAMPLER_KNUTH_YAO, 64), (O.SAMPLER_KNUTH_YAO, 32), (O.SAMPLER_KNUTH_YAO, 128),
+                                               (O.SAMPLER_BERNOULLI, 64)])
 @pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
 @pytest.mark.parametrize("tail,sigma,n", [(13.42, 215.0, 96), (13.0, 4.5, 512)])
 def test_ky_bernoulli_samples(sampler, precision, prng, tail, sigma, n):
@@ -136,6 +137,45 @@ def test_ky_bernoulli_samples(sampler, precision, prng, tail, sigma, n):
     got = gpu_samples(sampler, precision, 0, prng, tail, sigma, seeds, n)
     exp = O.port().gauss_streams(sampler, precision, 0, prng, tail, sigma, seeds, n)
     assert np.array_equal(got, exp)
+    if O.ref_available():
+        assert np.array_equal(exp, O.ref().gauss_streams(sampler, precision, 0, prng, tail, sigma, seeds, n))
+
+
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+def test_ky_bernoulli_vector_modes_and_ragged_batches(prng):
+    """Knuth-Yao (rank / select walk) and Bernoulli (one-draw-per-trip lanes) beyond the plain case: stream counts
+    that are not a multiple of a warp or a CTA, several calls, a centre, discard, and the shuffle / blinding vector
+    wrappers (sampler-agnostic in the reference, sampling.c:127-191; Knuth-Yao's blinding table is built from
+    sigma / sqrt 2, gaussian_knuth_yao.c:144-146, checked against the compiled reference's table)."""
+    for count in (1, 33, 130):
+        seeds = seeds_for(count, 44, salt=count)
+        for sampler, prec in ((O.SAMPLER_KNUTH_YAO, 64), (O.SAMPLER_BERNOULLI, 64)):
+            for discard, n, calls, centre in ((0, 50, 2, 3), (4, 37, 1, 0), (6, 5, 3, -7)):
+                got = gpu_samples(sampler, prec, 0, prng, 13.42, 215.0, seeds, n, calls=calls, centre=centre, discard=discard)
+                exp = O.port().gauss_streams(sampler, prec, 0, prng, 13.42, 215.0, seeds, n, discard=discard, centre=centre, calls=calls)
+                assert np.array_equal(got, exp), (count, sampler, discard)
+    seeds = seeds_for(9, 40, salt=5)
+    for sampler, prec, tail, sigma in ((O.SAMPLER_KNUTH_YAO, 64, 13.0, 19.53), (O.SAMPLER_KNUTH_YAO, 32, 13.0, 4.5), (O.SAMPLER_BERNOULLI, 64, 13.0, 19.53)):
+        for blinding in (O.SHUFFLE_SAMPLES, O.BLINDING_SAMPLES):
+            for discard, n in ((0, 64), (2, 77)):
+                got = gpu_samples(sampler, prec, blinding, prng, tail, sigma, seeds, n, calls=2, centre=1, discard=discard)
+                exp = O.port().gauss_streams(sampler, prec, blinding, prng, tail, sigma, seeds, n, discard=discard, centre=1, calls=2)
+                assert np.array_equal(got, exp), (sampler, blinding, discard)
+    if O.ref_available():
+        for bw in (32, 64, 128):
+            a, ba = O.port().ky_table(bw, 13.42, 215.0, 1)
+            b, bb = O.ref().ky_table(bw, 13.42, 215.0, 1)
+            assert ba == bb and np.array_equal(a, b)
+
+
+def test_bernoulli_and_knuth_yao_at_scale():
+    """2^13 streams x 256 samples of each: every sample against the port, moments as a sanity check."""
+    seeds = np.random.default_rng(11).integers(0, 256, size=(1 << 13, 40)).astype(np.uint8)
+    for sampler, lo, hi in ((O.SAMPLER_BERNOULLI, 205.0, 225.0), (O.SAMPLER_KNUTH_YAO, 150.0, 260.0)):
+        got = gpu_samples(sampler, 64, 0, O.PRNG_CHACHA, 13.42, 215.0, seeds, 256)
+        exp = O.port().gauss_streams(sampler, 64, 0, O.PRNG_CHACHA, 13.42, 215.0, seeds, 256)
+        assert np.array_equal(got, exp)
+        assert abs(got.mean()) < 2.0 and lo < got.std() < hi, (sampler, got.std())
 
 
 def test_sampling_statistics_at_scale():
