@@ -353,7 +353,13 @@ def main():
                 sv = torch.randint(-4, 5, (inst, k, nn), dtype=torch.int32, device=dev, generator=g)
                 to = torch.empty((inst, k, nn), dtype=torch.int32, device=dev)
                 put("kyber_matvec_k3_n256_q7681", inst, timed(lambda: pl.matvec(to, A, sv, k, k)), 4 * nn * (k * k + 2 * k), "instance")
-                del A, sv, to
+                # the same product with the matrix sampled on the device from a 32-byte seed per instance
+                # (create_rand_product_16_csprng): 4 n (l + k) + 32 bytes of HBM per instance, generator-bound
+                sd = torch.randint(0, 256, (inst, 32), dtype=torch.uint8, device=dev, generator=g)
+                for pname, prng in (("chacha20", sc.PRNG_CHACHA), ("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG)):
+                    put("kyber_rand_product_k3_%s" % pname, inst, timed(lambda: pl.rand_product(to, sv, sd, prng, 13, k, k), reps=5),
+                        4 * nn * 2 * k + 32, "instance")
+                del A, sv, to, sd
             del xa, xb, xo, pl
         # BLISS sign / verify core: v = INTT(NTT(t) o key), one shared SINT16 key (bliss_b.c:1378-1384): 8 n bytes
         key = torch.randint(0, Q, (N_COEF,), dtype=torch.int32, device=dev, generator=g).to(torch.int16)
@@ -409,6 +415,40 @@ def main():
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 4 * N_COEF * E2E_BATCH,
            "d2h_bytes_per_step": 4 * N_COEF * E2E_BATCH, "pairs_per_step": E2E_BATCH, "steps": e2e_steps,
            "api": "scgpu_polymul_batch_host (pinned host buffers, chunked 3-stream H2D/kernel/D2H pipeline)"}
+
+    # ---- strong scaling of ONE host batch from ONE process: the fixed 2^20-pair batch of BASELINE configs[1] split over
+    # all GPUs by scgpu_polymul_batch_host_multi (host-side scatter / gather, one thread per device).  Rank 0 drives
+    # every device; the other ranks wait on the rendezvous store (a host wait, their GPUs are idle).
+    e2e_multi = None
+    if world > 1:
+        from torch.distributed.distributed_c10d import _get_default_store
+        store = _get_default_store()
+        barrier()
+        if rank == 0:
+            from libsafecrypto_b200 import binding as B
+            ps = B.NttPlanSet(N_COEF, Q, sc.REFERENCE, w, r, max_devices=world)
+            mb = 1 << 20
+            ma = torch.randint(0, Q, (mb, N_COEF), dtype=torch.int32).pin_memory()
+            mbb = torch.randint(0, Q, (mb, N_COEF), dtype=torch.int32).pin_memory()
+            mo = torch.empty((mb, N_COEF), dtype=torch.int32).pin_memory()
+            e2e_multi = {"pairs": mb, "api": "scgpu_polymul_batch_host_multi (one process, one thread per device)", "by_devices": {}}
+            nd = 1
+            while nd <= ps.ndev:
+                ps.polymul_host(mo, ma, mbb, ndev=nd)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    ps.polymul_host(mo, ma, mbb, ndev=nd)
+                dt = (time.perf_counter() - t0) / 3
+                e2e_multi["by_devices"][str(nd)] = {"polymul_per_s": mb / dt, "seconds": dt}
+                nd *= 2
+            exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, N_COEF, Q, 16, ma[-8:].numpy(), mbb[-8:].numpy(), w, r)
+            assert np.array_equal(mo[-8:].numpy(), exp), "multi-device host path differs from the oracle"
+            ps.close()
+            del ma, mbb, mo
+            store.set("scgpu_multi_done", "1")
+        else:
+            store.wait(["scgpu_multi_done"])
+        barrier()
 
     # ---- secondary metric: Gaussian samples/s (BASELINE config 5 shape), every rank its own streams -------------
     # CDF-64, sigma 215, both generators; "fixed_probe" = the default constant-time table search (the reference's
@@ -496,7 +536,7 @@ def main():
                        "n": N_COEF, "q": Q, "pairs_per_gpu": BATCH, "parallelism": "shard by polynomial index, no collective",
                        "cache": "operands 4 GiB + result 2 GiB per step >> 126 MB L2 (no flush needed)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
-            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss, "other_shapes": shapes, "parity": parity,
+            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss, "other_shapes": shapes, "parity": parity, "e2e_multi": e2e_multi,
         }
         emit(line)
     if world > 1:

@@ -50,6 +50,12 @@ def lib():
         L.scgpu_polymul_batch_host.argtypes = [vp, vp, vp, vp, sz, sz]
         L.scgpu_ntt_mul_key_batch.argtypes = [vp, vp, vp, vp, ctypes.c_int, sz, sz, vp]
         L.scgpu_matvec_batch.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, sz, vp]
+        L.scgpu_rand_product_csprng_batch.argtypes = [vp, vp, vp, vp, sz, ctypes.c_int, u32, ctypes.c_int, ctypes.c_int, ctypes.c_int, sz, vp]
+        L.scgpu_rand_product_csprng_batch_host.argtypes = [vp, vp, vp, vp, sz, ctypes.c_int, u32, ctypes.c_int, ctypes.c_int, ctypes.c_int, sz]
+        L.scgpu_rand_matrix_csprng_batch.argtypes = [vp, vp, sz, ctypes.c_int, i32, u32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, sz, vp]
+        L.scgpu_ntt_plans_create_all.argtypes = [ctypes.POINTER(vp), ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.scgpu_polymul_batch_host_multi.argtypes = [ctypes.POINTER(vp), ctypes.c_int, vp, vp, vp, sz, sz]
+        L.scgpu_ntt_batch_host_multi.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, vp, vp, vp, sz, sz, i32, vp]
         L.scgpu_gauss_plan_create_table.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, vp, sz, ctypes.c_int]
         L.scgpu_gauss_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_float, ctypes.c_float, ctypes.c_int]
@@ -179,6 +185,21 @@ class NttPlan:
         return _check(lib().scgpu_matvec_batch(self.handle, _ptr(out), _ptr(A), _ptr(s), k, l, count,
                                                _stream_handle(stream)), "scgpu_matvec_batch")
 
+    def rand_product(self, out, y, seeds, prng_type, q_bits, k, l, transpose=False, count=None, stream=None):
+        """create_rand_product_{16,32}_csprng with the matrix sampled on the device from seeds [count, seed_len]."""
+        if count is None:
+            count = y.shape[0]
+        return _check(lib().scgpu_rand_product_csprng_batch(self.handle, _ptr(out), _ptr(y), _ptr(seeds), seeds.shape[-1], prng_type,
+                                                            q_bits, k, l, 1 if transpose else 0, count, _stream_handle(stream)),
+                      "scgpu_rand_product_csprng_batch")
+
+    def rand_product_host(self, out, y, seeds, prng_type, q_bits, k, l, transpose=False, count=None):
+        if count is None:
+            count = y.shape[0]
+        return _check(lib().scgpu_rand_product_csprng_batch_host(self.handle, _ptr(out), _ptr(y), _ptr(seeds), seeds.shape[-1],
+                                                                 prng_type, q_bits, k, l, 1 if transpose else 0, count),
+                      "scgpu_rand_product_csprng_batch_host")
+
     # ---- host buffers (numpy arrays or pinned torch CPU tensors) -----------------------------------
     def batch_host(self, op, out, a, b=None, b_stride=None, count=None, scalar=0, rc=None):
         if count is None:
@@ -200,6 +221,51 @@ class NttPlan:
         b_stride = 0 if len(b.shape) == 1 else b.shape[-1]
         return _check(lib().scgpu_polymul_batch_host(self.handle, _ptr(out), _ptr(a), _ptr(b), b_stride, count),
                       "scgpu_polymul_batch_host")
+
+
+class NttPlanSet:
+    """One plan per device of this process (scgpu_ntt_plans_create_all) for the *_host_multi entry points."""
+
+    def __init__(self, n, q, variant, w, r, max_devices=64):
+        self.params = make_params(n, q)
+        w = np.ascontiguousarray(w)
+        r = np.ascontiguousarray(r, dtype=w.dtype)
+        self._w, self._r = w, r
+        self.handles = (ctypes.c_void_p * max_devices)()
+        got = lib().scgpu_ntt_plans_create_all(self.handles, max_devices, self.params, variant, _ptr(w), _ptr(r),
+                                               16 if w.dtype == np.int16 else 32)
+        _check(got, "scgpu_ntt_plans_create_all")
+        self.ndev = got
+        self.n = n
+
+    def polymul_host(self, out, a, b, ndev=None):
+        b_stride = 0 if len(b.shape) == 1 else b.shape[-1]
+        return _check(lib().scgpu_polymul_batch_host_multi(self.handles, ndev or self.ndev, _ptr(out), _ptr(a), _ptr(b), b_stride,
+                                                           a.shape[0]), "scgpu_polymul_batch_host_multi")
+
+    def batch_host(self, op, out, a, b=None, scalar=0, rc=None, ndev=None):
+        b_stride = 0 if (b is None or len(b.shape) == 1) else b.shape[-1]
+        return _check(lib().scgpu_ntt_batch_host_multi(self.handles, ndev or self.ndev, op, _ptr(out), _ptr(a), _ptr(b), b_stride,
+                                                       a.shape[0], int(scalar), _ptr(rc)), "scgpu_ntt_batch_host_multi")
+
+    def close(self):
+        for i in range(getattr(self, "ndev", 0)):
+            if self.handles[i]:
+                lib().scgpu_ntt_plan_destroy(self.handles[i])
+                self.handles[i] = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def rand_matrix(A, seeds, prng_type, q, q_bits, n, k, l, transpose=False, stream=None):
+    """The k x l matrix of every instance, ring by ring as uniform_random_ring_q_csprng draws it: A [count, k, l, n]."""
+    return _check(lib().scgpu_rand_matrix_csprng_batch(_ptr(A), _ptr(seeds), seeds.shape[-1], prng_type, q, q_bits, n, k, l,
+                                                       1 if transpose else 0, seeds.shape[0], _stream_handle(stream)),
+                  "scgpu_rand_matrix_csprng_batch")
 
 
 class GaussPlan:

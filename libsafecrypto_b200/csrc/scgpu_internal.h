@@ -80,6 +80,8 @@ struct ExactArgs {
 };
 
 int launch_exact(const NttPlanDev &plan, const ExactArgs &args, cudaStream_t stream);
+int launch_gen_rings(int prng_type, const uint8_t *seeds, size_t seed_len, size_t count, int32_t *out, int n, int k, int l,
+                     int transpose, int32_t q, uint32_t q_bits, cudaStream_t stream);
 int build_xw32_tables(NttPlanDev &plan, const int32_t *w_host, const int32_t *r_host);
 void free_xw32_tables(NttPlanDev &plan);
 int launch_exact_w32(const NttPlanDev &plan, int op, int32_t *out, const int32_t *a, size_t count, cudaStream_t stream);

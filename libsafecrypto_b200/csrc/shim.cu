@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -287,6 +289,110 @@ extern "C" int scgpu_matvec_batch(const scgpu_ntt_plan_t *plan, int32_t *out, co
     return launch_matvec(plan->dev, out, A, s, k, l, count, static_cast<cudaStream_t>(stream));
 }
 
+// ---- module product with the matrix sampled on the device (rand_product.cu) ----------------------------------------
+
+static int check_rand_args(const char *what, int prng_type, size_t seed_len, int n, int k, int l)
+{
+    if (prng_type != SCGPU_PRNG_AES_CTR_DRBG && prng_type != SCGPU_PRNG_CHACHA) {
+        set_error("%s: PRNG type %d is not on the GPU path (0 = AES-CTR-DRBG, 2 = ChaCha20)", what, prng_type);
+        return SCGPU_ERR_UNSUPPORTED;
+    }
+    if (seed_len == 0 || k < 1 || l < 1) { set_error("%s: bad shape (k=%d l=%d)", what, k, l); return SCGPU_ERR_ARG; }
+    if (n != 256) {
+        // uniform_random_ring_q_csprng (module_lwe.c:519-535) never advances its output pointer: for n > 256 every
+        // 256-coefficient block lands on a[0..255] and the rest of the ring keeps whatever the caller's buffer held.
+        // Kyber and Dilithium are n = 256; nothing else has a defined result.
+        set_error("%s: the reference's ring sampler is only defined for n = 256 (got %d)", what, n);
+        return SCGPU_ERR_UNSUPPORTED;
+    }
+    if ((size_t)k * l * n * 2 >= 0x01000000u) { set_error("%s: an instance would cross the generator's 16 MiB reseed period", what); return SCGPU_ERR_UNSUPPORTED; }
+    return SCGPU_OK;
+}
+
+extern "C" int scgpu_rand_matrix_csprng_batch(int32_t *A, const uint8_t *seeds, size_t seed_len, int prng_type, int32_t q,
+                                              uint32_t q_bits, int n, int k, int l, int transpose, size_t count, void *stream)
+{
+    if (!A || !seeds) { set_error("rand_matrix: null argument"); return SCGPU_ERR_ARG; }
+    const int e = check_rand_args("rand_matrix", prng_type, seed_len, n, k, l);
+    if (e != SCGPU_OK) return e;
+    return launch_gen_rings(prng_type, seeds, seed_len, count, A, n, k, l, transpose, q, q_bits, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int scgpu_rand_product_csprng_batch(const scgpu_ntt_plan_t *plan, int32_t *t, const int32_t *y, const uint8_t *seeds,
+                                               size_t seed_len, int prng_type, uint32_t q_bits, int k, int l, int transpose,
+                                               size_t count, void *stream)
+{
+    if (!plan || !t || !y || !seeds) { set_error("rand_product: null argument"); return SCGPU_ERR_ARG; }
+    if (!plan->dev.w || !plan->dev.r) { set_error("rand_product: the plan has no twiddle tables"); return SCGPU_ERR_ARG; }
+    const int n = plan->dev.n;
+    int e = check_rand_args("rand_product", prng_type, seed_len, n, k, l);
+    if (e != SCGPU_OK) return e;
+    if (transpose && plan->dev.tw_bits == 32 && l > 1) {
+        set_error("rand_product: create_rand_product_32_csprng's transposed branch adds the matrix ring instead of the running sum "
+                  "(module_lwe.c:623-628); no scheme calls it and it is not reproduced");
+        return SCGPU_ERR_UNSUPPORTED;
+    }
+    if (count == 0) return SCGPU_OK;
+    SCGPU_CUDA_CHECK(cudaSetDevice(plan->dev.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the matrix of a chunk of instances stays in the L2: 48 MB of the 126 MB
+    const size_t inst_bytes = (size_t)k * l * n * sizeof(int32_t);
+    size_t chunk = (48u << 20) / inst_bytes;
+    if (chunk < 1) chunk = 1;
+    if (chunk > count) chunk = count;
+    int32_t *scratch = nullptr;
+    SCGPU_CUDA_CHECK(cudaMallocAsync(&scratch, chunk * inst_bytes, st));
+    for (size_t off = 0; off < count && e == SCGPU_OK; off += chunk) {
+        const size_t cnt = count - off < chunk ? count - off : chunk;
+        e = launch_gen_rings(prng_type, seeds + off * seed_len, seed_len, cnt, scratch, n, k, l, transpose, plan->dev.rc.q, q_bits, st);
+        if (e == SCGPU_OK) e = launch_matvec(plan->dev, t + off * (size_t)k * n, scratch, y + off * (size_t)l * n, k, l, cnt, st);
+    }
+    SCGPU_CUDA_CHECK(cudaFreeAsync(scratch, st));
+    return e;
+}
+
+extern "C" int scgpu_rand_product_csprng_batch_host(const scgpu_ntt_plan_t *plan, int32_t *t, const int32_t *y, const uint8_t *seeds,
+                                                    size_t seed_len, int prng_type, uint32_t q_bits, int k, int l, int transpose,
+                                                    size_t count)
+{
+    if (!plan || !t || !y || !seeds) { set_error("rand_product_host: null argument"); return SCGPU_ERR_ARG; }
+    if (count == 0) return SCGPU_OK;
+    scgpu_ntt_plan *p = const_cast<scgpu_ntt_plan *>(plan);
+    std::lock_guard<std::mutex> lock(p->mu);
+    SCGPU_CUDA_CHECK(cudaSetDevice(p->dev.device));
+    for (int i = 0; i < scgpu_ntt_plan::kStreams; i++)
+        if (!p->streams[i]) SCGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking));
+    // three-stream pipeline over chunks of instances: seeds + y in, t out; the matrix never crosses the bus
+    const size_t n = (size_t)p->dev.n;
+    const size_t yb = (size_t)l * n * 4, tb = (size_t)k * n * 4;
+    size_t rows = (16u << 20) / (yb > tb ? yb : tb);
+    if (rows < 1) rows = 1;
+    if (rows > count) rows = count;
+    int status = SCGPU_OK;
+    void *dy[scgpu_ntt_plan::kStreams] = {}, *dt[scgpu_ntt_plan::kStreams] = {}, *ds[scgpu_ntt_plan::kStreams] = {};
+    for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) {
+        SCGPU_CUDA_CHECK(cudaMallocAsync(&dy[i], rows * yb, p->streams[i]));
+        SCGPU_CUDA_CHECK(cudaMallocAsync(&dt[i], rows * tb, p->streams[i]));
+        SCGPU_CUDA_CHECK(cudaMallocAsync(&ds[i], rows * seed_len, p->streams[i]));
+    }
+    for (size_t off = 0, ci = 0; off < count && status == SCGPU_OK; off += rows, ci++) {
+        const int s = (int)(ci % scgpu_ntt_plan::kStreams);
+        cudaStream_t st = p->streams[s];
+        const size_t cnt = count - off < rows ? count - off : rows;
+        SCGPU_CUDA_CHECK(cudaMemcpyAsync(dy[s], reinterpret_cast<const char *>(y) + off * yb, cnt * yb, cudaMemcpyHostToDevice, st));
+        SCGPU_CUDA_CHECK(cudaMemcpyAsync(ds[s], seeds + off * seed_len, cnt * seed_len, cudaMemcpyHostToDevice, st));
+        status = scgpu_rand_product_csprng_batch(plan, static_cast<int32_t *>(dt[s]), static_cast<const int32_t *>(dy[s]),
+                                                 static_cast<const uint8_t *>(ds[s]), seed_len, prng_type, q_bits, k, l, transpose, cnt, st);
+        if (status != SCGPU_OK) break;
+        SCGPU_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(t) + off * tb, dt[s], cnt * tb, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) {
+        cudaFreeAsync(dy[i], p->streams[i]); cudaFreeAsync(dt[i], p->streams[i]); cudaFreeAsync(ds[i], p->streams[i]);
+        SCGPU_CUDA_CHECK(cudaStreamSynchronize(p->streams[i]));
+    }
+    return status;
+}
+
 // ---- host-buffer entry points: chunked three-stream pipeline -----------------------------------------
 
 // Sizes the three staging buffers for THIS call and returns its chunk length in rows.  A chunk is a whole number of
@@ -421,6 +527,71 @@ extern "C" int scgpu_ntt_canonical_batch_host(const scgpu_ntt_plan_t *plan, int 
 {
     if (!plan || !out || !a) { set_error("ntt_canonical_batch_host: null argument"); return SCGPU_ERR_ARG; }
     return run_host_pipeline(const_cast<scgpu_ntt_plan *>(plan), 3, inverse ? 1 : 0, out, a, nullptr, 0, count, 0, nullptr);
+}
+
+// ---- one host batch over several devices (host-side scatter / gather, one thread per device) ---------------------
+
+extern "C" int scgpu_ntt_plans_create_all(scgpu_ntt_plan_t **plans, int max_plans, const void *params, int variant,
+                                          const void *w, const void *r, int tw_bits)
+{
+    if (!plans || max_plans < 1) { set_error("plans_create_all: null argument"); return SCGPU_ERR_ARG; }
+    int ndev = scgpu_device_count();
+    if (ndev < 1) { set_error("plans_create_all: no CUDA device"); return SCGPU_ERR_CUDA; }
+    if (ndev > max_plans) ndev = max_plans;
+    for (int d = 0; d < ndev; d++) {
+        const int e = scgpu_ntt_plan_create(&plans[d], params, variant, w, r, tw_bits, d);
+        if (e != SCGPU_OK) {
+            for (int i = 0; i < d; i++) { scgpu_ntt_plan_destroy(plans[i]); plans[i] = nullptr; }
+            return e;
+        }
+    }
+    return ndev;
+}
+
+template <class Fn>
+static int run_slabs(int nplans, size_t count, Fn fn)
+{
+    std::vector<std::thread> th;
+    std::vector<int> status((size_t)nplans, SCGPU_OK);
+    std::vector<std::string> msg((size_t)nplans);
+    for (int i = 0; i < nplans; i++) {
+        const size_t lo = count * (size_t)i / (size_t)nplans, hi = count * (size_t)(i + 1) / (size_t)nplans;
+        if (hi == lo) continue;
+        th.emplace_back([&, i, lo, hi] {
+            status[i] = fn(i, lo, hi - lo);
+            if (status[i] != SCGPU_OK) msg[i] = scgpu_last_error();          // the error text is per thread
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int i = 0; i < nplans; i++)
+        if (status[i] != SCGPU_OK) { set_error("device slab %d: %s", i, msg[i].c_str()); return status[i]; }
+    return SCGPU_OK;
+}
+
+extern "C" int scgpu_polymul_batch_host_multi(const scgpu_ntt_plan_t *const *plans, int nplans, int32_t *out, const int32_t *a,
+                                              const int32_t *b, size_t b_stride, size_t count)
+{
+    if (!plans || nplans < 1 || !out || !a || !b) { set_error("polymul_batch_host_multi: null argument"); return SCGPU_ERR_ARG; }
+    for (int i = 0; i < nplans; i++) if (!plans[i]) { set_error("polymul_batch_host_multi: plan %d is null", i); return SCGPU_ERR_ARG; }
+    const size_t n = (size_t)plans[0]->dev.n;
+    return run_slabs(nplans, count, [&](int i, size_t lo, size_t cnt) {
+        return scgpu_polymul_batch_host(plans[i], out + lo * n, a + lo * n, b + lo * b_stride, b_stride, cnt);
+    });
+}
+
+extern "C" int scgpu_ntt_batch_host_multi(const scgpu_ntt_plan_t *const *plans, int nplans, int op, int32_t *out, const void *a,
+                                          const void *b, size_t b_stride, size_t count, int32_t scalar, int32_t *rc)
+{
+    if (!plans || nplans < 1 || !out || !a) { set_error("ntt_batch_host_multi: null argument"); return SCGPU_ERR_ARG; }
+    for (int i = 0; i < nplans; i++) if (!plans[i]) { set_error("ntt_batch_host_multi: plan %d is null", i); return SCGPU_ERR_ARG; }
+    if (op < 0 || op > SCGPU_OP_SPARSE16) { set_error("ntt_batch_host_multi: unknown op %d", op); return SCGPU_ERR_ARG; }
+    const size_t n = (size_t)plans[0]->dev.n;
+    const size_t ea = a_elem_size(op), eb = b_elem_size(op);
+    return run_slabs(nplans, count, [&](int i, size_t lo, size_t cnt) {
+        const char *bp = b ? static_cast<const char *>(b) + lo * b_stride * eb : nullptr;
+        return scgpu_ntt_batch_host(plans[i], op, out + lo * n, static_cast<const char *>(a) + lo * n * ea, bp, b_stride, cnt, scalar,
+                                    rc ? rc + lo : nullptr);
+    });
 }
 
 // =======================================================================================================

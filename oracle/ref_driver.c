@@ -23,6 +23,7 @@
 #include "utils/sampling/gaussian_knuth_yao.h"
 #include "utils/sampling/gaussian_bernoulli.h"
 #include "utils/crypto/prng.h"
+#include "utils/arith/module_lwe.h"
 
 /* op codes shared with oracle/sc_oracle.h and include/scgpu.h (SCGPU_OP_*) */
 enum {
@@ -335,6 +336,53 @@ int ref_gauss_streams(int sampler, int precision, int blinding, int prng_type, f
             fail |= 1;
         }
         prng_destroy(ctx);
+    }
+    return fail;
+}
+
+/* ---- module product with a CSPRNG-sampled matrix (module_lwe.c:588-748) ------------------------------------------ */
+
+/* One create_rand_product_{16,32}_csprng call per instance, exactly as kyber / dilithium make it: a CSPRNG created as
+ * create_csprng() does (module_lwe.c:914-940: user-provided entropy = the instance's seed, 16 MiB reseed period).
+ * y: [count][l][n], t: [count][k][n].  Also returns the matrix the same generator state would draw
+ * (uniform_random_ring_q_csprng ring by ring) when A != NULL: [count][k l][n] in DRAW order. */
+int ref_rand_product(int tw_bits, int variant, int n, int q, int q_bits, int k, int l, int transpose, int prng_type,
+                     const uint8_t *seeds, size_t seed_len, const int32_t *y, int32_t *t, int32_t *A,
+                     const void *w, const void *r, size_t count, int threads)
+{
+    static const UINT8 nonce[16] = "dilithiumcrystal";
+    const utils_arith_ntt_t *T = utils_arith_ntt((safecrypto_ntt_e)variant);
+    const utils_arith_poly_t *P = utils_arith_poly();
+    int nt = max_threads(threads), fail = 0;
+#pragma omp parallel for schedule(static) num_threads(nt) reduction(|:fail)
+    for (size_t s = 0; s < count; s++) {
+        ntt_params_t p;
+        init_reduce(&p, (size_t)n, q);
+        int32_t *yb = NULL, *c = NULL, *tmp = NULL, *tb = NULL;
+        if (posix_memalign((void **)&yb, 64, sizeof(int32_t) * (size_t)l * n) || posix_memalign((void **)&c, 64, sizeof(int32_t) * (size_t)n) ||
+            posix_memalign((void **)&tmp, 64, sizeof(int32_t) * (size_t)(l + k) * n) || posix_memalign((void **)&tb, 64, sizeof(int32_t) * (size_t)(k + l) * n)) { fail |= 1; continue; }
+        memset(tb, 0, sizeof(int32_t) * (size_t)(k + l) * n);
+        for (int pass = 0; pass < (A ? 2 : 1); pass++) {
+            prng_ctx_t *ctx = prng_create(SC_ENTROPY_USER_PROVIDED, (safecrypto_prng_e)prng_type, SC_PRNG_THREADING_NONE, 0x01000000);
+            if (!ctx) { fail |= 1; break; }
+            prng_set_entropy(ctx, seeds + s * seed_len, seed_len);
+            prng_init(ctx, nonce, 16);
+            if (pass == 1) {
+                for (int ring = 0; ring < k * l; ring++)
+                    uniform_random_ring_q_csprng(ctx, A + (s * (size_t)(k * l) + ring) * n, (size_t)n, q, (UINT32)q_bits);
+            } else {
+                memcpy(yb, y + s * (size_t)l * n, sizeof(int32_t) * (size_t)l * n);
+                if (tw_bits == 16)
+                    create_rand_product_16_csprng(ctx, (UINT32)q, (UINT32)q_bits, tb, yb, (size_t)n, (size_t)k, (size_t)l, c, tmp,
+                                                  RND_PRD_DISABLE_OVERWRITE, transpose, (const SINT16 *)w, (const SINT16 *)r, P, T, &p);
+                else
+                    create_rand_product_32_csprng(ctx, (UINT32)q, (UINT32)q_bits, tb, yb, (size_t)n, (size_t)k, (size_t)l, c, tmp,
+                                                  RND_PRD_DISABLE_OVERWRITE, transpose, (const SINT32 *)w, (const SINT32 *)r, P, T, &p);
+                memcpy(t + s * (size_t)k * n, tb, sizeof(int32_t) * (size_t)k * n);
+            }
+            prng_destroy(ctx);
+        }
+        free(yb); free(c); free(tmp); free(tb);
     }
     return fail;
 }

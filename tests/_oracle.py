@@ -187,6 +187,23 @@ class Checker:
 class RefChecker(Checker):
     """The reference library also exports its generated twiddle tables as data symbols."""
 
+    def rand_product(self, tw_bits, variant, n, q, q_bits, k, l, transpose, prng_type, seeds, y, w, r, want_matrix=False, threads=0):
+        """create_rand_product_{16,32}_csprng (module_lwe.c:588-748) per instance, CSPRNG as create_csprng makes it.
+        Returns t [count, k, n] (and the matrix in DRAW order [count, k l, n])."""
+        f = self.lib.ref_rand_product
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int] * 9 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8)
+        count = seeds.shape[0]
+        y = aligned(np.asarray(y, dtype=np.int32).reshape(count, l, n))
+        t = aligned(np.zeros((count, k, n), dtype=np.int32))
+        A = aligned(np.zeros((count, k * l, n), dtype=np.int32)) if want_matrix else None
+        w, r = aligned(w), aligned(r)
+        assert f(tw_bits, variant, n, q, q_bits, k, l, 1 if transpose else 0, prng_type, _vp(seeds), seeds.shape[1], _vp(y), _vp(t),
+                 _vp(A), _vp(w), _vp(r), count, threads) == 0
+        return (t, A) if want_matrix else t
+
     def table(self, kind, q, n, tw_bits):
         ct = ctypes.c_int16 if tw_bits == 16 else ctypes.c_int32
         size = n // 2 if kind == "inv_w" else n

@@ -139,6 +139,36 @@ def main():
     np.savez_compressed(path, **out2)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out2), "arrays")
 
+    # ---- golden_v3 (round 2): the PRNG front end beyond the word stream, module products with a CSPRNG matrix,
+    # Knuth-Yao 128 ---------------------------------------------------------------------------------------------
+    out3 = {}
+    rng = np.random.default_rng(20261017)
+    rp_seeds = rng.integers(0, 256, size=(6, 32)).astype(np.uint8)
+    out3["rp_seeds"] = rp_seeds
+    for name, (q, n, tw, k, l, q_bits) in (("kyber3", (7681, 256, 16, 3, 3, 13)), ("dil", (8380417, 256, 32, 5, 4, 23))):
+        y = rng.integers(-4, 5, size=(6, l, n)).astype(np.int32)
+        out3["rp_y_%s" % name] = y
+        w, r = O.tables(q, n, tw)
+        for pname, pt in (("chacha", O.PRNG_CHACHA), ("aes", O.PRNG_AES_CTR_DRBG)):
+            out3["rp_t_%s_%s" % (name, pname)] = ref.rand_product(tw, O.REFERENCE, n, q, q_bits, k, l, False, pt, rp_seeds, y, w, r)
+            if tw == 16:
+                out3["rp_tT_%s_%s" % (name, pname)] = ref.rand_product(tw, O.REFERENCE, n, q, q_bits, k, l, True, pt, rp_seeds, y, w, r)
+    script = []
+    for i in range(300):
+        kind = int(rng.choice([32, 64, 8, 1, 16, 0, 128, 2, 3, 4, 4, 6, 5]))
+        arg = int(rng.integers(1, 33)) if kind == 0 else int(rng.choice([1, 7, 64, 65, 512, 1000, 4096])) if kind == 4 else 0
+        script.append((kind, arg))
+    out3["prng_script"] = np.array(script, dtype=np.int32)
+    out3["prng_script_seed"] = rng.integers(0, 256, size=48).astype(np.uint8)
+    out3["prng_script_aes"] = ref.prng_script(O.PRNG_AES_CTR_DRBG, out3["prng_script_seed"], script, 4096)
+    noreset = [(k, a) for k, a in script if k != 5]
+    out3["prng_script_chacha"] = ref.prng_script(O.PRNG_CHACHA, out3["prng_script_seed"], noreset, 4096)
+    for pname, pt in (("chacha", O.PRNG_CHACHA), ("aes", O.PRNG_AES_CTR_DRBG)):
+        out3["gauss_ky128_%s" % pname] = ref.gauss_streams(O.SAMPLER_KNUTH_YAO, 128, 0, pt, 13.0, 19.53, seeds, 96)
+    path = os.path.join(HERE, "golden_v3.npz")
+    np.savez_compressed(path, **out3)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(out3), "arrays")
+
 
 if __name__ == "__main__":
     main()

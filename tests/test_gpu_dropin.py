@@ -221,6 +221,21 @@ def test_prng_front_end_scripts(prng):
             assert np.array_equal(exp, O.ref().prng_script(prng, seed, script, period))
 
 
+def test_prng_front_end_golden_fixture():
+    """The same front-end script against outputs of the compiled reference committed in tests/golden/golden_v3.npz."""
+    G3 = np.load(os.path.join(ROOT, "tests", "golden", "golden_v3.npz"))
+    L = bind_prng(sc.lib())
+    script = [tuple(int(v) for v in row) for row in G3["prng_script"]]
+    seed = np.ascontiguousarray(G3["prng_script_seed"])
+    for prng, key, scr in ((O.PRNG_AES_CTR_DRBG, "prng_script_aes", script),
+                           (O.PRNG_CHACHA, "prng_script_chacha", [(k, a) for k, a in script if k != 5])):
+        ctx = L.prng_create(5, prng, 0, 4096)
+        assert ctx and L.prng_set_entropy(ctx, seed.ctypes.data, seed.size) == 0 and L.prng_init(ctx, b"SAFEcrypto nonce", 16) == 0
+        got = run_script(L, ctx, scr)
+        L.prng_destroy(ctx)
+        assert np.array_equal(got, G3[key])
+
+
 ENTROPY_CB = ctypes.CFUNCTYPE(None, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint8))
 
 

@@ -286,3 +286,19 @@ def test_sample_statistics():
     assert abs(x.mean()) < 0.2 and 3.5 < x.std() < 4.7
     x = P.gauss_streams(O.SAMPLER_BERNOULLI, 64, 0, O.PRNG_AES_CTR_DRBG, 13.0, 4.5, seeds, 256)
     assert abs(x.mean()) < 0.3 and abs(x.std() - 4.5) < 0.3
+
+
+def test_round2_fixtures_prng_front_end_and_ky128():
+    """golden_v3.npz (generated from the compiled reference): prng_128 / float / double / mem / reset / counters in a
+    random interleaving, and Knuth-Yao at 128 rows."""
+    import os
+    G3 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v3.npz"))
+    script = [tuple(int(v) for v in row) for row in G3["prng_script"]]
+    seed = G3["prng_script_seed"]
+    assert np.array_equal(O.port().prng_script(O.PRNG_AES_CTR_DRBG, seed, script, 4096), G3["prng_script_aes"])
+    noreset = [(k, a) for k, a in script if k != 5]
+    assert np.array_equal(O.port().prng_script(O.PRNG_CHACHA, seed, noreset, 4096), G3["prng_script_chacha"])
+    seeds = np.array([[(s * 131 + j * 7 + 3) & 0xFF for j in range(64)] for s in range(4)], dtype=np.uint8)
+    for pname, pt in (("chacha", O.PRNG_CHACHA), ("aes", O.PRNG_AES_CTR_DRBG)):
+        got = O.port().gauss_streams(O.SAMPLER_KNUTH_YAO, 128, 0, pt, 13.0, 19.53, seeds, 96)
+        assert np.array_equal(got, G3["gauss_ky128_%s" % pname])
