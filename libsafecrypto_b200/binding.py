@@ -12,7 +12,7 @@ REFERENCE, BARRETT, FP, AVX, SOLINAS_7681, SOLINAS_8380417 = range(6)
  OP_CENTER, OP_POLYMUL, OP_TRIPLE16, OP_MODN, OP_MULN, OP_SQRN, OP_FLIP, OP_INVERT, OP_DIV,
  OP_PWR, OP_SCALAR, OP_SPARSE32, OP_SPARSE16) = range(22)
 PRNG_AES_CTR_DRBG, PRNG_CHACHA = 0, 2
-SAMPLER_CDF, SAMPLER_KNUTH_YAO, SAMPLER_BERNOULLI = 0, 1, 5
+SAMPLER_CDF, SAMPLER_KNUTH_YAO, SAMPLER_BERNOULLI, SAMPLER_KNUTH_YAO_FAST = 0, 1, 5, 6
 NORMAL_SAMPLES, BLINDING_SAMPLES, SHUFFLE_SAMPLES = 0, 1, 2
 
 
@@ -56,6 +56,8 @@ def lib():
         L.scgpu_ntt_plans_create_all.argtypes = [ctypes.POINTER(vp), ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.scgpu_polymul_batch_host_multi.argtypes = [ctypes.POINTER(vp), ctypes.c_int, vp, vp, vp, sz, sz]
         L.scgpu_ntt_batch_host_multi.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, vp, vp, vp, sz, sz, i32, vp]
+        L.scgpu_gauss_plan_create_ky_fast.argtypes = [ctypes.POINTER(vp), vp, vp, sz, vp, ctypes.c_int, ctypes.c_int, u32, u32,
+                                                      ctypes.c_int, ctypes.c_int]
         L.scgpu_gauss_plan_create_table.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, vp, sz, ctypes.c_int]
         L.scgpu_gauss_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_float, ctypes.c_float, ctypes.c_int]
@@ -271,11 +273,16 @@ def rand_matrix(A, seeds, prng_type, q, q_bits, n, k, l, transpose=False, stream
 class GaussPlan:
     """scgpu_gauss_plan_t: sampler tables (built on the host with the reference's formulas) on the device."""
 
-    def __init__(self, sampler, precision, blinding, tail, sigma, device=0, table=None):
+    def __init__(self, sampler, precision, blinding, tail, sigma, device=0, table=None, ky_fast=None):
         h = ctypes.c_void_p()
-        if table is not None:
+        if ky_fast is not None:
+            # (lut1, lut2, pmat [rows, cols], dist1_mask, dist2_mask): gaussian_knuth_yao_fast.c's constants, caller supplied
+            lut1, lut2, pmat, d1, d2 = ky_fast
+            lut1, lut2, pmat = (np.ascontiguousarray(x, dtype=np.uint8) for x in (lut1, lut2, pmat))
+            _check(lib().scgpu_gauss_plan_create_ky_fast(ctypes.byref(h), _ptr(lut1), _ptr(lut2), lut2.size, _ptr(pmat), pmat.shape[0],
+                                                         pmat.shape[1], d1, d2, blinding, device), "scgpu_gauss_plan_create_ky_fast")
+        elif table is not None:
             # 128 / 192 / 256-bit CDF over a caller-built table: numpy uint64 [entries, precision / 64]
-            import numpy as np
             t = np.ascontiguousarray(table, dtype=np.uint64)
             assert t.ndim == 2 and t.shape[1] * 64 == precision
             _check(lib().scgpu_gauss_plan_create_table(ctypes.byref(h), precision, blinding, ctypes.c_void_p(t.ctypes.data),

@@ -238,6 +238,37 @@ __device__ __forceinline__ void chacha20_first16(const uint32_t key[8], uint32_t
     ks[0] = x0 + 0x61707865; ks[1] = x1 + 0x3320646e; ks[2] = x2 + 0x79622d32; ks[3] = x3 + 0x6b206574;
 }
 
+// ctr_drbg_create + the first ctr_drbg_reseed (ctr_drbg.c:37-70, 100-147) of a FRESH stream, inlined: zero key, zero
+// counter, three counter blocks encrypted, key = entropy[4..36) ^ those bytes, counter = 3 ^ entropy[0..4).  What
+// PrngStream::init computes for PRNG_AES, without the resumable state (the throughput kernels set up one generator
+// per stream and the out-of-line version kept the whole PrngState in local memory).
+__device__ __forceinline__ void drbg_instantiate(const AesTables &t, const uint8_t *seed, uint32_t seed_len, uint32_t *rk, uint32_t &counter)
+{
+    uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    aes256_expand(t, zero, rk);
+    uint32_t bytes_be[12];
+    uint32_t ctr = 0;
+    for (int block = 3; block > 0;) {
+        ctr++;
+        const uint32_t c = bswap32(ctr);
+        uint32_t o[4];
+        block--;
+        aes256_encrypt(t, rk, c, c, c, c, o);
+        for (int i = 0; i < 4; i++) bytes_be[4 * block + i] = o[i];
+    }
+    uint32_t e = 0;
+    auto le32 = [&]() {
+        uint32_t v = 0;
+        for (int b = 0; b < 4; b++) { v |= (uint32_t)seed[e] << (8 * b); if (++e == seed_len) e = 0; }
+        return v;
+    };
+    const uint32_t ctr_le = le32();
+    uint32_t key[8];
+    for (int i = 0; i < 8; i++) key[i] = bswap32(le32()) ^ bytes_be[3 + i];
+    counter = ctr ^ ctr_le;
+    aes256_expand(t, key, rk);
+}
+
 // ---- the sequential generator -------------------------------------------------------------------------
 struct PrngStream {
     PrngState s;

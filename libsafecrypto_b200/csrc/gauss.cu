@@ -180,10 +180,38 @@ __device__ __forceinline__ int32_t sample_ber(const GaussTablesDev &g, PrngStrea
     return s;
 }
 
+// gaussian_knuth_yao_fast_sample (gaussian_knuth_yao_fast.c:303-368): a byte indexes the first table; a miss carries a
+// distance into the second table (5 more random bits), a second miss walks the probability matrix from column 13 on,
+// bottom row first, one random bit per column.  prng_8 / prng_bit are prng_var(8) / prng_var(1).
+__device__ __forceinline__ int32_t sample_ky_fast(const GaussTablesDev &g, PrngStream &rng)
+{
+    int32_t sample = g.kf_lut1[rng.var(8) & 0xFF];
+    if ((sample & 16) == 0) {
+        sample &= 0xF;
+        return rng.var(1) ? -sample : sample;
+    }
+    int32_t distance = sample & (int32_t)g.kf_d1mask;
+    sample = g.kf_lut2[(int32_t)(rng.var(8) & 0x1F) + 32 * distance];
+    if ((sample & 0x20) == 0) {
+        sample &= 0x1F;
+        return rng.var(1) ? -sample : sample;
+    }
+    distance = sample & (int32_t)g.kf_d2mask;
+    for (int col = 13; col < g.kf_cols; col++) {
+        distance = distance * 2 + (int32_t)rng.var(1);
+        for (int row = g.kf_rows - 1; row >= 0; row--) {
+            distance -= g.kf_pmat[row * g.kf_cols + col];
+            if (distance < 0) return rng.var(1) ? -row : row;
+        }
+    }
+    return 0;
+}
+
 __device__ __forceinline__ int32_t draw(const GaussTablesDev &g, PrngStream &rng)
 {
     if (g.sampler == SCGPU_SAMPLER_CDF) return sample_cdf(g, rng);
     if (g.sampler == SCGPU_SAMPLER_KNUTH_YAO) return sample_ky(g, rng);
+    if (g.sampler == SCGPU_SAMPLER_KNUTH_YAO_FAST) return sample_ky_fast(g, rng);
     return sample_ber(g, rng);
 }
 
@@ -400,14 +428,11 @@ __global__ void __launch_bounds__(128) k_drbg_setup(FastArgs a)
     __syncthreads();
     const size_t sidx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (sidx >= a.nstreams) return;
-    PrngStream rng;
-    rng.aes = &aes;
-    rng.seed = a.seeds + sidx * a.seed_len;
-    rng.s.pooled = 0; rng.s.ent_fresh = 0; rng.s.ent_avail = 0;
-    rng.init(PRNG_AES, a.seed_len, a.seed_period);
+    uint32_t rk[60], counter;
+    drbg_instantiate(aes, a.seeds + sidx * a.seed_len, a.seed_len, rk, counter);
     uint32_t *k = a.keys + sidx * 64;
-    for (int i = 0; i < 60; i++) k[i] = rng.s.drbg_rk[i];
-    k[60] = rng.s.drbg_counter;
+    for (int i = 0; i < 60; i++) k[i] = rk[i];
+    k[60] = counter;
 }
 
 constexpr int kAesCta = 1024;            // one CTA per SM: 128 KiB of replicated AES tables are shared by 32 warps

@@ -32,6 +32,11 @@ struct GaussTablesDev {
     // the same matrix as a bitmap (bit p of word p / 32 = entry p) with the number of one-bits before each word:
     // rank(p) = ky_rank[p / 32] + popc(low bits), so a whole row of the walk costs two table reads instead of a scan
     const uint32_t *ky_bits, *ky_rank;
+    // Knuth-Yao "fast" (gaussian_knuth_yao_fast.c:303-368): two byte look-up tables and a small byte-per-bit matrix,
+    // all handed over by the caller (they are source-embedded constants of the reference)
+    const uint8_t *kf_lut1, *kf_lut2, *kf_pmat;
+    int kf_rows, kf_cols;
+    uint32_t kf_d1mask, kf_d2mask;
     // Bernoulli (gaussian_bernoulli.c:40-103): entries x 8 bytes, most significant byte first
     const uint8_t *ber_tab;
     int ber_entries, ber_maxval, ber_maxlog;

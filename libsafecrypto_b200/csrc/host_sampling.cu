@@ -27,7 +27,7 @@ struct scgpu_gauss_plan {
     int device, sm_count;
     void *d_cdf = nullptr;
     uint32_t *d_flat = nullptr, *d_kybits = nullptr, *d_kyrank = nullptr;
-    uint8_t *d_ber = nullptr;
+    uint8_t *d_ber = nullptr, *d_kf = nullptr;
     uint32_t *d_guide = nullptr;
     std::mutex mu;
     uint8_t *d_seeds = nullptr; size_t seeds_cap = 0;       // staging for *_host
@@ -303,13 +303,46 @@ extern "C" int scgpu_gauss_plan_create_table(scgpu_gauss_plan_t **out, int preci
     return SCGPU_OK;
 }
 
+extern "C" int scgpu_gauss_plan_create_ky_fast(scgpu_gauss_plan_t **out, const uint8_t *lut1, const uint8_t *lut2, size_t lut2_len,
+                                               const uint8_t *pmat, int rows, int cols, uint32_t dist1_mask, uint32_t dist2_mask,
+                                               int blinding, int device)
+{
+    if (!out || !lut1 || !lut2 || !pmat) { set_error("gauss_plan_create_ky_fast: null argument"); return SCGPU_ERR_ARG; }
+    if (rows < 1 || cols < 14 || rows > 4096 || cols > 4096) { set_error("gauss_plan_create_ky_fast: %d x %d matrix", rows, cols); return SCGPU_ERR_ARG; }
+    if (lut2_len < 32 * ((size_t)dist1_mask + 1)) { set_error("gauss_plan_create_ky_fast: lut2 holds %zu bytes, the first-level distances index %zu", lut2_len, 32 * ((size_t)dist1_mask + 1)); return SCGPU_ERR_ARG; }
+    if (blinding == SCGPU_BLINDING_SAMPLES) { set_error("gauss_plan_create_ky_fast: configure_sampler refuses blinding for this sampler (sampling.c:372-374)"); return SCGPU_ERR_UNSUPPORTED; }
+    if (blinding < 0 || blinding > 2) { set_error("gauss_plan_create_ky_fast: blinding %d", blinding); return SCGPU_ERR_ARG; }
+    int ndev = 0;
+    SCGPU_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("gauss_plan_create_ky_fast: device %d of %d", device, ndev); return SCGPU_ERR_ARG; }
+    SCGPU_CUDA_CHECK(cudaSetDevice(device));
+    scgpu_gauss_plan *p = new scgpu_gauss_plan();
+    memset(&p->t, 0, sizeof(p->t));
+    p->t.sampler = SCGPU_SAMPLER_KNUTH_YAO_FAST; p->t.precision = 64; p->t.blinding = blinding;
+    p->device = device;
+    cudaDeviceProp prop;
+    SCGPU_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    p->sm_count = prop.multiProcessorCount;
+    { const int e = init_work_counters(); if (e != SCGPU_OK) { delete p; return e; } }
+    std::vector<uint8_t> all(256 + lut2_len + (size_t)rows * cols);
+    memcpy(all.data(), lut1, 256);
+    memcpy(all.data() + 256, lut2, lut2_len);
+    memcpy(all.data() + 256 + lut2_len, pmat, (size_t)rows * cols);
+    const int rc = upload(&p->d_kf, all);
+    if (rc != SCGPU_OK) { scgpu_gauss_plan_destroy(p); return rc; }
+    p->t.kf_lut1 = p->d_kf; p->t.kf_lut2 = p->d_kf + 256; p->t.kf_pmat = p->d_kf + 256 + lut2_len;
+    p->t.kf_rows = rows; p->t.kf_cols = cols; p->t.kf_d1mask = dist1_mask; p->t.kf_d2mask = dist2_mask;
+    *out = p;
+    return SCGPU_OK;
+}
+
 extern "C" int scgpu_set_fixed_probe_search(int on) { return set_fixed_probe_search(on); }
 
 extern "C" void scgpu_gauss_plan_destroy(scgpu_gauss_plan_t *p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
-    cudaFree(p->d_cdf); cudaFree(p->d_flat); cudaFree(p->d_kybits); cudaFree(p->d_kyrank); cudaFree(p->d_ber); cudaFree(p->d_guide);
+    cudaFree(p->d_cdf); cudaFree(p->d_flat); cudaFree(p->d_kybits); cudaFree(p->d_kyrank); cudaFree(p->d_ber); cudaFree(p->d_kf); cudaFree(p->d_guide);
     cudaFree(p->d_seeds); cudaFree(p->d_out);
     delete p;
 }
@@ -803,6 +836,8 @@ utils_sampling_t *create_sampler(random_sampling_e type, sample_precision_e prec
 {
     if (!prng_ctx || !prng_ctx->inited) return NULL;
     if (bootstrapped != SAMPLING_DISABLE_BOOTSTRAP) return NULL;      // MW bootstrap: SURVEY.md 8f rank 4
+    // configure_sampler refuses blinding for the Knuth-Yao samplers (sampling.c:341-343, 372-374)
+    if ((type == KNUTH_YAO_GAUSSIAN_SAMPLING || type == KNUTH_YAO_FAST_GAUSSIAN_SAMPLING) && blinding == BLINDING_SAMPLES) return NULL;
     scgpu_gauss_plan *plan = nullptr;
     if (scgpu_gauss_plan_create(&plan, (int)type, (int)precision, (int)blinding, tail, sigma, prng_ctx->device) != SCGPU_OK)
         return NULL;

@@ -52,9 +52,15 @@ struct XConst {
 // position of word j (0..31) of thread t in the by-4 thread-major packing: a warp's 128-bit loads are contiguous
 __host__ __device__ constexpr int by4(int T, int t, int j) { return ((j >> 2) * T + t) * 4 + (j & 3); }
 
-template <int V>
+// V_AVXF: the AVX2 variant with the single-precision lanes (16-bit tables, 512 < q <= 12289, ntt_template.c.in:1367-1402):
+// a kernel of its own, so that no butterfly carries both lane flavours behind a run-time test of q
+constexpr int V_AVXF = 6;
+template <int V> struct PolicyOf { static constexpr int value = V == V_AVXF ? (int)V_AVX : V; };
+
+template <int V, bool TW16>
 __device__ __forceinline__ int32_t xmul(int32_t x, int32_t w, int32_t aux, const XConst &c)
 {
+    constexpr int EV = PolicyOf<V>::value;
     if constexpr (V == V_REFERENCE) {
         const int32_t s = x >> 31;
         const int32_t qe = __mulhi(x, aux);
@@ -70,7 +76,10 @@ __device__ __forceinline__ int32_t xmul(int32_t x, int32_t w, int32_t aux, const
         const uint32_t v = (uint32_t)x * (uint32_t)w + t * (uint32_t)c.nq;
         return cond_fix((int32_t)v, c.rc.q);
     } else {
-        return Exact<V>::muln(x, w, c.rc);
+        // fp and the scalar stages of avx: the double quotient with its two 64-bit conversions.  A conversion-free
+        // form (magic-number int -> double and truncation) was measured SLOWER: it trades two XU conversions for five
+        // more FP64-pipe operations (fp forward n = 512: 7.5e8 -> 5.3e8 transforms/s).
+        return Exact<EV>::muln(x, w, c.rc);
     }
 }
 
@@ -78,8 +87,9 @@ __device__ __forceinline__ int32_t xmul(int32_t x, int32_t w, int32_t aux, const
 template <int V, bool TW16>
 __device__ __forceinline__ int32_t xtwist(int32_t x, int32_t w, int32_t aux, const XConst &c)
 {
-    if constexpr (V == V_AVX) return TW16 ? Exact<V>::pw16(x, w, c.rc) : Exact<V>::pw32(x, w, c.rc);
-    else return xmul<V>(x, w, aux, c);
+    constexpr int EV = PolicyOf<V>::value;
+    if constexpr (EV == V_AVX) return TW16 ? Exact<EV>::pw16(x, w, c.rc) : Exact<EV>::pw32(x, w, c.rc);
+    else return xmul<V, TW16>(x, w, aux, c);
 }
 
 // one DIT butterfly of stage S (ntt_template.c.in:1144-1244 fft_32, :1341-1482 fft_16; the AVX2 branches
@@ -88,18 +98,18 @@ template <int V, int LOGN, int S, bool TW16>
 __device__ __forceinline__ void xbfly(int32_t &lo, int32_t &hi, int32_t w, int32_t aux, bool j0, const XConst &c)
 {
     constexpr int N = 1 << LOGN;
-    constexpr bool vec = (V == V_AVX) && ((1 << S) < (N >> 3));
+    constexpr int EV = PolicyOf<V>::value;
+    constexpr bool vec = (EV == V_AVX) && ((1 << S) < (N >> 3));
     int32_t x;
     if constexpr (vec) {
-        const int64_t prod = (int64_t)hi * (int64_t)w;
-        if (TW16) x = (c.rc.q <= 12289) ? lane_flt((int32_t)prod, c.rc) : lane_dbl(prod, false, c.rc);
-        else      x = lane_dbl(prod, false, c.rc);
+        if constexpr (V == V_AVXF) x = lane_flt_magic((int32_t)((uint32_t)hi * (uint32_t)w), c.rc);   // low 32 bits of the product
+        else                       x = lane_dbl((int64_t)hi * (int64_t)w, false, c.rc);
     } else {
         // column j = 0 is not multiplied: passed through (fft_16) or reduced only (fft_32)
-        const int32_t x0 = TW16 ? hi : Exact<V>::modn(hi, c.rc);
+        const int32_t x0 = TW16 ? hi : Exact<EV>::modn(hi, c.rc);
         if (S == 0) x = x0;
         else {
-            const int32_t xm = xmul<V>(hi, w, aux, c);
+            const int32_t xm = xmul<V, TW16>(hi, w, aux, c);
             x = j0 ? x0 : xm;
         }
     }
@@ -410,6 +420,13 @@ int launch_xv(const NttPlanDev &p, bool inverse, int32_t *out, const int32_t *a,
     } else if constexpr (V == V_SOL8380417) {
         if (p.logn != 8 || tw16) return SCGPU_ERR_UNSUPPORTED;
         return launch_x<V, 8, false>(p, inverse, out, a, count, c, st);
+    } else if constexpr (V == V_AVXF) {
+        switch (p.logn) {
+        case 8:  return launch_x<V, 8, true>(p, inverse, out, a, count, c, st);
+        case 9:  return launch_x<V, 9, true>(p, inverse, out, a, count, c, st);
+        case 10: return launch_x<V, 10, true>(p, inverse, out, a, count, c, st);
+        default: return SCGPU_ERR_UNSUPPORTED;
+        }
     } else
     // the parameter sets of the reference: 16-bit tables exist for n = 256 (7681), 512 / 1024 (12289, 18433);
     // 32-bit tables for n = 256 (8380417), 512, 1024
@@ -469,7 +486,13 @@ int launch_exact_w32(const NttPlanDev &p, int op, int32_t *out, const int32_t *a
     case V_FP:         return launch_xv<V_FP>(p, inverse, out, a, count, c, st);
 #endif
 #if XW32_VARIANTS & 8
-    case V_AVX:        return launch_xv<V_AVX>(p, inverse, out, a, count, c, st);
+    case V_AVX:
+        // single-precision lanes for 16-bit tables with q <= 12289 (:1367-1402); the magic-number rounding needs q > 512
+        if (p.tw_bits == 16 && p.rc.q <= 12289) {
+            if (p.rc.q <= 512) return SCGPU_ERR_UNSUPPORTED;
+            return launch_xv<V_AVXF>(p, inverse, out, a, count, c, st);
+        }
+        return launch_xv<V_AVX>(p, inverse, out, a, count, c, st);
 #endif
 #if XW32_VARIANTS & 16
     case V_SOL7681:    return launch_xv<V_SOL7681>(p, inverse, out, a, count, c, st);

@@ -54,10 +54,10 @@ __device__ __forceinline__ int32_t ring_coeff(uint32_t v16, const GenArgs &a)
 // word g of the stream -> coefficients c0, c0 + 1 (c0 even)
 __device__ __forceinline__ void emit_word(const GenArgs &a, int32_t *inst_out, size_t g, uint32_t word)
 {
-    const size_t c0 = 4 * (g >> 1) + ((g & 1) ? 0 : 2);
-    const size_t total = (size_t)a.rings * a.n;
+    const uint32_t c0 = 4u * (uint32_t)(g >> 1) + ((g & 1) ? 0u : 2u);
+    const uint32_t total = (uint32_t)a.rings << 8;                  // n = 256 (the only defined ring length)
     if (c0 >= total) return;
-    const int ring = (int)(c0 / a.n), pos = (int)(c0 % a.n);
+    const int ring = (int)(c0 >> 8), pos = (int)(c0 & 255u);
     int32_t *dst = inst_out + (size_t)dest_ring(a, ring) * a.n + pos;
     *reinterpret_cast<int2 *>(dst) = make_int2(ring_coeff(word & 0xFFFFu, a), ring_coeff(word >> 16, a));
 }
@@ -130,13 +130,10 @@ __global__ void __launch_bounds__(128) k_gen_rings(GenArgs a)
         }
     } else {
         if (lane == 0) {
-            PrngStream rng;
-            rng.aes = &aes;
-            rng.seed = seed;
-            rng.s.pooled = 0; rng.s.ent_fresh = 0; rng.s.ent_avail = 0;
-            rng.init(PRNG_AES, a.seed_len, a.seed_period);
-            for (int i = 0; i < 60; i++) s_rk[warp][i] = rng.s.drbg_rk[i];
-            s_rk[warp][60] = rng.s.drbg_counter;
+            uint32_t rk0[60], counter;
+            drbg_instantiate(aes, seed, a.seed_len, rk0, counter);
+            for (int i = 0; i < 60; i++) s_rk[warp][i] = rk0[i];
+            s_rk[warp][60] = counter;
         }
         __syncwarp();
         const uint32_t *rk = s_rk[warp];
@@ -150,11 +147,11 @@ __global__ void __launch_bounds__(128) k_gen_rings(GenArgs a)
             // little-endian UINT16 pair of word i is bswap(o[i]); coefficient index = byte offset / 2
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const size_t cidx = 8 * b + 2 * (size_t)i;
-                const size_t total = (size_t)a.rings * a.n;
+                const uint32_t cidx = 8u * (uint32_t)b + 2u * (uint32_t)i;
+                const uint32_t total = (uint32_t)a.rings << 8;
                 if (cidx >= total) continue;
                 const uint32_t word = bswap32(o[i]);
-                const int ring = (int)(cidx / a.n), pos = (int)(cidx % a.n);
+                const int ring = (int)(cidx >> 8), pos = (int)(cidx & 255u);
                 int32_t *dst = inst_out + (size_t)dest_ring(a, ring) * a.n + pos;
                 *reinterpret_cast<int2 *>(dst) = make_int2(ring_coeff(word & 0xFFFFu, a), ring_coeff(word >> 16, a));
             }
@@ -168,6 +165,7 @@ int launch_gen_rings(int prng_type, const uint8_t *seeds, size_t seed_len, size_
                      int transpose, int32_t q, uint32_t q_bits, cudaStream_t st)
 {
     if (count == 0) return SCGPU_OK;
+    if (n != 256) { set_error("gen_rings: n = %d (256 only)", n); return SCGPU_ERR_UNSUPPORTED; }
     GenArgs a;
     a.seeds = seeds; a.seed_len = (uint32_t)seed_len; a.seed_period = 0x01000000u;      // create_csprng, module_lwe.c:921
     a.count = count; a.out = out; a.n = n; a.rings = k * l; a.k = k; a.l = l; a.transpose = transpose;

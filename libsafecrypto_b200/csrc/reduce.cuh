@@ -143,9 +143,18 @@ __device__ __forceinline__ int32_t lane_dbl(int64_t prod, bool full_range, const
 __device__ __forceinline__ int32_t lane_flt(int32_t p32, const RedConst &c)
 {
     float quo_f = __fmul_rn(__int2float_rn(p32), c.qs_inv);
-    // cvtps_epi32 = round to nearest even.  |quo_f| <= 2^31 / q < 2^22 for every q > 512, so adding 1.5 * 2^23 performs
-    // exactly that rounding in the mantissa (one FADD + one IADD instead of a conversion on the XU pipe)
-    int32_t quo = c.q > 512 ? __float_as_int(__fadd_rn(quo_f, 12582912.0f)) - 0x4B400000 : __float2int_rn(quo_f);
+    int32_t quo = __float2int_rn(quo_f);
+    int32_t res = (int32_t)((uint32_t)p32 - (uint32_t)quo * (uint32_t)c.q);
+    if (res < 0) res = (int32_t)((uint32_t)res + (uint32_t)c.q);
+    return res;
+}
+
+// The same lane for 512 < q: cvtps_epi32 rounds to nearest even, and |quo_f| <= 2^31 / q < 2^22, so adding 1.5 * 2^23
+// performs exactly that rounding in the mantissa (one FADD + one IADD instead of a conversion on the XU pipe).
+__device__ __forceinline__ int32_t lane_flt_magic(int32_t p32, const RedConst &c)
+{
+    const float quo_f = __fmul_rn(__int2float_rn(p32), c.qs_inv);
+    const int32_t quo = __float_as_int(__fadd_rn(quo_f, 12582912.0f)) - 0x4B400000;
     int32_t res = (int32_t)((uint32_t)p32 - (uint32_t)quo * (uint32_t)c.q);
     if (res < 0) res = (int32_t)((uint32_t)res + (uint32_t)c.q);
     return res;

@@ -22,6 +22,7 @@
 #include "utils/sampling/gaussian_cdf.h"
 #include "utils/sampling/gaussian_knuth_yao.h"
 #include "utils/sampling/gaussian_bernoulli.h"
+#include "utils/sampling/gaussian_knuth_yao_fast.h"
 #include "utils/crypto/prng.h"
 #include "utils/arith/module_lwe.h"
 
@@ -275,6 +276,37 @@ int ref_ber_table(float tail, float sigma, uint8_t *tab, size_t cap, int32_t *en
     return (int)sz;
 }
 
+/* gauss_knuth_yao_fast_t, gaussian_knuth_yao_fast.c:27-38.  The tables are constants of the reference's source; tests
+ * read them out of the compiled library at run time and hand them to the GPU plan. */
+SC_STRUCT_PACK_START
+typedef struct { SINT32 num_rows, num_cols; UINT32 dist1_mask, dist2_mask; const UINT8 *pre_lut_1, *pre_lut_2, *pmat; prng_ctx_t *prng; } SC_STRUCT_PACKED drv_kyf_t;
+SC_STRUCT_PACK_END
+
+static void *kyfast_create(prng_ctx_t *ctx, int dimension)
+{
+    return dimension == 512 ? gaussian_knuth_yao_fast_512_create(ctx, 0.0f, 4.8591f, 0, NORMAL_SAMPLES)
+                            : gaussian_knuth_yao_fast_256_create(ctx, 0.0f, 4.5120f, 0, NORMAL_SAMPLES);
+}
+
+/* dims: rows, cols, dist1_mask, dist2_mask, lut2 length */
+int ref_kyfast_tables(int dimension, uint8_t *lut1, uint8_t *lut2, size_t lut2_cap, uint8_t *pmat, size_t pmat_cap, int32_t *dims)
+{
+    static const uint8_t z[64] = {0};
+    prng_ctx_t *ctx = make_prng(SC_PRNG_CHACHA, z, 64, 0);
+    drv_kyf_t *k = (drv_kyf_t *)kyfast_create(ctx, dimension);
+    if (!k) { prng_destroy(ctx); return 1; }
+    const size_t l2 = 32 * ((size_t)k->dist1_mask + 1), pm = (size_t)k->num_rows * (size_t)k->num_cols;
+    dims[0] = k->num_rows; dims[1] = k->num_cols; dims[2] = (int32_t)k->dist1_mask; dims[3] = (int32_t)k->dist2_mask; dims[4] = (int32_t)l2;
+    if (l2 > lut2_cap || pm > pmat_cap) { prng_destroy(ctx); return 2; }
+    memcpy(lut1, k->pre_lut_1, 256);
+    memcpy(lut2, k->pre_lut_2, l2);
+    memcpy(pmat, k->pmat, pm);
+    void *g = k;
+    gaussian_knuth_yao_fast_destroy(&g);
+    prng_destroy(ctx);
+    return 0;
+}
+
 /* Optional caller-supplied 128 / 192-bit CDF table written over the one create_sampler() built: the reference's
  * own table construction needs GMP/MPFR to be meaningful (with USE_SAFECRYPTO_FLOAT_MP every entry comes out
  * as {2, 2, ..}), the SAMPLING over a table is what the GPU path is compared against. */
@@ -328,6 +360,12 @@ int ref_gauss_streams(int sampler, int precision, int blinding, int prng_type, f
                     : (precision == 128) ? gaussian_knuth_yao_create_128(ctx, tail, sigma, 0, (sample_blinding_e)blinding)
                                          : gaussian_knuth_yao_create_64(ctx, tail, sigma, 0, (sample_blinding_e)blinding);
             for (size_t j = 0; j < n * calls_per_stream; j++) v[j] = gaussian_knuth_yao_sample(g) + centre;
+        } else if (sampler == KNUTH_YAO_FAST_GAUSSIAN_SAMPLING) {
+            /* `precision` carries the dimension (256 / 512) that selects the reference's table set */
+            void *g = kyfast_create(ctx, precision);
+            if (!g) { fail |= 1; prng_destroy(ctx); continue; }
+            for (size_t j = 0; j < n * calls_per_stream; j++) v[j] = gaussian_knuth_yao_fast_sample(g) + centre;
+            gaussian_knuth_yao_fast_destroy(&g);
         } else if (sampler == BERNOULLI_GAUSSIAN_SAMPLING) {
             void *g = bernoulli_create_64(ctx, tail, sigma, 0, NORMAL_SAMPLES);
             for (size_t j = 0; j < n * calls_per_stream; j++) v[j] = bernoulli_sample_64(g) + centre;

@@ -26,7 +26,7 @@ VARIANT_NAMES = {REFERENCE: "reference", BARRETT: "barrett", FP: "fp", AVX: "avx
  OP_PWR, OP_SCALAR, OP_SPARSE32, OP_SPARSE16) = range(22)
 
 PRNG_AES_CTR_DRBG, PRNG_CHACHA = 0, 2
-SAMPLER_CDF, SAMPLER_KNUTH_YAO, SAMPLER_BERNOULLI = 0, 1, 5
+SAMPLER_CDF, SAMPLER_KNUTH_YAO, SAMPLER_BERNOULLI, SAMPLER_KNUTH_YAO_FAST = 0, 1, 5, 6
 NORMAL_SAMPLES, BLINDING_SAMPLES, SHUFFLE_SAMPLES = 0, 1, 2
 
 # (tw_bits, q, n) of build_tools/ntt_table_gen/main.c:19-37
@@ -186,6 +186,18 @@ class Checker:
 
 class RefChecker(Checker):
     """The reference library also exports its generated twiddle tables as data symbols."""
+
+    def kyfast_tables(self, dimension):
+        """(lut1, lut2, pmat [rows, cols], dist1_mask, dist2_mask) of gaussian_knuth_yao_fast_{256,512}_create, read out of
+        the compiled reference."""
+        f = self.lib.ref_kyfast_tables
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        lut1, lut2, pmat = np.zeros(256, np.uint8), np.zeros(4096, np.uint8), np.zeros(1 << 16, np.uint8)
+        dims = np.zeros(5, np.int32)
+        assert f(dimension, _vp(lut1), _vp(lut2), lut2.size, _vp(pmat), pmat.size, _vp(dims)) == 0
+        rows, cols = int(dims[0]), int(dims[1])
+        return lut1, lut2[:int(dims[4])].copy(), pmat[:rows * cols].reshape(rows, cols).copy(), int(dims[2]), int(dims[3])
 
     def rand_product(self, tw_bits, variant, n, q, q_bits, k, l, transpose, prng_type, seeds, y, w, r, want_matrix=False, threads=0):
         """create_rand_product_{16,32}_csprng (module_lwe.c:588-748) per instance, CSPRNG as create_csprng makes it.

@@ -168,6 +168,27 @@ def test_ky_bernoulli_vector_modes_and_ragged_batches(prng):
             assert ba == bb and np.array_equal(a, b)
 
 
+@pytest.mark.skipif(not O.ref_available(), reason="the look-up tables are constants of the reference: read from oracle/_ref/libscref.so")
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+@pytest.mark.parametrize("dimension", [256, 512])
+def test_knuth_yao_fast_over_the_references_tables(prng, dimension):
+    """gaussian_knuth_yao_fast_sample (gaussian_knuth_yao_fast.c:303-368): the tables are read out of the compiled
+    reference at run time and handed to scgpu_gauss_plan_create_ky_fast; samples against the reference's own."""
+    tabs = O.ref().kyfast_tables(dimension)
+    plan = sc.GaussPlan(sc.SAMPLER_KNUTH_YAO_FAST, 64, 0, 0.0, 0.0, ky_fast=tabs)
+    seeds = seeds_for(70, 40, salt=dimension)
+    for n, calls, centre in ((512, 2, 0), (77, 1, 5)):
+        out = torch.full((seeds.shape[0], n * calls), 99, dtype=torch.int32, device=DEV)
+        plan.streams(prng, torch.from_numpy(seeds).to(DEV), n, out, calls=calls, centre=centre)
+        torch.cuda.synchronize()
+        exp = O.ref().gauss_streams(O.SAMPLER_KNUTH_YAO_FAST, dimension, 0, prng, 0.0, 0.0, seeds, n, centre=centre, calls=calls)
+        assert np.array_equal(out.cpu().numpy(), exp)
+    got = out.cpu().numpy() - 5
+    assert abs(got.std() - (4.51 if dimension == 256 else 4.86)) < 0.25
+    with pytest.raises(sc.ScgpuError):
+        sc.GaussPlan(sc.SAMPLER_KNUTH_YAO_FAST, 64, 1, 0.0, 0.0, ky_fast=tabs)         # blinding: refused as configure_sampler does
+
+
 def test_bernoulli_and_knuth_yao_at_scale():
     """2^13 streams x 256 samples of each: every sample against the port, moments as a sanity check."""
     seeds = np.random.default_rng(11).integers(0, 256, size=(1 << 13, 40)).astype(np.uint8)
