@@ -183,8 +183,8 @@ def test_knuth_yao_fast_over_the_references_tables(prng, dimension):
         torch.cuda.synchronize()
         exp = O.ref().gauss_streams(O.SAMPLER_KNUTH_YAO_FAST, dimension, 0, prng, 0.0, 0.0, seeds, n, centre=centre, calls=calls)
         assert np.array_equal(out.cpu().numpy(), exp)
-    got = out.cpu().numpy() - 5
-    assert abs(got.std() - (4.51 if dimension == 256 else 4.86)) < 0.25
+        if n == 512:        # sanity: sigma 4.512 / 4.8591 (a ChaCha20 stream opens with three zero words, skip them)
+            assert abs(out.cpu().numpy()[:, 16:].std() - (4.51 if dimension == 256 else 4.86)) < 0.2
     with pytest.raises(sc.ScgpuError):
         sc.GaussPlan(sc.SAMPLER_KNUTH_YAO_FAST, 64, 1, 0.0, 0.0, ky_fast=tabs)         # blinding: refused as configure_sampler does
 

@@ -39,5 +39,29 @@ if what in ("gauss", "all"):
     for prng in (sc.PRNG_AES_CTR_DRBG, sc.PRNG_CHACHA):
         for _ in range(3):
             gp.streams(prng, seeds, n, smp)
+if what in ("exact_avx",):
+    p = sc.NttPlan(n, q, sc.AVX, w, r)
+    for _ in range(2):
+        p.batch(sc.OP_FWD, out, a)
+    p.batch(sc.OP_INV, out, a)
+if what in ("ber", "ky"):
+    sid = sc.SAMPLER_BERNOULLI if what == "ber" else sc.SAMPLER_KNUTH_YAO
+    gp = sc.GaussPlan(sid, 64, 0, 13.42, 215.0)
+    ns = 1 << 16
+    seeds = torch.randint(0, 256, (ns, 40), dtype=torch.uint8, device=dev, generator=g)
+    smp = torch.empty((ns, 128), dtype=torch.int32, device=dev)
+    for _ in range(2):
+        gp.streams(sc.PRNG_CHACHA, seeds, 128, smp)
+if what in ("randprod",):
+    q3, k = 7681, 3
+    w3, r3 = O.tables(q3, 256, 16)
+    p3 = sc.NttPlan(256, q3, sc.REFERENCE, w3, r3)
+    inst = 1 << 15
+    sd = torch.randint(0, 256, (inst, 32), dtype=torch.uint8, device=dev, generator=g)
+    sv = torch.randint(-4, 5, (inst, k, 256), dtype=torch.int32, device=dev, generator=g)
+    to = torch.empty((inst, k, 256), dtype=torch.int32, device=dev)
+    for prng in (sc.PRNG_CHACHA, sc.PRNG_AES_CTR_DRBG):
+        for _ in range(2):
+            p3.rand_product(to, sv, sd, prng, 13, k, k)
 torch.cuda.synchronize()
 print("done")
