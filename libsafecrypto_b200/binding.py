@@ -58,6 +58,8 @@ def lib():
         L.scgpu_ntt_batch_host_multi.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, vp, vp, vp, sz, sz, i32, vp]
         L.scgpu_gauss_plan_create_ky_fast.argtypes = [ctypes.POINTER(vp), vp, vp, sz, vp, ctypes.c_int, ctypes.c_int, u32, u32,
                                                       ctypes.c_int, ctypes.c_int]
+        L.scgpu_gauss_plan_create_mw.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int]
+        L.scgpu_gauss_mw_streams.argtypes = [vp, ctypes.c_int, vp, sz, sz, sz, ctypes.c_float, ctypes.c_float, vp, vp, vp]
         L.scgpu_gauss_plan_create_table.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, vp, sz, ctypes.c_int]
         L.scgpu_gauss_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_float, ctypes.c_float, ctypes.c_int]
@@ -273,9 +275,12 @@ def rand_matrix(A, seeds, prng_type, q, q_bits, n, k, l, transpose=False, stream
 class GaussPlan:
     """scgpu_gauss_plan_t: sampler tables (built on the host with the reference's formulas) on the device."""
 
-    def __init__(self, sampler, precision, blinding, tail, sigma, device=0, table=None, ky_fast=None):
+    def __init__(self, sampler, precision, blinding, tail, sigma, device=0, table=None, ky_fast=None, mw=False):
         h = ctypes.c_void_p()
-        if ky_fast is not None:
+        if mw:
+            # Micciancio-Walter bootstrap over a CDF base sampler of sigma 16 (sigma argument unused)
+            _check(lib().scgpu_gauss_plan_create_mw(ctypes.byref(h), precision, blinding, tail, device), "scgpu_gauss_plan_create_mw")
+        elif ky_fast is not None:
             # (lut1, lut2, pmat [rows, cols], dist1_mask, dist2_mask): gaussian_knuth_yao_fast.c's constants, caller supplied
             lut1, lut2, pmat, d1, d2 = ky_fast
             lut1, lut2, pmat = (np.ascontiguousarray(x, dtype=np.uint8) for x in (lut1, lut2, pmat))
@@ -308,6 +313,11 @@ class GaussPlan:
         return _check(lib().scgpu_gauss_streams(self.handle, prng_type, _ptr(seeds), seed_len, nstreams, n, calls,
                                                 centre, discard, _ptr(out), _stream_handle(stream)),
                       "scgpu_gauss_streams")
+
+    def mw_streams(self, prng_type, seeds, n, out, sigma, centre=0.0, centres=None, stream=None):
+        nstreams, seed_len = seeds.shape
+        return _check(lib().scgpu_gauss_mw_streams(self.handle, prng_type, _ptr(seeds), seed_len, nstreams, n, sigma, centre,
+                                                   _ptr(centres), _ptr(out), _stream_handle(stream)), "scgpu_gauss_mw_streams")
 
     def streams_host(self, prng_type, seeds, n, out, calls=1, centre=0, discard=0):
         nstreams, seed_len = seeds.shape

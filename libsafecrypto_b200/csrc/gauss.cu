@@ -14,6 +14,7 @@
 #include "scgpu_internal.h"
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 #include "csprng.cuh"
 #include "gauss_plan.h"
 #include "../../include/scgpu.h"
@@ -207,6 +208,38 @@ __device__ __forceinline__ int32_t sample_ky_fast(const GaussTablesDev &g, PrngS
     return 0;
 }
 
+// mw_bootstrap_sample (mw_bootstrap.c:243-259) over the CDF base sampler of sigma 16.  One sample is a fixed function
+// of 8 base samples (the combiner network, left operand first, :85-99), one prng_64 and 29 more base samples:
+//  * c = centre + x * scale, ci = floor(c);
+//  * mw_flip_and_round (:213-241) scales the fractional part by 1UL << precision with precision = 64, i.e. by 1 on
+//    x86-64 (the shift count wraps), so the scaled centre is 0: the coin flips consume random bits up to the first
+//    one-bit and always end in mw_round(0);
+//  * mw_round (:193-211): 29 steps of  sample = base_centre[center & 1] + base sample  (FLOAT + int, truncated),
+//    minus one for an odd negative centre, center = center / 2 + sample.
+__device__ __forceinline__ int32_t sample_mw(const GaussTablesDev &g, const MwParams &m, PrngStream &rng, float centre)
+{
+    int32_t b[8];
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) b[i] = sample_cdf(g, rng);
+    int32_t l0[4], l1[2];
+    for (int i = 0; i < 4; i++) l0[i] = m.z[0][0] * b[2 * i] + m.z[0][1] * b[2 * i + 1];
+    for (int i = 0; i < 2; i++) l1[i] = m.z[1][0] * l0[2 * i] + m.z[1][1] * l0[2 * i + 1];
+    const int32_t x = m.z[2][0] * l1[0] + m.z[2][1] * l1[1];
+    const double c = __dadd_rn((double)centre, __dmul_rn((double)x, m.scale));
+    const double ci = floor(c);
+    while (rng.next64() == 0) { }                       // the flips stop at the first one-bit
+    long long center = 0;
+#pragma unroll 1
+    for (int it = 0; it < m.k; it++) {
+        const int32_t smp = sample_cdf(g, rng);
+        int32_t sample = (int32_t)__fadd_rn((center & 1) ? 0.5f : 0.0f, (float)smp);      // truncation toward zero
+        if ((center & 1) && center < 0) sample--;
+        center /= 2;
+        center += sample;
+    }
+    return (int32_t)ci + (int32_t)center;
+}
+
 __device__ __forceinline__ int32_t draw(const GaussTablesDev &g, PrngStream &rng)
 {
     if (g.sampler == SCGPU_SAMPLER_CDF) return sample_cdf(g, rng);
@@ -239,6 +272,7 @@ struct SeqArgs {
     int mode;                   // 0 sampler vector calls, 1 raw words, 2 single get_sample, 3 instantiate only,
                                 // 4 prng_mem (n = 64-byte blocks), 5 prng_reset, 6 refill the bit pool
     uint32_t *pool_mem;         // pooled states (drop-in prng_ctx_t): kPoolWords + kDrbgBufWords words per stream
+    MwParams mw;                // mode 7: Micciancio-Walter bootstrap samples
 };
 
 __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
@@ -278,6 +312,14 @@ __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
         rng.reset_pooled();
     } else if (a.mode == 6) {
         rng.pool_refill();
+    } else if (a.mode == 7) {
+        // get_vector_32's bootstrap branch (sampling.c:560-573) / get_bootstrap_sample (:519-538)
+        for (size_t i = 0; i < a.n * a.calls; i++) {
+            const float centre = a.mw.centres ? a.mw.centres[sidx * a.n * a.calls + i] : a.mw.centre;
+            int32_t r = sample_mw(a.g, a.mw, rng, centre);
+            if (a.mw.clamp) r = r < a.mw.lim_lo ? a.mw.lim_lo : (r > a.mw.lim_hi ? a.mw.lim_hi : r);
+            v[i] = r;
+        }
     } else {
         for (size_t call = 0; call < a.calls; call++, v += a.n) {
             const size_t n = a.n;
@@ -330,12 +372,15 @@ __global__ void __launch_bounds__(128) k_stream_seq(SeqArgs a)
 // sample() call per lane per trip a warp always waits for its one lane that is inside an accepted candidate
 // (3.4e7 samples/s in round 1).  Here every lane advances its own state machine by one draw per trip -- candidate,
 // byte (j, i), zero / sign, discard -- so all lanes make progress all the time, and the generator is stepped for the
-// whole warp at once: each lane keeps a four-word FIFO, and when any lane runs dry every lane with room draws its next
-// 64 bits, so the ChaCha20 / AES blocks of the 32 streams are computed side by side instead of one lane at a time.
+// whole warp at once: each lane keeps a 16-word FIFO in shared memory, and when any lane runs dry every lane with room
+// draws its next generator block, so the ChaCha20 / AES blocks of the 32 streams are computed side by side instead of
+// one lane at a time (with a 4-word FIFO only 17 of 32 lanes took part in an average refill, profiles/ber_lanes_r2_ncu.json).
 // Fresh streams, NORMAL_SAMPLES (any discard setting); everything else stays on k_stream_seq.
+constexpr int kBerFifo = 16;            // words per lane; refills add one generator block (4 words) at a time
 __global__ void __launch_bounds__(128) k_ber_lanes(SeqArgs a)
 {
     __shared__ AesTables aes;
+    __shared__ uint32_t fifo[kBerFifo][128];            // lane-interleaved: conflict-free
     aes_tables_init(aes);
     __syncthreads();
     const size_t sidx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -347,10 +392,11 @@ __global__ void __launch_bounds__(128) k_ber_lanes(SeqArgs a)
     rng.s.pooled = 0; rng.s.ent_fresh = 0; rng.s.ent_avail = 0;
     if (!done) rng.init(a.prng_type, a.seed_len, a.seed_period);
     int32_t *v = a.out + (done ? 0 : sidx) * total;
-    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-    int cnt = 0;                                        // words in the FIFO
+    uint32_t (*q)[128] = fifo;
+    const int tid = threadIdx.x;
+    int head = 0, cnt = 0;                              // ring buffer state of this lane
     uint32_t var_buf = 0, var_bits = 0;                 // prng_var's bit buffer (prng.c:1017-1048)
-    auto pop = [&]() { const uint32_t x = w0; w0 = w1; w1 = w2; w2 = w3; cnt--; return x; };
+    auto pop = [&]() { const uint32_t x = q[head][tid]; head = (head + 1) & (kBerFifo - 1); cnt--; return x; };
     auto var = [&](uint32_t n) {                         // n < 32 here
         uint32_t ret = var_buf;
         if (var_bits < n) {
@@ -371,12 +417,19 @@ __global__ void __launch_bounds__(128) k_ber_lanes(SeqArgs a)
     uint32_t val = 0, x = 0, accept_mask = 0;
     size_t idx = 0;
     while (__any_sync(0xFFFFFFFFu, !done)) {
+        // Refill event: some lane is dry.  Every lane with room for a whole generator block (two 64-bit draws) takes
+        // one, so the 32 ChaCha20 / AES blocks run side by side; the deep FIFO averages out the differences in the
+        // lanes' consumption so that (almost) every lane takes part in (almost) every event.
         if (__any_sync(0xFFFFFFFFu, !done && cnt == 0)) {
-            if (!done && cnt <= 2) {
-                uint32_t hi, lo;
-                rng.draw64(hi, lo);
-                if (cnt == 0) { w0 = hi; w1 = lo; } else if (cnt == 1) { w1 = hi; w2 = lo; } else { w2 = hi; w3 = lo; }
-                cnt += 2;
+            if (!done && cnt <= kBerFifo - 4) {
+#pragma unroll 1
+                for (int d = 0; d < 2; d++) {
+                    uint32_t hi, lo;
+                    rng.draw64(hi, lo);
+                    q[(head + cnt) & (kBerFifo - 1)][tid] = hi;
+                    q[(head + cnt + 1) & (kBerFifo - 1)][tid] = lo;
+                    cnt += 2;
+                }
             }
         }
         if (done) continue;
@@ -628,7 +681,8 @@ unsigned cap_grid(size_t want, int sms, int per_sm)
 
 int launch_gauss_seq(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
                      uint32_t seed_period, PrngState *states, size_t nstreams, size_t n, size_t calls,
-                     int32_t centre, uint32_t discard, int32_t *out, int mode, cudaStream_t st, uint32_t *pool_mem)
+                     int32_t centre, uint32_t discard, int32_t *out, int mode, cudaStream_t st, uint32_t *pool_mem,
+                     const MwParams *mw)
 {
     if (nstreams == 0 || (n * calls == 0 && mode != 2 && mode != 3 && mode != 5 && mode != 6)) return SCGPU_OK;
     SeqArgs a;
@@ -636,6 +690,8 @@ int launch_gauss_seq(const GaussTablesDev &g, int prng_type, const uint8_t *seed
     a.prng_type = (uint32_t)prng_type; a.nstreams = nstreams; a.n = n; a.calls = calls; a.centre = centre;
     a.thresh = discard == 2 ? 1u << 28 : discard == 4 ? 1u << 30 : discard == 6 ? 1u << 31 : 0;   // sampling.c:85-92
     a.out = out; a.mode = mode; a.pool_mem = pool_mem;
+    memset(&a.mw, 0, sizeof(a.mw));
+    if (mw) a.mw = *mw;
     const unsigned grid = (unsigned)((nstreams + 127) / 128);
     if (mode == 0 && states == nullptr && g.sampler == SCGPU_SAMPLER_BERNOULLI && g.blinding == SCGPU_NORMAL_SAMPLES && g.ber_maxlog < 32)
         k_ber_lanes<<<grid, 128, 0, st>>>(a);

@@ -42,10 +42,20 @@ struct GaussTablesDev {
     int ber_entries, ber_maxval, ber_maxlog;
 };
 
+// Micciancio-Walter bootstrap (mw_bootstrap.c) over a base sampler of sigma 16: constants of one launch
+struct MwParams {
+    int32_t z[3][2];        // combiner weights of the three levels (mw_bootstrap_create, :112-160)
+    int32_t k;              // rounding steps (29)
+    double scale;           // sqrt((sigma^2 - rr_sigma2) / wide_sigma2), computed on the host in long double
+    float centre;           // used when centres == nullptr
+    const float *centres;   // optional per-sample centres, [nstreams][n]
+    int32_t clamp, lim_lo, lim_hi;      // get_vector_32's integer limits (sampling.c:560-573)
+};
+
 int launch_gauss_seq(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
                      uint32_t seed_period, PrngState *states, size_t nstreams, size_t n, size_t calls,
                      int32_t centre, uint32_t discard, int32_t *out, int mode, cudaStream_t st,
-                     uint32_t *pool_mem = nullptr);
+                     uint32_t *pool_mem = nullptr, const MwParams *mw = nullptr);
 int set_fixed_probe_search(int on);
 int launch_gauss_fast(const GaussTablesDev &g, int prng_type, const uint8_t *seeds, size_t seed_len,
                       uint32_t seed_period, size_t nstreams, size_t per_stream, int32_t centre, int32_t *out,

@@ -30,6 +30,12 @@ struct scgpu_gauss_plan {
     uint8_t *d_ber = nullptr, *d_kf = nullptr;
     uint32_t *d_guide = nullptr;
     std::mutex mu;
+    // Micciancio-Walter network constants (mw_bootstrap_create, mw_bootstrap.c:112-175), long double as in the reference
+    bool mw = false;
+    int32_t mw_z[3][2] = {};
+    int32_t mw_k = 0;
+    float mw_tail = 0;
+    long double mw_inv_wide_sigma2 = 0, mw_rr_sigma2 = 0;
     uint8_t *d_seeds = nullptr; size_t seeds_cap = 0;       // staging for *_host
     int32_t *d_out = nullptr; size_t out_cap = 0;
 };
@@ -334,6 +340,69 @@ extern "C" int scgpu_gauss_plan_create_ky_fast(scgpu_gauss_plan_t **out, const u
     p->t.kf_rows = rows; p->t.kf_cols = cols; p->t.kf_d1mask = dist1_mask; p->t.kf_d2mask = dist2_mask;
     *out = p;
     return SCGPU_OK;
+}
+
+// mw_bootstrap_create(sampler, base, 16.0f, 4, 1, 64, 35, 2.5f) -- the only configuration create_sampler uses
+static void mw_constants(scgpu_gauss_plan *p)
+{
+    const float base_sigma = 16.0f, eta = 2.5f;
+    const size_t max_slevels = 4, log_base = 1, precision = 64, max_flips = 35;
+    const double inv_two_eta_2 = 1.0 / (2.0 * eta * eta);
+    long double wide = (long double)base_sigma * (long double)base_sigma;
+    const long double base_sigma2 = wide;
+    for (size_t i = 0; i < max_slevels - 1; i++) {
+        const int32_t z1 = (int32_t)floor(sqrt((double)(wide * inv_two_eta_2)));
+        const int32_t z2 = z1 - 1 > 1 ? z1 - 1 : 1;
+        p->mw_z[i][0] = z1; p->mw_z[i][1] = z2;
+        wide = (z1 * z1 + z2 * z2) * wide;
+    }
+    p->mw_inv_wide_sigma2 = 1 / wide;
+    p->mw_k = (int32_t)ceil((double)(precision - max_flips) / log_base);
+    long double rr = 1, t = 1.0 / (1UL << (2 * log_base)), s = 1.0;
+    for (size_t i = (size_t)p->mw_k - 1; i--;) { s *= t; rr += s; }
+    p->mw_rr_sigma2 = rr * base_sigma2;
+    p->mw = true;
+}
+
+// the per-launch constants for (sigma^2 as the FLOAT product the reference forms, centre); false: sigma below the floor
+static bool mw_params(const scgpu_gauss_plan *p, float sigma2, float centre, MwParams *m)
+{
+    memset(m, 0, sizeof(*m));
+    memcpy(m->z, p->mw_z, sizeof(m->z));
+    m->k = p->mw_k;
+    const long double v = ((long double)(double)sigma2 - p->mw_rr_sigma2) * p->mw_inv_wide_sigma2;
+    if (!(v >= 0)) return false;
+    m->scale = sqrt((double)v);
+    m->centre = centre;
+    return true;
+}
+
+extern "C" int scgpu_gauss_plan_create_mw(scgpu_gauss_plan_t **out, int precision, int blinding, float tail, int device)
+{
+    if (precision != 32 && precision != 64) { set_error("gauss_plan_create_mw: base sampler precision %d (32 or 64)", precision); return SCGPU_ERR_UNSUPPORTED; }
+    const int e = scgpu_gauss_plan_create(out, SCGPU_SAMPLER_CDF, precision, blinding, tail, 16.0f, device);
+    if (e != SCGPU_OK) return e;
+    mw_constants(*out);
+    (*out)->mw_tail = tail;
+    return SCGPU_OK;
+}
+
+extern "C" int scgpu_gauss_mw_streams(const scgpu_gauss_plan_t *plan, int prng_type, const uint8_t *seeds, size_t seed_len,
+                                      size_t nstreams, size_t n, float sigma, float centre, const float *centres, int32_t *out,
+                                      void *stream)
+{
+    if (!plan || !seeds || !out || seed_len == 0) { set_error("gauss_mw_streams: null/empty argument"); return SCGPU_ERR_ARG; }
+    if (!plan->mw) { set_error("gauss_mw_streams: the plan was not created by scgpu_gauss_plan_create_mw"); return SCGPU_ERR_ARG; }
+    if (prng_type != PRNG_AES && prng_type != PRNG_CHACHA20) { set_error("PRNG type %d is not on the GPU path", prng_type); return SCGPU_ERR_UNSUPPORTED; }
+    MwParams m;
+    if (!mw_params(plan, sigma * sigma, centre, &m)) { set_error("gauss_mw_streams: sigma %g is below the combiner network's noise floor", (double)sigma); return SCGPU_ERR_ARG; }
+    m.centres = centres;
+    const float limit = sigma * plan->mw_tail;
+    m.clamp = centres ? 0 : 1;                        // integer limits exist per call; per-sample centres are clamped by the caller
+    m.lim_lo = (int32_t)(-limit + centre); m.lim_hi = (int32_t)(limit + centre);
+    SCGPU_CUDA_CHECK(cudaSetDevice(plan->device));
+    return launch_gauss_seq(plan->t, prng_type, seeds, seed_len, kDefaultSeedPeriod, nullptr, nstreams, n, 1, 0, 0, out, 7,
+                            static_cast<cudaStream_t>(stream), nullptr, &m);
 }
 
 extern "C" int scgpu_set_fixed_probe_search(int on) { return set_fixed_probe_search(on); }
@@ -771,6 +840,40 @@ struct GaussObj {            // what utils_sampling_t::gauss points at
     prng_ctx_t *prng;
 };
 
+// one launch of mw_bootstrap_sample calls on the context's device state (unclamped)
+void run_mw_on_ctx(GaussObj *o, int32_t *host_out, size_t n, float sigma2, float centre)
+{
+    prng_ctx_t *c = o->prng;
+    MwParams m;
+    if (!mw_params(o->plan, sigma2, centre, &m)) { set_error("bootstrap sampler: sigma^2 = %g is below the combiner network's noise floor", (double)sigma2); prng_fatal("get_bootstrap_sample"); }
+    std::lock_guard<std::mutex> lock(c->mu);
+    int32_t *d = ensure_out(c, n);
+    PRNG_CUDA(cudaSetDevice(c->device));
+    const size_t words = n * (size_t)(40 * (o->plan->t.precision > 32 ? 2 : 1)) + 65536;
+    top_up_entropy(c, reseeds_for(c, words));
+    if (c->ring_dirty) {
+        if (c->d_ring_cap < c->ring.size()) {
+            if (c->d_ring) cudaFree(c->d_ring);
+            PRNG_CUDA(cudaMalloc(&c->d_ring, c->ring.size()));
+            c->d_ring_cap = c->ring.size();
+        }
+        PRNG_CUDA(cudaMemcpyAsync(c->d_ring, c->ring.data(), c->ring.size(), cudaMemcpyHostToDevice, c->st));
+        c->ring_dirty = false;
+    }
+    PRNG_CUDA(cudaMemcpyAsync(c->d_state, &c->hs, sizeof(PrngState), cudaMemcpyHostToDevice, c->st));
+    if (launch_gauss_seq(o->plan->t, c->type, c->d_ring, c->ring.size(), (uint32_t)c->seed_period, c->d_state, 1, n, 1, 0, 0, d, 7,
+                         c->st, c->d_poolmem, &m) != SCGPU_OK)
+        prng_fatal("bootstrap sampler kernel");
+    PRNG_CUDA(cudaMemcpyAsync(&c->hs, c->d_state, sizeof(PrngState), cudaMemcpyDeviceToHost, c->st));
+    PRNG_CUDA(cudaMemcpyAsync(host_out, d, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->st));
+    PRNG_CUDA(cudaStreamSynchronize(c->st));
+    if (c->hs.error) { set_error("the device ran out of fresh entropy inside one launch"); prng_fatal("prng entropy"); }
+    if (c->hs.pool_fill) {
+        PRNG_CUDA(cudaMemcpyAsync(c->pool, c->d_poolmem, sizeof(c->pool), cudaMemcpyDeviceToHost, c->st));
+        PRNG_CUDA(cudaStreamSynchronize(c->st));
+    }
+}
+
 void *gauss_create_stub(prng_ctx_t *, FLOAT, FLOAT, size_t, sample_blinding_e) { return nullptr; }
 
 SINT32 gauss_destroy(void **g)
@@ -835,7 +938,24 @@ utils_sampling_t *create_sampler(random_sampling_e type, sample_precision_e prec
                                  FLOAT tail, FLOAT sigma)
 {
     if (!prng_ctx || !prng_ctx->inited) return NULL;
-    if (bootstrapped != SAMPLING_DISABLE_BOOTSTRAP) return NULL;      // MW bootstrap: SURVEY.md 8f rank 4
+    if (bootstrapped == SAMPLING_MW_BOOTSTRAP) {
+        // sampling.c:449-457: a base sampler of sigma 16 of the configured type, combined by mw_bootstrap_create(.., 16.0f,
+        // 4, 1, 64, 35, 2.5f); the CDF base samplers are on the GPU path
+        if (type != CDF_GAUSSIAN_SAMPLING || (precision != SAMPLING_32BIT && precision != SAMPLING_64BIT)) return NULL;
+        scgpu_gauss_plan *mplan = nullptr;
+        if (scgpu_gauss_plan_create_mw(&mplan, (int)precision, (int)blinding, tail, prng_ctx->device) != SCGPU_OK) return NULL;
+        utils_sampling_t *s = static_cast<utils_sampling_t *>(calloc(1, sizeof(utils_sampling_t)));
+        if (!s) { scgpu_gauss_plan_destroy(mplan); return NULL; }
+        GaussObj *o = new GaussObj{mplan, prng_ctx};
+        s->create = gauss_create_stub; s->destroy = gauss_destroy; s->get_prng = gauss_get_prng; s->sample = gauss_sample;
+        s->vector_16 = vector_16; s->vector_32 = vector_32;
+        s->precision = precision; s->dimension = dimension; s->bootstrapped = bootstrapped;
+        s->tail = tail; s->sigma = sigma; s->sigma2 = sigma * sigma;
+        s->gauss = o; s->prng_ctx = prng_ctx; s->discard = 0;
+        s->bootstrap = o;                         // mw_bootstrap_destroy's counterpart is gauss_destroy
+        return s;
+    }
+    if (bootstrapped != SAMPLING_DISABLE_BOOTSTRAP) return NULL;
     // configure_sampler refuses blinding for the Knuth-Yao samplers (sampling.c:341-343, 372-374)
     if ((type == KNUTH_YAO_GAUSSIAN_SAMPLING || type == KNUTH_YAO_FAST_GAUSSIAN_SAMPLING) && blinding == BLINDING_SAMPLES) return NULL;
     scgpu_gauss_plan *plan = nullptr;
@@ -874,17 +994,38 @@ SINT32 destroy_sampler(utils_sampling_t **sampler)
 
 SINT32 set_discard(utils_sampling_t *sampler, UINT32 discard) { sampler->discard = discard; return SC_FUNC_SUCCESS; }
 SINT32 get_sample(utils_sampling_t *sampler) { return sampler->sample(sampler->gauss); }
+// sampling.c:519-538
 SINT32 get_bootstrap_sample(utils_sampling_t *sampler, FLOAT sigma, FLOAT centre)
 {
-    (void)sampler; (void)sigma; (void)centre;
-    return 0;                                  // sampling.c:519-538: 0 unless a bootstrap sampler was requested
+    if (sampler->bootstrapped != SAMPLING_MW_BOOTSTRAP) return 0;
+    SINT32 sample = 0;
+    run_mw_on_ctx(static_cast<GaussObj *>(sampler->gauss), &sample, 1, sigma * sigma, centre);
+    const FLOAT limit = sigma * sampler->tail;
+    if (sample < (-limit + centre)) sample = (-limit + centre);
+    if (sample > (limit + centre)) sample = (limit + centre);
+    return sample;
+}
+// sampling.c:540-580: the bootstrap branch clamps to integer limits, the plain branch truncates the centre
+static void mw_vector(utils_sampling_t *sampler, SINT32 *v, size_t n, FLOAT centre)
+{
+    run_mw_on_ctx(static_cast<GaussObj *>(sampler->gauss), v, n, sampler->sigma2, centre);
+    const FLOAT limit = sampler->sigma * sampler->tail;
+    const SINT32 limits[2] = {(SINT32)(-limit + centre), (SINT32)(limit + centre)};
+    for (size_t i = 0; i < n; i++) v[i] = v[i] < limits[0] ? limits[0] : (v[i] > limits[1] ? limits[1] : v[i]);
 }
 SINT32 get_vector_16(utils_sampling_t *sampler, SINT16 *v, size_t n, FLOAT centre)
 {
+    if (sampler->bootstrapped == SAMPLING_MW_BOOTSTRAP) {
+        std::vector<SINT32> tmp(n);
+        mw_vector(sampler, tmp.data(), n, centre);
+        for (size_t i = 0; i < n; i++) v[i] = (SINT16)tmp[i];
+        return SC_FUNC_SUCCESS;
+    }
     return sampler->vector_16(sampler, v, n, (SINT32)centre);
 }
 SINT32 get_vector_32(utils_sampling_t *sampler, SINT32 *v, size_t n, FLOAT centre)
 {
+    if (sampler->bootstrapped == SAMPLING_MW_BOOTSTRAP) { mw_vector(sampler, v, n, centre); return SC_FUNC_SUCCESS; }
     return sampler->vector_32(sampler, v, n, (SINT32)centre);
 }
 

@@ -425,4 +425,31 @@ int ref_rand_product(int tw_bits, int variant, int n, int q, int q_bits, int k, 
     return fail;
 }
 
+/* ---- Micciancio-Walter bootstrap (mw_bootstrap.c, wired by create_sampler, sampling.c:449-457) ------------------- */
+
+/* Per stream: create_sampler(CDF, 64-bit, NORMAL, SAMPLING_MW_BOOTSTRAP) and either n get_vector_32 samples at
+ * (sigma, centre[0]) when per_sample == 0, or n get_bootstrap_sample(sigma_i, centre_i) calls with the arrays
+ * sigmas / centres ([nstreams][n]) when per_sample != 0.  sigma2 is the create-time sigma squared in FLOAT. */
+int ref_mw_streams(int prng_type, const uint8_t *seeds, size_t seed_len, size_t nstreams, size_t n, float tail, float sigma,
+                   const float *sigmas, const float *centres, int per_sample, int32_t *out, int threads)
+{
+    int fail = 0, nt = max_threads(threads);
+#pragma omp parallel for schedule(static) num_threads(nt) reduction(|:fail)
+    for (size_t s = 0; s < nstreams; s++) {
+        prng_ctx_t *ctx = make_prng(prng_type, seeds + s * seed_len, seed_len, 0);
+        if (!ctx) { fail |= 1; continue; }
+        utils_sampling_t *smp = create_sampler(CDF_GAUSSIAN_SAMPLING, SAMPLING_64BIT, NORMAL_SAMPLES, (SINT32)n,
+                                               SAMPLING_MW_BOOTSTRAP, ctx, tail, sigma);
+        if (!smp) { fail |= 1; prng_destroy(ctx); continue; }
+        if (per_sample) {
+            for (size_t i = 0; i < n; i++) out[s * n + i] = get_bootstrap_sample(smp, sigmas[s * n + i], centres[s * n + i]);
+        } else {
+            get_vector_32(smp, out + s * n, n, centres[0]);
+        }
+        destroy_sampler(&smp);
+        prng_destroy(ctx);
+    }
+    return fail;
+}
+
 int ref_num_threads(void) { return omp_get_max_threads(); }

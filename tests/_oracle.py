@@ -199,6 +199,25 @@ class RefChecker(Checker):
         rows, cols = int(dims[0]), int(dims[1])
         return lut1, lut2[:int(dims[4])].copy(), pmat[:rows * cols].reshape(rows, cols).copy(), int(dims[2]), int(dims[3])
 
+    def mw_streams(self, prng_type, seeds, n, tail, sigma, centre=0.0, sigmas=None, centres=None, threads=0):
+        """create_sampler(CDF, 64-bit, SAMPLING_MW_BOOTSTRAP) per stream; n get_vector_32 samples at (sigma, centre), or
+        n get_bootstrap_sample(sigmas[s, i], centres[s, i]) calls when the arrays are given."""
+        f = self.lib.ref_mw_streams
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float, ctypes.c_float,
+                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8)
+        out = np.zeros((seeds.shape[0], n), dtype=np.int32)
+        per = centres is not None
+        if per:
+            centres = np.ascontiguousarray(centres, dtype=np.float32)
+            sigmas = np.ascontiguousarray(sigmas if sigmas is not None else np.full(centres.shape, sigma), dtype=np.float32)
+        else:
+            centres = np.array([centre], dtype=np.float32)
+        assert f(prng_type, _vp(seeds), seeds.shape[1], seeds.shape[0], n, tail, sigma, _vp(sigmas) if per else None, _vp(centres),
+                 1 if per else 0, _vp(out), threads) == 0
+        return out
+
     def rand_product(self, tw_bits, variant, n, q, q_bits, k, l, transpose, prng_type, seeds, y, w, r, want_matrix=False, threads=0):
         """create_rand_product_{16,32}_csprng (module_lwe.c:588-748) per instance, CSPRNG as create_csprng makes it.
         Returns t [count, k, n] (and the matrix in DRAW order [count, k l, n])."""

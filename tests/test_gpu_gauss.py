@@ -292,3 +292,76 @@ def test_dropin_sampler_api():
         h = ctypes.c_void_p(smp)
         assert L.destroy_sampler(ctypes.byref(h)) == 0
         L.prng_destroy(ctx)
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libscref.so not built")
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+def test_mw_bootstrap_against_the_reference(prng):
+    """Micciancio-Walter bootstrap (mw_bootstrap.c through create_sampler(.., SAMPLING_MW_BOOTSTRAP, ..)): arbitrary sigma
+    and real-valued centres from the sigma-16 CDF base sampler; get_vector_32's clamped vectors and the per-sample
+    centres of get_bootstrap_sample, against the compiled reference making the same calls."""
+    plan = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.0, 0.0, mw=True)
+    seeds = seeds_for(48, 40, salt=3)
+    d_seeds = torch.from_numpy(seeds).to(DEV)
+    for sigma, centre, n in ((100.0, 0.3, 300), (215.0, -7.625, 128), (19.0, 1000.5, 64), (40.0, 0.0, 33)):
+        out = torch.zeros((seeds.shape[0], n), dtype=torch.int32, device=DEV)
+        plan.mw_streams(prng, d_seeds, n, out, sigma, centre)
+        torch.cuda.synchronize()
+        exp = O.ref().mw_streams(prng, seeds, n, 13.0, sigma, centre)
+        assert np.array_equal(out.cpu().numpy(), exp), (sigma, centre)
+    got = out.cpu().numpy()
+    assert abs(got.std() - 40.0) < 3.0 and abs(got.mean()) < 3.0
+    rng = np.random.default_rng(4)
+    n = 200
+    centres = rng.uniform(-50, 50, size=(seeds.shape[0], n)).astype(np.float32)
+    out = torch.zeros((seeds.shape[0], n), dtype=torch.int32, device=DEV)
+    plan.mw_streams(prng, d_seeds, n, out, 60.0, 0.0, centres=torch.from_numpy(centres).to(DEV))
+    torch.cuda.synchronize()
+    exp = O.ref().mw_streams(prng, seeds, n, 13.0, 60.0, sigmas=np.full(centres.shape, 60.0, np.float32), centres=centres)
+    assert np.array_equal(out.cpu().numpy(), exp)            # the tail (13 sigma) never clamps here
+    with pytest.raises(sc.ScgpuError):                        # below the network's own noise floor
+        plan.mw_streams(prng, d_seeds, 4, out, 10.0, 0.0)
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libscref.so not built")
+def test_mw_bootstrap_dropin_api():
+    """create_sampler(CDF, 64-bit, NORMAL, n, SAMPLING_MW_BOOTSTRAP, ..): get_vector_32, get_bootstrap_sample with varying
+    sigma and centre, get_sample (the base sampler) and prng_32 interleaved on one context -- the same calls on libscref."""
+    results = []
+    seed = bytes(((i * 11 + 5) & 0xFF) for i in range(48))
+    for L in (sc.lib(), O.ref().lib):
+        L.prng_create.restype = ctypes.c_void_p
+        L.prng_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t]
+        L.prng_set_entropy.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.prng_init.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.prng_32.restype = ctypes.c_uint32
+        L.prng_32.argtypes = [ctypes.c_void_p]
+        L.prng_destroy.argtypes = [ctypes.c_void_p]
+        L.create_sampler.restype = ctypes.c_void_p
+        L.create_sampler.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int32, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_float, ctypes.c_float]
+        L.get_vector_32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float]
+        L.get_bootstrap_sample.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_float]
+        L.get_bootstrap_sample.restype = ctypes.c_int32
+        L.get_sample.argtypes = [ctypes.c_void_p]
+        L.get_sample.restype = ctypes.c_int32
+        L.destroy_sampler.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+        ctx = L.prng_create(5, O.PRNG_AES_CTR_DRBG, 0, 0x00100000)
+        assert ctx and L.prng_set_entropy(ctx, seed, len(seed)) == 0 and L.prng_init(ctx, b"SAFEcrypto nonce", 16) == 0
+        smp = L.create_sampler(0, 64, 0, 256, 1, ctx, 13.0, 150.0)          # SAMPLING_MW_BOOTSTRAP = 1
+        assert smp
+        got = []
+        v = np.zeros(256, dtype=np.int32)
+        L.get_vector_32(smp, v.ctypes.data, 256, 2.75)
+        got += list(v)
+        got.append(L.prng_32(ctx))
+        for sg, ce in ((33.5, 0.25), (90.0, -3.5), (500.0, 17.125), (20.0, 1e4)):
+            got.append(L.get_bootstrap_sample(smp, sg, ce))
+        got.append(L.get_sample(smp))
+        L.get_vector_32(smp, v.ctypes.data, 100, -0.5)
+        got += list(v[:100])
+        h = ctypes.c_void_p(smp)
+        assert L.destroy_sampler(ctypes.byref(h)) == 0
+        L.prng_destroy(ctx)
+        results.append([int(x) for x in got])
+    assert results[0] == results[1]
