@@ -416,6 +416,47 @@ def main():
            "d2h_bytes_per_step": 4 * N_COEF * E2E_BATCH, "pairs_per_step": E2E_BATCH, "steps": e2e_steps,
            "api": "scgpu_polymul_batch_host (pinned host buffers, chunked 3-stream H2D/kernel/D2H pipeline)"}
 
+    # ---- composed end-to-end leg: the BLISS-B sign core (bliss_b.c:1372-1384) through the C-ABI, seeds in, v out ------
+    # t = get_vector_32(sigma 215) on the device from a 40-byte seed per signature, v = INTT(NTT(t) o a) with the public
+    # key a resident on the device; only the seeds cross the bus on the way in (40 B) and v on the way out (4 n B).
+    sign_core = None
+    if rank == 0:
+        gps = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0, device=local_rank)
+        nsig = 1 << 18
+        chunk = 1 << 16
+        hseed = torch.randint(0, 256, (nsig, 40), dtype=torch.uint8).pin_memory()
+        hv = torch.empty((nsig, N_COEF), dtype=torch.int32).pin_memory()
+        keyd = torch.randint(0, Q, (N_COEF,), dtype=torch.int32, device=dev, generator=g).to(torch.int16)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        bufs = [(torch.empty((chunk, 40), dtype=torch.uint8, device=dev), torch.empty((chunk, N_COEF), dtype=torch.int32, device=dev),
+                 torch.empty((chunk, N_COEF), dtype=torch.int32, device=dev)) for _ in range(3)]
+
+        def sign_pass():
+            for ci, off in enumerate(range(0, nsig, chunk)):
+                st = streams[ci % 3]
+                dseed, dt, dv = bufs[ci % 3]
+                with torch.cuda.stream(st):
+                    dseed.copy_(hseed[off:off + chunk], non_blocking=True)
+                    gps.streams(sc.PRNG_CHACHA, dseed, N_COEF, dt, stream=st)
+                    plan.mul_key(dv, dt, keyd, stream=st)
+                    hv[off:off + chunk].copy_(dv, non_blocking=True)
+            for st in streams:
+                st.synchronize()
+
+        sign_pass()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            sign_pass()
+        dt_s = (time.perf_counter() - t0) / 3
+        # parity of the composition on a few signatures: the port's sampler, then the oracle's triple
+        tt = O.port().gauss_streams(O.SAMPLER_CDF, 64, 0, O.PRNG_CHACHA, 13.42, 215.0, hseed[:4].numpy(), N_COEF)
+        vv = O.port().ntt_batch(O.REFERENCE, O.OP_TRIPLE16, N_COEF, Q, 16, tt, keyd.cpu().numpy(), w, r)
+        assert np.array_equal(hv[:4].numpy(), vv), "sign-core composition differs from the oracle"
+        sign_core = {"value": nsig / dt_s, "unit": "sign cores/s (get_vector_32 + fwd_ntt, mul_32_pointwise_16, inv_ntt)", "signatures": nsig,
+                     "h2d_bytes_per_step": 40 * nsig, "d2h_bytes_per_step": 4 * N_COEF * nsig,
+                     "api": "scgpu_gauss_streams -> scgpu_ntt_mul_key_batch on device buffers, seeds H2D and v D2H inside the timed region"}
+        del hseed, hv, bufs
+
     # ---- strong scaling of ONE host batch from ONE process: the fixed 2^20-pair batch of BASELINE configs[1] split over
     # all GPUs by scgpu_polymul_batch_host_multi (host-side scatter / gather, one thread per device).  Rank 0 drives
     # every device; the other ranks wait on the rendezvous store (a host wait, their GPUs are idle).
@@ -536,7 +577,7 @@ def main():
                        "n": N_COEF, "q": Q, "pairs_per_gpu": BATCH, "parallelism": "shard by polynomial index, no collective",
                        "cache": "operands 4 GiB + result 2 GiB per step >> 126 MB L2 (no flush needed)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
-            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss, "other_shapes": shapes, "parity": parity, "e2e_multi": e2e_multi,
+            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss, "other_shapes": shapes, "parity": parity, "e2e_multi": e2e_multi, "e2e_bliss_sign_core": sign_core,
         }
         emit(line)
     if world > 1:

@@ -6,8 +6,9 @@ harness the tests and ``bench.py`` use to drive that library with torch-owned de
 streams: every call below forwards to one exported C symbol.  There is no CPU implementation
 here and no fallback: if the library is missing or a CUDA call fails, an exception is raised.
 """
+from . import binding  # noqa: F401
 from .binding import (  # noqa: F401
-    ScgpuError, lib, lib_path, NttPlan, GaussPlan, make_params, launch_count, int_peak_gops,
+    ScgpuError, lib, lib_path, NttPlan, NttPlanSet, GaussPlan, rand_matrix, make_params, launch_count, int_peak_gops,
     REFERENCE, BARRETT, FP, AVX, SOLINAS_7681, SOLINAS_8380417,
     OP_FWD, OP_INV, OP_FWD_LARGE, OP_INV_LARGE, OP_FFT, OP_FFT_LARGE, OP_PW, OP_PW16, OP_NORMALIZE,
     OP_CENTER, OP_POLYMUL, OP_TRIPLE16, OP_MODN, OP_MULN, OP_SQRN, OP_FLIP, OP_INVERT, OP_DIV,

@@ -1,0 +1,92 @@
+"""Regressions for the round-1 review findings: concurrent sampler calls on one plan, host staging sized per call,
+launches inside a CUDA graph capture."""
+import numpy as np
+import pytest
+
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import libsafecrypto_b200 as sc  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def test_two_streams_share_one_sampler_plan():
+    """scgpu_gauss_streams on the AES fast path from two CUDA streams at once (and back to back without a sync): the
+    DRBG round keys of a call live in stream-ordered scratch, not in a buffer of the plan."""
+    plan = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0)
+    rng = np.random.default_rng(3)
+    seeds = [rng.integers(0, 256, size=(4096, 40)).astype(np.uint8) for _ in range(4)]
+    d_seeds = [torch.from_numpy(s).to(DEV) for s in seeds]
+    outs = [torch.zeros((4096, 512), dtype=torch.int32, device=DEV) for _ in range(4)]
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i in range(4):
+            plan.streams(sc.PRNG_AES_CTR_DRBG, d_seeds[i], 512, outs[i], stream=streams[i % 2])
+    torch.cuda.synchronize()
+    for i in range(4):
+        exp = O.port().gauss_streams(O.SAMPLER_CDF, 64, 0, O.PRNG_AES_CTR_DRBG, 13.42, 215.0, seeds[i][:64], 512)
+        assert np.array_equal(outs[i][:64].cpu().numpy(), exp), i
+    # whole outputs agree with a serial re-run
+    ref = torch.zeros_like(outs[0])
+    for i in range(4):
+        plan.streams(sc.PRNG_AES_CTR_DRBG, d_seeds[i], 512, ref)
+        torch.cuda.synchronize()
+        assert torch.equal(ref, outs[i])
+
+
+def test_host_staging_follows_the_widest_row_of_each_call():
+    """A *_host call with padded second-operand rows (b_stride = 2n) after one with b_stride = n on the same plan."""
+    q, n = 12289, 512
+    w, r = O.tables(q, n, 16)
+    plan = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    rng = np.random.default_rng(4)
+    count = 20000
+    a = rng.integers(0, q, size=(count, n)).astype(np.int32)
+    b = rng.integers(0, q, size=(count, n)).astype(np.int32)
+    out = np.zeros_like(a)
+    plan.batch_host(sc.OP_PW, out, a, b)
+    exp = O.port().ntt_batch(O.REFERENCE, O.OP_PW, n, q, 16, a, b, w, r)
+    assert np.array_equal(out, exp)
+    bpad = np.zeros((count, 2 * n), dtype=np.int32)
+    bpad[:, :n] = b
+    out2 = np.zeros_like(a)
+    plan.batch_host(sc.OP_PW, out2, a, bpad, b_stride=2 * n)
+    assert np.array_equal(out2, exp)
+    out3 = np.zeros_like(a)
+    plan.polymul_host(out3, a, b)
+    assert np.array_equal(out3[:50], O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, 16, a[:50], b[:50], w, r))
+
+
+def test_launches_inside_a_cuda_graph_capture():
+    """Captured launches keep the static stride (no work-counter slot is baked into the graph); replays agree."""
+    q, n = 12289, 512
+    w, r = O.tables(q, n, 16)
+    plan = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    count = 1 << 16                                   # more than one grid-full: the eager launch uses the counter
+    a = torch.randint(0, q, (count, n), dtype=torch.int32, device=DEV, generator=g)
+    b = torch.randint(0, q, (count, n), dtype=torch.int32, device=DEV, generator=g)
+    eager = torch.empty_like(a)
+    plan.polymul(eager, a, b)
+    torch.cuda.synchronize()
+    out = torch.zeros_like(a)
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream(device=DEV)
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(graph, stream=s):
+            plan.polymul(out, a, b, stream=s)
+            plan.batch(sc.OP_FWD, out, out, stream=s)
+    ref = torch.empty_like(a)
+    plan.batch(sc.OP_FWD, ref, eager)
+    for _ in range(3):
+        out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
