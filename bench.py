@@ -537,7 +537,7 @@ def main():
     assert np.array_equal(smp[:4].cpu().numpy(), exp), "sampler output differs from the oracle"
     # Knuth-Yao-64 and Bernoulli-64 (the other two samplers north_star names), sigma 215, smaller batches
     if rank == 0:
-        for sname, sid, ns in (("knuth_yao64", sc.SAMPLER_KNUTH_YAO, 1 << 15), ("bernoulli64", sc.SAMPLER_BERNOULLI, 1 << 15)):
+        for sname, sid, ns in (("knuth_yao64", sc.SAMPLER_KNUTH_YAO, 1 << 17), ("bernoulli64", sc.SAMPLER_BERNOULLI, 1 << 17)):
             gpx = sc.GaussPlan(sid, 64, 0, 13.42, 215.0, device=local_rank)
             sx = torch.empty((ns, n), dtype=torch.int32, device=dev)
             for prng_name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):

@@ -364,7 +364,8 @@ def test_matvec_matches_reference_composition(q, tw, k, eta, arithmetic):
 def test_full_size_properties():
     """BASELINE config C2 at full size (2^20 polynomials): size-independent properties.
     (1) a * 1 == a mod q; (2) linearity: (a + a') * b == a*b + a'*b mod q; (3) commutativity;
-    (4) x^(n-1) * x == -1: negacyclic wrap; (5) a checksum of the whole output against per-chunk runs."""
+    (4) x^(n-1) * x == -1: negacyclic wrap; (5) the whole output against per-chunk runs; (6) all 2^20 rows against the
+    compiled reference."""
     q, n, B = 12289, 512, 1 << 20
     p, _, _ = plan(q, n, 16, O.REFERENCE)
     g = torch.Generator(device=DEV).manual_seed(1)
@@ -398,8 +399,13 @@ def test_full_size_properties():
     for start in (0, 123456, B - 4096):
         p.polymul(chk, a[start:start + 4096], b[start:start + 4096])
         assert torch.equal(chk, ab[start:start + 4096])
-    # and a slice against the oracle
+    # and EVERY row against the checker: the compiled reference's own fwd, fwd, pointwise, inv over all host threads
+    # (a few seconds for 2^20 pairs); the port on a slice when libscref is not available
     w, r = O.tables(q, n, 16)
+    if O.ref_available():
+        exp = O.ref().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, 16, a.cpu().numpy(), b.cpu().numpy(), w, r, threads=os.cpu_count() or 1)
+        assert np.array_equal(ab.cpu().numpy(), exp)
+        del exp
     sl = slice(777, 777 + 64)
     exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, 16, a[sl].cpu().numpy(), b[sl].cpu().numpy(), w, r)
     assert np.array_equal(ab[sl].cpu().numpy(), exp)
