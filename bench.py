@@ -535,6 +535,20 @@ def main():
     # spot check against the oracle
     exp = O.port().gauss_streams(O.SAMPLER_CDF, 64, 0, sc.PRNG_CHACHA, 13.42, 215.0, seeds[:4].cpu().numpy(), n)
     assert np.array_equal(smp[:4].cpu().numpy(), exp), "sampler output differs from the oracle"
+    # end to end through the C-ABI with HOST buffers: seeds in (40 B per stream), samples out (4 B each), copies inside
+    if rank == 0:
+        hs = seeds.cpu().pin_memory()
+        ho_s = torch.empty((nstreams, n), dtype=torch.int32).pin_memory()
+        for name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
+            gp.streams_host(prng, hs, n, ho_s)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                gp.streams_host(prng, hs, n, ho_s)
+            dt = (time.perf_counter() - t0) / 3
+            gauss["cdf64_sigma215_%s_e2e" % name] = {"samples_per_s": nstreams * n / dt, "h2d_bytes_per_step": 40 * nstreams,
+                                                     "d2h_bytes_per_step": 4 * nstreams * n, "api": "scgpu_gauss_streams_host"}
+        assert np.array_equal(ho_s[:4].numpy(), exp), "host-path sampler output differs from the oracle"
+        del hs, ho_s
     # Knuth-Yao-64 and Bernoulli-64 (the other two samplers north_star names), sigma 215, smaller batches
     if rank == 0:
         for sname, sid, ns in (("knuth_yao64", sc.SAMPLER_KNUTH_YAO, 1 << 17), ("bernoulli64", sc.SAMPLER_BERNOULLI, 1 << 17)):

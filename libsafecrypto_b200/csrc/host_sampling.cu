@@ -36,8 +36,7 @@ struct scgpu_gauss_plan {
     int32_t mw_k = 0;
     float mw_tail = 0;
     long double mw_inv_wide_sigma2 = 0, mw_rr_sigma2 = 0;
-    uint8_t *d_seeds = nullptr; size_t seeds_cap = 0;       // staging for *_host
-    int32_t *d_out = nullptr; size_t out_cap = 0;
+    cudaStream_t hstreams[3] = {nullptr, nullptr, nullptr};     // pipeline of the *_host entry point
 };
 
 namespace {
@@ -412,7 +411,7 @@ extern "C" void scgpu_gauss_plan_destroy(scgpu_gauss_plan_t *p)
     if (!p) return;
     cudaSetDevice(p->device);
     cudaFree(p->d_cdf); cudaFree(p->d_flat); cudaFree(p->d_kybits); cudaFree(p->d_kyrank); cudaFree(p->d_ber); cudaFree(p->d_kf); cudaFree(p->d_guide);
-    cudaFree(p->d_seeds); cudaFree(p->d_out);
+    for (int i = 0; i < 3; i++) if (p->hstreams[i]) { cudaStreamSynchronize(p->hstreams[i]); cudaStreamDestroy(p->hstreams[i]); }
     delete p;
 }
 
@@ -451,19 +450,45 @@ extern "C" int scgpu_gauss_streams_host(const scgpu_gauss_plan_t *plan, int prng
                                         uint32_t discard, int32_t *out)
 {
     if (!plan || !seeds || !out) { set_error("gauss_streams_host: null argument"); return SCGPU_ERR_ARG; }
+    if (nstreams == 0 || n * calls == 0) return SCGPU_OK;
     scgpu_gauss_plan *p = const_cast<scgpu_gauss_plan *>(plan);
     std::lock_guard<std::mutex> lock(p->mu);
     SCGPU_CUDA_CHECK(cudaSetDevice(p->device));
-    int e = ensure_cap(&p->d_seeds, &p->seeds_cap, nstreams * seed_len);
-    if (e != SCGPU_OK) return e;
-    e = ensure_cap(&p->d_out, &p->out_cap, nstreams * n * calls);
-    if (e != SCGPU_OK) return e;
-    SCGPU_CUDA_CHECK(cudaMemcpyAsync(p->d_seeds, seeds, nstreams * seed_len, cudaMemcpyHostToDevice, 0));
-    e = gauss_dispatch(p, prng_type, p->d_seeds, seed_len, nstreams, n, calls, centre, discard, p->d_out, 0);
-    if (e != SCGPU_OK) return e;
-    SCGPU_CUDA_CHECK(cudaMemcpyAsync(out, p->d_out, nstreams * n * calls * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
-    SCGPU_CUDA_CHECK(cudaStreamSynchronize(0));
-    return SCGPU_OK;
+    // chunks of streams through three streams: the D2H of one chunk (4 bytes per sample, the long pole) overlaps the
+    // kernels of the next ones
+    constexpr int kS = 3;
+    for (int i = 0; i < kS; i++)
+        if (!p->hstreams[i]) SCGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&p->hstreams[i], cudaStreamNonBlocking));
+    const size_t row = n * calls * sizeof(int32_t);
+    size_t rows = (32u << 20) / row;
+    if (rows < 1) rows = 1;
+    if (rows > nstreams) rows = nstreams;
+    int status = SCGPU_OK;
+    void *ds[kS] = {}, *dout[kS] = {};
+    auto cuda_ok = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && status == SCGPU_OK) { set_error("%s failed: %s", what, cudaGetErrorString(e)); status = SCGPU_ERR_CUDA; }
+        return e == cudaSuccess;
+    };
+    for (int i = 0; i < kS && status == SCGPU_OK; i++) {
+        cuda_ok(cudaMallocAsync(&ds[i], rows * seed_len, p->hstreams[i]), "cudaMallocAsync");
+        cuda_ok(cudaMallocAsync(&dout[i], rows * row, p->hstreams[i]), "cudaMallocAsync");
+    }
+    for (size_t off = 0, ci = 0; off < nstreams && status == SCGPU_OK; off += rows, ci++) {
+        const int s = (int)(ci % kS);
+        cudaStream_t st = p->hstreams[s];
+        const size_t cnt = nstreams - off < rows ? nstreams - off : rows;
+        if (!cuda_ok(cudaMemcpyAsync(ds[s], seeds + off * seed_len, cnt * seed_len, cudaMemcpyHostToDevice, st), "H2D copy")) break;
+        const int e = gauss_dispatch(p, prng_type, static_cast<const uint8_t *>(ds[s]), seed_len, cnt, n, calls, centre, discard,
+                                     static_cast<int32_t *>(dout[s]), st);
+        if (e != SCGPU_OK) { status = e; break; }
+        cuda_ok(cudaMemcpyAsync(reinterpret_cast<char *>(out) + off * row, dout[s], cnt * row, cudaMemcpyDeviceToHost, st), "D2H copy");
+    }
+    for (int i = 0; i < kS; i++) {
+        if (ds[i]) cudaFreeAsync(ds[i], p->hstreams[i]);
+        if (dout[i]) cudaFreeAsync(dout[i], p->hstreams[i]);
+        cuda_ok(cudaStreamSynchronize(p->hstreams[i]), "cudaStreamSynchronize");
+    }
+    return status;
 }
 
 extern "C" int scgpu_prng_words(int prng_type, const uint8_t *seeds, size_t seed_len, size_t seed_period,
@@ -595,7 +620,7 @@ void top_up_entropy(prng_ctx_t *c, size_t reseeds)
 // One kernel on the context's state: push the header (and the ring if the host refreshed it), run, pull the header
 // and -- when the kernel refilled it -- the pool.  `words` bounds the 32-bit words the launch may hand out.
 void run_state_kernel(prng_ctx_t *c, const GaussTablesDev &t, size_t n, size_t calls, int32_t centre, uint32_t discard,
-                      int mode, int32_t *d_out, size_t words)
+                      int mode, int32_t *d_out, size_t words, const MwParams *mw = nullptr)
 {
     PRNG_CUDA(cudaSetDevice(c->device));
     top_up_entropy(c, reseeds_for(c, words));
@@ -611,7 +636,7 @@ void run_state_kernel(prng_ctx_t *c, const GaussTablesDev &t, size_t n, size_t c
     const uint64_t draws_before = c->hs.draws64;
     PRNG_CUDA(cudaMemcpyAsync(c->d_state, &c->hs, sizeof(PrngState), cudaMemcpyHostToDevice, c->st));
     if (launch_gauss_seq(t, c->type, c->d_ring, c->ring.size(), (uint32_t)c->seed_period, c->d_state, 1, n, calls, centre,
-                         discard, d_out, mode, c->st, c->d_poolmem) != SCGPU_OK)
+                         discard, d_out, mode, c->st, c->d_poolmem, mw) != SCGPU_OK)
         prng_fatal("prng kernel");
     PRNG_CUDA(cudaMemcpyAsync(&c->hs, c->d_state, sizeof(PrngState), cudaMemcpyDeviceToHost, c->st));
     PRNG_CUDA(cudaStreamSynchronize(c->st));
@@ -848,30 +873,10 @@ void run_mw_on_ctx(GaussObj *o, int32_t *host_out, size_t n, float sigma2, float
     if (!mw_params(o->plan, sigma2, centre, &m)) { set_error("bootstrap sampler: sigma^2 = %g is below the combiner network's noise floor", (double)sigma2); prng_fatal("get_bootstrap_sample"); }
     std::lock_guard<std::mutex> lock(c->mu);
     int32_t *d = ensure_out(c, n);
-    PRNG_CUDA(cudaSetDevice(c->device));
-    const size_t words = n * (size_t)(40 * (o->plan->t.precision > 32 ? 2 : 1)) + 65536;
-    top_up_entropy(c, reseeds_for(c, words));
-    if (c->ring_dirty) {
-        if (c->d_ring_cap < c->ring.size()) {
-            if (c->d_ring) cudaFree(c->d_ring);
-            PRNG_CUDA(cudaMalloc(&c->d_ring, c->ring.size()));
-            c->d_ring_cap = c->ring.size();
-        }
-        PRNG_CUDA(cudaMemcpyAsync(c->d_ring, c->ring.data(), c->ring.size(), cudaMemcpyHostToDevice, c->st));
-        c->ring_dirty = false;
-    }
-    PRNG_CUDA(cudaMemcpyAsync(c->d_state, &c->hs, sizeof(PrngState), cudaMemcpyHostToDevice, c->st));
-    if (launch_gauss_seq(o->plan->t, c->type, c->d_ring, c->ring.size(), (uint32_t)c->seed_period, c->d_state, 1, n, 1, 0, 0, d, 7,
-                         c->st, c->d_poolmem, &m) != SCGPU_OK)
-        prng_fatal("bootstrap sampler kernel");
-    PRNG_CUDA(cudaMemcpyAsync(&c->hs, c->d_state, sizeof(PrngState), cudaMemcpyDeviceToHost, c->st));
+    // 8 + 29 base samples and one flip word per sample, 64-bit draws
+    run_state_kernel(c, o->plan->t, n, 1, 0, 0, 7, d, n * 80 + 65536, &m);
     PRNG_CUDA(cudaMemcpyAsync(host_out, d, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->st));
     PRNG_CUDA(cudaStreamSynchronize(c->st));
-    if (c->hs.error) { set_error("the device ran out of fresh entropy inside one launch"); prng_fatal("prng entropy"); }
-    if (c->hs.pool_fill) {
-        PRNG_CUDA(cudaMemcpyAsync(c->pool, c->d_poolmem, sizeof(c->pool), cudaMemcpyDeviceToHost, c->st));
-        PRNG_CUDA(cudaStreamSynchronize(c->st));
-    }
 }
 
 void *gauss_create_stub(prng_ctx_t *, FLOAT, FLOAT, size_t, sample_blinding_e) { return nullptr; }

@@ -370,25 +370,32 @@ extern "C" int scgpu_rand_product_csprng_batch_host(const scgpu_ntt_plan_t *plan
     if (rows > count) rows = count;
     int status = SCGPU_OK;
     void *dy[scgpu_ntt_plan::kStreams] = {}, *dt[scgpu_ntt_plan::kStreams] = {}, *ds[scgpu_ntt_plan::kStreams] = {};
-    for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) {
-        SCGPU_CUDA_CHECK(cudaMallocAsync(&dy[i], rows * yb, p->streams[i]));
-        SCGPU_CUDA_CHECK(cudaMallocAsync(&dt[i], rows * tb, p->streams[i]));
-        SCGPU_CUDA_CHECK(cudaMallocAsync(&ds[i], rows * seed_len, p->streams[i]));
+    auto cuda_ok = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && status == SCGPU_OK) { set_error("%s failed: %s", what, cudaGetErrorString(e)); status = SCGPU_ERR_CUDA; }
+        return e == cudaSuccess;
+    };
+    for (int i = 0; i < scgpu_ntt_plan::kStreams && status == SCGPU_OK; i++) {
+        cuda_ok(cudaMallocAsync(&dy[i], rows * yb, p->streams[i]), "cudaMallocAsync");
+        cuda_ok(cudaMallocAsync(&dt[i], rows * tb, p->streams[i]), "cudaMallocAsync");
+        cuda_ok(cudaMallocAsync(&ds[i], rows * seed_len, p->streams[i]), "cudaMallocAsync");
     }
     for (size_t off = 0, ci = 0; off < count && status == SCGPU_OK; off += rows, ci++) {
         const int s = (int)(ci % scgpu_ntt_plan::kStreams);
         cudaStream_t st = p->streams[s];
         const size_t cnt = count - off < rows ? count - off : rows;
-        SCGPU_CUDA_CHECK(cudaMemcpyAsync(dy[s], reinterpret_cast<const char *>(y) + off * yb, cnt * yb, cudaMemcpyHostToDevice, st));
-        SCGPU_CUDA_CHECK(cudaMemcpyAsync(ds[s], seeds + off * seed_len, cnt * seed_len, cudaMemcpyHostToDevice, st));
-        status = scgpu_rand_product_csprng_batch(plan, static_cast<int32_t *>(dt[s]), static_cast<const int32_t *>(dy[s]),
-                                                 static_cast<const uint8_t *>(ds[s]), seed_len, prng_type, q_bits, k, l, transpose, cnt, st);
-        if (status != SCGPU_OK) break;
-        SCGPU_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(t) + off * tb, dt[s], cnt * tb, cudaMemcpyDeviceToHost, st));
+        if (!cuda_ok(cudaMemcpyAsync(dy[s], reinterpret_cast<const char *>(y) + off * yb, cnt * yb, cudaMemcpyHostToDevice, st), "H2D copy")) break;
+        if (!cuda_ok(cudaMemcpyAsync(ds[s], seeds + off * seed_len, cnt * seed_len, cudaMemcpyHostToDevice, st), "H2D copy")) break;
+        const int e = scgpu_rand_product_csprng_batch(plan, static_cast<int32_t *>(dt[s]), static_cast<const int32_t *>(dy[s]),
+                                                      static_cast<const uint8_t *>(ds[s]), seed_len, prng_type, q_bits, k, l, transpose, cnt, st);
+        if (e != SCGPU_OK) { status = e; break; }
+        cuda_ok(cudaMemcpyAsync(reinterpret_cast<char *>(t) + off * tb, dt[s], cnt * tb, cudaMemcpyDeviceToHost, st), "D2H copy");
     }
+    // every path releases the staging buffers and drains the streams
     for (int i = 0; i < scgpu_ntt_plan::kStreams; i++) {
-        cudaFreeAsync(dy[i], p->streams[i]); cudaFreeAsync(dt[i], p->streams[i]); cudaFreeAsync(ds[i], p->streams[i]);
-        SCGPU_CUDA_CHECK(cudaStreamSynchronize(p->streams[i]));
+        if (dy[i]) cudaFreeAsync(dy[i], p->streams[i]);
+        if (dt[i]) cudaFreeAsync(dt[i], p->streams[i]);
+        if (ds[i]) cudaFreeAsync(ds[i], p->streams[i]);
+        cuda_ok(cudaStreamSynchronize(p->streams[i]), "cudaStreamSynchronize");
     }
     return status;
 }
