@@ -13,7 +13,7 @@ from .binding import (  # noqa: F401
     OP_FWD, OP_INV, OP_FWD_LARGE, OP_INV_LARGE, OP_FFT, OP_FFT_LARGE, OP_PW, OP_PW16, OP_NORMALIZE,
     OP_CENTER, OP_POLYMUL, OP_TRIPLE16, OP_MODN, OP_MULN, OP_SQRN, OP_FLIP, OP_INVERT, OP_DIV,
     OP_PWR, OP_SCALAR, OP_SPARSE32, OP_SPARSE16,
-    PRNG_AES_CTR_DRBG, PRNG_CHACHA, SAMPLER_CDF, SAMPLER_KNUTH_YAO, SAMPLER_BERNOULLI, SAMPLER_KNUTH_YAO_FAST,
+    PRNG_AES_CTR_DRBG, PRNG_CHACHA, PLAN_INPUTS_IN_RANGE, SAMPLER_CDF, SAMPLER_KNUTH_YAO, SAMPLER_BERNOULLI, SAMPLER_KNUTH_YAO_FAST,
     NORMAL_SAMPLES, BLINDING_SAMPLES, SHUFFLE_SAMPLES,
 )
 

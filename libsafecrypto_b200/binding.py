@@ -12,6 +12,7 @@ REFERENCE, BARRETT, FP, AVX, SOLINAS_7681, SOLINAS_8380417 = range(6)
  OP_CENTER, OP_POLYMUL, OP_TRIPLE16, OP_MODN, OP_MULN, OP_SQRN, OP_FLIP, OP_INVERT, OP_DIV,
  OP_PWR, OP_SCALAR, OP_SPARSE32, OP_SPARSE16) = range(22)
 PRNG_AES_CTR_DRBG, PRNG_CHACHA = 0, 2
+PLAN_INPUTS_IN_RANGE = 1
 SAMPLER_CDF, SAMPLER_KNUTH_YAO, SAMPLER_BERNOULLI, SAMPLER_KNUTH_YAO_FAST = 0, 1, 5, 6
 NORMAL_SAMPLES, BLINDING_SAMPLES, SHUFFLE_SAMPLES = 0, 1, 2
 
@@ -44,6 +45,7 @@ def lib():
         L.scgpu_ntt_plan_create.argtypes = [ctypes.POINTER(vp), vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int]
         L.scgpu_ntt_plan_destroy.argtypes = [vp]
         L.scgpu_ntt_plan_destroy.restype = None
+        L.scgpu_ntt_plan_set_flags.argtypes = [vp, ctypes.c_uint]
         L.scgpu_ntt_batch.argtypes = [vp, ctypes.c_int, vp, vp, vp, sz, sz, i32, vp, vp]
         L.scgpu_ntt_batch_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, sz, sz, i32, vp]
         L.scgpu_polymul_batch.argtypes = [vp, vp, vp, vp, sz, sz, vp]
@@ -141,6 +143,10 @@ class NttPlan:
                                            tw_bits, device), "scgpu_ntt_plan_create")
         self.handle = h
         self.device = device
+
+    def set_flags(self, flags):
+        """scgpu_ntt_plan_set_flags (PLAN_INPUTS_IN_RANGE: the fused product skips its range vote)."""
+        return _check(lib().scgpu_ntt_plan_set_flags(self.handle, int(flags)), "scgpu_ntt_plan_set_flags")
 
     def close(self):
         if getattr(self, "handle", None):

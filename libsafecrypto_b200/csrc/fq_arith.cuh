@@ -94,5 +94,69 @@ FQ_HD int32_t mul_var(int32_t a, int32_t b, float invq, int32_t pwk, int32_t nq)
     return mad(as_i(f), nq, p);
 }
 
+FQ_HD float mul_rn(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    return a * b;                                  // compiled with -ffp-contract=off
+#endif
+}
+FQ_HD float i2f(int32_t a)
+{
+#ifdef __CUDA_ARCH__
+    return __int2float_rn(a);
+#else
+    return (float)a;
+#endif
+}
+
+// x UNBIASED with its float copy xf (|x| < 2^22): x * w - qe * q, unbiased.  Only tw.w / tw.wq are read:
+// the magic number is the FMA's addend, pwk = kBias * q cancels the bias of the quotient's bit pattern.
+FQ_HD int32_t mul_unb(int32_t x, float xf, int32_t w, float wq, int32_t pwk, int32_t nq)
+{
+    const float f = fma_rn(xf, wq, kBiasF);
+    const int32_t p = mad(x, w, pwk);
+    return mad(as_i(f), nq, p);
+}
+
+// ---- degree-3 base multiplication: the transform stops two stages early -------------------------------------
+// After stage logn - 3 the polynomial is split into n/4 residues modulo X^4 - zeta_b (four consecutive elements,
+// natural order).  Their products
+//     c0 = a0 b0 + zeta (a1 b3 + a2 b2 + a3 b1)      c1 = a0 b1 + a1 b0 + zeta (a2 b3 + a3 b2)
+//     c2 = a0 b2 + a1 b1 + a2 b0 + zeta a3 b3        c3 = a0 b3 + a1 b2 + a2 b1 + a3 b0
+// replace the last two forward stages of both operands, the n pointwise products and the first two inverse stages
+// (92 instructions per four coefficients) by 3 products with zeta, 16 multiply-adds on the integer side, 16 on the
+// float side and ONE quotient per output coefficient (60 instructions).  The integer sums wrap around; the float
+// sums only have to estimate the quotient: |sum| < 2^22 q, four roundings of half an ulp each (fq_host.h:
+// analyse32_bm bounds the error of the quotient and the size of the result).
+// a, b UNBIASED (the stage before emits them so inside its 3-input adds); c is BIASED.  pwb = kBias * q + kBias.
+FQ_HD void basemul4(int32_t (&c)[4], const int32_t (&a)[4], const int32_t (&b)[4], int32_t zw, float zwq,
+                    float invq, int32_t pwk, int32_t pwb, int32_t nq)
+{
+    float af[4], bf[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { af[i] = i2f(a[i]); bf[i] = i2f(b[i]); }
+    int32_t z[4]; float zf[4];
+    z[0] = 0; zf[0] = 0.0f;
+#pragma unroll
+    for (int i = 1; i < 4; i++) { z[i] = mul_unb(a[i], af[i], zw, zwq, pwk, nq); zf[i] = i2f(z[i]); }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        // terms i + j = k use a_i, terms i + j = k + 4 use zeta a_i
+        int32_t p = mad(a[0], b[k], pwb);
+        float f = mul_rn(af[0], bf[k]);
+#pragma unroll
+        for (int i = 1; i < 4; i++) {
+            const int j = (k - i) & 3;
+            const bool wrap = i > k;
+            p = mad(wrap ? z[i] : a[i], b[j], p);
+            f = fma_rn(wrap ? zf[i] : af[i], bf[j], f);
+        }
+        const float g = fma_rn(f, invq, kBiasF);
+        c[k] = mad(as_i(g), nq, p);
+    }
+}
+
 }  // namespace fq
 }  // namespace scgpu

@@ -146,6 +146,67 @@ inline bool analyse32(int logn, int64_t qi, int accumulate, int *r0_out, int32_t
     return false;
 }
 
+// Bounds of the warp-local schedule with the degree-3 base multiplication (fq_arith.cuh: basemul4): logn - 2
+// forward stages, n/4 products modulo X^4 - zeta, logn - 2 inverse stages.  x0 = |input| bound.
+struct BmBounds { double fwd_max, sum_max, pw_max; };
+inline bool analyse32_bm(int logn, int64_t qi, int32_t x0, int *r0_out, BmBounds *bounds = nullptr)
+{
+    const double q = (double)qi, lim = (double)kLimit - 2.0;
+    if (qi < 257 || qi >= (1 << 18) || (qi & 1) == 0 || logn < 8) return false;
+    double b = (double)x0;
+    for (int st = 0; st < logn - 2; st++) {
+        if (b >= lim) return false;
+        b += mul_bound(b, q);
+    }
+    if (b >= lim) return false;                                  // read as a float by the conversions
+    const double zb = mul_bound(b, q);                           // |zeta a_i|
+    const double big = b > zb ? b : zb;
+    const double sum = 4.0 * big * b;                            // four products per output coefficient
+    if (sum / q >= lim) return false;
+    // the float sum: one rounding per term, each at most half an ulp of a partial sum below `sum`; 1/q is rounded
+    // (2^-24 relative); the FMA that adds the magic number rounds to an integer (1/2)
+    double ferr = 0;
+    for (int t = 1; t <= 4; t++) ferr += 0.5 * std::ldexp(1.0, std::ilogb(t * big * b) - 23);   // partial sum of t terms
+    const double pw = q * (0.5 + 2.0 * (sum / q) / 16777216.0) + ferr + 2.0;
+    if (bounds) { bounds->fwd_max = b; bounds->sum_max = sum; bounds->pw_max = pw; }
+    for (int r0 = 0; r0 <= 1; r0++) {
+        double v = pw;
+        bool ok = true;
+        for (int st = logn - 3; st >= 0 && ok; st--) {
+            if (st == 4 && r0) { if (v >= lim) { ok = false; break; } v = mul_bound(v, q); }
+            const double d = 2.0 * v;
+            if (d >= lim) { ok = false; break; }
+            const double prod = mul_bound(d, q);
+            if (st == 0) { if (prod >= q) ok = false; v = prod; }
+            else v = d > prod ? d : prod;
+        }
+        if (ok) { *r0_out = r0; return true; }
+    }
+    return false;
+}
+
+// zeta_b = zf[n/4 + b]^2 (the modulus X^4 - zeta_b of block b after stage logn - 3) as (w, wq) pairs, and the two
+// entries of the last inverse stage with (n/4)^-1 instead of n^-1 (two Gentleman-Sande stages fewer double the
+// result twice less)
+inline void build_bm_tables(int logn, int64_t q, const int32_t *w_host, std::vector<int32_t> &zeta_w,
+                            std::vector<float> &zeta_wq, Tw &ninv_bm, Tw &i01_bm)
+{
+    const int n = 1 << logn, nb = n / 4;
+    zeta_w.resize(nb); zeta_wq.resize(nb);
+    for (int b = 0; b < nb; b++) {
+        const int k = nb + b;
+        int e = 0;
+        for (int t = 0; t < logn; t++) e |= ((k >> t) & 1) << (logn - 1 - t);
+        const int64_t z = (((int64_t)w_host[e] % q) + q) % q;
+        const Tw tw = make_tw((int64_t)(((__int128)z * z) % q), q, false);
+        zeta_w[b] = tw.w; zeta_wq[b] = tw.wq;
+    }
+    const int64_t nin4 = powmod(n / 4, q - 2, q);
+    const int64_t zinv1 = (q - (((int64_t)w_host[n - n / 2] % q) + q) % q) % q;       // zi[1] without n^-1 (brv(1) = n/2)
+    ninv_bm = make_tw(nin4, q, false);
+    i01_bm = make_tw((int64_t)(((__int128)zinv1 * nin4) % q), q, false);
+}
+
 // zf[k] = psi^brv(k) (k = 2^s + b: stage s, block b); zi[k] = its inverse, zi[1] also carries n^-1.
 // Forward products and the two final-stage products are unbiased, every other inverse product is biased.
 inline bool build_tables(int logn, int64_t q, const int32_t *w_host, std::vector<Tw> &zf, std::vector<Tw> &zi,

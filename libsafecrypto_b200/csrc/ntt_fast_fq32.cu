@@ -33,8 +33,9 @@ using w32::u32;
 // Arithmetic policy: float-quotient products (fq_arith.cuh); coefficients travel biased by kBias.
 struct ArFq {
     typedef Tw E;
-    struct K { int32_t nq, q, pwk; float invq; };
+    struct K { int32_t nq, q, pwk; float invq; int32_t pwb; };
     static constexpr bool STASH16 = true;          // mat-vec may keep the transformed vectors as int16
+    static constexpr bool BASEMUL = true;          // two-operand products stop two stages early (fq::basemul4)
     static constexpr int WORDS = 4;
     static __device__ __forceinline__ u32 enc(int32_t x) { return (u32)x + (u32)kBias; }
     static __device__ __forceinline__ int32_t dec(u32 x) { return (int32_t)(x - (u32)kBias); }
@@ -72,6 +73,31 @@ struct ArFq {
         hi = lo - t + (u32)kBias;
         lo = lo + t + (u32)kBias;
 #endif
+    }
+    // both results UNBIASED (the stage in front of the base multiplication): the bias leaves inside the 3-input adds
+    static __device__ __forceinline__ void ct_unb(u32 &lo, u32 &hi, const E &z, const K &k)
+    {
+        const u32 t = (u32)fq::mul((int32_t)hi, z, k.nq);
+#ifdef __CUDA_ARCH__
+        u32 kb1, kb2;                                    // opaque copies, see ct0
+        asm("mov.u32 %0, 0x4B400000;" : "=r"(kb1));
+        asm("mov.u32 %0, 1262485504;" : "=r"(kb2));
+        hi = lo - t - kb1;
+        lo = lo + t - kb2;
+#else
+        hi = lo - t - (u32)kBias;
+        lo = lo + t - (u32)kBias;
+#endif
+    }
+    // xa[0..3] (unbiased) <- xa * xb modulo X^4 - zeta, biased
+    static __device__ __forceinline__ void bm4(u32 *xa, const u32 *xb, int32_t zw, int32_t zwq, const K &k)
+    {
+        int32_t a[4], b[4], c[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { a[i] = (int32_t)xa[i]; b[i] = (int32_t)xb[i]; }
+        fq::basemul4(c, a, b, zw, __int_as_float(zwq), k.invq, k.pwk, k.pwb, k.nq);
+#pragma unroll
+        for (int i = 0; i < 4; i++) xa[i] = (u32)c[i];
     }
     static __device__ __forceinline__ void gs(u32 &lo, u32 &hi, const E &z, const K &k)
     {
@@ -117,20 +143,26 @@ struct ArFq {
 
 typedef w32::W32Const<ArFq> FqConst32;
 
-FqConst32 fq32_const(const NttPlanDev &p, int r0)
+FqConst32 fq32_const(const NttPlanDev &p, int r0, bool bm = false)
 {
     FqConst32 c;
     const int n = p.n;
     c.pf = static_cast<const int32_t *>(p.fq32_tab);
     c.pi = c.pf + 4 * n;
+    c.pz = static_cast<const int32_t *>(p.fq32_zeta);
     memcpy(c.f0, p.fq32_pass0, sizeof(Tw) * 31);
     memcpy(c.i0, p.fq32_pass0 + sizeof(Tw) * 31, sizeof(Tw) * 31);
     memcpy(&c.ninv, p.fq_ninv, sizeof(Tw));
+    if (bm) {                                       // two inverse stages fewer: (n/4)^-1 in the last stage
+        memcpy(&c.ninv, p.fq32_ninv_bm, sizeof(Tw));
+        memcpy(&c.i0[0], p.fq32_i01_bm, sizeof(Tw));
+    }
     memcpy(&c.one, p.fq_one, sizeof(Tw));
     c.q = p.rc.q; c.nq = -p.rc.q; c.x0 = p.fq32_x0;
     c.k.q = p.rc.q; c.k.nq = -p.rc.q;
     c.k.pwk = (int32_t)((uint32_t)kBias * (uint32_t)p.rc.q);
     c.k.invq = (float)(1.0 / (double)p.rc.q);
+    c.k.pwb = (int32_t)((uint32_t)c.k.pwk + (uint32_t)kBias);
     c.M = (uint32_t)((1ull << 32) / (uint64_t)p.rc.q);
     c.r0 = r0;
     return c;
@@ -141,6 +173,7 @@ FqConst32 fq32_const(const NttPlanDev &p, int r0)
 int build_fq32_tables(NttPlanDev &p, const int32_t *w_host)
 {
     p.fq32_ok = 0; p.fq32_tab = nullptr;
+    p.fq32_bm_ok = 0; p.fq32_zeta = nullptr;
     if (p.logn < 8 || p.logn > 10) return SCGPU_OK;
     int r0 = 0; int32_t x0 = 0;
     if (!fq::analyse32(p.logn, p.rc.q, 1, &r0, &x0)) return SCGPU_OK;
@@ -167,14 +200,38 @@ int build_fq32_tables(NttPlanDev &p, const int32_t *w_host)
     p.fq32_r0 = r0;
     p.fq32_x0 = x0;
     p.fq32_ok = 1;
+    // base multiplication of the two-operand product: zeta pairs thread-major, [pair pr][tau][w, wq, w, wq]
+    // (blocks 8 tau + 2 pr and 8 tau + 2 pr + 1 of thread tau)
+    int r0_bm = 0;
+    const char *no_bm = getenv("SCGPU_NO_BASEMUL");
+    if (!(no_bm && atoi(no_bm) != 0) && fq::analyse32_bm(p.logn, p.rc.q, x0, &r0_bm)) {
+        std::vector<int32_t> zw; std::vector<float> zwq; Tw ninv_bm, i01_bm;
+        fq::build_bm_tables(p.logn, p.rc.q, w_host, zw, zwq, ninv_bm, i01_bm);
+        const int T = n / 32;
+        std::vector<int32_t> zp((size_t)n / 2);
+        for (int pr = 0; pr < 4; pr++)
+            for (int tau = 0; tau < T; tau++)
+                for (int u = 0; u < 2; u++) {
+                    const int blk = 8 * tau + 2 * pr + u;
+                    zp[((size_t)pr * T + tau) * 4 + 2 * u] = zw[blk];
+                    memcpy(&zp[((size_t)pr * T + tau) * 4 + 2 * u + 1], &zwq[blk], 4);
+                }
+        SCGPU_CUDA_CHECK(cudaMalloc(&p.fq32_zeta, sizeof(int32_t) * zp.size()));
+        SCGPU_CUDA_CHECK(cudaMemcpy(p.fq32_zeta, zp.data(), sizeof(int32_t) * zp.size(), cudaMemcpyHostToDevice));
+        memcpy(p.fq32_ninv_bm, &ninv_bm, sizeof(Tw));
+        memcpy(p.fq32_i01_bm, &i01_bm, sizeof(Tw));
+        p.fq32_r0_bm = r0_bm;
+        p.fq32_bm_ok = 1;
+    }
     return SCGPU_OK;
 }
 
 void free_fq32_tables(NttPlanDev &p)
 {
     if (p.fq32_tab) cudaFree(p.fq32_tab);
-    p.fq32_tab = nullptr;
-    p.fq32_ok = 0;
+    if (p.fq32_zeta) cudaFree(p.fq32_zeta);
+    p.fq32_tab = nullptr; p.fq32_zeta = nullptr;
+    p.fq32_ok = 0; p.fq32_bm_ok = 0;
 }
 
 // n = 256 (Kyber); returns SCGPU_ERR_UNSUPPORTED when this schedule does not apply (the caller falls back)
@@ -188,7 +245,9 @@ int launch_matvec_fq32(const NttPlanDev &p, int32_t *out, const int32_t *A, cons
 int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32_t *a, const void *b,
                         size_t b_stride, size_t count, cudaStream_t st)
 {
-    return w32::launch_polymul_w32<ArFq>(fq32_const(p, p.fq32_r0), p.logn, p.sm_count, mode, out, a, b, b_stride, count, st);
+    const bool bm = mode == w32::FQ_POLYMUL && p.fq32_bm_ok;
+    return w32::launch_polymul_w32<ArFq>(fq32_const(p, bm ? p.fq32_r0_bm : p.fq32_r0, bm), p.logn, p.sm_count, mode, out, a, b,
+                                         b_stride, count, st, bm, !p.inputs_in_range);
 }
 
 int launch_ntt_fq32(const NttPlanDev &p, int inverse, int32_t *out, const int32_t *a, size_t count, cudaStream_t st)

@@ -23,6 +23,7 @@ using w32::u32;
 struct ArSh {
     struct E { int32_t w, wp; };
     struct K { int32_t q, nq, qinv; };
+    static constexpr bool BASEMUL = false;         // Montgomery pointwise products: no shared-quotient sums
     static constexpr bool STASH16 = false;          // mat-vec may keep the transformed vectors as int16
     static constexpr int WORDS = 2;
     static __device__ __forceinline__ u32 enc(int32_t x) { return (u32)x; }
@@ -141,6 +142,7 @@ ShConst32 sh32_const(const NttPlanDev &p, int r0)
     const int n = p.n;
     c.pf = static_cast<const int32_t *>(p.sh32_tab);
     c.pi = c.pf + 2 * n;
+    c.pz = nullptr;
     memcpy(c.f0, p.sh32_pass0, sizeof(ArSh::E) * 31);
     memcpy(c.i0, p.sh32_pass0 + sizeof(ArSh::E) * 31, sizeof(ArSh::E) * 31);
     memcpy(&c.ninv, p.sh32_ninv, sizeof(ArSh::E));
@@ -220,7 +222,7 @@ int launch_matvec_sh32(const NttPlanDev &p, int32_t *out, const int32_t *A, cons
 int launch_polymul_sh32(const NttPlanDev &p, int mode, int32_t *out, const int32_t *a, const void *b,
                         size_t b_stride, size_t count, cudaStream_t st)
 {
-    return w32::launch_polymul_w32<ArSh>(sh32_const(p, p.sh32_r0), p.logn, p.sm_count, mode, out, a, b, b_stride, count, st);
+    return w32::launch_polymul_w32<ArSh>(sh32_const(p, p.sh32_r0), p.logn, p.sm_count, mode, out, a, b, b_stride, count, st, false, !p.inputs_in_range);
 }
 
 int launch_ntt_sh32(const NttPlanDev &p, int inverse, int32_t *out, const int32_t *a, size_t count, cudaStream_t st)

@@ -52,6 +52,11 @@ struct NttPlanDev {
     int32_t fq32_x0;
     void *fq32_tab;                      // forward [w | wq | k | c], inverse [w | wq | k | c], n words each
     alignas(16) unsigned char fq32_pass0[2 * 31 * 16];
+    // degree-3 base multiplication of the two-operand product (fq_arith.cuh: basemul4); 0: (q, n) outside its bounds
+    int fq32_bm_ok, fq32_r0_bm;
+    void *fq32_zeta;                     // (w, wq) of zeta per block of four, [pair][tau][4 words]: n/2 words
+    alignas(16) unsigned char fq32_ninv_bm[16], fq32_i01_bm[16];      // last inverse stage with (n/4)^-1
+    int inputs_in_range;                 // SCGPU_PLAN_INPUTS_IN_RANGE: the fused products skip the range vote
     // Shoup / Montgomery arithmetic on the same schedule, for moduli up to 2^25 (ntt_fast_sh32.cu)
     int sh32_ok, sh32_r0, sh32_mv_ok, sh32_r0_mv;
     int32_t sh32_x0;

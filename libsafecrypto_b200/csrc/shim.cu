@@ -205,6 +205,14 @@ extern "C" int scgpu_ntt_plan_create(scgpu_ntt_plan_t **out, const void *params,
     return SCGPU_OK;
 }
 
+extern "C" int scgpu_ntt_plan_set_flags(scgpu_ntt_plan_t *plan, unsigned flags)
+{
+    if (!plan || (flags & ~SCGPU_PLAN_INPUTS_IN_RANGE)) { set_error("plan_set_flags: bad argument"); return SCGPU_ERR_ARG; }
+    const int prev = plan->dev.inputs_in_range ? (int)SCGPU_PLAN_INPUTS_IN_RANGE : 0;
+    plan->dev.inputs_in_range = (flags & SCGPU_PLAN_INPUTS_IN_RANGE) ? 1 : 0;
+    return prev;
+}
+
 extern "C" void scgpu_ntt_plan_destroy(scgpu_ntt_plan_t *plan)
 {
     if (!plan) return;

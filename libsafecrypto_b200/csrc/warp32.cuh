@@ -161,6 +161,8 @@ template <class AR>
 struct W32Const {
     const int32_t *pf;                           // pass-1 forward table, thread-major (slot32): WORDS arrays of n words
     const int32_t *pi;                           // pass-1 inverse table
+    const int32_t *pz;                           // base multiplication: (w, wq) of zeta for the thread's 8 blocks of four,
+                                                 // [pair of blocks][tau][4 words] (policies with AR::BASEMUL)
     typename AR::E f0[31], i0[31];               // entries 1..31: stages 0..4
     typename AR::E ninv, one;
     typename AR::K k;
@@ -251,7 +253,8 @@ static __device__ __forceinline__ void load_entries(E (&tw)[CNT], const int32_t 
 }
 
 // one radix-2 stage S (forward: Cooley-Tukey, inverse: Gentleman-Sande) on sub-chunk h of NOPS operands
-template <int LOGN, int S, int NOPS, bool INV, int CH>
+// UNB (forward only): the butterflies emit unbiased values (the stage in front of the base multiplication)
+template <int LOGN, int S, int NOPS, bool INV, int CH, bool UNB = false>
 static __device__ __forceinline__ void stage1(u32 (&xa)[CH], u32 (&xb)[CH], const Const &c, int tau, int h)
 {
     using C = Cfg32<LOGN>;
@@ -270,6 +273,9 @@ static __device__ __forceinline__ void stage1(u32 (&xa)[CH], u32 (&xb)[CH], cons
                 const int i = (g0 + g) * 2 * LEN + j;
                 if (INV) {
                     AR::gs(xa[i], xa[i + LEN], tw[g], c.k);
+                } else if constexpr (UNB) {
+                    AR::ct_unb(xa[i], xa[i + LEN], tw[g], c.k);
+                    if (NOPS == 2) AR::ct_unb(xb[i], xb[i + LEN], tw[g], c.k);
                 } else {
                     AR::ct(xa[i], xa[i + LEN], tw[g], c.k);
                     if (NOPS == 2) AR::ct(xb[i], xb[i + LEN], tw[g], c.k);
@@ -288,6 +294,33 @@ static __device__ __forceinline__ void fwd_stages1(u32 (&xa)[Cfg32<LOGN>::SUB], 
         fwd_stages1<LOGN, S + 1, NOPS>(xa, xb, c, tau, h);
     }
 }
+// forward stages S .. LOGN - 3 of both operands, the last one emitting unbiased values
+template <int LOGN, int S>
+static __device__ __forceinline__ void fwd_stages1_bm(u32 (&xa)[Cfg32<LOGN>::SUB], u32 (&xb)[Cfg32<LOGN>::SUB],
+                                               const Const &c, int tau, int h)
+{
+    if constexpr (S < LOGN - 3) {
+        stage1<LOGN, S, 2, false, Cfg32<LOGN>::SUB>(xa, xb, c, tau, h);
+        fwd_stages1_bm<LOGN, S + 1>(xa, xb, c, tau, h);
+    } else {
+        stage1<LOGN, S, 2, false, Cfg32<LOGN>::SUB, true>(xa, xb, c, tau, h);
+    }
+}
+// xa <- xa * xb modulo X^4 - zeta for the SUB / 4 blocks of sub-chunk h (fq_arith.cuh: basemul4)
+template <int LOGN>
+static __device__ __forceinline__ void basemul_sub(u32 (&xa)[Cfg32<LOGN>::SUB], const u32 (&xb)[Cfg32<LOGN>::SUB],
+                                            const Const &c, int tau, int h)
+{
+    using C = Cfg32<LOGN>;
+    constexpr int PAIRS = C::SUB / 8;
+#pragma unroll
+    for (int pr = 0; pr < PAIRS; pr++) {
+        const int4 z = __ldg(reinterpret_cast<const int4 *>(c.pz) + (h * PAIRS + pr) * C::T + tau);
+        AR::bm4(&xa[8 * pr], &xb[8 * pr], z.x, z.y, c.k);
+        AR::bm4(&xa[8 * pr + 4], &xb[8 * pr + 4], z.z, z.w, c.k);
+    }
+}
+
 template <int LOGN, int S>
 static __device__ __forceinline__ void inv_stages1(u32 (&x)[Cfg32<LOGN>::SUB], const Const &c, int tau, int h)
 {
@@ -309,7 +342,8 @@ static __device__ __forceinline__ void chunk_stage5(int32_t *p, const Const &c, 
     }
 }
 
-template <int LOGN>
+// CHK = false: the caller vouches for |coefficient| <= c.x0 (SCGPU_PLAN_INPUTS_IN_RANGE); no range vote
+template <int LOGN, bool CHK = true>
 static __device__ __forceinline__ void load_operand(u32 (&x)[32], const int32_t *row, int tau, const Const &c)
 {
     constexpr int T = Cfg32<LOGN>::T;
@@ -318,9 +352,9 @@ static __device__ __forceinline__ void load_operand(u32 (&x)[32], const int32_t 
 #pragma unroll
     for (int m = 0; m < 32; m++) {
         v[m] = __ldg(row + tau + m * T);
-        wide |= out_of_range(v[m], c);
+        if (CHK) wide |= out_of_range(v[m], c);
     }
-    if (__any_sync(0xFFFFFFFFu, wide)) {
+    if (CHK && __any_sync(0xFFFFFFFFu, wide)) {
 #pragma unroll
         for (int m = 0; m < 32; m++) v[m] = bred(v[m], c);
     }
@@ -330,7 +364,7 @@ static __device__ __forceinline__ void load_operand(u32 (&x)[32], const int32_t 
 }
 
 // same, from a raw row that a bulk copy (TMA) has staged at the start of the tile region
-template <int LOGN>
+template <int LOGN, bool CHK = true>
 static __device__ __forceinline__ void load_operand_staged(u32 (&x)[32], const int32_t *raw, int tau, const Const &c)
 {
     constexpr int T = Cfg32<LOGN>::T;
@@ -339,9 +373,9 @@ static __device__ __forceinline__ void load_operand_staged(u32 (&x)[32], const i
 #pragma unroll
     for (int m = 0; m < 32; m++) {
         v[m] = raw[tau + m * T];
-        wide |= out_of_range(v[m], c);
+        if (CHK) wide |= out_of_range(v[m], c);
     }
-    if (__any_sync(0xFFFFFFFFu, wide)) {
+    if (CHK && __any_sync(0xFFFFFFFFu, wide)) {
 #pragma unroll
         for (int m = 0; m < 32; m++) v[m] = bred(v[m], c);
     }
@@ -353,7 +387,9 @@ static __device__ __forceinline__ void load_operand_staged(u32 (&x)[32], const i
 };  // struct W32
 
 // TMA = true: operand rows arrive by bulk copy (16-byte aligned rows); false: plain LDG (any alignment)
-template <class AR, int LOGN, int MODE, bool TMA>
+// BM = true (FQ_POLYMUL, policies with AR::BASEMUL): the transforms stop two stages early and the residues modulo
+// X^4 - zeta are multiplied directly (c carries the last-stage entries for (n/4)^-1).  CHK = false: no range vote.
+template <class AR, int LOGN, int MODE, bool TMA, bool BM = false, bool CHK = true>
 __global__ void __launch_bounds__(kThreads32, FQ32_MINB)
 k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const void *__restrict__ bsrc,
                size_t b_stride, size_t count, unsigned long long *ctr, const __grid_constant__ W32Const<AR> c)
@@ -413,11 +449,11 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
             int32_t *tile = op == 0 ? ta : tb;
             if (TMA) {
                 mbar_wait(&bars[warp][op], parity);
-                W::template load_operand_staged<LOGN>(x, tile, tau, c);
+                W::template load_operand_staged<LOGN, CHK>(x, tile, tau, c);
                 __syncwarp();                     // the padded result overwrites the raw row in place
             } else {
                 const int32_t *row = op == 0 ? a + prow * N : static_cast<const int32_t *>(bsrc) + prow * b_stride;
-                W::template load_operand<LOGN>(x, row, tau, c);
+                W::template load_operand<LOGN, CHK>(x, row, tau, c);
             }
             W::fwd_pass0(x, c);
             store_pass0<LOGN>(tile, x, tau);
@@ -432,7 +468,11 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
             u32 xa[SUB], xb[SUB];
             int32_t *pa = ta + 36 * tau + SUB * h;
             load_sub<SUB>(pa, xa);
-            if (MODE == FQ_POLYMUL) {
+            if constexpr (MODE == FQ_POLYMUL && BM) {
+                load_sub<SUB>(tb + 36 * tau + SUB * h, xb);
+                W::template fwd_stages1_bm<LOGN, C::S1>(xa, xb, c, tau, h);
+                W::template basemul_sub<LOGN>(xa, xb, c, tau, h);
+            } else if constexpr (MODE == FQ_POLYMUL) {
                 load_sub<SUB>(tb + 36 * tau + SUB * h, xb);
                 W::template fwd_stages1<LOGN, C::S1, 2>(xa, xb, c, tau, h);
 #pragma unroll
@@ -463,7 +503,7 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
                 for (int i = 0; i < SUB; i++)
                     xa[i] = AR::pwraw(xa[i], kv[i], c.k);
             }
-            W::template inv_stages1<LOGN, LOGN - 1>(xa, c, tau, h);
+            W::template inv_stages1<LOGN, BM ? LOGN - 3 : LOGN - 1>(xa, c, tau, h);
             store_sub<SUB>(pa, xa);
         }
         W::template chunk_stage5<LOGN, true>(ta + 36 * tau, c, tau);
@@ -1047,15 +1087,30 @@ inline bool tma_allowed()
     return !(no_tma && atoi(no_tma) != 0);
 }
 
+// bm: base-multiplication kernel (FQ_POLYMUL, policies with AR::BASEMUL; c must carry the (n/4)^-1 entries);
+// chk = false: no range vote on the operands (FQ_POLYMUL only)
 template <class AR>
 int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, int32_t *out, const int32_t *a,
-                       const void *b, size_t b_stride, size_t count, cudaStream_t st)
+                       const void *b, size_t b_stride, size_t count, cudaStream_t st, bool bm = false, bool chk = true)
 {
     const int sms = sm_count > 0 ? sm_count : 148;
     // bulk copies need 16-byte aligned rows; the second operand is only staged in FQ_POLYMUL mode
     bool tma = ((uintptr_t)a % 16) == 0 && tma_allowed();
     if (mode == FQ_POLYMUL) tma = tma && ((uintptr_t)b % 16) == 0 && (b_stride % 4) == 0;
     unsigned long long *ctr = nullptr;               // work counter, only when the batch exceeds one grid-full
+    if (mode != FQ_POLYMUL) { bm = false; chk = true; }
+    if (!AR::BASEMUL) bm = false;
+#define W32_GO(L, MODE, TMA_, BM_, CHK_) \
+    k_polymul_w32<AR, L, MODE, TMA_, BM_, CHK_><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c)
+#define W32_PM(L, TMA_)                                                                                    \
+    {                                                                                                      \
+        if constexpr (AR::BASEMUL) {                                                                       \
+            if (bm && chk) W32_GO(L, FQ_POLYMUL, TMA_, true, true);                                        \
+            else if (bm)   W32_GO(L, FQ_POLYMUL, TMA_, true, false);                                       \
+        }                                                                                                  \
+        if (!bm && chk) W32_GO(L, FQ_POLYMUL, TMA_, false, true);                                          \
+        else if (!bm)   W32_GO(L, FQ_POLYMUL, TMA_, false, false);                                         \
+    }
 #define W32_LAUNCH(L)                                                                                      \
     {                                                                                                      \
         const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
@@ -1064,13 +1119,13 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
         if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; } \
         if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }     \
         if (tma) {                                                                                         \
-            if (mode == FQ_POLYMUL)    k_polymul_w32<AR, L, FQ_POLYMUL, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c); \
-            else if (mode == FQ_KEY16) k_polymul_w32<AR, L, FQ_KEY16, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c);   \
-            else                       k_polymul_w32<AR, L, FQ_KEY32, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c);   \
+            if (mode == FQ_POLYMUL)    W32_PM(L, true)                                                     \
+            else if (mode == FQ_KEY16) W32_GO(L, FQ_KEY16, true, false, true);                             \
+            else                       W32_GO(L, FQ_KEY32, true, false, true);                             \
         } else {                                                                                           \
-            if (mode == FQ_POLYMUL)    k_polymul_w32<AR, L, FQ_POLYMUL, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c); \
-            else if (mode == FQ_KEY16) k_polymul_w32<AR, L, FQ_KEY16, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c);   \
-            else                       k_polymul_w32<AR, L, FQ_KEY32, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c);   \
+            if (mode == FQ_POLYMUL)    W32_PM(L, false)                                                    \
+            else if (mode == FQ_KEY16) W32_GO(L, FQ_KEY16, false, false, true);                            \
+            else                       W32_GO(L, FQ_KEY32, false, false, true);                            \
         }                                                                                                  \
     }
     switch (logn) {
@@ -1080,6 +1135,8 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
     default: set_error("unsupported n=%d", 1 << logn); return SCGPU_ERR_UNSUPPORTED;
     }
 #undef W32_LAUNCH
+#undef W32_PM
+#undef W32_GO
     count_launch();
     SCGPU_CUDA_CHECK(cudaGetLastError());
     return SCGPU_OK;

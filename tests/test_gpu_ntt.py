@@ -637,3 +637,57 @@ def test_work_counter_batches_beyond_one_grid(q, n, tw):
             t = P.ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw, np.mod(acc, q).astype(np.int32))
             t = P.ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, t, None, w, r)
             assert np.array_equal(om[:64, i].cpu().numpy(), P.ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw, t))
+
+
+@pytest.mark.parametrize("q,n", [(12289, 512), (12289, 1024), (7681, 256), (12289, 256)])
+def test_base_multiplication_and_in_range_flag(q, n):
+    """The two-operand product stops its transforms two stages early and multiplies the residues modulo X^4 - zeta
+    (fq_arith.cuh: basemul4).  Same bits as the full-length schedule (SCGPU_NO_BASEMUL=1 at plan creation), as the
+    oracle, and -- for operands inside the +-4q window the flag promises -- as the kernel without the range vote
+    (SCGPU_PLAN_INPUTS_IN_RANGE), at the window's edges and with adversarial sign patterns."""
+    w, r = O.tables(q, n, 16)
+    p_bm = sc.NttPlan(n, q, O.REFERENCE, w, r)
+    os.environ["SCGPU_NO_BASEMUL"] = "1"
+    try:
+        p_full = sc.NttPlan(n, q, O.REFERENCE, w, r)
+    finally:
+        del os.environ["SCGPU_NO_BASEMUL"]
+    p_flag = sc.NttPlan(n, q, O.REFERENCE, w, r)
+    assert p_flag.set_flags(sc.PLAN_INPUTS_IN_RANGE) == 0
+    assert p_flag.set_flags(sc.PLAN_INPUTS_IN_RANGE) == sc.PLAN_INPUTS_IN_RANGE
+    rng = np.random.default_rng(q + n)
+    x0 = 4 * q
+    cases = [(rand_inputs(rng, "uniform", q, (1031, n)), rand_inputs(rng, "uniform", q, (1031, n))),
+             (rand_inputs(rng, "signed", q, (65, n)), rand_inputs(rng, "small", q, (65, n))),
+             (rng.integers(-x0, x0 + 1, size=(257, n)).astype(np.int32), rng.integers(-x0, x0 + 1, size=(257, n)).astype(np.int32)),
+             (np.full((3, n), x0, dtype=np.int32), np.full((3, n), -x0, dtype=np.int32)),
+             ((x0 * rng.choice([-1, 1], size=(33, n))).astype(np.int32), (x0 * rng.choice([-1, 1], size=(33, n))).astype(np.int32)),
+             (np.full((2, n), q - 1, dtype=np.int32), np.full((2, n), q - 1, dtype=np.int32))]
+    one_hot = np.zeros((n, n), dtype=np.int32)
+    one_hot[np.arange(n), np.arange(n)] = x0                     # x0 * X^i times a dense operand: every zeta is exercised
+    cases.append((one_hot, np.full((n, n), -x0, dtype=np.int32)))
+    for a, b in cases:
+        exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, 16, a, b, w, r)
+        for name, p in (("basemul", p_bm), ("full", p_full), ("flag", p_flag)):
+            for aligned in (True, False):                        # bulk-copy and plain-load variants of the kernel
+                if aligned:
+                    da, db = dev(a), dev(b)
+                else:
+                    fa = torch.zeros(a.size + 1, dtype=torch.int32, device=DEV)
+                    fb = torch.zeros(b.size + 1, dtype=torch.int32, device=DEV)
+                    fa[1:] = dev(a).flatten(); fb[1:] = dev(b).flatten()
+                    da, db = fa[1:].view(a.shape), fb[1:].view(b.shape)
+                out = torch.full(a.shape, -7, dtype=torch.int32, device=DEV)
+                p.polymul(out, da, db)
+                torch.cuda.synchronize()
+                assert np.array_equal(out.cpu().numpy(), exp), (name, aligned, a.shape)
+    # arbitrary SINT32 operands stay exact without the flag
+    a, b = rand_inputs(rng, "extreme", q, (129, n)), rand_inputs(rng, "lazy", q, (129, n))
+    exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, 16, a, b, w, r)
+    for p in (p_bm, p_full):
+        out = torch.empty(a.shape, dtype=torch.int32, device=DEV)
+        p.polymul(out, dev(a), dev(b))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), exp)
+    for p in (p_bm, p_full, p_flag):
+        p.close()
