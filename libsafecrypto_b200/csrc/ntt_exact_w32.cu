@@ -227,13 +227,14 @@ k_exact_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t cou
         if (lane == 0 && first < count) fetch(first);
     }
 
-    for (unsigned g = blockIdx.x; (size_t)g * C::POLYS < count;) {
-        const size_t base = (size_t)g * C::POLYS;
+    w32::Claim cl;
+    for (cl.init(); (size_t)cl.g * C::POLYS < count;) {
+        const size_t base = (size_t)cl.g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;
         const size_t prow = live ? poly : 0;
-        const unsigned gnext = claim_next(ctr, g, lane);
-        const size_t nbase = (size_t)gnext * C::POLYS;
+        cl.issue(ctr, lane);
+        const size_t nbase = (size_t)cl.gn * C::POLYS;
         {
             int32_t x[32];
             if (TMA) {
@@ -298,7 +299,7 @@ k_exact_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t cou
             }
         }
         __syncwarp();
-        g = share_next(ctr, gnext);
+        cl.advance(ctr);
     }
 }
 

@@ -129,6 +129,24 @@ __device__ __forceinline__ unsigned share_next(unsigned long long *ctr, unsigned
 {
     return ctr == nullptr ? gnext : __shfl_sync(0xFFFFFFFFu, gnext, 0);
 }
+// Pipelined claim: a warp knows its current group g AND its next group gn (whose rows it prefetches); at the top of
+// an iteration lane 0 claims the group AFTER the next one and nobody reads the atomic's result before the end of the
+// iteration.  (Claiming the next group itself left the atomic's latency exposed wherever the prefetch is issued early
+// in the iteration: the add that consumed its result was the most-sampled stall of the kernel,
+// profiles/polymul_r2bm_ncu_mix.txt.)  The first two groups of a warp are static, the counter hands out the rest.
+struct Claim {
+    unsigned g, gn, raw;
+    __device__ __forceinline__ void init() { g = blockIdx.x; gn = blockIdx.x + gridDim.x; raw = 0; }
+    __device__ __forceinline__ void issue(unsigned long long *ctr, int lane)
+    {
+        if (ctr != nullptr && lane == 0) raw = atomicAdd(reinterpret_cast<unsigned *>(ctr), 1u);
+    }
+    __device__ __forceinline__ void advance(unsigned long long *ctr)
+    {
+        g = gn;
+        gn = ctr == nullptr ? gn + gridDim.x : __shfl_sync(0xFFFFFFFFu, raw, 0) + 2u * gridDim.x;
+    }
+};
 
 template <int LOGN>
 __device__ __forceinline__ void store_pass0(int32_t *tile, const u32 (&x)[32], int tau)
@@ -434,13 +452,14 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
         }
     }
 
-    for (unsigned g = blockIdx.x; (size_t)g * C::POLYS < count;) {
-        const size_t base = (size_t)g * C::POLYS;
+    Claim cl;
+    for (cl.init(); (size_t)cl.g * C::POLYS < count;) {
+        const size_t base = (size_t)cl.g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;
         const size_t prow = live ? poly : 0;
-        const unsigned gnext = claim_next(ctr, g, lane);
-        const size_t nbase = (size_t)gnext * C::POLYS;
+        cl.issue(ctr, lane);
+        const size_t nbase = (size_t)cl.gn * C::POLYS;
         // rolled loops (operand, sub-chunk): the fully unrolled body was 60 KB of SASS and spent 2 of every
         // 7 stall cycles waiting for instructions (profiles/polymul_r02c_*); the L1.5 I-cache holds 32 KB
 #pragma unroll 1
@@ -537,7 +556,7 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
         } else {
             __syncwarp();
         }
-        g = share_next(ctr, gnext);
+        cl.advance(ctr);
     }
 }
 
@@ -588,13 +607,14 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
         if (lane == 0 && first < count) fetch(first);
     }
 
-    for (unsigned g = blockIdx.x; (size_t)g * C::POLYS < count;) {
-        const size_t base = (size_t)g * C::POLYS;
+    Claim cl;
+    for (cl.init(); (size_t)cl.g * C::POLYS < count;) {
+        const size_t base = (size_t)cl.g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;
         const size_t prow = live ? poly : 0;
-        const unsigned gnext = claim_next(ctr, g, lane);
-        const size_t nbase = (size_t)gnext * C::POLYS;
+        cl.issue(ctr, lane);
+        const size_t nbase = (size_t)cl.gn * C::POLYS;
         if (!INV) {
             {
                 u32 x[32];
@@ -681,7 +701,7 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
             }
             __syncwarp();
         }
-        g = share_next(ctr, gnext);
+        cl.advance(ctr);
     }
     (void)taurev;
 }
@@ -749,13 +769,14 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
         if (lane == 0 && first < count) { fetch_s(first); fetch_a(first, 0); }
     }
 
-    for (unsigned g = blockIdx.x; (size_t)g * C::POLYS < count;) {
-        const size_t base = (size_t)g * C::POLYS;
+    Claim cl;
+    for (cl.init(); (size_t)cl.g * C::POLYS < count;) {
+        const size_t base = (size_t)cl.g * C::POLYS;
         const size_t inst = base + slot;
         const bool live = inst < count;
         const size_t irow = live ? inst : 0;
-        const unsigned gnext = claim_next(ctr, g, lane);
-        const size_t nbase = (size_t)gnext * C::POLYS;
+        cl.issue(ctr, lane);
+        const size_t nbase = (size_t)cl.gn * C::POLYS;
         if (TMA) { mbar_wait(&bars[warp][0], par_s); par_s ^= 1u; }
 #pragma unroll 1
         for (int j = 0; j < l; j++) {
@@ -863,7 +884,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
             }
             __syncwarp();
         }
-        g = share_next(ctr, gnext);
+        cl.advance(ctr);
     }
 }
 
@@ -1079,7 +1100,7 @@ inline void pack_pass1(int logn, const Vec &zf, const Vec &zi, Get get, int32_t 
 }
 
 // group indices are 32-bit in the kernels (claim_next)
-inline bool groups_fit(size_t groups, size_t grid) { return groups + grid < 0xFFFFFFFFull; }
+inline bool groups_fit(size_t groups, size_t grid) { return groups + 3 * grid < 0xFFFFFFFFull; }
 
 inline bool tma_allowed()
 {
