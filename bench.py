@@ -229,6 +229,10 @@ def main():
 
     w, r = O.tables(Q, N_COEF, 16)        # twiddle tables (host set-up; validated against the reference's generated ones)
     plan = sc.NttPlan(N_COEF, Q, sc.REFERENCE, w, r, device=local_rank)
+    # the operands are canonical residues (as at every call site of the reference): the plan says so and the fused
+    # product skips its per-coefficient range vote; the default path (exact for ANY SINT32) is timed below as well
+    plan.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+    plan_checked = sc.NttPlan(N_COEF, Q, sc.REFERENCE, w, r, device=local_rank)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     a = torch.randint(0, Q, (BATCH, N_COEF), dtype=torch.int32, device=dev, generator=g)
     b = torch.randint(0, Q, (BATCH, N_COEF), dtype=torch.int32, device=dev, generator=g)
@@ -288,7 +292,7 @@ def main():
     alg_bytes = 12 * N_COEF * BATCH                     # read a, b (4n each) + write out (4n) per product
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "k_polymul_w32<ArFq,9,POLYMUL,TMA>",
+                "traffic": None, "peak_source": peak_src, "kernel": "k_polymul_w32<ArFq,9,POLYMUL,TMA,BM=1,CHK=0>",
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes}
     prof = os.path.join(ROOT, "profiles", "polymul_traffic.json")
     if os.path.exists(prof):
@@ -306,17 +310,18 @@ def main():
         smi = sampler.summary() if sampler.rows else {}
         sm_mhz = smi.get("sm_max_mhz") or props.clock_rate / 1e3
         peak_issue = issue_peak(sm_count, sm_mhz)
-        wipp = counts.get("k_polymul_w32_n512", {}).get("per_unit")
-        bfly = 3 * (N_COEF // 2) * 9 + N_COEF + N_COEF // 2
+        ckey = "k_polymul_w32_n512_inrange" if "k_polymul_w32_n512_inrange" in counts else "k_polymul_w32_n512"
+        wipp = counts.get(ckey, {}).get("per_unit")
+        # arithmetic floor of the schedule: 3 transforms x (log n - 2) stages x n/2 butterflies x 5 instructions, plus
+        # n/4 base multiplications x 60, per warp-instruction of 32 lanes
+        arith = (3 * (N_COEF // 2) * 7 * 5 + (N_COEF // 4) * 60) / 32.0
         int_roof = {"bound": "issue", "unit": "warp-instructions/s", "peak": peak_issue, "sm_count": sm_count, "sm_mhz": sm_mhz,
-                    "warp_instr_per_product": wipp, "butterfly_equivalents_per_product": bfly,
-                    "source": counts.get("k_polymul_w32_n512", {}).get("source"),
+                    "warp_instr_per_product": wipp, "arithmetic_warp_instr_per_product": arith,
+                    "source": counts.get(ckey, {}).get("source"), "counted_kernel": ckey,
                     "peak_source": "SMs x 4 schedulers x max SM clock"}
         if wipp:
             ach = wipp * BATCH / (k_ms * 1e-3)
-            int_roof.update({"achieved": ach, "frac": ach / peak_issue,
-                             "butterfly_instr_frac": 5.0 * bfly / 32.0 / wipp})
-    # other parameter shapes of BASELINE.json configs[1..3] (device-resident, 1 GiB per operand; parity is in tests/)
+            int_roof.update({"achieved": ach, "frac": ach / peak_issue, "arithmetic_instr_frac": arith / wipp})
     def timed(fn, reps=10):
         for _ in range(3):
             fn()
@@ -330,7 +335,13 @@ def main():
         return s0.elapsed_time(e0) / reps * 1e-3
 
     shapes = None
+    checked_path = None
     if rank == 0:
+        # the default path of the same kernel: range vote on every coefficient, exact for any SINT32 operand
+        tc = timed(lambda: plan_checked.polymul(out, a, b))
+        checked_path = {"value": BATCH / tc, "unit": UNIT, "hbm_frac": alg_bytes / tc / 1e9 / peak,
+                        "kernel": "k_polymul_w32<ArFq,9,POLYMUL,TMA,BM=1,CHK=1>",
+                        "note": "scgpu_polymul_batch without SCGPU_PLAN_INPUTS_IN_RANGE (any SINT32 input exact), same operands, same output"}
         shapes = {}
 
         def put(name, units, secs, bytes_per_unit, unit):
@@ -345,6 +356,9 @@ def main():
             xb = torch.randint(0, qq, (bb, nn), dtype=torch.int32, device=dev, generator=g)
             xo = torch.empty_like(xa)
             put("polymul_n%d_q%d" % (nn, qq), bb, timed(lambda: pl.polymul(xo, xa, xb)), 12 * nn, "polymul")
+            pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+            put("polymul_n%d_q%d_inputs_in_range" % (nn, qq), bb, timed(lambda: pl.polymul(xo, xa, xb)), 12 * nn, "polymul")
+            pl.set_flags(0)
             if nn == 256:
                 # Kyber module product t = A s, k = l = 3 (module_lwe.c:669-748), A in the NTT domain: 4 n (k^2 + 2 k) bytes
                 k = 3
@@ -589,9 +603,11 @@ def main():
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": "batched NTT polymul n=512 q=12289 (BASELINE configs[1]), 2^20 pairs per GPU, fused fwd/fwd/pointwise/inv, canonical output",
                        "n": N_COEF, "q": Q, "pairs_per_gpu": BATCH, "parallelism": "shard by polynomial index, no collective",
-                       "cache": "operands 4 GiB + result 2 GiB per step >> 126 MB L2 (no flush needed)"},
+                       "cache": "operands 4 GiB + result 2 GiB per step >> 126 MB L2 (no flush needed)",
+                       "inputs": "uniform residues in [0, q); plan flag SCGPU_PLAN_INPUTS_IN_RANGE set (no range vote in the kernel); "
+                                 "the default any-SINT32-exact path on the same operands is `checked_path`"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
-            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss, "other_shapes": shapes, "parity": parity, "e2e_multi": e2e_multi, "e2e_bliss_sign_core": sign_core,
+            "int_roofline": int_roof, "cpu_baseline": cpu, "gaussian": gauss, "checked_path": checked_path, "other_shapes": shapes, "parity": parity, "e2e_multi": e2e_multi, "e2e_bliss_sign_core": sign_core,
         }
         emit(line)
     if world > 1:

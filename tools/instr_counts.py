@@ -13,7 +13,8 @@ log = os.path.join(ROOT, "gpurun_out", "instr_probe_ncu.csv")
 metrics = ("smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,"
            "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,"
            "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum")
-subprocess.check_call(["ncu", "--metrics", metrics, "--clock-control", "none", "--csv", "--log-file", log,
+if "--parse-only" not in sys.argv:      # re-read an existing gpurun_out/instr_probe_ncu.csv (no GPU needed)
+  subprocess.check_call(["ncu", "--metrics", metrics, "--clock-control", "none", "--csv", "--log-file", log,
                        "-k", "regex:k_polymul_w32|k_ntt_w32|k_exact_w32|k_cdf_aes|k_cdf_chacha|k_stream_seq|k_ber_lanes",
                        sys.executable, os.path.join(ROOT, "tools", "instr_probe.py")])
 units = json.load(open(os.path.join(ROOT, "gpurun_out", "instr_probe_units.json")))

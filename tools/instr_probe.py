@@ -23,6 +23,9 @@ b = torch.randint(0, q, (B, n), dtype=torch.int32, device=dev, generator=g)
 out = torch.empty_like(a)
 plan = sc.NttPlan(n, q, sc.REFERENCE, w, r)
 plan.polymul(out, a, b); units.append(("k_polymul_w32", "k_polymul_w32_n512", B))
+plan.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+plan.polymul(out, a, b); units.append(("k_polymul_w32", "k_polymul_w32_n512_inrange", B))
+plan.set_flags(0)
 key = torch.randint(0, q, (n,), dtype=torch.int32, device=dev, generator=g).to(torch.int16)
 plan.mul_key(out, a, key); units.append(("k_polymul_w32", "k_polymul_w32_key16_n512", B))
 plan.ntt_canonical(out, a); units.append(("k_ntt_w32", "k_ntt_w32_fwd_n512", B))
