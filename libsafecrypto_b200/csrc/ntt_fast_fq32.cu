@@ -239,7 +239,7 @@ int launch_matvec_fq32(const NttPlanDev &p, int32_t *out, const int32_t *A, cons
                        size_t count, cudaStream_t st)
 {
     if (!p.fq32_ok || !p.fq32_mv_ok || p.logn != 8 || l > 4) return SCGPU_ERR_UNSUPPORTED;
-    return w32::launch_matvec_w32<ArFq>(fq32_const(p, p.fq32_r0_mv), p.sm_count, out, A, s, k, l, count, st);
+    return w32::launch_matvec_w32<ArFq>(fq32_const(p, p.fq32_r0_mv), p.sm_count, out, A, s, k, l, count, st, !p.inputs_in_range);
 }
 
 int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32_t *a, const void *b,

@@ -511,10 +511,10 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
                     if (MODE == FQ_KEY16) kv[i] = (int32_t)__ldg(static_cast<const int16_t *>(bsrc) + kbase + off);
                     else {
                         kv[i] = __ldg(static_cast<const int32_t *>(bsrc) + kbase + off);
-                        wide |= W::out_of_range(kv[i], c);
+                        if (CHK) wide |= W::out_of_range(kv[i], c);
                     }
                 }
-                if (MODE == FQ_KEY32 && __any_sync(0xFFFFFFFFu, wide)) {
+                if (CHK && MODE == FQ_KEY32 && __any_sync(0xFFFFFFFFu, wide)) {
 #pragma unroll
                     for (int i = 0; i < SUB; i++) kv[i] = W::bred(kv[i], c);
                 }
@@ -718,7 +718,7 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
 // brev5(e) * (n/32) + brev(tau) of the row (ntt_index), so for a fixed e the lanes of an instance read n/32
 // consecutive words: conflict-free from the staging row (instances 8 banks apart), one full sector from HBM
 // in the LDG variant.
-template <class AR, int LOGN, bool TMA>
+template <class AR, int LOGN, bool TMA, bool CHK = true>
 __global__ void __launch_bounds__(kThreads32)
 k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t *__restrict__ s,
               int k, int l, size_t count, unsigned long long *ctr, const __grid_constant__ W32Const<AR> c)
@@ -783,10 +783,10 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
             u32 x[32];
             int32_t *tile = dyn_tiles + ((size_t)(j + 1) * C::POLYS + slot) * C::TS;
             if (TMA) {
-                W::template load_operand_staged<LOGN>(x, tile, tau, c);
+                W::template load_operand_staged<LOGN, CHK>(x, tile, tau, c);
                 __syncwarp();
             } else {
-                W::template load_operand<LOGN>(x, s + (irow * l + j) * N, tau, c);
+                W::template load_operand<LOGN, CHK>(x, s + (irow * l + j) * N, tau, c);
             }
             W::fwd_pass0(x, c);
             store_pass0<LOGN>(tile, x, tau);
@@ -819,7 +819,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
 #pragma unroll
                     for (int e = 0; e < 32; e++) {
                         av[e] = astage[taurev + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5))];
-                        wide |= W::out_of_range(av[e], c);
+                        if (CHK) wide |= W::out_of_range(av[e], c);
                     }
                     // the staging row is in registers: put the next row (this instance's next step, or step 0
                     // of the warp's next instances) in flight before the arithmetic
@@ -835,11 +835,11 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
 #pragma unroll
                     for (int e = 0; e < 32; e++) {
                         av[e] = __ldg(arow + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5)));
-                        wide |= W::out_of_range(av[e], c);
+                        if (CHK) wide |= W::out_of_range(av[e], c);
                     }
                 }
                 // A is canonical in the reference (sampled in [0, q)); anything else is reduced first
-                if (__any_sync(0xFFFFFFFFu, wide)) {
+                if (CHK && __any_sync(0xFFFFFFFFu, wide)) {
 #pragma unroll
                     for (int e = 0; e < 32; e++) av[e] = W::bred(av[e], c);
                 }
@@ -895,7 +895,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
 // forward transforms run through the one exchange tile, and EVERY row of the instance -- s_0 .. s_{l-1}, then
 // A_00 .. A_{k-1,l-1} -- travels through ONE staging row and ONE mbarrier: as soon as a row is in registers the
 // next row of the sequence (or s_0 of the warp's next instances) is put in flight.  13-15 warps per SM.
-template <class AR, int LOGN, bool TMA>
+template <class AR, int LOGN, bool TMA, bool CHK = true>
 __global__ void __launch_bounds__(kThreads32, 16)        // 128 registers: 4 warps per scheduler fit (140 allowed 3)
 k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t *__restrict__ s,
                int k, int l, size_t count, unsigned long long *ctr, const __grid_constant__ W32Const<AR> c)
@@ -972,10 +972,10 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
             u32 x[32];
             if (TMA) {
                 mbar_wait(&bars[warp], parity); parity ^= 1u;
-                W::template load_operand_staged<LOGN>(x, stage, tau, c);
+                W::template load_operand_staged<LOGN, CHK>(x, stage, tau, c);
                 advance();
             } else {
-                W::template load_operand<LOGN>(x, s + (irow * l + j) * N, tau, c);
+                W::template load_operand<LOGN, CHK>(x, s + (irow * l + j) * N, tau, c);
             }
             W::fwd_pass0(x, c);
             store_pass0<LOGN>(xt, x, tau);
@@ -1014,7 +1014,7 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
 #pragma unroll
                     for (int e = 0; e < 32; e++) {
                         av[e] = stage[taurev + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5))];
-                        wide |= W::out_of_range(av[e], c);
+                        if (CHK) wide |= W::out_of_range(av[e], c);
                     }
                     advance();
                 } else {
@@ -1022,10 +1022,10 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
 #pragma unroll
                     for (int e = 0; e < 32; e++) {
                         av[e] = __ldg(arow + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5)));
-                        wide |= W::out_of_range(av[e], c);
+                        if (CHK) wide |= W::out_of_range(av[e], c);
                     }
                 }
-                if (__any_sync(0xFFFFFFFFu, wide)) {
+                if (CHK && __any_sync(0xFFFFFFFFu, wide)) {
 #pragma unroll
                     for (int e = 0; e < 32; e++) av[e] = W::bred(av[e], c);
                 }
@@ -1109,7 +1109,7 @@ inline bool tma_allowed()
 }
 
 // bm: base-multiplication kernel (FQ_POLYMUL, policies with AR::BASEMUL; c must carry the (n/4)^-1 entries);
-// chk = false: no range vote on the operands (FQ_POLYMUL only)
+// chk = false: no range vote on the operands
 template <class AR>
 int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, int32_t *out, const int32_t *a,
                        const void *b, size_t b_stride, size_t count, cudaStream_t st, bool bm = false, bool chk = true)
@@ -1119,7 +1119,7 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
     bool tma = ((uintptr_t)a % 16) == 0 && tma_allowed();
     if (mode == FQ_POLYMUL) tma = tma && ((uintptr_t)b % 16) == 0 && (b_stride % 4) == 0;
     unsigned long long *ctr = nullptr;               // work counter, only when the batch exceeds one grid-full
-    if (mode != FQ_POLYMUL) { bm = false; chk = true; }
+    if (mode != FQ_POLYMUL) bm = false;
     if (!AR::BASEMUL) bm = false;
 #define W32_GO(L, MODE, TMA_, BM_, CHK_) \
     k_polymul_w32<AR, L, MODE, TMA_, BM_, CHK_><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c)
@@ -1141,12 +1141,12 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
         if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }     \
         if (tma) {                                                                                         \
             if (mode == FQ_POLYMUL)    W32_PM(L, true)                                                     \
-            else if (mode == FQ_KEY16) W32_GO(L, FQ_KEY16, true, false, true);                             \
-            else                       W32_GO(L, FQ_KEY32, true, false, true);                             \
+            else if (mode == FQ_KEY16) { if (chk) W32_GO(L, FQ_KEY16, true, false, true); else W32_GO(L, FQ_KEY16, true, false, false); } \
+            else                       { if (chk) W32_GO(L, FQ_KEY32, true, false, true); else W32_GO(L, FQ_KEY32, true, false, false); } \
         } else {                                                                                           \
             if (mode == FQ_POLYMUL)    W32_PM(L, false)                                                    \
-            else if (mode == FQ_KEY16) W32_GO(L, FQ_KEY16, false, false, true);                            \
-            else                       W32_GO(L, FQ_KEY32, false, false, true);                            \
+            else if (mode == FQ_KEY16) { if (chk) W32_GO(L, FQ_KEY16, false, false, true); else W32_GO(L, FQ_KEY16, false, false, false); } \
+            else                       { if (chk) W32_GO(L, FQ_KEY32, false, false, true); else W32_GO(L, FQ_KEY32, false, false, false); } \
         }                                                                                                  \
     }
     switch (logn) {
@@ -1200,7 +1200,7 @@ int launch_ntt_w32(const W32Const<AR> &c, int logn, int sm_count, int inverse, i
 // n = 256 (Kyber, Dilithium)
 template <class AR>
 int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
-                      size_t count, cudaStream_t st)
+                      size_t count, cudaStream_t st, bool chk = true)
 {
     using C = Cfg32<8>;
     const bool tma = ((uintptr_t)A % 16) == 0 && ((uintptr_t)s % 16) == 0 && tma_allowed();
@@ -1216,7 +1216,8 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
     const int minl = minl_env ? atoi(minl_env) : 1;
     if (AR::STASH16 && c.q < 59000 && l >= minl && tma && !(no16 && atoi(no16) != 0)) {
         const size_t smem = ((size_t)C::POLYS * (C::TS + (C::N + C::T)) + (size_t)l * C::POLYS * (20 * C::T + C::T)) * sizeof(int32_t);
-        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         int per_sm = (int)((227 * 1024) / (smem + 1024 + 64));
         if (per_sm > 16) per_sm = 16;
         if (per_sm < 1) per_sm = 1;
@@ -1224,15 +1225,21 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
         if (grid > groups) grid = groups;
         if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; }
         if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }
-        k_matvec16_w32<AR, 8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+        if (chk) k_matvec16_w32<AR, 8, true, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+        else     k_matvec16_w32<AR, 8, true, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
         count_launch();
         SCGPU_CUDA_CHECK(cudaGetLastError());
         return SCGPU_OK;
     }
     const size_t smem = ((size_t)(l + 1) * C::POLYS * C::TS + (tma ? (size_t)C::POLYS * (C::N + C::T) : 0)) * sizeof(int32_t);
     // per launch, not once: the attribute belongs to the current device's context and plans exist per device
-    if (tma) SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    else     SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (tma) {
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    } else {
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_w32<AR, 8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
     if (smem > 200 * 1024) { set_error("matvec: l=%d needs %zu bytes of shared memory", l, smem); return SCGPU_ERR_UNSUPPORTED; }
     int per_sm = (int)((227 * 1024) / (smem + 1024 + 64));
     if (per_sm > 16) per_sm = 16;
@@ -1241,8 +1248,10 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
     if (grid > groups) grid = groups;
     if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; }
     if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }
-    if (tma) k_matvec_w32<AR, 8, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
-    else     k_matvec_w32<AR, 8, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+    if (tma && chk)  k_matvec_w32<AR, 8, true, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+    else if (tma)    k_matvec_w32<AR, 8, true, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+    else if (chk)    k_matvec_w32<AR, 8, false, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+    else             k_matvec_w32<AR, 8, false, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
     count_launch();
     SCGPU_CUDA_CHECK(cudaGetLastError());
     return SCGPU_OK;

@@ -691,3 +691,49 @@ def test_base_multiplication_and_in_range_flag(q, n):
         assert np.array_equal(out.cpu().numpy(), exp)
     for p in (p_bm, p_full, p_flag):
         p.close()
+
+
+@pytest.mark.parametrize("q,tw", [(7681, 16), (12289, 16), (8380417, 32)])
+def test_in_range_flag_on_key_products_and_matvec(q, tw):
+    """SCGPU_PLAN_INPUTS_IN_RANGE also drops the range votes of the key product and of the module mat-vec; for
+    operands inside the promised window the flagged plan returns the bits of the default plan (which the tests above
+    pin to the oracle), window edges included."""
+    n = 256
+    w, r = O.tables(q, n, tw)
+    p_def, _, _ = plan(q, n, tw, O.REFERENCE)
+    p_flag = sc.NttPlan(n, q, O.REFERENCE, w, r)
+    p_flag.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+    rng = np.random.default_rng(q)
+    x0 = 4 * q
+    for t in (rand_inputs(rng, "uniform", q, (131, n)), rand_inputs(rng, "signed", q, (131, n)),
+              rng.integers(-x0, x0 + 1, size=(131, n)).astype(np.int32), np.full((5, n), -x0, dtype=np.int32)):
+        rows = t.shape[0]
+        keys = [rng.integers(0, q, size=(rows, n)).astype(np.int32), rng.integers(-x0, x0 + 1, size=n).astype(np.int32)]
+        if tw == 16:
+            keys.append(rng.integers(-32768, 32768, size=n).astype(np.int16))
+        for key in keys:
+            o1 = torch.empty((rows, n), dtype=torch.int32, device=DEV)
+            o2 = torch.empty((rows, n), dtype=torch.int32, device=DEV)
+            p_def.mul_key(o1, dev(t), dev(key))
+            p_flag.mul_key(o2, dev(t), dev(key))
+            torch.cuda.synchronize()
+            assert torch.equal(o1, o2)
+            if key.dtype == np.int32 or tw == 16:
+                kk = key if key.ndim == 2 else np.tile(key, (rows, 1))
+                if key.dtype == np.int16:
+                    exp = O.port().ntt_batch(O.REFERENCE, O.OP_TRIPLE16, n, q, tw, t, key, w, r)
+                    assert np.array_equal(o2.cpu().numpy(), exp)
+    for k, l in ((2, 2), (3, 2), (4, 4)):
+        count = 37
+        A = rng.integers(0, q, size=(count, k, l, n)).astype(np.int32)
+        A[0] = x0
+        A[1] = -x0
+        s = rng.integers(-x0, x0 + 1, size=(count, l, n)).astype(np.int32)
+        s[2:] = rng.integers(-5, 6, size=(count - 2, l, n))
+        o1 = torch.empty((count, k, n), dtype=torch.int32, device=DEV)
+        o2 = torch.empty((count, k, n), dtype=torch.int32, device=DEV)
+        p_def.matvec(o1, dev(A), dev(s), k, l)
+        p_flag.matvec(o2, dev(A), dev(s), k, l)
+        torch.cuda.synchronize()
+        assert torch.equal(o1, o2), (k, l)
+    p_flag.close()

@@ -48,5 +48,28 @@ for n, q in ((512, 12289), (1024, 12289), (256, 7681)):
     same = torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     ok &= same
     print(line, " outputs", "equal" if same else "DIFFER", flush=True)
-    del a, b, outs
+    key = torch.randint(0, q, (n,), dtype=torch.int32, device=dev, generator=g).to(torch.int16)
+    o1, o2 = torch.empty((B, n), dtype=torch.int32, device=dev), torch.empty((B, n), dtype=torch.int32, device=dev)
+    t1 = timeit(lambda: p_bm.mul_key(o1, a, key)); t2 = timeit(lambda: p_flag.mul_key(o2, a, key))
+    same = torch.equal(o1, o2); ok &= same
+    print("key product n=%d: checked %.4g/s (%.3f)  in-range %.4g/s (%.3f)  outputs %s" % (
+        n, B / t1, 8 * n * B / t1 / PEAK, B / t2, 8 * n * B / t2 / PEAK, "equal" if same else "DIFFER"), flush=True)
+    del a, b, outs, o1, o2
+for q, tw, shapes in ((7681, 16, ((2, 2), (3, 3), (4, 4))), (8380417, 32, ((5, 4),))):
+    n = 256
+    w, r = O.tables(q, n, tw)
+    p_def = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    p_flag = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    p_flag.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+    for k, l in shapes:
+        Bm = 1 << 17
+        A = torch.randint(0, q, (Bm, k * l, n), dtype=torch.int32, device=dev, generator=g)
+        sv = torch.randint(-4, 5, (Bm, l, n), dtype=torch.int32, device=dev, generator=g)
+        o1 = torch.empty((Bm, k, n), dtype=torch.int32, device=dev); o2 = torch.empty_like(o1)
+        t1 = timeit(lambda: p_def.matvec(o1, A, sv, k, l)); t2 = timeit(lambda: p_flag.matvec(o2, A, sv, k, l))
+        same = torch.equal(o1, o2); ok &= same
+        bpi = 4 * n * (k * l + l + k)
+        print("mat-vec q=%d k=%d l=%d: checked %.4g/s (%.3f)  in-range %.4g/s (%.3f)  outputs %s" % (
+            q, k, l, Bm / t1, bpi * Bm / t1 / PEAK, Bm / t2, bpi * Bm / t2 / PEAK, "equal" if same else "DIFFER"), flush=True)
+        del A, sv, o1, o2
 sys.exit(0 if ok else 1)
