@@ -158,5 +158,32 @@ FQ_HD void basemul4(int32_t (&c)[4], const int32_t (&a)[4], const int32_t (&b)[4
     }
 }
 
+// The same product against a KEY whose residues modulo X^4 - zeta were prepared once per launch (ntt_fast_fq32.cu:
+// k_key_residues): b[0..3] and zb[i] = zeta b[i] (centred, |.| <= q/2) with their float copies, so the run-time side
+// needs no product with zeta and converts only a:
+//     c_k = sum_{i <= k} a_i b_{k-i}  +  sum_{i > k} a_i zb_{k-i+4}
+// a UNBIASED, c BIASED.  4 conversions + 16 + 16 multiply-adds + 4 quotients = 44 instructions per four coefficients.
+FQ_HD void basemul4_key(int32_t (&c)[4], const int32_t (&a)[4], const int32_t (&b)[4], const float (&bf)[4],
+                        const int32_t (&zb)[4], const float (&zbf)[4], float invq, int32_t pwb, int32_t nq)
+{
+    float af[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) af[i] = i2f(a[i]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int32_t p = mad(a[0], b[k], pwb);
+        float f = mul_rn(af[0], bf[k]);
+#pragma unroll
+        for (int i = 1; i < 4; i++) {
+            const int j = (k - i) & 3;
+            const bool wrap = i > k;
+            p = mad(a[i], wrap ? zb[j] : b[j], p);
+            f = fma_rn(af[i], wrap ? zbf[j] : bf[j], f);
+        }
+        const float g = fma_rn(f, invq, kBiasF);
+        c[k] = mad(as_i(g), nq, p);
+    }
+}
+
 }  // namespace fq
 }  // namespace scgpu

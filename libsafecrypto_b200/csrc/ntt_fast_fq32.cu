@@ -99,6 +99,19 @@ struct ArFq {
 #pragma unroll
         for (int i = 0; i < 4; i++) xa[i] = (u32)c[i];
     }
+    // xa[0..3] (unbiased) <- xa * key modulo X^4 - zeta, biased; the four vectors are one block of the residue table
+    static __device__ __forceinline__ void bmk4(u32 *xa, const int4 &vb, const int4 &vbf, const int4 &vz, const int4 &vzf, const K &k)
+    {
+        int32_t a[4], c[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = (int32_t)xa[i];
+        const int32_t b[4] = {vb.x, vb.y, vb.z, vb.w}, zb[4] = {vz.x, vz.y, vz.z, vz.w};
+        const float bf[4] = {__int_as_float(vbf.x), __int_as_float(vbf.y), __int_as_float(vbf.z), __int_as_float(vbf.w)};
+        const float zbf[4] = {__int_as_float(vzf.x), __int_as_float(vzf.y), __int_as_float(vzf.z), __int_as_float(vzf.w)};
+        fq::basemul4_key(c, a, b, bf, zb, zbf, k.invq, k.pwb, k.nq);
+#pragma unroll
+        for (int i = 0; i < 4; i++) xa[i] = (u32)c[i];
+    }
     static __device__ __forceinline__ void gs(u32 &lo, u32 &hi, const E &z, const K &k)
     {
         const u32 d = lo - hi + (u32)kBias;
@@ -168,12 +181,49 @@ FqConst32 fq32_const(const NttPlanDev &p, int r0, bool bm = false)
     return c;
 }
 
+// ---- key residues for the base-multiplication key product -------------------------------------------------------
+// The key arrives fully transformed (the reference's NTT-domain order).  Two Gentleman-Sande stages and a factor 1/4
+// take the four point values of block b back to the residue modulo X^4 - zeta_b; the table also holds zeta_b times
+// the residue and float copies of both (fq_arith.cuh: basemul4_key).  One thread per block, 64-bit arithmetic: n/4
+// threads per launch, negligible against the batch.  ktab (plan): [zi of stage logn-2 (n/4) | zi of stage logn-1
+// (n/2) | zeta (n/4)], residues in [0, q).
+template <class KT>
+__global__ void k_key_residues(int32_t *__restrict__ kres, const KT *__restrict__ key, const int32_t *__restrict__ ktab,
+                               int logn, int32_t q, int32_t inv4)
+{
+    const int n = 1 << logn, nb = n >> 2, T = n >> 5;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    auto modq = [q](long long v) { long long r = v % q; return r < 0 ? r + q : r; };
+    long long v[4];
+    for (int i = 0; i < 4; i++) {
+        const unsigned pos = (unsigned)(4 * b + i);
+        const unsigned idx = __brev(pos) >> (32 - logn);                  // reference index of internal position pos
+        v[i] = modq((long long)key[idx]);
+    }
+    const long long zc = ktab[b], za = ktab[nb + 2 * b], zb_ = ktab[nb + 2 * b + 1], zeta = ktab[nb + 2 * nb + b];
+    const long long u0 = v[0] + v[1], u1 = modq((v[0] - v[1]) * za), u2 = v[2] + v[3], u3 = modq((v[2] - v[3]) * zb_);
+    long long r[4] = {u0 + u2, u1 + u3, modq((u0 - u2) * zc), modq((u1 - u3) * zc)};
+    const int tau = b >> 3, j = b & 7;
+    int32_t *o = kres + ((size_t)(4 * j) * T + tau) * 4;          // vector v of the block at o + 4 T v
+    for (int i = 0; i < 4; i++) {
+        long long x = modq(modq(r[i]) * inv4);
+        long long z = modq(x * zeta);
+        if (x > q / 2) x -= q;
+        if (z > q / 2) z -= q;
+        o[i] = (int32_t)x;
+        o[4 * T + i] = __float_as_int((float)(int32_t)x);
+        o[8 * T + i] = i ? (int32_t)z : 0;
+        o[12 * T + i] = i ? __float_as_int((float)(int32_t)z) : 0;
+    }
+}
+
 }  // namespace
 
 int build_fq32_tables(NttPlanDev &p, const int32_t *w_host)
 {
     p.fq32_ok = 0; p.fq32_tab = nullptr;
-    p.fq32_bm_ok = 0; p.fq32_zeta = nullptr;
+    p.fq32_bm_ok = 0; p.fq32_zeta = nullptr; p.fq32_ktab = nullptr;
     if (p.logn < 8 || p.logn > 10) return SCGPU_OK;
     int r0 = 0; int32_t x0 = 0;
     if (!fq::analyse32(p.logn, p.rc.q, 1, &r0, &x0)) return SCGPU_OK;
@@ -220,6 +270,13 @@ int build_fq32_tables(NttPlanDev &p, const int32_t *w_host)
         SCGPU_CUDA_CHECK(cudaMemcpy(p.fq32_zeta, zp.data(), sizeof(int32_t) * zp.size(), cudaMemcpyHostToDevice));
         memcpy(p.fq32_ninv_bm, &ninv_bm, sizeof(Tw));
         memcpy(p.fq32_i01_bm, &i01_bm, sizeof(Tw));
+        // table of k_key_residues: inverse twiddles of the last two stages (natural index) and zeta, in [0, q)
+        std::vector<int32_t> kt((size_t)n);
+        for (int b = 0; b < n / 4; b++) { kt[b] = zi[n / 4 + b].w; kt[n / 4 + n / 2 + b] = zw[b]; }
+        for (int b = 0; b < n / 2; b++) kt[n / 4 + b] = zi[n / 2 + b].w;
+        SCGPU_CUDA_CHECK(cudaMalloc(&p.fq32_ktab, sizeof(int32_t) * kt.size()));
+        SCGPU_CUDA_CHECK(cudaMemcpy(p.fq32_ktab, kt.data(), sizeof(int32_t) * kt.size(), cudaMemcpyHostToDevice));
+        p.fq32_inv4 = (int32_t)fq::powmod(4, p.rc.q - 2, p.rc.q);
         p.fq32_r0_bm = r0_bm;
         p.fq32_bm_ok = 1;
     }
@@ -230,7 +287,8 @@ void free_fq32_tables(NttPlanDev &p)
 {
     if (p.fq32_tab) cudaFree(p.fq32_tab);
     if (p.fq32_zeta) cudaFree(p.fq32_zeta);
-    p.fq32_tab = nullptr; p.fq32_zeta = nullptr;
+    if (p.fq32_ktab) cudaFree(p.fq32_ktab);
+    p.fq32_tab = nullptr; p.fq32_zeta = nullptr; p.fq32_ktab = nullptr;
     p.fq32_ok = 0; p.fq32_bm_ok = 0;
 }
 
@@ -245,6 +303,23 @@ int launch_matvec_fq32(const NttPlanDev &p, int32_t *out, const int32_t *A, cons
 int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32_t *a, const void *b,
                         size_t b_stride, size_t count, cudaStream_t st)
 {
+    if (mode != w32::FQ_POLYMUL && b_stride == 0 && p.fq32_bm_ok) {
+        // shared key (the BLISS signing product): its residues modulo X^4 - zeta are prepared once for the launch in
+        // a stream-ordered scratch, then the batch runs the base-multiplication key product
+        int32_t *kres = nullptr;
+        SCGPU_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&kres), sizeof(int32_t) * 4 * (size_t)p.n, st));
+        const int nb = p.n / 4, th = 64;
+        if (mode == w32::FQ_KEY16)
+            k_key_residues<int16_t><<<(nb + th - 1) / th, th, 0, st>>>(kres, static_cast<const int16_t *>(b), static_cast<const int32_t *>(p.fq32_ktab), p.logn, p.rc.q, p.fq32_inv4);
+        else
+            k_key_residues<int32_t><<<(nb + th - 1) / th, th, 0, st>>>(kres, static_cast<const int32_t *>(b), static_cast<const int32_t *>(p.fq32_ktab), p.logn, p.rc.q, p.fq32_inv4);
+        count_launch();
+        int e = w32::launch_polymul_w32<ArFq>(fq32_const(p, p.fq32_r0_bm, true), p.logn, p.sm_count, w32::FQ_KEYBM, out, a, kres, 0,
+                                              count, st, true, !p.inputs_in_range);
+        const cudaError_t fe = cudaFreeAsync(kres, st);
+        if (e == SCGPU_OK && fe != cudaSuccess) { set_error("cudaFreeAsync failed: %s", cudaGetErrorString(fe)); e = SCGPU_ERR_CUDA; }
+        return e;
+    }
     const bool bm = mode == w32::FQ_POLYMUL && p.fq32_bm_ok;
     return w32::launch_polymul_w32<ArFq>(fq32_const(p, bm ? p.fq32_r0_bm : p.fq32_r0, bm), p.logn, p.sm_count, mode, out, a, b,
                                          b_stride, count, st, bm, !p.inputs_in_range);

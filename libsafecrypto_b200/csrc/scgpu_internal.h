@@ -55,6 +55,8 @@ struct NttPlanDev {
     // degree-3 base multiplication of the two-operand product (fq_arith.cuh: basemul4); 0: (q, n) outside its bounds
     int fq32_bm_ok, fq32_r0_bm;
     void *fq32_zeta;                     // (w, wq) of zeta per block of four, [pair][tau][4 words]: n/2 words
+    void *fq32_ktab;                     // k_key_residues: [zi stage logn-2 | zi stage logn-1 | zeta], n words
+    int32_t fq32_inv4;                   // 4^-1 mod q
     alignas(16) unsigned char fq32_ninv_bm[16], fq32_i01_bm[16];      // last inverse stage with (n/4)^-1
     int inputs_in_range;                 // SCGPU_PLAN_INPUTS_IN_RANGE: the fused products skip the range vote
     // Shoup / Montgomery arithmetic on the same schedule, for moduli up to 2^25 (ntt_fast_sh32.cu)

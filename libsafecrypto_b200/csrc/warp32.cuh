@@ -163,7 +163,8 @@ __device__ __forceinline__ void load_pass0(const int32_t *tile, u32 (&x)[32], in
     for (int m = 0; m < 32; m++) x[m] = (u32)tile[tau + pos32(T * m)];
 }
 
-enum { FQ_POLYMUL = 0, FQ_KEY16 = 1, FQ_KEY32 = 2 };
+// FQ_KEYBM: key product against a residue table prepared per launch (base multiplication, policies with AR::BASEMUL)
+enum { FQ_POLYMUL = 0, FQ_KEY16 = 1, FQ_KEY32 = 2, FQ_KEYBM = 3 };
 
 // reference NTT-domain index of the thread's pass-1 element e (position 32 tau + e of the bit-reversed order):
 // brev(32 tau + e) = brev5(e) << (LOGN - 5) | brev_{LOGN-5}(tau); for fixed e the lanes of a polynomial read
@@ -312,16 +313,30 @@ static __device__ __forceinline__ void fwd_stages1(u32 (&xa)[Cfg32<LOGN>::SUB], 
         fwd_stages1<LOGN, S + 1, NOPS>(xa, xb, c, tau, h);
     }
 }
-// forward stages S .. LOGN - 3 of both operands, the last one emitting unbiased values
-template <int LOGN, int S>
+// forward stages S .. LOGN - 3 of NOPS operands, the last one emitting unbiased values
+template <int LOGN, int S, int NOPS = 2>
 static __device__ __forceinline__ void fwd_stages1_bm(u32 (&xa)[Cfg32<LOGN>::SUB], u32 (&xb)[Cfg32<LOGN>::SUB],
                                                const Const &c, int tau, int h)
 {
     if constexpr (S < LOGN - 3) {
-        stage1<LOGN, S, 2, false, Cfg32<LOGN>::SUB>(xa, xb, c, tau, h);
-        fwd_stages1_bm<LOGN, S + 1>(xa, xb, c, tau, h);
+        stage1<LOGN, S, NOPS, false, Cfg32<LOGN>::SUB>(xa, xb, c, tau, h);
+        fwd_stages1_bm<LOGN, S + 1, NOPS>(xa, xb, c, tau, h);
     } else {
-        stage1<LOGN, S, 2, false, Cfg32<LOGN>::SUB, true>(xa, xb, c, tau, h);
+        stage1<LOGN, S, NOPS, false, Cfg32<LOGN>::SUB, true>(xa, xb, c, tau, h);
+    }
+}
+// xa <- xa * key modulo X^4 - zeta for the SUB / 4 blocks of sub-chunk h; kres = the launch's residue table,
+// 16 words per block as four 128-bit vectors [b | float b | zeta b | float zeta b]; vector v of block j of thread tau
+// at ((4 j + v) T + tau) 4: the lanes of a polynomial read contiguous 16-byte words
+template <int LOGN>
+static __device__ __forceinline__ void keymul_sub(u32 (&xa)[Cfg32<LOGN>::SUB], const int32_t *kres, const Const &c, int tau, int h)
+{
+    using C = Cfg32<LOGN>;
+    constexpr int GROUPS = C::SUB / 4;
+#pragma unroll
+    for (int g = 0; g < GROUPS; g++) {
+        const int4 *p = reinterpret_cast<const int4 *>(kres) + (h * GROUPS + g) * 4 * C::T + tau;
+        AR::bmk4(&xa[4 * g], __ldg(p), __ldg(p + C::T), __ldg(p + 2 * C::T), __ldg(p + 3 * C::T), c.k);
     }
 }
 // xa <- xa * xb modulo X^4 - zeta for the SUB / 4 blocks of sub-chunk h (fq_arith.cuh: basemul4)
@@ -468,6 +483,13 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
             int32_t *tile = op == 0 ? ta : tb;
             if (TMA) {
                 mbar_wait(&bars[warp][op], parity);
+                if (MODE != FQ_POLYMUL) {
+                    // key product: only one operand streams, so the other region is free for the WHOLE iteration --
+                    // the next product's rows are put in flight a full iteration ahead (its group is known: Claim)
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && nbase < count) fetch(0, nbase, tb - (lane / T) * C::TS);
+                }
                 W::template load_operand_staged<LOGN, CHK>(x, tile, tau, c);
                 __syncwarp();                     // the padded result overwrites the raw row in place
             } else {
@@ -487,7 +509,11 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
             u32 xa[SUB], xb[SUB];
             int32_t *pa = ta + 36 * tau + SUB * h;
             load_sub<SUB>(pa, xa);
-            if constexpr (MODE == FQ_POLYMUL && BM) {
+            if constexpr (MODE == FQ_KEYBM) {
+                static_assert(MODE != FQ_KEYBM || BM, "the residue-table key product is a base multiplication");
+                W::template fwd_stages1_bm<LOGN, C::S1, 1>(xa, xb, c, tau, h);
+                W::template keymul_sub<LOGN>(xa, static_cast<const int32_t *>(bsrc), c, tau, h);
+            } else if constexpr (MODE == FQ_POLYMUL && BM) {
                 load_sub<SUB>(tb + 36 * tau + SUB * h, xb);
                 W::template fwd_stages1_bm<LOGN, C::S1>(xa, xb, c, tau, h);
                 W::template basemul_sub<LOGN>(xa, xb, c, tau, h);
@@ -529,7 +555,7 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
         if (TMA) fence_proxy_async();
         __syncwarp();
         // tb is free from here on: the next product's a rows go there
-        if (TMA && lane == 0 && nbase < count) fetch(0, nbase, tb - (lane / T) * C::TS);
+        if (TMA && MODE == FQ_POLYMUL && lane == 0 && nbase < count) fetch(0, nbase, tb - (lane / T) * C::TS);
         {
             u32 x[32];
             load_pass0<LOGN>(ta, x, tau);
@@ -1119,7 +1145,8 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
     bool tma = ((uintptr_t)a % 16) == 0 && tma_allowed();
     if (mode == FQ_POLYMUL) tma = tma && ((uintptr_t)b % 16) == 0 && (b_stride % 4) == 0;
     unsigned long long *ctr = nullptr;               // work counter, only when the batch exceeds one grid-full
-    if (mode != FQ_POLYMUL) bm = false;
+    if (mode == FQ_KEYBM && !(AR::BASEMUL && bm)) { set_error("key residue product: not available for this arithmetic"); return SCGPU_ERR_UNSUPPORTED; }
+    if (mode != FQ_POLYMUL && mode != FQ_KEYBM) bm = false;
     if (!AR::BASEMUL) bm = false;
 #define W32_GO(L, MODE, TMA_, BM_, CHK_) \
     k_polymul_w32<AR, L, MODE, TMA_, BM_, CHK_><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, b, b_stride, count, ctr, c)
@@ -1132,6 +1159,12 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
         if (!bm && chk) W32_GO(L, FQ_POLYMUL, TMA_, false, true);                                          \
         else if (!bm)   W32_GO(L, FQ_POLYMUL, TMA_, false, false);                                         \
     }
+#define W32_KB(L, TMA_)                                                                                    \
+    {                                                                                                      \
+        if constexpr (AR::BASEMUL) {                                                                       \
+            if (chk) W32_GO(L, FQ_KEYBM, TMA_, true, true); else W32_GO(L, FQ_KEYBM, TMA_, true, false);   \
+        }                                                                                                  \
+    }
 #define W32_LAUNCH(L)                                                                                      \
     {                                                                                                      \
         const size_t groups = (count + Cfg32<L>::POLYS - 1) / Cfg32<L>::POLYS;                             \
@@ -1139,7 +1172,8 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
         if (grid > groups) grid = groups;                                                                  \
         if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; } \
         if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }     \
-        if (tma) {                                                                                         \
+        if (mode == FQ_KEYBM) { if (tma) W32_KB(L, true) else W32_KB(L, false) }                           \
+        else if (tma) {                                                                                    \
             if (mode == FQ_POLYMUL)    W32_PM(L, true)                                                     \
             else if (mode == FQ_KEY16) { if (chk) W32_GO(L, FQ_KEY16, true, false, true); else W32_GO(L, FQ_KEY16, true, false, false); } \
             else                       { if (chk) W32_GO(L, FQ_KEY32, true, false, true); else W32_GO(L, FQ_KEY32, true, false, false); } \
@@ -1156,6 +1190,7 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
     default: set_error("unsupported n=%d", 1 << logn); return SCGPU_ERR_UNSUPPORTED;
     }
 #undef W32_LAUNCH
+#undef W32_KB
 #undef W32_PM
 #undef W32_GO
     count_launch();
