@@ -367,6 +367,9 @@ def main():
                 sv = torch.randint(-4, 5, (inst, k, nn), dtype=torch.int32, device=dev, generator=g)
                 to = torch.empty((inst, k, nn), dtype=torch.int32, device=dev)
                 put("kyber_matvec_k3_n256_q7681", inst, timed(lambda: pl.matvec(to, A, sv, k, k)), 4 * nn * (k * k + 2 * k), "instance")
+                pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+                put("kyber_matvec_k3_n256_q7681_inputs_in_range", inst, timed(lambda: pl.matvec(to, A, sv, k, k)), 4 * nn * (k * k + 2 * k), "instance")
+                pl.set_flags(0)
                 # the same product with the matrix sampled on the device from a 32-byte seed per instance
                 # (create_rand_product_16_csprng): 4 n (l + k) + 32 bytes of HBM per instance, generator-bound
                 sd = torch.randint(0, 256, (inst, 32), dtype=torch.uint8, device=dev, generator=g)
@@ -377,7 +380,8 @@ def main():
             del xa, xb, xo, pl
         # BLISS sign / verify core: v = INTT(NTT(t) o key), one shared SINT16 key (bliss_b.c:1378-1384): 8 n bytes
         key = torch.randint(0, Q, (N_COEF,), dtype=torch.int32, device=dev, generator=g).to(torch.int16)
-        put("bliss_key_product_n512_q12289", BATCH, timed(lambda: plan.mul_key(out, a, key)), 8 * N_COEF, "product")
+        put("bliss_key_product_n512_q12289", BATCH, timed(lambda: plan_checked.mul_key(out, a, key)), 8 * N_COEF, "product")
+        put("bliss_key_product_n512_q12289_inputs_in_range", BATCH, timed(lambda: plan.mul_key(out, a, key)), 8 * N_COEF, "product")
         # single transforms with canonical output (normalize_32 o fwd_ntt, inv_ntt), n = 512: 8 n bytes each
         put("fwd_ntt_canonical_n512_q12289", BATCH, timed(lambda: plan.ntt_canonical(out, a)), 8 * N_COEF, "ntt")
         put("inv_ntt_canonical_n512_q12289", BATCH, timed(lambda: plan.ntt_canonical(out, a, inverse=True)), 8 * N_COEF, "ntt")
@@ -402,6 +406,8 @@ def main():
         sv = torch.randint(-2, 3, (inst, 4, nn), dtype=torch.int32, device=dev, generator=g)
         to = torch.empty((inst, 5, nn), dtype=torch.int32, device=dev)
         put("dilithium_matvec_k5_l4_n256", inst, timed(lambda: pl.matvec(to, A, sv, 5, 4)), 4 * nn * (20 + 4 + 5), "instance")
+        pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+        put("dilithium_matvec_k5_l4_n256_inputs_in_range", inst, timed(lambda: pl.matvec(to, A, sv, 5, 4)), 4 * nn * (20 + 4 + 5), "instance")
         del A, sv, to, pl
 
     # ---- end-to-end leg: host buffers through the C-ABI ----------------------------------------------------

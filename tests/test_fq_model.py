@@ -19,3 +19,6 @@ def test_float_quotient_model_matches_schoolbook_and_bounds(tmp_path):
     # the headline parameter sets are served by this arithmetic
     for line in ("q=12289 n=512 ok=1", "q=12289 n=1024 ok=1", "q=7681 n=256 ok=1"):
         assert line in out.stdout
+    # ... and their two-operand products by the degree-3 base multiplication (fq_arith.cuh: basemul4), without the
+    # extra reduction pass (r0 = 0) -- three of the four served sets (q = 12289 at n = 256 too)
+    assert out.stdout.count("warp-local schedule with base multiplication: r0=0") >= 4

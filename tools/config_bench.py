@@ -35,6 +35,10 @@ def report(name, units, secs, bytes_per_unit, unit="polymul"):
     print("%-44s %10.4g %s/s  %7.0f GB/s  %.3f of HBM peak" % (name, rate, unit, rate * bytes_per_unit / 1e9, rate * bytes_per_unit / 1e9 / PEAK))
 
 
+# SCGPU_BENCH_IN_RANGE=1: the fused plans carry SCGPU_PLAN_INPUTS_IN_RANGE (no range votes; the operands here are canonical)
+IN_RANGE = os.environ.get("SCGPU_BENCH_IN_RANGE", "0") not in ("", "0")
+
+
 def rnd(q, shape):
     return torch.randint(0, q, shape, dtype=torch.int32, device=dev, generator=g)
 
@@ -44,6 +48,7 @@ for n in (512, 1024):
     q, B = 12289, (1 << 29) // (4 * n)
     w, r = O.tables(q, n, 16)
     pl = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    if IN_RANGE: pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
     a, b, o = rnd(q, (B, n)), rnd(q, (B, n)), torch.empty((B, n), dtype=torch.int32, device=dev)
     report("C2 polymul n=%d q=12289" % n, B, timeit(lambda: pl.polymul(o, a, b)), 12 * n)
     key = rnd(q, (n,)).to(torch.int16)
@@ -61,6 +66,7 @@ for n in (512, 1024):
 q, n = 7681, 256
 w, r = O.tables(q, n, 16)
 pl = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+if IN_RANGE: pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
 for k in (2, 3, 4):
     B = 1 << 17
     A, s = rnd(q, (B, k * k, n)), torch.randint(-4, 5, (B, k, n), dtype=torch.int32, device=dev, generator=g)
@@ -74,6 +80,7 @@ report("C3 polymul n=256 q=7681", 1 << 20, timeit(lambda: pl.polymul(o, a, b)), 
 q = 8380417
 w, r = O.tables(q, n, 32)
 pl = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+if IN_RANGE: pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
 a, b = rnd(q, (1 << 20, n)), rnd(q, (1 << 20, n))
 report("C4 polymul n=256 q=8380417 (Shoup, warp-local)", 1 << 20, timeit(lambda: pl.polymul(o, a, b)), 12 * n)
 report("C4 canonical fwd NTT n=256 q=8380417", 1 << 20, timeit(lambda: pl.ntt_canonical(o, a)), 8 * n, "ntt")

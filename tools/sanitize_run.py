@@ -17,6 +17,24 @@ for q, n, tw in ((12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417,
     pl.polymul(out, torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))
     torch.cuda.synchronize()
     ok &= np.array_equal(out.cpu().numpy()[:64], O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a[:64], b[:64], w, r))
+    # round 2: shared-key product (k_key_residues + the residue-table kernel), per-row keys, and the kernels without range
+    # votes (SCGPU_PLAN_INPUTS_IN_RANGE)
+    ta = torch.from_numpy(a).to(dev)
+    key = torch.from_numpy(rng.integers(0, q, n).astype(np.int16 if tw == 16 else np.int32)).to(dev)
+    pl.mul_key(out, ta, key)
+    torch.cuda.synchronize()
+    if tw == 16:
+        ok &= np.array_equal(out.cpu().numpy()[:64], O.port().ntt_batch(O.REFERENCE, O.OP_TRIPLE16, n, q, tw, a[:64], key.cpu().numpy(), w, r))
+    keys = torch.from_numpy(rng.integers(0, q, (rows, n)).astype(np.int32)).to(dev)
+    pl.mul_key(out, ta, keys)
+    pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+    pl.polymul(out, ta, torch.from_numpy(b).to(dev))
+    pl.mul_key(out, ta, key)
+    pl.ntt_canonical(out, ta)
+    pl.ntt_canonical(out, ta, inverse=True)
+    torch.cuda.synchronize()
+    ok &= np.array_equal(out.cpu().numpy()[:16], O.port().ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, a[:16], None, w, r))
+    pl.set_flags(0)
     if n == 256:
         k = 3
         A = rng.integers(0, q, (9000, k * k, n)).astype(np.int32); s = rng.integers(-4, 5, (9000, k, n)).astype(np.int32)
