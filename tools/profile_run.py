@@ -21,10 +21,17 @@ g = torch.Generator(device=dev).manual_seed(1)
 a = torch.randint(0, q, (B, n), dtype=torch.int32, device=dev, generator=g)
 b = torch.randint(0, q, (B, n), dtype=torch.int32, device=dev, generator=g)
 out = torch.empty_like(a)
-if what in ("polymul", "all"):
+if what in ("polymul", "polymul_inrange", "all"):
     plan = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    if what == "polymul_inrange":
+        plan.set_flags(sc.PLAN_INPUTS_IN_RANGE)          # the bench's headline configuration: no range vote
     for _ in range(5):
         plan.polymul(out, a, b)
+if what == "keyproduct":
+    plan = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    key = torch.randint(0, q, (n,), dtype=torch.int32, device=dev, generator=g).to(torch.int16)
+    for _ in range(5):
+        plan.mul_key(out, a, key)
 if what in ("fwd", "all"):
     for v in (sc.REFERENCE, sc.FP, sc.BARRETT):
         p = sc.NttPlan(n, q, v, w, r)
