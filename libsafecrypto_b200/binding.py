@@ -46,6 +46,7 @@ def lib():
         L.scgpu_ntt_plan_destroy.argtypes = [vp]
         L.scgpu_ntt_plan_destroy.restype = None
         L.scgpu_ntt_plan_set_flags.argtypes = [vp, ctypes.c_uint]
+        L.scgpu_gauss_cdf_table_high.argtypes = [vp, sz, ctypes.POINTER(sz), ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float]
         L.scgpu_ntt_batch.argtypes = [vp, ctypes.c_int, vp, vp, vp, sz, sz, i32, vp, vp]
         L.scgpu_ntt_batch_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, sz, sz, i32, vp]
         L.scgpu_polymul_batch.argtypes = [vp, vp, vp, vp, sz, sz, vp]

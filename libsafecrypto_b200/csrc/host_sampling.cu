@@ -194,6 +194,13 @@ extern "C" int scgpu_gauss_plan_create(scgpu_gauss_plan_t **out, int sampler, in
     SCGPU_CUDA_CHECK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { set_error("gauss_plan_create: device %d of %d", device, ndev); return SCGPU_ERR_ARG; }
     SCGPU_CUDA_CHECK(cudaSetDevice(device));
+    if (sampler == SCGPU_SAMPLER_CDF && (precision == 128 || precision == 192)) {
+        // gaussian_cdf_create_128 / _192 (gaussian_cdf.c:385-397): the table of gauss_cdf_create_high_precision is built
+        // on the host (cdf_hp.cu), the sampling runs over it as over a caller-built table
+        if (!(tail * sigma >= 2.0f)) { set_error("gauss_plan_create: tail * sigma too small"); return SCGPU_ERR_ARG; }
+        const std::vector<uint64_t> t = build_cdf_high(precision, blinding, tail, sigma);
+        return scgpu_gauss_plan_create_table(out, precision, blinding, t.data(), t.size() / (size_t)(precision / 64), device);
+    }
     scgpu_gauss_plan *p = new scgpu_gauss_plan();
     memset(&p->t, 0, sizeof(p->t));
     p->t.sampler = sampler; p->t.precision = precision; p->t.blinding = blinding;

@@ -1,5 +1,6 @@
 // scgpu_internal.h -- shared between the translation units of libscgpu.so (not installed).
 #pragma once
+#include <vector>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstddef>
@@ -87,6 +88,8 @@ struct ExactArgs {
 };
 
 int launch_exact(const NttPlanDev &plan, const ExactArgs &args, cudaStream_t stream);
+// cdf_hp.cu: table of gauss_cdf_create_high_precision (host set-up): entries x precision/64 words, word 0 least significant
+std::vector<uint64_t> build_cdf_high(int precision, int blinding, float tail, float sigma);
 int launch_gen_rings(int prng_type, const uint8_t *seeds, size_t seed_len, size_t count, int32_t *out, int n, int k, int l,
                      int transpose, int32_t q, uint32_t q_bits, cudaStream_t stream);
 int build_xw32_tables(NttPlanDev &plan, const int32_t *w_host, const int32_t *r_host);

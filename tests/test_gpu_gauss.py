@@ -292,6 +292,30 @@ def test_dropin_sampler_api():
         h = ctypes.c_void_p(smp)
         assert L.destroy_sampler(ctypes.byref(h)) == 0
         L.prng_destroy(ctx)
+        # 128 / 192-bit CDF through the drop-in (func_alg_bliss_b.c:118 asks for SAMPLING_128BIT): the table is built by the
+        # library (csrc/cdf_hp.cu), the samples are those of the port's sampler over that table on the same word stream
+        for precision in (128, 192):
+            ctx = L.prng_create(5, prng, 0, 0x00100000)
+            assert L.prng_set_entropy(ctx, seed, len(seed)) == 0 and L.prng_init(ctx, b"SAFEcrypto nonce", 16) == 0
+            smp = L.create_sampler(0, precision, 0, 512, 0, ctx, 13.42, 215.0)
+            assert smp, precision
+            v = np.zeros(300, dtype=np.int32)
+            L.get_vector_32(smp, v.ctypes.data, 300, 0.0)
+            nent = ctypes.c_size_t(0)
+            assert L.scgpu_gauss_cdf_table_high(None, 0, ctypes.byref(nent), precision, 0, 13.42, 215.0) == 0
+            tabh = np.zeros((nent.value, precision // 64), dtype=np.uint64)
+            assert L.scgpu_gauss_cdf_table_high(tabh.ctypes.data, nent.value, ctypes.byref(nent), precision, 0, 13.42, 215.0) == 0
+            O.port().set_high_table(precision, tabh)
+            sd = np.frombuffer(seed, dtype=np.uint8)[None, :].copy()
+            exp = O.port().gauss_streams(O.SAMPLER_CDF, precision, 0, prng, 13.42, 215.0, sd, 300)
+            assert np.array_equal(v, exp[0]), precision
+            h = ctypes.c_void_p(smp)
+            assert L.destroy_sampler(ctypes.byref(h)) == 0
+            L.prng_destroy(ctx)
+        ctx = L.prng_create(5, prng, 0, 0x00100000)
+        assert L.prng_set_entropy(ctx, seed, len(seed)) == 0 and L.prng_init(ctx, b"SAFEcrypto nonce", 16) == 0
+        assert not L.create_sampler(0, 256, 0, 512, 0, ctx, 13.42, 215.0)      # the reference's 256-bit sampler reads an uninitialised word
+        L.prng_destroy(ctx)
 
 
 @pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libscref.so not built")
@@ -365,3 +389,35 @@ def test_mw_bootstrap_dropin_api():
         L.prng_destroy(ctx)
         results.append([int(x) for x in got])
     assert results[0] == results[1]
+
+
+@pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
+@pytest.mark.parametrize("precision,tail,sigma", [(128, 13.42, 215.0), (192, 10.0, 19.53), (128, 12.0, 4.5)])
+def test_high_precision_cdf_table_built_by_the_library(prng, precision, tail, sigma):
+    """scgpu_gauss_plan_create(CDF, 128 | 192, ...) builds the table of gauss_cdf_create_high_precision itself
+    (csrc/cdf_hp.cu; pinned in tests/test_cdf_high.py): the samples are those of the port's sampler over that table,
+    in every vector mode (blinding scales sigma inside the table construction, gaussian_cdf.c:225-228)."""
+    import ctypes
+    seeds = seeds_for(29, 40, salt=precision)
+    for blinding in (O.NORMAL_SAMPLES, O.BLINDING_SAMPLES, O.SHUFFLE_SAMPLES):
+        nent = ctypes.c_size_t(0)
+        assert sc.lib().scgpu_gauss_cdf_table_high(None, 0, ctypes.byref(nent), precision, blinding, tail, sigma) == 0
+        tab = np.zeros((nent.value, precision // 64), dtype=np.uint64)
+        assert sc.lib().scgpu_gauss_cdf_table_high(tab.ctypes.data, nent.value, ctypes.byref(nent), precision, blinding, tail, sigma) == 0
+        O.port().set_high_table(precision, tab)
+        plan = sc.GaussPlan(sc.SAMPLER_CDF, precision, blinding, tail, sigma)
+        for n, calls, centre, discard in ((256, 2, 0, 0), (33, 1, -4, 4)):
+            out = torch.full((seeds.shape[0], n * calls), 777, dtype=torch.int32, device=DEV)
+            plan.streams(prng, torch.from_numpy(seeds).to(DEV), n, out, calls=calls, centre=centre, discard=discard)
+            torch.cuda.synchronize()
+            exp = O.port().gauss_streams(O.SAMPLER_CDF, precision, blinding, prng, tail, sigma, seeds, n,
+                                         discard=discard, centre=centre, calls=calls)
+            assert np.array_equal(out.cpu().numpy(), exp), (blinding, n)
+        if blinding == O.NORMAL_SAMPLES and sigma > 100:
+            x = out.cpu().numpy()
+            plan2 = sc.GaussPlan(sc.SAMPLER_CDF, precision, 0, tail, sigma)
+            big = torch.empty((seeds.shape[0], 2048), dtype=torch.int32, device=DEV)
+            plan2.streams(prng, torch.from_numpy(seeds).to(DEV), 2048, big)
+            torch.cuda.synchronize()
+            y = big.cpu().numpy()[:, 16:]
+            assert abs(y.std() - sigma) < 0.02 * sigma and abs(y.mean()) < 0.05 * sigma
