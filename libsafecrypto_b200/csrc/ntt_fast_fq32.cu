@@ -303,19 +303,30 @@ int launch_matvec_fq32(const NttPlanDev &p, int32_t *out, const int32_t *A, cons
 int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32_t *a, const void *b,
                         size_t b_stride, size_t count, cudaStream_t st)
 {
-    if (mode != w32::FQ_POLYMUL && b_stride == 0 && p.fq32_bm_ok) {
-        // shared key (the BLISS signing product): its residues modulo X^4 - zeta are prepared once for the launch in
-        // a stream-ordered scratch, then the batch runs the base-multiplication key product
+    if (b_stride == 0 && p.fq32_bm_ok && (mode != w32::FQ_POLYMUL || count >= 64)) {
+        // One second operand for the whole batch.  A shared key (the BLISS signing product) arrives transformed: its
+        // residues modulo X^4 - zeta are prepared once for the launch in a stream-ordered scratch, then the batch runs
+        // the base-multiplication key product.  A shared RAW operand (scgpu_polymul_batch with b_stride = 0) is first
+        // taken to the reference's NTT domain by the canonical forward transform (one row) and is a shared key from
+        // there on: the batch reads 8 n instead of 12 n bytes per product and transforms one operand instead of two.
         int32_t *kres = nullptr;
-        SCGPU_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&kres), sizeof(int32_t) * 4 * (size_t)p.n, st));
+        SCGPU_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&kres), sizeof(int32_t) * 5 * (size_t)p.n, st));
+        int32_t *hat = kres + 4 * (size_t)p.n;
         const int nb = p.n / 4, th = 64;
-        if (mode == w32::FQ_KEY16)
-            k_key_residues<int16_t><<<(nb + th - 1) / th, th, 0, st>>>(kres, static_cast<const int16_t *>(b), static_cast<const int32_t *>(p.fq32_ktab), p.logn, p.rc.q, p.fq32_inv4);
-        else
-            k_key_residues<int32_t><<<(nb + th - 1) / th, th, 0, st>>>(kres, static_cast<const int32_t *>(b), static_cast<const int32_t *>(p.fq32_ktab), p.logn, p.rc.q, p.fq32_inv4);
-        count_launch();
-        int e = w32::launch_polymul_w32<ArFq>(fq32_const(p, p.fq32_r0_bm, true), p.logn, p.sm_count, w32::FQ_KEYBM, out, a, kres, 0,
+        int e = SCGPU_OK;
+        if (mode == w32::FQ_POLYMUL) {
+            e = launch_ntt_fq32(p, 0, hat, static_cast<const int32_t *>(b), 1, st);
+            b = hat;
+        }
+        if (e == SCGPU_OK) {
+            if (mode == w32::FQ_KEY16)
+                k_key_residues<int16_t><<<(nb + th - 1) / th, th, 0, st>>>(kres, static_cast<const int16_t *>(b), static_cast<const int32_t *>(p.fq32_ktab), p.logn, p.rc.q, p.fq32_inv4);
+            else
+                k_key_residues<int32_t><<<(nb + th - 1) / th, th, 0, st>>>(kres, static_cast<const int32_t *>(b), static_cast<const int32_t *>(p.fq32_ktab), p.logn, p.rc.q, p.fq32_inv4);
+            count_launch();
+            e = w32::launch_polymul_w32<ArFq>(fq32_const(p, p.fq32_r0_bm, true), p.logn, p.sm_count, w32::FQ_KEYBM, out, a, kres, 0,
                                               count, st, true, !p.inputs_in_range);
+        }
         const cudaError_t fe = cudaFreeAsync(kres, st);
         if (e == SCGPU_OK && fe != cudaSuccess) { set_error("cudaFreeAsync failed: %s", cudaGetErrorString(fe)); e = SCGPU_ERR_CUDA; }
         return e;

@@ -19,6 +19,7 @@
 //                    L, L + 32, ...; lane 0 instantiates the DRBG (ctr_drbg.c:37-147) and shares the round keys.
 // No reseed can fall inside an instance: create_csprng uses a 16 MiB period, an instance draws k l n 2 bytes.
 #include "scgpu_internal.h"
+#include <cstdlib>
 #include "csprng.cuh"
 #include "../../include/scgpu.h"
 
@@ -159,6 +160,66 @@ __global__ void __launch_bounds__(128) k_gen_rings(GenArgs a)
     }
 }
 
+// ---- AES-CTR-DRBG, throughput form (the library's default generator, so create_csprng's default too) ---------------
+// One warp per instance left 31 lanes idle while lane 0 instantiated the DRBG (key schedule + entropy mix, about as much
+// work as a lane's share of the blocks) and read a 1 KiB T-table with bank conflicts.  Now: k_gen_setup_aes instantiates
+// one DRBG per THREAD into a scratch of round keys, and k_gen_rings_aes encrypts one counter-addressed block per thread
+// over the bank-replicated tables of the CDF kernel (csprng.cuh: aes_rep_init, 128 KiB, one 1024-thread CTA per SM).
+__global__ void __launch_bounds__(128) k_gen_setup_aes(const uint8_t *seeds, uint32_t seed_len, size_t count, uint32_t *keys)
+{
+    __shared__ AesTables aes;
+    aes_tables_init(aes);
+    __syncthreads();
+    const size_t inst = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (inst >= count) return;
+    uint32_t rk[60], counter;
+    drbg_instantiate(aes, seeds + inst * seed_len, seed_len, rk, counter);
+    uint32_t *k = keys + inst * 64;
+    for (int i = 0; i < 60; i++) k[i] = rk[i];
+    k[60] = counter;
+}
+
+constexpr int kGenAesCta = 1024;
+constexpr size_t kGenAesTabBytes = 4 * 32768;
+
+__global__ void __launch_bounds__(kGenAesCta) k_gen_rings_aes(GenArgs a, const uint32_t *__restrict__ keys)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *te0r = reinterpret_cast<uint32_t *>(smem_raw);
+    aes_rep_init(te0r);
+    __syncthreads();
+    const uint32_t l4 = (threadIdx.x & 31) * 4;
+    const uint32_t total_c = (uint32_t)a.rings << 8;                 // coefficients per instance (n = 256)
+    const size_t nblocks = ((size_t)total_c + 7) / 8;                // 8 coefficients per 16-byte block
+    const size_t total = a.count * nblocks;
+    for (size_t item = blockIdx.x * (size_t)blockDim.x + threadIdx.x; item < total; item += (size_t)gridDim.x * blockDim.x) {
+        const size_t inst = item / nblocks, b = item % nblocks;
+        const uint32_t *k = keys + inst * 64;
+        const uint32_t c = bswap32(__ldg(k + 60) + (uint32_t)b);
+        uint32_t o[4];
+        aes256_encrypt_rep(te0r, l4, k, c, c, c, c, o);
+        int32_t *inst_out = a.out + inst * (size_t)a.rings * a.n;
+        // ciphertext bytes in order are the little-endian UINT16 pairs of bswap(o[i]) (see k_gen_rings); the eight
+        // coefficients of a block lie in one ring (256 is a multiple of 8): two 128-bit stores
+        const uint32_t cidx = 8u * (uint32_t)b;
+        const int ring = (int)(cidx >> 8), pos = (int)(cidx & 255u);
+        int32_t *dst = inst_out + (size_t)dest_ring(a, ring) * a.n + pos;
+        int32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t word = bswap32(o[i]);
+            v[2 * i] = ring_coeff(word & 0xFFFFu, a);
+            v[2 * i + 1] = ring_coeff(word >> 16, a);
+        }
+        if (cidx + 8 <= total_c) {
+            *reinterpret_cast<int4 *>(dst) = make_int4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<int4 *>(dst + 4) = make_int4(v[4], v[5], v[6], v[7]);
+        } else {
+            for (uint32_t i = 0; cidx + i < total_c; i++) dst[i] = v[i];
+        }
+    }
+}
+
 }  // namespace
 
 int launch_gen_rings(int prng_type, const uint8_t *seeds, size_t seed_len, size_t count, int32_t *out, int n, int k, int l,
@@ -179,8 +240,22 @@ int launch_gen_rings(int prng_type, const uint8_t *seeds, size_t seed_len, size_
         const size_t smem = (size_t)4 * a.cache_blocks * 32 * 16;
         SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_gen_rings<PRNG_CHACHA20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         k_gen_rings<PRNG_CHACHA20><<<grid, 128, smem, st>>>(a);
+    } else if (getenv("SCGPU_GEN_AES_WARP") && atoi(getenv("SCGPU_GEN_AES_WARP")) != 0) {
+        k_gen_rings<PRNG_AES><<<grid, 128, 0, st>>>(a);              // one warp per instance (round-2 first version; A/B)
     } else {
-        k_gen_rings<PRNG_AES><<<grid, 128, 0, st>>>(a);
+        uint32_t *keys = nullptr;
+        SCGPU_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&keys), count * 64 * sizeof(uint32_t), st));
+        k_gen_setup_aes<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(seeds, (uint32_t)seed_len, count, keys);
+        count_launch();
+        const size_t items = count * (((size_t)k * l * n + 7) / 8);
+        int sms = 148;
+        { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        size_t g2 = (items + kGenAesCta - 1) / kGenAesCta;
+        if (g2 > (size_t)sms) g2 = (size_t)sms;
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_gen_rings_aes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGenAesTabBytes));
+        k_gen_rings_aes<<<(unsigned)g2, kGenAesCta, kGenAesTabBytes, st>>>(a, keys);
+        const cudaError_t fe = cudaFreeAsync(keys, st);
+        if (fe != cudaSuccess) { set_error("cudaFreeAsync failed: %s", cudaGetErrorString(fe)); return SCGPU_ERR_CUDA; }
     }
     count_launch();
     SCGPU_CUDA_CHECK(cudaGetLastError());

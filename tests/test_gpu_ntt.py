@@ -253,6 +253,15 @@ def test_fused_polymul_matches_reference_composition(q, n, tw, arithmetic):
     p.polymul(out, dev(a), dev(b))
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a, np.tile(b, (33, 1)), w, r))
+    # ... and on a batch large enough for the shared-operand route of the float-quotient policy (one canonical forward
+    # transform of b, then the residue-table key product), with any SINT32 in the shared row
+    for kb in ("uniform", "signed", "extreme"):
+        a = rand_inputs(rng, "lazy" if kb == "extreme" else "uniform", q, (257, n))
+        b = rand_inputs(rng, kb, q, (n,))
+        out = torch.empty((257, n), dtype=torch.int32, device=DEV)
+        p.polymul(out, dev(a), dev(b))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a, np.tile(b, (257, 1)), w, r)), kb
 
 
 def test_fused_polymul_is_schoolbook_product():

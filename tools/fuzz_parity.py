@@ -22,7 +22,9 @@ def plan(q, n, tw):
     key = (q, n)
     if key not in plans:
         w, r = O.tables(q, n, tw)
-        plans[key] = (sc.NttPlan(n, q, sc.REFERENCE, w, r), w, r)
+        flagged = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+        flagged.set_flags(sc.PLAN_INPUTS_IN_RANGE)          # no range votes: only used with operands inside +-4q
+        plans[key] = (sc.NttPlan(n, q, sc.REFERENCE, w, r), w, r, flagged)
     return plans[key]
 
 
@@ -47,7 +49,8 @@ t0, iters, fails = time.time(), 0, 0
 counts = {}
 while time.time() - t0 < budget:
     q, n, tw = PARAMS[rng.integers(len(PARAMS))]
-    pl, w, r = plan(q, n, tw)
+    pl0, w, r, plf = plan(q, n, tw)
+    pl = pl0
     mode = int(rng.choice([0, 0, 0, 1, 2, 3, 4]))
     sc.lib().scgpu_set_fast_arith(mode)
     what = int(rng.integers(5))
@@ -57,7 +60,10 @@ while time.time() - t0 < budget:
     try:
         if what == 0:
             name = "polymul"
-            a, b = inputs(rng.integers(5), q, (rows, n)), inputs(rng.integers(5), q, (rows, n))
+            ka, kb = int(rng.integers(5)), int(rng.integers(5))
+            a, b = inputs(ka, q, (rows, n)), inputs(kb, q, (rows, n))
+            if ka <= 2 and kb <= 2 and rng.random() < 0.5:
+                pl, name = plf, "polymul_inrange"
             out = torch.empty((rows, n), dtype=torch.int32, device=dev)
             if rng.random() < 0.2:
                 b = b[:1]
@@ -69,8 +75,11 @@ while time.time() - t0 < budget:
             exp = P.ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a, bb, w, r)
         elif what == 1 and tw == 16:
             name = "key16"
-            a = inputs(rng.integers(5), q, (rows, n))
-            key = rng.integers(-32768, 32768, (rows, n)).astype(np.int16) if rng.random() < 0.5 else rng.integers(0, q, (n,)).astype(np.int16)
+            ka = int(rng.integers(5))
+            a = inputs(ka, q, (rows, n))
+            key = rng.integers(-32768, 32768, (rows, n)).astype(np.int16) if rng.random() < 0.4 else rng.integers(-32768, 32768, (n,)).astype(np.int16)
+            if ka <= 2 and rng.random() < 0.5:
+                pl, name = plf, "key16_inrange"
             out = torch.empty((rows, n), dtype=torch.int32, device=dev)
             pl.mul_key(out, dev_rows(a, offa), torch.from_numpy(key).to(dev))
             exp = P.ntt_batch(O.REFERENCE, O.OP_TRIPLE16, n, q, tw, a, key if key.ndim == 2 else np.tile(key, (rows, 1)), w, r)
@@ -91,7 +100,10 @@ while time.time() - t0 < budget:
             k, l = int(rng.integers(1, 6)), int(rng.integers(1, 5))
             rows = min(rows, 300)
             A = inputs(rng.integers(3), q, (rows, k * l, n))
-            s = inputs(int(rng.choice([0, 1, 4])), q, (rows, l, n))
+            ks = int(rng.choice([0, 1, 4]))
+            s = inputs(ks, q, (rows, l, n))
+            if ks <= 1 and rng.random() < 0.5:
+                pl, name = plf, "matvec_inrange"
             out = torch.empty((rows, k, n), dtype=torch.int32, device=dev)
             pl.matvec(out, dev_rows(A, offa), dev_rows(s, offb), k, l)
             sh = P.ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, s.reshape(-1, n), None, w, r).reshape(rows, l, n)
