@@ -29,7 +29,19 @@
 //               (w > 0): 9 instructions, no 64-bit arithmetic, no bound on x.
 //   barrett     ntt.c:366-378 literally, with the twiddle-times-m product precomputed: (x w) m == x (w m) mod 2^64,
 //               w m < 2^30, so t = bits [k, k+32) of the 64-bit product x (w m): IMAD + IMAD.HI + funnel shift.
-//   fp / avx / solinas   Exact<V> as is (double quotient, AVX2 lane emulation, folds).
+//   fp          (int64)(double(x w) * (1/q)) truncated, v - q qi (ntt_template.c.in:766-767).  With v = x w = m q + r:
+//               the double product differs from v / q by less than 2^-21 (|v / q| < 2^31: 2^-22 from the rounded
+//               reciprocal, 2^-23 from the product's own rounding), and r / q >= 1/q > 2^-21 for q < 2^21, so for
+//               r != 0 the truncation is m and the result is the C remainder -- the reference variant's 9 instructions.
+//               Only when q divides x w can the rounding fall below m (result q instead of 0, depending on q's
+//               reciprocal and on m's position in its binade): that case -- one product in q -- takes the double
+//               arithmetic itself.  For 32-bit tables (q up to 2^30) the bound needs |x| < 2^29; beyond it: doubles.
+//   avx         scalar stages: the fp code.  Double lanes on 16-bit tables (|x w| < 2^46 < 2^51: the magic-number
+//               conversion is exact): quotient = RN(x w (1/q)) in ONE rounding (FMA), and x w / q is never within
+//               2^-21 of a half-integer (q odd), so the lane returns x w - round(x w / q) q, +q if negative: the
+//               CANONICAL residue -- a Shoup product and two unsigned minima, no FP64.  Float lanes, full-range double
+//               lanes (32-bit tables) and the q = 7681 twist stay lane emulation (Exact<V>).
+//   solinas     Exact<V> as is (folds).
 #include "warp32.cuh"
 
 #include <cstring>
@@ -55,30 +67,56 @@ __host__ __device__ constexpr int by4(int T, int t, int j) { return ((j >> 2) * 
 // V_AVXF: the AVX2 variant with the single-precision lanes (16-bit tables, 512 < q <= 12289, ntt_template.c.in:1367-1402):
 // a kernel of its own, so that no butterfly carries both lane flavours behind a run-time test of q
 constexpr int V_AVXF = 6;
-template <int V> struct PolicyOf { static constexpr int value = V == V_AVXF ? (int)V_AVX : V; };
+// Integer forms of the double arithmetic (file header), selected per plan (xw32_fpint: 16-bit tables, 0 <= w < q < 2^15,
+// and no quotient m < 2^31 whose product m q rounds below m): fp, avx with double lanes, avx with float lanes
+constexpr int V_FPI = 7, V_AVXI = 8, V_AVXFI = 9;
+template <int V> struct PolicyOf {
+    static constexpr int value = (V == V_AVXF || V == V_AVXI || V == V_AVXFI) ? (int)V_AVX : (V == V_FPI ? (int)V_FP : V);
+};
+template <int V> constexpr bool kIntFp = (V == V_FPI || V == V_AVXI || V == V_AVXFI);
+template <int V> constexpr bool kFloatLanes = (V == V_AVXF || V == V_AVXFI);
+
+// C remainder of x * w (sign of x), w > 0 given centred with wp = round(wc 2^32 / q); any int32 x
+__device__ __forceinline__ int32_t ref_mul(int32_t x, int32_t wc, int32_t wp, const XConst &c)
+{
+    const int32_t s = x >> 31;
+    const int32_t qe = __mulhi(x, wp);
+    const uint32_t p = (uint32_t)x * (uint32_t)wc + (uint32_t)s;
+    uint32_t t = (uint32_t)qe * (uint32_t)c.nq + p;
+    t = min(t, t + (uint32_t)c.rc.q);
+    t = min(t, t - (uint32_t)c.rc.q);
+    return (int32_t)((uint32_t)s * (uint32_t)c.qm1 + t);
+}
+// canonical residue of x * w in [0, q), same entry
+__device__ __forceinline__ int32_t canon_mul(int32_t x, int32_t wc, int32_t wp, const XConst &c)
+{
+    const int32_t qe = __mulhi(x, wp);
+    uint32_t t = (uint32_t)x * (uint32_t)wc + (uint32_t)qe * (uint32_t)c.nq;        // in (-q/4, 5q/4)
+    t = min(t, t + (uint32_t)c.rc.q);
+    t = min(t, t - (uint32_t)c.rc.q);
+    return (int32_t)t;
+}
 
 template <int V, bool TW16>
 __device__ __forceinline__ int32_t xmul(int32_t x, int32_t w, int32_t aux, const XConst &c)
 {
     constexpr int EV = PolicyOf<V>::value;
     if constexpr (V == V_REFERENCE) {
-        const int32_t s = x >> 31;
-        const int32_t qe = __mulhi(x, aux);
-        const uint32_t p = (uint32_t)x * (uint32_t)w + (uint32_t)s;                 // w is the centred twiddle here
-        uint32_t t = (uint32_t)qe * (uint32_t)c.nq + p;
-        t = min(t, t + (uint32_t)c.rc.q);
-        t = min(t, t - (uint32_t)c.rc.q);
-        return (int32_t)((uint32_t)s * (uint32_t)c.qm1 + t);
+        return ref_mul(x, w, aux, c);                                               // w is the centred twiddle here
     } else if constexpr (V == V_BARRETT) {
         const uint32_t lo = (uint32_t)x * (uint32_t)aux;                            // aux = w * m
         const uint32_t hi = (uint32_t)__mulhi(x, aux);
         const uint32_t t = __funnelshift_r(lo, hi, c.rc.k);
         const uint32_t v = (uint32_t)x * (uint32_t)w + t * (uint32_t)c.nq;
         return cond_fix((int32_t)v, c.rc.q);
+    } else if constexpr (kIntFp<V>) {
+        // fp and the scalar stages of avx where the truncated double quotient provably IS the C remainder (file header):
+        // entries are (wc, wp) as for the reference variant
+        return ref_mul(x, w, aux, c);
     } else {
-        // fp and the scalar stages of avx: the double quotient with its two 64-bit conversions.  A conversion-free
-        // form (magic-number int -> double and truncation) was measured SLOWER: it trades two XU conversions for five
-        // more FP64-pipe operations (fp forward n = 512: 7.5e8 -> 5.3e8 transforms/s).
+        // fp and the scalar stages of avx otherwise: the double quotient with its two 64-bit conversions.  A
+        // conversion-free form (magic-number int -> double and truncation) was measured SLOWER: it trades two XU
+        // conversions for five more FP64-pipe operations (fp forward n = 512: 7.5e8 -> 5.3e8 transforms/s).
         return Exact<EV>::muln(x, w, c.rc);
     }
 }
@@ -88,8 +126,12 @@ template <int V, bool TW16>
 __device__ __forceinline__ int32_t xtwist(int32_t x, int32_t w, int32_t aux, const XConst &c)
 {
     constexpr int EV = PolicyOf<V>::value;
-    if constexpr (EV == V_AVX) return TW16 ? Exact<EV>::pw16(x, w, c.rc) : Exact<EV>::pw32(x, w, c.rc);
-    else return xmul<V, TW16>(x, w, aux, c);
+    if constexpr (EV == V_AVX) {
+        if constexpr (kIntFp<V>) return canon_mul(x, w, aux, c);       // double lane on 16-bit tables, q != 7681: canonical residue
+        else return TW16 ? Exact<EV>::pw16(x, w, c.rc) : Exact<EV>::pw32(x, w, c.rc);
+    } else {
+        return xmul<V, TW16>(x, w, aux, c);
+    }
 }
 
 // one DIT butterfly of stage S (ntt_template.c.in:1144-1244 fft_32, :1341-1482 fft_16; the AVX2 branches
@@ -102,8 +144,9 @@ __device__ __forceinline__ void xbfly(int32_t &lo, int32_t &hi, int32_t w, int32
     constexpr bool vec = (EV == V_AVX) && ((1 << S) < (N >> 3));
     int32_t x;
     if constexpr (vec) {
-        if constexpr (V == V_AVXF) x = lane_flt_magic((int32_t)((uint32_t)hi * (uint32_t)w), c.rc);   // low 32 bits of the product
-        else                       x = lane_dbl((int64_t)hi * (int64_t)w, false, c.rc);
+        if constexpr (kFloatLanes<V>)  x = lane_flt_magic((int32_t)((uint32_t)hi * (uint32_t)w), c.rc);   // low 32 bits of the product
+        else if constexpr (kIntFp<V>)  x = canon_mul(hi, w, aux, c);                                      // double lane, 16-bit tables
+        else                           x = lane_dbl((int64_t)hi * (int64_t)w, false, c.rc);
     } else {
         // column j = 0 is not multiplied: passed through (fft_16) or reduced only (fft_32)
         const int32_t x0 = TW16 ? hi : Exact<EV>::modn(hi, c.rc);
@@ -309,11 +352,22 @@ struct ArX { static constexpr int WORDS = 2; };       // two words per entry for
 
 int32_t centre(int32_t w, int32_t q) { return w > q / 2 ? w - q : w; }
 
-// the two words of a twiddle entry for the plan's variant
-void make_entry(const NttPlanDev &p, int32_t w, int32_t *ow, int32_t *oa)
+// the two words of a twiddle entry for the plan's variant.  kind: 0 = stage with the AVX2 vector lanes (avx only),
+// 1 = scalar stage, 2 = pre / post twist
+void make_entry(const NttPlanDev &p, int32_t w, int kind, int32_t *ow, int32_t *oa)
 {
     const int32_t q = p.rc.q;
-    if (p.variant == V_REFERENCE) {
+    const bool tw16 = p.tw_bits == 16;
+    bool centred = false;
+    if (p.variant == V_REFERENCE) centred = true;
+    else if (p.variant == V_FP) centred = p.xw32_fpint != 0;
+    else if (p.variant == V_AVX && p.xw32_fpint) {
+        const bool avxf = tw16 && q <= 12289;                    // float lanes in the vector stages
+        if (kind == 0) centred = tw16 && !avxf;                  // double lanes on 16-bit tables: canonical Shoup product
+        else if (kind == 1) centred = true;                      // fp code
+        else centred = tw16 && q != 7681;                        // twist: double lanes unless q = 7681 (float lanes)
+    }
+    if (centred) {
         const int32_t wc = centre(w, q);
         const double wp = nearbyint((double)wc * 4294967296.0 / (double)q);           // |wp| < 2^31
         *ow = wc;
@@ -339,15 +393,29 @@ int build_xw32_tables(NttPlanDev &p, const int32_t *w_host, const int32_t *r_hos
     const int n = p.n, L = p.logn, T = n / 32;
     const int32_t q = p.rc.q;
     if (q < 3 || q >= (1 << 30)) return SCGPU_OK;
+    p.xw32_fpint = 0;
+    bool canonical = true;
+    for (int i = 0; i < n; i++) {
+        if (w_host[i] < 0 || w_host[i] >= q) canonical = false;
+        if (r_host && (r_host[i] < 0 || r_host[i] >= q)) canonical = false;
+    }
     if (p.variant == V_REFERENCE || p.variant == V_BARRETT) {
-        for (int i = 0; i < n; i++) {
-            if (w_host[i] < 0 || w_host[i] >= q) return SCGPU_OK;
-            if (r_host && (r_host[i] < 0 || r_host[i] >= q)) return SCGPU_OK;
-        }
+        if (!canonical) return SCGPU_OK;
         if (p.variant == V_BARRETT) {
             if (p.rc.k < 0 || p.rc.k > 31 || p.rc.m < 0) return SCGPU_OK;
             if ((int64_t)(q - 1) * (int64_t)p.rc.m > 0x7FFFFFFFll) return SCGPU_OK;
         }
+    }
+    if ((p.variant == V_FP || p.variant == V_AVX) && canonical && p.tw_bits == 16 && q < (1 << 15) && (q & 1)) {
+        // Integer forms (file header).  The truncated quotient of an exact multiple m q is m unless RN(m (1 + delta)) < m,
+        // delta = inv_q_dbl q - 1 (the caller's reciprocal, not recomputed): impossible for delta >= 0, and for delta < 0
+        // only when m |delta| exceeds half the spacing below m, i.e. (m / 2^k) |delta| 2^53 > 1 with m / 2^k < 2.
+        const long double delta = (long double)p.rc.inv_q_dbl * (long double)q - 1.0L;      // exact: 53 + 15 bits < 64
+        const long double D = -delta * 9007199254740992.0L;                                  // |delta| 2^53 when delta < 0
+        if (delta >= 0.0L || D <= 0.5L) p.xw32_fpint = 1;
+        if (p.variant == V_AVX && q == 7681) p.xw32_fpint = 0;      // its twist runs the float lanes (mul_32_pointwise_16, :1081-1094)
+        const char *off = getenv("SCGPU_EXACT_FP_DOUBLES");
+        if (off && atoi(off) != 0) p.xw32_fpint = 0;
     }
     auto brev_bits = [](int v, int bits) { int r = 0; for (int b = 0; b < bits; b++) if (v & (1 << b)) r |= 1 << (bits - 1 - b); return r; };
     // natural table: entry 2^s + g = w[brev_s(g) * n / 2^s]
@@ -356,7 +424,8 @@ int build_xw32_tables(NttPlanDev &p, const int32_t *w_host, const int32_t *r_hos
     for (int s = 0; s < L; s++)
         for (int g = 0; g < (1 << s); g++) {
             Ent e;
-            make_entry(p, w_host[(size_t)brev_bits(g, s) << (L - s)], &e.w, &e.a);
+            const int vec = (p.variant == V_AVX && (1 << s) < (n >> 3)) ? 0 : 1;       // ntt_template.c.in:1164, :1361
+            make_entry(p, w_host[(size_t)brev_bits(g, s) << (L - s)], vec, &e.w, &e.a);
             z[(1 << s) + g] = e;
         }
     // layout: [pass-1 w | pass-1 aux | fwd twist w | fwd twist aux | inv twist w | inv twist aux], n words each
@@ -367,11 +436,11 @@ int build_xw32_tables(NttPlanDev &p, const int32_t *w_host, const int32_t *r_hos
     for (int t = 0; t < T; t++)
         for (int j = 0; j < 32; j++) {
             int32_t ew, ea;
-            make_entry(p, w_host[t + T * j], &ew, &ea);                               // pre-twist of element tau + T m
+            make_entry(p, w_host[t + T * j], 2, &ew, &ea);                            // pre-twist of element tau + T m
             pack[2 * n + by4(T, t, j)] = ew; pack[3 * n + by4(T, t, j)] = ea;
             if (r_host) {
                 const int k = (brev_bits(j, 5) << (L - 5)) | brev_bits(t, L - 5);      // coefficient of element j, thread t
-                make_entry(p, r_host[k], &ew, &ea);
+                make_entry(p, r_host[k], 2, &ew, &ea);
                 pack[4 * n + by4(T, t, j)] = ew; pack[5 * n + by4(T, t, j)] = ea;
             }
         }
@@ -421,7 +490,8 @@ int launch_xv(const NttPlanDev &p, bool inverse, int32_t *out, const int32_t *a,
     } else if constexpr (V == V_SOL8380417) {
         if (p.logn != 8 || tw16) return SCGPU_ERR_UNSUPPORTED;
         return launch_x<V, 8, false>(p, inverse, out, a, count, c, st);
-    } else if constexpr (V == V_AVXF) {
+    } else if constexpr (V == V_AVXF || kIntFp<V>) {
+        if (!tw16) return SCGPU_ERR_UNSUPPORTED;
         switch (p.logn) {
         case 8:  return launch_x<V, 8, true>(p, inverse, out, a, count, c, st);
         case 9:  return launch_x<V, 9, true>(p, inverse, out, a, count, c, st);
@@ -484,16 +554,16 @@ int launch_exact_w32(const NttPlanDev &p, int op, int32_t *out, const int32_t *a
     case V_BARRETT:    return launch_xv<V_BARRETT>(p, inverse, out, a, count, c, st);
 #endif
 #if XW32_VARIANTS & 4
-    case V_FP:         return launch_xv<V_FP>(p, inverse, out, a, count, c, st);
+    case V_FP:         return p.xw32_fpint ? launch_xv<V_FPI>(p, inverse, out, a, count, c, st) : launch_xv<V_FP>(p, inverse, out, a, count, c, st);
 #endif
 #if XW32_VARIANTS & 8
     case V_AVX:
         // single-precision lanes for 16-bit tables with q <= 12289 (:1367-1402); the magic-number rounding needs q > 512
         if (p.tw_bits == 16 && p.rc.q <= 12289) {
             if (p.rc.q <= 512) return SCGPU_ERR_UNSUPPORTED;
-            return launch_xv<V_AVXF>(p, inverse, out, a, count, c, st);
+            return p.xw32_fpint ? launch_xv<V_AVXFI>(p, inverse, out, a, count, c, st) : launch_xv<V_AVXF>(p, inverse, out, a, count, c, st);
         }
-        return launch_xv<V_AVX>(p, inverse, out, a, count, c, st);
+        return p.xw32_fpint ? launch_xv<V_AVXI>(p, inverse, out, a, count, c, st) : launch_xv<V_AVX>(p, inverse, out, a, count, c, st);
 #endif
 #if XW32_VARIANTS & 16
     case V_SOL7681:    return launch_xv<V_SOL7681>(p, inverse, out, a, count, c, st);

@@ -68,6 +68,7 @@ struct NttPlanDev {
     alignas(16) unsigned char sh32_ninv_plain[8], sh32_zi1_plain[8];   // last-stage multipliers without the factor R
     // variant-exact transforms on the warp-local schedule (ntt_exact_w32.cu): 0 not applicable, 1 forward only (no r), 2 both
     int xw32_ok;
+    int xw32_fpint;                      // fp / avx: the double quotient is evaluated in integers (ntt_exact_w32.cu header)
     void *xw32_tab;                      // [pass-1 w | aux | fwd twist w | aux | inv twist w | aux], n words each
     int32_t xw32_f0[62];                 // stages 0..4: 31 x w, 31 x aux
 };

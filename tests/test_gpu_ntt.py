@@ -746,3 +746,34 @@ def test_in_range_flag_on_key_products_and_matvec(q, tw):
         torch.cuda.synchronize()
         assert torch.equal(o1, o2), (k, l)
     p_flag.close()
+
+
+@pytest.mark.parametrize("q,n,tw", PARAMS + [(18433, 512, 16), (12289, 256, 16)])
+def test_exact_transforms_when_q_divides_the_products(q, n, tw):
+    """The warp-local exact kernels evaluate the fp / avx double quotient in integers wherever that is provably the same
+    (ntt_exact_w32.cu header): the C remainder unless q divides the product, the canonical residue for the double
+    lanes.  The exceptional case is forced here: inputs that are multiples of q (sums of multiples stay multiples, so
+    every butterfly of every stage is in the exceptional case), zeros, sparse rows, rows at +-2^29 / +-2^31 (beyond the
+    bound of the 32-bit-table form), against the compiled reference and the port, all variants, forward and inverse."""
+    rng = np.random.default_rng(q - n)
+    w, r = O.tables(q, n, tw)
+    kmax = (2**31 - 1) // q
+    rows = []
+    rows.append(q * rng.integers(-3, 4, size=(9, n)))
+    rows.append(q * rng.integers(-kmax, kmax + 1, size=(9, n)))
+    rows.append(np.zeros((2, n), dtype=np.int64))
+    sparse = np.zeros((6, n), dtype=np.int64)
+    sparse[np.arange(6), rng.integers(0, n, size=6)] = [1, -1, q, -q, q * kmax, 12345]
+    rows.append(sparse)
+    big = rng.choice([2**29, -(2**29), 2**29 - 1, 2**29 + 1, 2**31 - 1, -(2**31)], size=(6, n))
+    rows.append(big)
+    mixed = rng.integers(0, q, size=(8, n))
+    mixed[:, ::3] = q * rng.integers(-5, 6, size=mixed[:, ::3].shape)
+    rows.append(mixed)
+    a = np.concatenate(rows).astype(np.int32)
+    for variant in variants_for(q):
+        for op in (O.OP_FWD, O.OP_INV):
+            got, _ = run_gpu(q, n, tw, variant, op, a)
+            for chk in checkers():
+                exp = chk.ntt_batch(variant, op, n, q, tw, a, None, w, r)
+                assert np.array_equal(got, exp), (O.VARIANT_NAMES[variant], op, chk.prefix, np.argwhere(got != exp)[:4])

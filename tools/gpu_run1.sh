@@ -1,1 +1,2 @@
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+set -x
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
