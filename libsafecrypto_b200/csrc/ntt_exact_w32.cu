@@ -333,10 +333,19 @@ k_exact_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t cou
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const int e = e4 + u;
-                        int32_t v = xtwist<V, TW16>(x[e], ws[u], as[u], c);
                         const int k = k0 + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5));
-                        if (e == 0) v = (k == 0) ? (int32_t)(0u - (uint32_t)v) : v;
-                        if (live) out[poly * N + ((N - k) & (N - 1))] = cond_fix(v, c.rc.q);
+                        int32_t v;
+                        if constexpr (V == V_REFERENCE || kIntFp<V>) {
+                            // cond_fix of the C remainder (and of the double lane's residue) IS the canonical residue:
+                            // one Shoup product and two minima instead of remainder + sign + fix-up; -v for k = 0
+                            v = canon_mul(x[e], ws[u], as[u], c);
+                            if (e == 0) v = (k == 0 && v != 0) ? c.rc.q - v : v;
+                        } else {
+                            v = xtwist<V, TW16>(x[e], ws[u], as[u], c);
+                            if (e == 0) v = (k == 0) ? (int32_t)(0u - (uint32_t)v) : v;
+                            v = cond_fix(v, c.rc.q);
+                        }
+                        if (live) out[poly * N + ((N - k) & (N - 1))] = v;
                     }
                 }
             }
