@@ -59,6 +59,7 @@ struct XConst {
     int32_t f0w[31], f0a[31];   // stages 0..4: entry (1 << s) - 1 + g, g = m >> (5 - s)
     RedConst rc;
     int32_t nq, qm1;
+    int32_t wp1;                // round(2^32 / q): the entry (1, wp1) turns ref_mul into x % q (modn of the integer fp form)
 };
 
 // position of word j (0..31) of thread t in the by-4 thread-major packing: a warp's 128-bit loads are contiguous
@@ -70,11 +71,21 @@ constexpr int V_AVXF = 6;
 // Integer forms of the double arithmetic (file header), selected per plan (xw32_fpint: 16-bit tables, 0 <= w < q < 2^15,
 // and no quotient m < 2^31 whose product m q rounds below m): fp, avx with double lanes, avx with float lanes
 constexpr int V_FPI = 7, V_AVXI = 8, V_AVXFI = 9;
+// 32-bit tables: the same integer forms hold while every multiplicand stays below 2^29 (and every lane product below
+// 2^51), which a row guarantees when all its INPUTS are at most 2^27 (multiplicands are inputs, or sums of an input and
+// a few residues below 2^26.4; twiddles are below 2^23.01).  V_FPG / V_AVXG vote on that per row; a row beyond the bound runs the double arithmetic over the same
+// (centred) table entries, V_FPC / V_AVXC.
+constexpr int V_FPG = 10, V_AVXG = 11, V_FPC = 12, V_AVXC = 13;
 template <int V> struct PolicyOf {
-    static constexpr int value = (V == V_AVXF || V == V_AVXI || V == V_AVXFI) ? (int)V_AVX : (V == V_FPI ? (int)V_FP : V);
+    static constexpr int value = (V == V_AVXF || V == V_AVXI || V == V_AVXFI || V == V_AVXG || V == V_AVXC) ? (int)V_AVX
+                               : ((V == V_FPI || V == V_FPG || V == V_FPC) ? (int)V_FP : V);
 };
-template <int V> constexpr bool kIntFp = (V == V_FPI || V == V_AVXI || V == V_AVXFI);
+template <int V> constexpr bool kIntFp = (V == V_FPI || V == V_AVXI || V == V_AVXFI || V == V_FPG || V == V_AVXG);
 template <int V> constexpr bool kFloatLanes = (V == V_AVXF || V == V_AVXFI);
+template <int V> constexpr bool kGuarded = (V == V_FPG || V == V_AVXG);
+template <int V> constexpr bool kCentredDoubles = (V == V_FPC || V == V_AVXC);       // doubles over (wc, wp) entries
+template <int V> struct SlowOf { static constexpr int value = V == V_FPG ? V_FPC : (V == V_AVXG ? V_AVXC : V); };
+template <int V> struct XTag { static constexpr int value = V; };
 
 // C remainder of x * w (sign of x), w > 0 given centred with wp = round(wc 2^32 / q); any int32 x
 __device__ __forceinline__ int32_t ref_mul(int32_t x, int32_t wc, int32_t wp, const XConst &c)
@@ -117,7 +128,7 @@ __device__ __forceinline__ int32_t xmul(int32_t x, int32_t w, int32_t aux, const
         // fp and the scalar stages of avx otherwise: the double quotient with its two 64-bit conversions.  A
         // conversion-free form (magic-number int -> double and truncation) was measured SLOWER: it trades two XU
         // conversions for five more FP64-pipe operations (fp forward n = 512: 7.5e8 -> 5.3e8 transforms/s).
-        return Exact<EV>::muln(x, w, c.rc);
+        return Exact<EV>::muln(x, kCentredDoubles<V> ? w + ((w >> 31) & c.rc.q) : w, c.rc);
     }
 }
 
@@ -127,8 +138,11 @@ __device__ __forceinline__ int32_t xtwist(int32_t x, int32_t w, int32_t aux, con
 {
     constexpr int EV = PolicyOf<V>::value;
     if constexpr (EV == V_AVX) {
-        if constexpr (kIntFp<V>) return canon_mul(x, w, aux, c);       // double lane on 16-bit tables, q != 7681: canonical residue
-        else return TW16 ? Exact<EV>::pw16(x, w, c.rc) : Exact<EV>::pw32(x, w, c.rc);
+        if constexpr (kIntFp<V>) return canon_mul(x, w, aux, c);       // double lane (16-bit tables with q != 7681, guarded rows of 32-bit tables): canonical residue
+        else {
+            const int32_t wu = kCentredDoubles<V> ? w + ((w >> 31) & c.rc.q) : w;
+            return TW16 ? Exact<EV>::pw16(x, wu, c.rc) : Exact<EV>::pw32(x, wu, c.rc);
+        }
     } else {
         return xmul<V, TW16>(x, w, aux, c);
     }
@@ -146,10 +160,14 @@ __device__ __forceinline__ void xbfly(int32_t &lo, int32_t &hi, int32_t w, int32
     if constexpr (vec) {
         if constexpr (kFloatLanes<V>)  x = lane_flt_magic((int32_t)((uint32_t)hi * (uint32_t)w), c.rc);   // low 32 bits of the product
         else if constexpr (kIntFp<V>)  x = canon_mul(hi, w, aux, c);                                      // double lane, 16-bit tables
-        else                           x = lane_dbl((int64_t)hi * (int64_t)w, false, c.rc);
+        else                           x = lane_dbl((int64_t)hi * (int64_t)(kCentredDoubles<V> ? w + ((w >> 31) & c.rc.q) : w), false, c.rc);
     } else {
-        // column j = 0 is not multiplied: passed through (fft_16) or reduced only (fft_32)
-        const int32_t x0 = TW16 ? hi : Exact<EV>::modn(hi, c.rc);
+        // column j = 0 is not multiplied: passed through (fft_16) or reduced only (fft_32); the integer fp form of
+        // modn is the remainder x % q (|x| / q < 2^9: no bound on x is needed)
+        int32_t x0;
+        if constexpr (TW16) x0 = hi;
+        else if constexpr (kIntFp<V>) x0 = ref_mul(hi, 1, c.wp1, c);
+        else x0 = Exact<EV>::modn(hi, c.rc);
         if (S == 0) x = x0;
         else {
             const int32_t xm = xmul<V, TW16>(hi, w, aux, c);
@@ -278,32 +296,39 @@ k_exact_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t cou
         const size_t prow = live ? poly : 0;
         cl.issue(ctr, lane);
         const size_t nbase = (size_t)cl.gn * C::POLYS;
+        int32_t xr[32];                                             // the raw row
         {
-            int32_t x[32];
             if (TMA) {
                 mbar_wait(&bars[warp], parity); parity ^= 1u;
 #pragma unroll
-                for (int m = 0; m < 32; m++) x[m] = stage[tau + m * T];
+                for (int m = 0; m < 32; m++) xr[m] = stage[tau + m * T];
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && nbase < count) fetch(nbase);        // the staging row is in registers
             } else {
 #pragma unroll
-                for (int m = 0; m < 32; m++) x[m] = __ldg(a + prow * N + tau + m * T);
+                for (int m = 0; m < 32; m++) xr[m] = __ldg(a + prow * N + tau + m * T);
             }
+        }
+        auto row_body = [&](auto tag) {
+        constexpr int VV = decltype(tag)::value;
+        {
+            int32_t x[32];
+#pragma unroll
+            for (int m = 0; m < 32; m++) x[m] = xr[m];
             if (!INV) {
                 // pre-twist v[i] = t[i] * w[i], i = tau + T m (mult_pointwise, :956-1141)
 #pragma unroll
                 for (int m4 = 0; m4 < 32; m4 += 4) {
                     const int4 w4 = __ldg(reinterpret_cast<const int4 *>(c.tw + by4(T, tau, m4)));
                     const int4 a4 = __ldg(reinterpret_cast<const int4 *>(c.tw + N + by4(T, tau, m4)));
-                    x[m4] = xtwist<V, TW16>(x[m4], w4.x, a4.x, c);
-                    x[m4 + 1] = xtwist<V, TW16>(x[m4 + 1], w4.y, a4.y, c);
-                    x[m4 + 2] = xtwist<V, TW16>(x[m4 + 2], w4.z, a4.z, c);
-                    x[m4 + 3] = xtwist<V, TW16>(x[m4 + 3], w4.w, a4.w, c);
+                    x[m4] = xtwist<VV, TW16>(x[m4], w4.x, a4.x, c);
+                    x[m4 + 1] = xtwist<VV, TW16>(x[m4 + 1], w4.y, a4.y, c);
+                    x[m4 + 2] = xtwist<VV, TW16>(x[m4 + 2], w4.z, a4.z, c);
+                    x[m4 + 3] = xtwist<VV, TW16>(x[m4 + 3], w4.w, a4.w, c);
                 }
             }
-            xpass0<V, LOGN, TW16>(x, c);
+            xpass0<VV, LOGN, TW16>(x, c);
 #pragma unroll
             for (int m = 0; m < 32; m++) tile[tau + pos32(T * m)] = x[m];
         }
@@ -315,7 +340,7 @@ k_exact_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t cou
                 const int4 v = *reinterpret_cast<const int4 *>(tile + 36 * tau + k4);
                 x[k4] = v.x; x[k4 + 1] = v.y; x[k4 + 2] = v.z; x[k4 + 3] = v.w;
             }
-            xstages1<V, LOGN, 5, TW16>(x, c, tau);
+            xstages1<VV, LOGN, 5, TW16>(x, c, tau);
             if (!INV) {
                 if (live) {
                     int32_t *orow = out + poly * N + ntt_index<LOGN>(tau, 0);
@@ -335,13 +360,13 @@ k_exact_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t cou
                         const int e = e4 + u;
                         const int k = k0 + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5));
                         int32_t v;
-                        if constexpr (V == V_REFERENCE || kIntFp<V>) {
+                        if constexpr (VV == V_REFERENCE || kIntFp<VV>) {
                             // cond_fix of the C remainder (and of the double lane's residue) IS the canonical residue:
                             // one Shoup product and two minima instead of remainder + sign + fix-up; -v for k = 0
                             v = canon_mul(x[e], ws[u], as[u], c);
                             if (e == 0) v = (k == 0 && v != 0) ? c.rc.q - v : v;
                         } else {
-                            v = xtwist<V, TW16>(x[e], ws[u], as[u], c);
+                            v = xtwist<VV, TW16>(x[e], ws[u], as[u], c);
                             if (e == 0) v = (k == 0) ? (int32_t)(0u - (uint32_t)v) : v;
                             v = cond_fix(v, c.rc.q);
                         }
@@ -349,6 +374,16 @@ k_exact_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t cou
                     }
                 }
             }
+        }
+        };
+        if constexpr (kGuarded<V>) {
+            bool big = false;
+#pragma unroll
+            for (int m = 0; m < 32; m++) big |= ((uint32_t)xr[m] + 0x08000000u) > 0x10000000u;      // |input| > 2^27
+            if (__any_sync(0xFFFFFFFFu, big)) row_body(XTag<SlowOf<V>::value>{});
+            else row_body(XTag<V>{});
+        } else {
+            row_body(XTag<V>{});
         }
         __syncwarp();
         cl.advance(ctr);
@@ -372,9 +407,9 @@ void make_entry(const NttPlanDev &p, int32_t w, int kind, int32_t *ow, int32_t *
     else if (p.variant == V_FP) centred = p.xw32_fpint != 0;
     else if (p.variant == V_AVX && p.xw32_fpint) {
         const bool avxf = tw16 && q <= 12289;                    // float lanes in the vector stages
-        if (kind == 0) centred = tw16 && !avxf;                  // double lanes on 16-bit tables: canonical Shoup product
+        if (kind == 0) centred = !avxf;                          // double lanes: canonical Shoup product
         else if (kind == 1) centred = true;                      // fp code
-        else centred = tw16 && q != 7681;                        // twist: double lanes unless q = 7681 (float lanes)
+        else centred = !tw16 || q != 7681;                       // twist: double lanes unless 16-bit tables with q = 7681 (float lanes)
     }
     if (centred) {
         const int32_t wc = centre(w, q);
@@ -415,7 +450,10 @@ int build_xw32_tables(NttPlanDev &p, const int32_t *w_host, const int32_t *r_hos
             if ((int64_t)(q - 1) * (int64_t)p.rc.m > 0x7FFFFFFFll) return SCGPU_OK;
         }
     }
-    if ((p.variant == V_FP || p.variant == V_AVX) && canonical && p.tw_bits == 16 && q < (1 << 15) && (q & 1)) {
+    if ((p.variant == V_FP || p.variant == V_AVX) && canonical && (q & 1) &&
+        ((p.tw_bits == 16 && q < (1 << 15)) || (p.tw_bits != 16 && q < 8400000))) {
+        // (32-bit tables: rows are guarded, see V_FPG; q < 2^23.002 keeps the guarded bounds -- quotient error
+        // 1.5 * 2^-25.3 below 1/q, lane products below 2^51)
         // Integer forms (file header).  The truncated quotient of an exact multiple m q is m unless RN(m (1 + delta)) < m,
         // delta = inv_q_dbl q - 1 (the caller's reciprocal, not recomputed): impossible for delta >= 0, and for delta < 0
         // only when m |delta| exceeds half the spacing below m, i.e. (m / 2^k) |delta| 2^53 > 1 with m / 2^k < 2.
@@ -499,6 +537,14 @@ int launch_xv(const NttPlanDev &p, bool inverse, int32_t *out, const int32_t *a,
     } else if constexpr (V == V_SOL8380417) {
         if (p.logn != 8 || tw16) return SCGPU_ERR_UNSUPPORTED;
         return launch_x<V, 8, false>(p, inverse, out, a, count, c, st);
+    } else if constexpr (kGuarded<V>) {
+        if (tw16) return SCGPU_ERR_UNSUPPORTED;
+        switch (p.logn) {
+        case 8:  return launch_x<V, 8, false>(p, inverse, out, a, count, c, st);
+        case 9:  return launch_x<V, 9, false>(p, inverse, out, a, count, c, st);
+        case 10: return launch_x<V, 10, false>(p, inverse, out, a, count, c, st);
+        default: return SCGPU_ERR_UNSUPPORTED;
+        }
     } else if constexpr (V == V_AVXF || kIntFp<V>) {
         if (!tw16) return SCGPU_ERR_UNSUPPORTED;
         switch (p.logn) {
@@ -552,6 +598,7 @@ int launch_exact_w32(const NttPlanDev &p, int op, int32_t *out, const int32_t *a
     c.rc = p.rc;
     c.nq = -p.rc.q;
     c.qm1 = p.rc.q - 1;
+    c.wp1 = (int32_t)(int64_t)nearbyint(4294967296.0 / (double)p.rc.q);
 #ifndef XW32_VARIANTS
 #define XW32_VARIANTS 0x3F
 #endif
@@ -563,7 +610,9 @@ int launch_exact_w32(const NttPlanDev &p, int op, int32_t *out, const int32_t *a
     case V_BARRETT:    return launch_xv<V_BARRETT>(p, inverse, out, a, count, c, st);
 #endif
 #if XW32_VARIANTS & 4
-    case V_FP:         return p.xw32_fpint ? launch_xv<V_FPI>(p, inverse, out, a, count, c, st) : launch_xv<V_FP>(p, inverse, out, a, count, c, st);
+    case V_FP:
+        if (!p.xw32_fpint) return launch_xv<V_FP>(p, inverse, out, a, count, c, st);
+        return p.tw_bits == 16 ? launch_xv<V_FPI>(p, inverse, out, a, count, c, st) : launch_xv<V_FPG>(p, inverse, out, a, count, c, st);
 #endif
 #if XW32_VARIANTS & 8
     case V_AVX:
@@ -572,7 +621,8 @@ int launch_exact_w32(const NttPlanDev &p, int op, int32_t *out, const int32_t *a
             if (p.rc.q <= 512) return SCGPU_ERR_UNSUPPORTED;
             return p.xw32_fpint ? launch_xv<V_AVXFI>(p, inverse, out, a, count, c, st) : launch_xv<V_AVXF>(p, inverse, out, a, count, c, st);
         }
-        return p.xw32_fpint ? launch_xv<V_AVXI>(p, inverse, out, a, count, c, st) : launch_xv<V_AVX>(p, inverse, out, a, count, c, st);
+        if (!p.xw32_fpint) return launch_xv<V_AVX>(p, inverse, out, a, count, c, st);
+        return p.tw_bits == 16 ? launch_xv<V_AVXI>(p, inverse, out, a, count, c, st) : launch_xv<V_AVXG>(p, inverse, out, a, count, c, st);
 #endif
 #if XW32_VARIANTS & 16
     case V_SOL7681:    return launch_xv<V_SOL7681>(p, inverse, out, a, count, c, st);
