@@ -147,6 +147,12 @@ struct ArFq {
         a.p = (u32)fq::mad(av, sv, (int32_t)a.p);
         a.f = __fmaf_rn(__int2float_rn(av), __int2float_rn(sv), a.f);
     }
+    // the same from an exact 32-bit sum (no wrap-around): one conversion, one quotient
+    static __device__ __forceinline__ u32 acc_fin_int(int32_t p, const K &k)
+    {
+        const float f = __fmaf_rn(__int2float_rn(p), k.invq, fq::kBiasF);
+        return (u32)fq::mad(fq::as_i(f), k.nq, (int32_t)((u32)p + (u32)k.pwk)) + (u32)kBias;
+    }
     static __device__ __forceinline__ u32 acc_fin(const Acc &a, const K &k)
     {
         const float f = __fmaf_rn(a.f, k.invq, fq::kBiasF);

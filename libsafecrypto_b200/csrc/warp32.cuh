@@ -921,7 +921,10 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
 // forward transforms run through the one exchange tile, and EVERY row of the instance -- s_0 .. s_{l-1}, then
 // A_00 .. A_{k-1,l-1} -- travels through ONE staging row and ONE mbarrier: as soon as a row is in registers the
 // next row of the sequence (or s_0 of the warp's next instances) is put in flight.  13-15 warps per SM.
-template <class AR, int LOGN, bool TMA, bool CHK = true>
+// IACC: the l products of an output coefficient cannot leave 32 bits (l |a| |s| < 2^31 with |a| <= x0 and the stash
+// reduced to |s| <= 0.55 q), so they are summed by plain IMADs and the quotient comes from ONE conversion of the sum --
+// instead of an IMAD, an FFMA and two conversions per term (AR::Acc), and in 32 instead of 64 accumulator registers.
+template <class AR, int LOGN, bool TMA, bool CHK = true, bool IACC = false>
 __global__ void __launch_bounds__(kThreads32, 16)        // 128 registers: 4 warps per scheduler fit (140 allowed 3)
 k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t *__restrict__ s,
                int k, int l, size_t count, unsigned long long *ctr, const __grid_constant__ W32Const<AR> c)
@@ -1028,9 +1031,10 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
         }
 #pragma unroll 1
         for (int i = 0; i < k; i++) {
-            typename AR::Acc part[32];
+            typename AR::Acc part[IACC ? 1 : 32];
+            int32_t ipart[IACC ? 32 : 1];
 #pragma unroll
-            for (int e = 0; e < 32; e++) part[e] = AR::acc_zero();
+            for (int e = 0; e < 32; e++) { if (IACC) ipart[e] = 0; else part[e] = AR::acc_zero(); }
 #pragma unroll 1
             for (int j = 0; j < l; j++) {
                 int32_t av[32];
@@ -1062,14 +1066,23 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
                     const uint32_t wds[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        AR::acc_add(part[e + 2 * u], av[e + 2 * u], (int32_t)(int16_t)(wds[u] & 0xFFFFu), c.k);
-                        AR::acc_add(part[e + 2 * u + 1], av[e + 2 * u + 1], (int32_t)wds[u] >> 16, c.k);
+                        const int32_t s0 = (int32_t)(int16_t)(wds[u] & 0xFFFFu), s1 = (int32_t)wds[u] >> 16;
+                        if constexpr (IACC) {
+                            ipart[e + 2 * u] += av[e + 2 * u] * s0;
+                            ipart[e + 2 * u + 1] += av[e + 2 * u + 1] * s1;
+                        } else {
+                            AR::acc_add(part[e + 2 * u], av[e + 2 * u], s0, c.k);
+                            AR::acc_add(part[e + 2 * u + 1], av[e + 2 * u + 1], s1, c.k);
+                        }
                     }
                 }
             }
             u32 acc[NSUB][SUB];
 #pragma unroll
-            for (int e = 0; e < 32; e++) acc[e / SUB][e % SUB] = AR::acc_fin(part[e], c.k);
+            for (int e = 0; e < 32; e++) {
+                if constexpr (IACC) acc[e / SUB][e % SUB] = AR::acc_fin_int(ipart[e], c.k);
+                else acc[e / SUB][e % SUB] = AR::acc_fin(part[e], c.k);
+            }
 #pragma unroll
             for (int h = 0; h < NSUB; h++) {
                 W::template inv_stages1<LOGN, LOGN - 1>(acc[h], c, tau, h);
@@ -1251,8 +1264,16 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
     const int minl = minl_env ? atoi(minl_env) : 1;
     if (AR::STASH16 && c.q < 59000 && l >= minl && tma && !(no16 && atoi(no16) != 0)) {
         const size_t smem = ((size_t)C::POLYS * (C::TS + (C::N + C::T)) + (size_t)l * C::POLYS * (20 * C::T + C::T)) * sizeof(int32_t);
-        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        // integer accumulators: l |a| |s| < 2^31 with |a| <= x0 (the range vote's window, also what the flag promises) and
+        // |s| <= 0.55 q + 2 (the reduced stash)
+        const char *facc = getenv("SCGPU_MATVEC_FLOAT_ACC");
+        const bool iacc = (double)l * (double)c.x0 * (0.55 * (double)c.q + 2.0) < 2147483648.0 && !(facc && atoi(facc) != 0);
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if constexpr (AR::STASH16) {
+            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec16_w32<AR, 8, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        }
         int per_sm = (int)((227 * 1024) / (smem + 1024 + 64));
         if (per_sm > 16) per_sm = 16;
         if (per_sm < 1) per_sm = 1;
@@ -1260,8 +1281,18 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
         if (grid > groups) grid = groups;
         if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; }
         if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }
-        if (chk) k_matvec16_w32<AR, 8, true, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
-        else     k_matvec16_w32<AR, 8, true, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+        bool launched = false;
+        if constexpr (AR::STASH16) {
+            if (iacc) {
+                if (chk) k_matvec16_w32<AR, 8, true, true, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+                else     k_matvec16_w32<AR, 8, true, false, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+                launched = true;
+            }
+        }
+        if (!launched) {
+            if (chk) k_matvec16_w32<AR, 8, true, true, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+            else     k_matvec16_w32<AR, 8, true, false, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
+        }
         count_launch();
         SCGPU_CUDA_CHECK(cudaGetLastError());
         return SCGPU_OK;
