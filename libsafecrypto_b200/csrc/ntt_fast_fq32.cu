@@ -344,7 +344,7 @@ int launch_polymul_fq32(const NttPlanDev &p, int mode, int32_t *out, const int32
 
 int launch_ntt_fq32(const NttPlanDev &p, int inverse, int32_t *out, const int32_t *a, size_t count, cudaStream_t st)
 {
-    return w32::launch_ntt_w32<ArFq>(fq32_const(p, p.fq32_r0), p.logn, p.sm_count, inverse, out, a, count, st);
+    return w32::launch_ntt_w32<ArFq>(fq32_const(p, p.fq32_r0), p.logn, p.sm_count, inverse, out, a, count, st, !p.inputs_in_range);
 }
 
 }  // namespace scgpu

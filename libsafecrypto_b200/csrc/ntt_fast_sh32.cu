@@ -241,7 +241,7 @@ int launch_ntt_sh32(const NttPlanDev &p, int inverse, int32_t *out, const int32_
         memcpy(&c.ninv, p.sh32_ninv_plain, sizeof(ArSh::E));
         memcpy(&c.i0[0], p.sh32_zi1_plain, sizeof(ArSh::E));
     }
-    return w32::launch_ntt_w32<ArSh>(c, p.logn, p.sm_count, inverse, out, a, count, st);
+    return w32::launch_ntt_w32<ArSh>(c, p.logn, p.sm_count, inverse, out, a, count, st, !p.inputs_in_range);
 }
 
 }  // namespace scgpu

@@ -594,7 +594,7 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
 // variant-exact kernels of ntt_exact.cu remain the way to get fwd_ntt's lazily reduced representative itself.
 // TMA = true: the next polynomial's row is bulk-copied into a staging row while the current one is transformed
 // (16-byte aligned rows); false: plain loads.
-template <class AR, int LOGN, bool INV, bool TMA>
+template <class AR, int LOGN, bool INV, bool TMA, bool CHK = true>
 __global__ void __launch_bounds__(kThreads32, FQ32_MINB)
 k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count, unsigned long long *ctr,
           const __grid_constant__ W32Const<AR> c)
@@ -646,12 +646,12 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
                 u32 x[32];
                 if (TMA) {
                     mbar_wait(&bars[warp], parity); parity ^= 1u;
-                    W::template load_operand_staged<LOGN>(x, stage, tau, c);
+                    W::template load_operand_staged<LOGN, CHK>(x, stage, tau, c);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0 && nbase < count) fetch(nbase);    // the staging row is in registers
                 } else {
-                    W::template load_operand<LOGN>(x, a + prow * N, tau, c);
+                    W::template load_operand<LOGN, CHK>(x, a + prow * N, tau, c);
                 }
                 W::fwd_pass0(x, c);
                 store_pass0<LOGN>(tile, x, tau);
@@ -684,17 +684,17 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
 #pragma unroll
                     for (int i = 0; i < SUB; i++) {
                         v[i] = irow[(int)((__brev((unsigned)i) >> 27) << (LOGN - 5))];
-                        wide |= W::out_of_range(v[i], c);
+                        if (CHK) wide |= W::out_of_range(v[i], c);
                     }
                 } else {
                     const int32_t *irow = a + prow * N + ntt_index<LOGN>(tau, SUB * h);
 #pragma unroll
                     for (int i = 0; i < SUB; i++) {
                         v[i] = __ldg(irow + (int)((__brev((unsigned)i) >> 27) << (LOGN - 5)));
-                        wide |= W::out_of_range(v[i], c);
+                        if (CHK) wide |= W::out_of_range(v[i], c);
                     }
                 }
-                if (__any_sync(0xFFFFFFFFu, wide)) {
+                if (CHK && __any_sync(0xFFFFFFFFu, wide)) {
 #pragma unroll
                     for (int i = 0; i < SUB; i++) v[i] = W::bred(v[i], c);
                 }
@@ -1213,7 +1213,7 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
 
 template <class AR>
 int launch_ntt_w32(const W32Const<AR> &c, int logn, int sm_count, int inverse, int32_t *out, const int32_t *a, size_t count,
-                   cudaStream_t st)
+                   cudaStream_t st, bool chk = true)
 {
     const int sms = sm_count > 0 ? sm_count : 148;
     const bool tma = ((uintptr_t)a % 16) == 0 && tma_allowed();
@@ -1225,12 +1225,18 @@ int launch_ntt_w32(const W32Const<AR> &c, int logn, int sm_count, int inverse, i
         if (grid > groups) grid = groups;                                                                  \
         if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; } \
         if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }     \
-        if (tma) {                                                                                         \
-            if (inverse) k_ntt_w32<AR, L, true, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);   \
-            else         k_ntt_w32<AR, L, false, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);  \
+        if (tma && chk) {                                                                                  \
+            if (inverse) k_ntt_w32<AR, L, true, true, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);   \
+            else         k_ntt_w32<AR, L, false, true, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);  \
+        } else if (tma) {                                                                                  \
+            if (inverse) k_ntt_w32<AR, L, true, true, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);  \
+            else         k_ntt_w32<AR, L, false, true, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c); \
+        } else if (chk) {                                                                                  \
+            if (inverse) k_ntt_w32<AR, L, true, false, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);  \
+            else         k_ntt_w32<AR, L, false, false, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c); \
         } else {                                                                                           \
-            if (inverse) k_ntt_w32<AR, L, true, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);  \
-            else         k_ntt_w32<AR, L, false, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c); \
+            if (inverse) k_ntt_w32<AR, L, true, false, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c); \
+            else         k_ntt_w32<AR, L, false, false, false><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);\
         }                                                                                                  \
     }
     switch (logn) {

@@ -732,6 +732,15 @@ def test_in_range_flag_on_key_products_and_matvec(q, tw):
                 if key.dtype == np.int16:
                     exp = O.port().ntt_batch(O.REFERENCE, O.OP_TRIPLE16, n, q, tw, t, key, w, r)
                     assert np.array_equal(o2.cpu().numpy(), exp)
+    # canonical single transforms: forward of in-window operands, inverse of in-window NTT-domain values
+    for t in (rand_inputs(rng, "uniform", q, (259, n)), rng.integers(-x0, x0 + 1, size=(259, n)).astype(np.int32)):
+        for inverse in (False, True):
+            o1 = torch.empty((259, n), dtype=torch.int32, device=DEV)
+            o2 = torch.empty((259, n), dtype=torch.int32, device=DEV)
+            p_def.ntt_canonical(o1, dev(t), inverse=inverse)
+            p_flag.ntt_canonical(o2, dev(t), inverse=inverse)
+            torch.cuda.synchronize()
+            assert torch.equal(o1, o2), inverse
     for k, l in ((2, 2), (3, 2), (4, 4)):
         count = 37
         A = rng.integers(0, q, size=(count, k, l, n)).astype(np.int32)
