@@ -289,7 +289,7 @@ k_exact_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t cou
     }
 
     w32::Claim cl;
-    for (cl.init(); (size_t)cl.g * C::POLYS < count;) {
+    for (cl.init(ctr); (size_t)cl.g * C::POLYS < count;) {
         const size_t base = (size_t)cl.g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;

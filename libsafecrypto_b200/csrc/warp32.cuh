@@ -136,15 +136,32 @@ __device__ __forceinline__ unsigned share_next(unsigned long long *ctr, unsigned
 // profiles/polymul_r2bm_ncu_mix.txt.)  The first two groups of a warp are static, the counter hands out the rest.
 struct Claim {
     unsigned g, gn, raw;
-    __device__ __forceinline__ void init() { g = blockIdx.x; gn = blockIdx.x + gridDim.x; raw = 0; }
+    unsigned *p;                                             // the counter, through an opaque per-lane register (see issue)
+    __device__ __forceinline__ void init(unsigned long long *ctr)
+    {
+        g = blockIdx.x; gn = blockIdx.x + gridDim.x; raw = 0;
+        // ptxas turns an atomic add on a provably warp-uniform address into a warp-aggregated atomic -- leader election,
+        // POPC, and a SHFL that broadcasts the result -- even when one lane issues it through inline PTX, and that shuffle
+        // waits for the atomic on the spot (it was the most-sampled instruction of the kernel,
+        // profiles/polymul_r2c_ncu_mix.txt).  An address that is not provably uniform keeps the atomic a plain one whose
+        // result nobody reads before advance().
+        // (the high word of the 64-bit slot is zero -- the launcher clears the slot and only the low word counts -- but
+        // only at run time: the address below depends on a value each lane loaded for itself)
+        p = reinterpret_cast<unsigned *>(ctr);
+        if (ctr != nullptr) p += (threadIdx.x + 1u) * reinterpret_cast<volatile unsigned *>(ctr)[1];
+    }
     __device__ __forceinline__ void issue(unsigned long long *ctr, int lane)
     {
-        if (ctr != nullptr && lane == 0) raw = atomicAdd(reinterpret_cast<unsigned *>(ctr), 1u);
+        if (ctr != nullptr && lane == 0)
+            asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(raw) : "l"(p) : "memory");
     }
     __device__ __forceinline__ void advance(unsigned long long *ctr)
     {
         g = gn;
-        gn = ctr == nullptr ? gn + gridDim.x : __shfl_sync(0xFFFFFFFFu, raw, 0) + 2u * gridDim.x;
+        if (ctr == nullptr) { gn = gn + gridDim.x; return; }
+        unsigned v;
+        asm volatile("shfl.sync.idx.b32 %0, %1, 0, 0x1f, 0xffffffff;" : "=r"(v) : "r"(raw) : "memory");
+        gn = v + 2u * gridDim.x;
     }
 };
 
@@ -468,7 +485,7 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
     }
 
     Claim cl;
-    for (cl.init(); (size_t)cl.g * C::POLYS < count;) {
+    for (cl.init(ctr); (size_t)cl.g * C::POLYS < count;) {
         const size_t base = (size_t)cl.g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;
@@ -634,7 +651,7 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
     }
 
     Claim cl;
-    for (cl.init(); (size_t)cl.g * C::POLYS < count;) {
+    for (cl.init(ctr); (size_t)cl.g * C::POLYS < count;) {
         const size_t base = (size_t)cl.g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;
@@ -796,7 +813,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
     }
 
     Claim cl;
-    for (cl.init(); (size_t)cl.g * C::POLYS < count;) {
+    for (cl.init(ctr); (size_t)cl.g * C::POLYS < count;) {
         const size_t base = (size_t)cl.g * C::POLYS;
         const size_t inst = base + slot;
         const bool live = inst < count;
