@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(kAesCta) k_cdf_aes(FastArgs a)
     constexpr int SPB = PREC == 64 ? 2 : 4;                   // samples per 16-byte DRBG block
     const size_t blocks_per_stream = (a.per_stream + SPB - 1) / SPB;
     const size_t total = a.nstreams * blocks_per_stream;
+#pragma unroll 2
     for (size_t item = blockIdx.x * (size_t)blockDim.x + threadIdx.x; item < total; item += (size_t)gridDim.x * blockDim.x) {
         const size_t sidx = item / blocks_per_stream, blk = item % blocks_per_stream;
         const uint32_t *k = a.keys + sidx * 64;
