@@ -289,7 +289,7 @@ k_exact_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t cou
     }
 
     w32::Claim cl;
-    for (cl.init(ctr); (size_t)cl.g * C::POLYS < count;) {
+    for (cl.init(ctr, (unsigned)((count + C::POLYS - 1) / C::POLYS)); (size_t)cl.g * C::POLYS < count;) {
         const size_t base = (size_t)cl.g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;
@@ -519,7 +519,7 @@ int launch_x(const NttPlanDev &p, bool inverse, int32_t *out, const int32_t *a, 
     if (grid > groups) grid = groups;
     if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; }
     unsigned long long *ctr = nullptr;
-    if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }
+    if (groups > grid) { const int e = next_work_counter(st, &ctr, 4); if (e != SCGPU_OK) return e; }
     if (inverse) k_exact_w32<V, LOGN, TW16, true, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);
     else         k_exact_w32<V, LOGN, TW16, false, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);
     count_launch();

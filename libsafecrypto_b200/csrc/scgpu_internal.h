@@ -11,7 +11,7 @@ namespace scgpu {
 
 void set_error(const char *fmt, ...);
 void count_launch();
-int next_work_counter(cudaStream_t stream, unsigned long long **ctr);   // nullptr: static stride
+int next_work_counter(cudaStream_t stream, unsigned long long **ctr, int chunk = 1);   // nullptr: static stride; chunk: groups per claim (1, 2, 4)
 int init_work_counters();      // per-device ring of counters, allocated at plan creation
 
 #define SCGPU_CUDA_CHECK(expr)                                                              \

@@ -38,8 +38,13 @@ namespace {
 constexpr int kCtrMaxDev = 64;
 constexpr unsigned kCtrSlots = 8192;
 std::mutex g_ctr_mu;
+// A slot is 16 bytes: the 64-bit counter (cleared per launch; only its low word counts) and, written once when the
+// ring is created, the number of groups one claim of that slot hands out (warp32.cuh: Claim).  Slot i serves the
+// chunk size 1 << (i % 3), so a launcher picks its chunk size by picking the slot class -- no extra kernel argument.
+constexpr unsigned kCtrClasses = 3;
+constexpr unsigned kCtrPerClass = kCtrSlots / kCtrClasses;
 unsigned long long *g_ctr_pool[kCtrMaxDev] = {};
-unsigned g_ctr_next[kCtrMaxDev] = {};
+unsigned g_ctr_next[kCtrMaxDev][kCtrClasses] = {};
 }  // namespace
 
 // Stream-ordered scratch (cudaMallocAsync: DRBG round keys, the L2-resident matrix chunk, staging of the *_host twins)
@@ -69,13 +74,26 @@ int init_work_counters()
     SCGPU_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= kCtrMaxDev) return SCGPU_OK;
     std::lock_guard<std::mutex> lk(g_ctr_mu);
-    if (!g_ctr_pool[dev]) SCGPU_CUDA_CHECK(cudaMalloc(&g_ctr_pool[dev], sizeof(unsigned long long) * kCtrSlots));
+    if (!g_ctr_pool[dev]) {
+        std::vector<unsigned> img((size_t)kCtrSlots * 4, 0u);
+        for (unsigned i = 0; i < kCtrSlots; i++) img[(size_t)i * 4 + 2] = 1u << (i % kCtrClasses);
+        unsigned long long *pool = nullptr;
+        SCGPU_CUDA_CHECK(cudaMalloc(&pool, img.size() * sizeof(unsigned)));
+        if (cudaMemcpy(pool, img.data(), img.size() * sizeof(unsigned), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(pool);
+            set_error("work counters: cudaMemcpy failed");
+            return SCGPU_ERR_CUDA;
+        }
+        g_ctr_pool[dev] = pool;
+    }
     return init_mempool();
 }
 
-int next_work_counter(cudaStream_t st, unsigned long long **ctr)
+int next_work_counter(cudaStream_t st, unsigned long long **ctr, int chunk)
 {
     *ctr = nullptr;
+    if (const char *ce = getenv("SCGPU_CLAIM_CHUNK")) { const int v = atoi(ce); if (v == 1 || v == 2 || v == 4) chunk = v; }
+    const unsigned cls = chunk >= 4 ? 2u : chunk == 2 ? 1u : 0u;
     const char *env = getenv("SCGPU_STATIC_SCHED");
     if (env && atoi(env) != 0) return SCGPU_OK;
     // A captured graph would bake its slot into every replay, long after the ring has handed the slot to other
@@ -89,7 +107,7 @@ int next_work_counter(cudaStream_t st, unsigned long long **ctr)
     {
         std::lock_guard<std::mutex> lk(g_ctr_mu);
         if (!g_ctr_pool[dev]) return SCGPU_OK;             // no plan was created on this device: static stride
-        slot = g_ctr_pool[dev] + (g_ctr_next[dev]++ % kCtrSlots);
+        slot = g_ctr_pool[dev] + 2 * (size_t)((g_ctr_next[dev][cls]++ % kCtrPerClass) * kCtrClasses + cls);
     }
     SCGPU_CUDA_CHECK(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), st));
     *ctr = slot;
@@ -817,6 +835,12 @@ struct ThreadCtx {
     char *d[3] = {nullptr, nullptr, nullptr};
     size_t cap[3] = {0, 0, 0};
     int32_t *d_rc = nullptr;
+    // Small calls go through one pinned, device-mapped buffer instead: the kernel reads its operands from host memory
+    // and writes the result there, so a call is two host memcpy, one launch and one stream synchronisation -- no copy
+    // engine work (three cudaMemcpyAsync cost more than the kernel at these sizes: 31 us -> see
+    // profiles/dropin_latency_r2.txt).
+    char *h = nullptr, *h_dev = nullptr;
+    size_t hcap = 0;
     int device = -1;
     PlanKey last_key;
     int32_t last_sent[4] = {0, 0, 0, 0};
@@ -833,11 +857,25 @@ struct ThreadCtx {
         }
         return d[i];
     }
+    char *mapped(size_t bytes)
+    {
+        if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) dropin_fatal("stream");
+        if (hcap < bytes) {
+            if (h) { cudaStreamSynchronize(st); cudaFreeHost(h); h = nullptr; }
+            size_t want = bytes < 32768 ? 32768 : bytes;
+            if (cudaHostAlloc(reinterpret_cast<void **>(&h), want, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+                dropin_fatal("cudaHostAlloc");
+            if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&h_dev), h, 0) != cudaSuccess) dropin_fatal("cudaHostGetDevicePointer");
+            hcap = want;
+        }
+        return h;
+    }
     ~ThreadCtx()
     {
         // errors are ignored: at process exit the context may already have been torn down
         if (device >= 0 && cudaSetDevice(device) == cudaSuccess) {
             if (st) cudaStreamSynchronize(st);
+            if (h) cudaFreeHost(h);
             for (int i = 0; i < 3; i++) cudaFree(d[i]);
             cudaFree(d_rc);
             if (st) cudaStreamDestroy(st);
@@ -859,6 +897,14 @@ struct ThreadCtx {
 };
 thread_local ThreadCtx t_ctx;
 
+// rows up to this size are read and written by the kernel in place in mapped host memory (ThreadCtx::mapped)
+constexpr size_t kZeroCopyMax = 64 * 1024;
+bool zero_copy_enabled()
+{
+    static const int on = [] { const char *e = getenv("SCGPU_DROPIN_ZERO_COPY"); return (e && atoi(e) == 0) ? 0 : 1; }();
+    return on != 0;
+}
+
 // One reference call = one row through the batch kernel.
 SINT32 run_one(int variant, int op, const ntt_params_t *p, size_t n, SINT32 *out, const void *a, const void *b,
                size_t b_elems, const void *w, const void *r, int tw_bits, int32_t scalar)
@@ -872,6 +918,21 @@ SINT32 run_one(int variant, int op, const ntt_params_t *p, size_t n, SINT32 *out
     if (cudaSetDevice(plan->dev.device) != cudaSuccess) dropin_fatal("cudaSetDevice");
     c.device = plan->dev.device;
     const size_t abytes = n * a_elem_size(op), obytes = n * 4, bbytes = b_elems * b_elem_size(op);
+    if (abytes + bbytes + obytes <= kZeroCopyMax && zero_copy_enabled()) {
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t bo = up(abytes), oo = bo + up(b ? bbytes : 0), ro = oo + up(obytes);
+        char *h = c.mapped(ro + 256);
+        char *hd = c.h_dev;
+        memcpy(h, a, abytes);
+        if (b) memcpy(h + bo, b, bbytes);
+        *reinterpret_cast<int32_t *>(h + ro) = 0;
+        if (scgpu_ntt_batch(plan, op, reinterpret_cast<int32_t *>(hd + oo), hd, b ? hd + bo : nullptr, b_elems, 1, scalar,
+                            reinterpret_cast<int32_t *>(hd + ro), c.st) != SCGPU_OK)
+            dropin_fatal("kernel launch");
+        if (cudaStreamSynchronize(c.st) != cudaSuccess) dropin_fatal("kernel");
+        memcpy(out, h + oo, obytes);
+        return (op == SCGPU_OP_INVERT || op == SCGPU_OP_DIV) ? *reinterpret_cast<int32_t *>(h + ro) : 0;
+    }
     void *da = c.ensure(0, abytes);
     void *dout = c.ensure(1, obytes);
     void *db = b ? c.ensure(2, bbytes) : nullptr;

@@ -135,11 +135,25 @@ __device__ __forceinline__ unsigned share_next(unsigned long long *ctr, unsigned
 // in the iteration: the add that consumed its result was the most-sampled stall of the kernel,
 // profiles/polymul_r2bm_ncu_mix.txt.)  The first two groups of a warp are static, the counter hands out the rest.
 struct Claim {
-    unsigned g, gn, raw;
+    // Chunked claims: one atomic hands a warp kChunk consecutive groups while plenty of work is left, single groups near
+    // the end.  With one atomic per group the canonical transforms asked one address for 0.7 atomics per ns (2^19 claims
+    // in 0.75 ms, n = 512) -- about the rate at which an L2 slice serialises same-address atomics: depending on the
+    // slot's slice the kernel ran at 0.87 or at 0.46 of HBM peak (profiles/ab_canonical_r2.txt).
+    // The counter counts claims, every claim adds 1: claim c < nb is the chunk [2 grid + c kChunk, + kChunk), the later
+    // ones are the single groups behind the chunks (the last 8 grid-fulls), so a claim's extent follows from its number.
+    unsigned kChunk;                                         // groups per claim (1, 2 or 4: word 2 of the launch's slot)
+    unsigned g, gn;                                          // current group, the group after it (prefetched)
+    unsigned gend;                                           // end of the current chunk
+    unsigned ns, nend;                                       // the next chunk
+    unsigned raw, nb;                                        // claim in flight (lane 0); number of kChunk-sized claims
     unsigned *p;                                             // the counter, through an opaque per-lane register (see issue)
-    __device__ __forceinline__ void init(unsigned long long *ctr)
+    __device__ __forceinline__ void init(unsigned long long *ctr, unsigned total)
     {
         g = blockIdx.x; gn = blockIdx.x + gridDim.x; raw = 0;
+        gend = g + 1; ns = gn; nend = gn + 1;
+        kChunk = ctr != nullptr ? reinterpret_cast<volatile unsigned *>(ctr)[2] : 1u;
+        const unsigned reserve = 10u * gridDim.x;            // 2 static grid-fulls + 8 of single groups
+        nb = (kChunk > 1u && total > reserve) ? (total - reserve) / kChunk : 0u;
         // ptxas turns an atomic add on a provably warp-uniform address into a warp-aggregated atomic -- leader election,
         // POPC, and a SHFL that broadcasts the result -- even when one lane issues it through inline PTX, and that shuffle
         // waits for the atomic on the spot (it was the most-sampled instruction of the kernel,
@@ -150,18 +164,25 @@ struct Claim {
         p = reinterpret_cast<unsigned *>(ctr);
         if (ctr != nullptr) p += (threadIdx.x + 1u) * reinterpret_cast<volatile unsigned *>(ctr)[1];
     }
+    // in the last group of a chunk: claim the chunk after the next one (read at the end of this iteration)
     __device__ __forceinline__ void issue(unsigned long long *ctr, int lane)
     {
-        if (ctr != nullptr && lane == 0)
+        if (ctr != nullptr && lane == 0 && g + 1u == gend)
             asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(raw) : "l"(p) : "memory");
     }
     __device__ __forceinline__ void advance(unsigned long long *ctr)
     {
-        g = gn;
-        if (ctr == nullptr) { gn = gn + gridDim.x; return; }
-        unsigned v;
-        asm volatile("shfl.sync.idx.b32 %0, %1, 0, 0x1f, 0xffffffff;" : "=r"(v) : "r"(raw) : "memory");
-        gn = v + 2u * gridDim.x;
+        if (ctr == nullptr) { g = gn; gn = gn + gridDim.x; return; }
+        g++;
+        if (g == gend) {
+            unsigned c;
+            asm volatile("shfl.sync.idx.b32 %0, %1, 0, 0x1f, 0xffffffff;" : "=r"(c) : "r"(raw) : "memory");
+            g = ns; gend = nend;
+            const unsigned base = 2u * gridDim.x;
+            ns = c < nb ? base + c * kChunk : base + nb * kChunk + (c - nb);
+            nend = ns + (c < nb ? kChunk : 1u);
+        }
+        gn = g + 1u < gend ? g + 1u : ns;
     }
 };
 
@@ -485,7 +506,7 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
     }
 
     Claim cl;
-    for (cl.init(ctr); (size_t)cl.g * C::POLYS < count;) {
+    for (cl.init(ctr, (unsigned)((count + C::POLYS - 1) / C::POLYS)); (size_t)cl.g * C::POLYS < count;) {
         const size_t base = (size_t)cl.g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;
@@ -651,7 +672,7 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
     }
 
     Claim cl;
-    for (cl.init(ctr); (size_t)cl.g * C::POLYS < count;) {
+    for (cl.init(ctr, (unsigned)((count + C::POLYS - 1) / C::POLYS)); (size_t)cl.g * C::POLYS < count;) {
         const size_t base = (size_t)cl.g * C::POLYS;
         const size_t poly = base + slot;
         const bool live = poly < count;
@@ -813,7 +834,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
     }
 
     Claim cl;
-    for (cl.init(ctr); (size_t)cl.g * C::POLYS < count;) {
+    for (cl.init(ctr, (unsigned)((count + C::POLYS - 1) / C::POLYS)); (size_t)cl.g * C::POLYS < count;) {
         const size_t base = (size_t)cl.g * C::POLYS;
         const size_t inst = base + slot;
         const bool live = inst < count;
@@ -1156,7 +1177,7 @@ inline void pack_pass1(int logn, const Vec &zf, const Vec &zi, Get get, int32_t 
 }
 
 // group indices are 32-bit in the kernels (claim_next)
-inline bool groups_fit(size_t groups, size_t grid) { return groups + 3 * grid < 0xFFFFFFFFull; }
+inline bool groups_fit(size_t groups, size_t grid) { return groups + 12 * grid < 0xFFFFFFFFull; }   // chunked claims overshoot by up to 2 chunks per warp
 
 inline bool tma_allowed()
 {
@@ -1201,7 +1222,7 @@ int launch_polymul_w32(const W32Const<AR> &c, int logn, int sm_count, int mode, 
         size_t grid = (size_t)sms * FQ32_MINB;                                                             \
         if (grid > groups) grid = groups;                                                                  \
         if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; } \
-        if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }     \
+        if (groups > grid) { const int e = next_work_counter(st, &ctr, 2); if (e != SCGPU_OK) return e; }     \
         if (mode == FQ_KEYBM) { if (tma) W32_KB(L, true) else W32_KB(L, false) }                           \
         else if (tma) {                                                                                    \
             if (mode == FQ_POLYMUL)    W32_PM(L, true)                                                     \
@@ -1241,7 +1262,7 @@ int launch_ntt_w32(const W32Const<AR> &c, int logn, int sm_count, int inverse, i
         size_t grid = (size_t)sms * FQ32_MINB;                                                             \
         if (grid > groups) grid = groups;                                                                  \
         if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; } \
-        if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }     \
+        if (groups > grid) { const int e = next_work_counter(st, &ctr, 2); if (e != SCGPU_OK) return e; }  \
         if (tma && chk) {                                                                                  \
             if (inverse) k_ntt_w32<AR, L, true, true, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);   \
             else         k_ntt_w32<AR, L, false, true, true><<<(unsigned)grid, kThreads32, 0, st>>>(out, a, count, ctr, c);  \
@@ -1303,7 +1324,7 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
         size_t grid = (size_t)sms * per_sm;
         if (grid > groups) grid = groups;
         if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; }
-        if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }
+        if (groups > grid) { const int e = next_work_counter(st, &ctr, 2); if (e != SCGPU_OK) return e; }
         bool launched = false;
         if constexpr (AR::STASH16) {
             if (iacc) {
@@ -1336,7 +1357,7 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
     size_t grid = (size_t)sms * per_sm;
     if (grid > groups) grid = groups;
     if (!groups_fit(groups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; }
-    if (groups > grid) { const int e = next_work_counter(st, &ctr); if (e != SCGPU_OK) return e; }
+    if (groups > grid) { const int e = next_work_counter(st, &ctr, 2); if (e != SCGPU_OK) return e; }
     if (tma && chk)  k_matvec_w32<AR, 8, true, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
     else if (tma)    k_matvec_w32<AR, 8, true, false><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);
     else if (chk)    k_matvec_w32<AR, 8, false, true><<<(unsigned)grid, kThreads32, smem, st>>>(out, A, s, k, l, count, ctr, c);

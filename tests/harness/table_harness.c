@@ -8,7 +8,10 @@
  * compares every output word and return code.  With --threads T the whole sweep additionally runs from T pthreads
  * at once on one table (BLISS-B's worker threads call the members concurrently, bliss_b.c:74-175).
  *
- *   table_harness <libA.so> <libB.so> [--threads T] [--rounds R]
+ *   table_harness <libA.so> <libB.so> [--threads T] [--rounds R] [--time REPS]
+ *
+ * --time REPS: after the comparison, wall-clock per call of four members (BASELINE config C1: one polynomial per call
+ * through the table, n = 512, q = 12289) on each library.
  *
  * Prints one line per (q, n, variant) and a summary; exit status 0 iff no word differs.
  */
@@ -18,6 +21,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/scgpu_dropin.h"
 
@@ -217,11 +221,44 @@ static void *worker(void *arg)
     return NULL;
 }
 
+static double now_us(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
+/* per-call latency of the members BLISS-B's sign core calls (bliss_b.c:1372-1384), n = 512, q = 12289 */
+static void time_members(const lib_t *L, const pset_t *ps, int variant, int reps)
+{
+    const utils_arith_ntt_t *T = L->table((safecrypto_ntt_e)variant);
+    ntt_params_t p;
+    const int n = ps->n, q = ps->q;
+    uint64_t s = 99;
+    L->init_reduce(&p, (size_t)n, q);
+    SINT32 *a = xalloc(sizeof(SINT32) * MAXLEN), *b = xalloc(sizeof(SINT32) * MAXLEN), *t = xalloc(sizeof(SINT32) * MAXLEN);
+    SINT16 *h = xalloc(sizeof(SINT16) * MAXLEN);
+    for (int i = 0; i < n; i++) { a[i] = rnd_range(&s, 0, q - 1); b[i] = rnd_range(&s, 0, q - 1); h[i] = (SINT16)rnd_range(&s, -2, 2); }
+    double t0, us[5];
+    for (int pass = 0; pass < 2; pass++) {           /* pass 0 warms up (plans, contexts, caches) */
+        const int r = pass ? reps : 20;
+        t0 = now_us(); for (int i = 0; i < r; i++) T->fwd_ntt_32_16(t, &p, a, ps->w16); us[0] = (now_us() - t0) / r;
+        t0 = now_us(); for (int i = 0; i < r; i++) T->mul_32_pointwise_16(t, &p, t, h); us[1] = (now_us() - t0) / r;
+        t0 = now_us(); for (int i = 0; i < r; i++) T->inv_ntt_32_16(t, &p, t, ps->w16, ps->r16); us[2] = (now_us() - t0) / r;
+        t0 = now_us(); for (int i = 0; i < r; i++) T->normalize_32(t, (size_t)n, &p); us[3] = (now_us() - t0) / r;
+        t0 = now_us(); for (int i = 0; i < r; i++) b[0] = T->muln_32(a[i % n], b[0] | 1, &p); us[4] = (now_us() - t0) / r;
+    }
+    printf("TIME %s variant=%d n=%d q=%d: fwd_ntt_32_16 %.2f us, mul_32_pointwise_16 %.2f us, inv_ntt_32_16 %.2f us, "
+           "normalize_32 %.2f us, muln_32 %.2f us per call\n", L->path, variant, n, q, us[0], us[1], us[2], us[3], us[4]);
+    free(a); free(b); free(t); free(h);
+}
+
 int main(int argc, char **argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: %s libA.so libB.so [--threads T] [--rounds R]\n", argv[0]); return 2; }
-    int threads = 0, rounds = 2;
+    int threads = 0, rounds = 2, time_reps = 0;
     for (int i = 3; i + 1 < argc; i += 2) {
+        if (!strcmp(argv[i], "--time")) time_reps = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "--threads")) threads = atoi(argv[i + 1]);
         if (!strcmp(argv[i], "--rounds")) rounds = atoi(argv[i + 1]);
     }
@@ -256,6 +293,10 @@ int main(int argc, char **argv)
             total_bad += bad;
             printf("q=%d n=%d: %d threads concurrently, %d mismatches\n", ps.q, ps.n, threads, bad);
         }
+    }
+    if (time_reps > 0) {
+        pset_t ps = make_pset(&B, 12289, 512);
+        for (int variant = 0; variant < 4; variant += 3) { time_members(&A, &ps, variant, time_reps); time_members(&B, &ps, variant, time_reps); }
     }
     printf("SUMMARY member_calls=%d mismatches=%d\n", total_members, total_bad);
     return total_bad ? 1 : 0;

@@ -90,3 +90,41 @@ def test_launches_inside_a_cuda_graph_capture():
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("chunk", ["1", "2", "4"])
+def test_chunked_work_claims_cover_every_row_once(chunk, monkeypatch):
+    """The persistent kernels claim their groups from a counter, several groups per claim while plenty of work is left
+    and single groups at the end (warp32.cuh: Claim).  A ragged batch that goes through both phases: whole output of
+    the fused product, the canonical transforms and a variant-exact transform against the checker, for every chunk
+    size (SCGPU_CLAIM_CHUNK overrides the launchers' choice)."""
+    monkeypatch.setenv("SCGPU_CLAIM_CHUNK", chunk)
+    q, n = 7681, 256
+    w, r = O.tables(q, n, 16)
+    count = 200003                                   # 50001 groups of 4 rows > 10 grid-fulls of 2960 warps
+    g = torch.Generator(device=DEV).manual_seed(int(chunk))
+    a = torch.randint(0, q, (count, n), dtype=torch.int32, device=DEV, generator=g)
+    b = torch.randint(0, q, (count, n), dtype=torch.int32, device=DEV, generator=g)
+    out = torch.full_like(a, -1)
+    chk = O.ref() if O.ref_available() else O.port()
+    an, bn = a.cpu().numpy(), b.cpu().numpy()
+    for flags in (0, sc.PLAN_INPUTS_IN_RANGE):
+        plan = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+        if flags:
+            plan.set_flags(flags)
+        out.fill_(-1)
+        plan.polymul(out, a, b)
+        exp = chk.ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, 16, an, bn, w, r, threads=8)
+        assert np.array_equal(out.cpu().numpy(), exp)
+        out.fill_(-1)
+        plan.ntt_canonical(out, a)
+        fwd = chk.ntt_batch(O.REFERENCE, O.OP_FWD, n, q, 16, an, None, w, r, threads=8)
+        assert np.array_equal(out.cpu().numpy(), np.mod(fwd, q))
+        back = torch.full_like(a, -1)
+        plan.ntt_canonical(back, out, inverse=True)
+        assert torch.equal(back, a)
+    pe = sc.NttPlan(n, q, sc.BARRETT, w, r)
+    out.fill_(-1)
+    pe.batch(sc.OP_FWD, out, a)
+    exp = chk.ntt_batch(O.BARRETT, O.OP_FWD, n, q, 16, an, None, w, r, threads=8)
+    assert np.array_equal(out.cpu().numpy(), exp)

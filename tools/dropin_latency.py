@@ -32,3 +32,22 @@ for pname, prng in (("aes_ctr_drbg", O.PRNG_AES_CTR_DRBG), ("chacha20", O.PRNG_C
         dt = (time.perf_counter() - t0) / reps
         print("get_vector_32(512) %-12s %-12s %8.1f us per call  (%.3g samples/s)" % (sname, pname, dt * 1e6, 512 / dt))
     L.prng_destroy(ctx)
+
+# one polynomial per call through the batch entry point with host buffers (what a table member does: plan lookup, H2D,
+# one launch, D2H, stream synchronisation)
+for q, n, tw in ((12289, 512, 16), (8380417, 256, 32)):
+    w, r = O.tables(q, n, tw)
+    a = np.random.default_rng(1).integers(0, q, size=(1, n)).astype(np.int32)
+    b = np.random.default_rng(2).integers(0, q, size=(1, n)).astype(np.int32)
+    out = np.zeros((1, n), dtype=np.int32)
+    for vname, v in (("reference", sc.REFERENCE), ("avx", sc.AVX)):
+        pl = sc.NttPlan(n, q, v, w, r)
+        for label, fn in (("fwd_ntt (exact)", lambda: pl.batch_host(sc.OP_FWD, out, a)),
+                          ("polymul (fused)", lambda: pl.polymul_host(out, a, b))):
+            for _ in range(5):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(200):
+                fn()
+            dt = (time.perf_counter() - t0) / 200
+            print("count=1 %-16s n=%d q=%d %-9s %7.1f us per call" % (label, n, q, vname, dt * 1e6))
