@@ -68,9 +68,11 @@ struct ArSh {
     // a b R^-1 in (-q, q) for |a b| < q 2^31
     static __device__ __forceinline__ u32 mont(int32_t a, int32_t b, const K &k)
     {
-        const int64_t p = (int64_t)a * (int64_t)b;
-        const int32_t m = (int32_t)((u32)p * (u32)k.qinv);
-        return (u32)((int32_t)(p >> 32) - __mulhi(m, k.q));
+        // low and high word by IMAD + IMAD.HI (3 issue units of the fma-heavy pipe; the 64-bit product as one
+        // IMAD.WIDE measures 4.5, profiles/int_peaks_r02.txt -- the kernel is bound by that pipe, profiles/dil_polymul_r2_ncu.json)
+        const u32 lo = (u32)a * (u32)b;
+        const int32_t m = (int32_t)(lo * (u32)k.qinv);
+        return (u32)(__mulhi(a, b) - __mulhi(m, k.q));
     }
     static __device__ __forceinline__ u32 pw(u32 a, u32 b, const K &k) { return mont((int32_t)a, (int32_t)b, k); }
     static __device__ __forceinline__ u32 pwraw(u32 a, int32_t kv, const K &k) { return mont((int32_t)a, kv, k); }

@@ -72,3 +72,40 @@ if what in ("randprod",):
             p3.rand_product(to, sv, sd, prng, 13, k, k)
 torch.cuda.synchronize()
 print("done")
+if what in ("dilithium",):
+    # C4: q = 8380417, n = 256, Shoup-policy fused product (k_polymul_w32<ArSh, 8, ...>)
+    qq, nn = 8380417, 256
+    ww, rr = O.tables(qq, nn, 32)
+    pd = sc.NttPlan(nn, qq, sc.REFERENCE, ww, rr)
+    pd.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+    xa = torch.randint(0, qq, (B, nn), dtype=torch.int32, device=dev, generator=g)
+    xb = torch.randint(0, qq, (B, nn), dtype=torch.int32, device=dev, generator=g)
+    xo = torch.empty_like(xa)
+    for _ in range(5):
+        pd.polymul(xo, xa, xb)
+if what in ("exact_barrett",):
+    p = sc.NttPlan(n, q, sc.BARRETT, w, r)
+    for _ in range(3):
+        p.batch(sc.OP_INV, out, a)
+if what in ("dil_matvec",):
+    qq, nn, kk, ll = 8380417, 256, 5, 4
+    inst = 1 << 15
+    ww, rr = O.tables(qq, nn, 32)
+    pd = sc.NttPlan(nn, qq, sc.REFERENCE, ww, rr)
+    pd.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+    A3 = torch.randint(0, qq, (inst, kk * ll, nn), dtype=torch.int32, device=dev, generator=g)
+    s3 = torch.randint(0, qq, (inst, ll, nn), dtype=torch.int32, device=dev, generator=g)
+    t3 = torch.empty((inst, kk, nn), dtype=torch.int32, device=dev)
+    for _ in range(5):
+        pd.matvec(t3, A3, s3, kk, ll)
+if what in ("polymul1024", "key1024"):
+    w1, r1 = O.tables(q, 1024, 16)
+    p1 = sc.NttPlan(1024, q, sc.REFERENCE, w1, r1)
+    p1.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+    a1, b1, o1 = a.view(B // 2, 1024), b.view(B // 2, 1024), out.view(B // 2, 1024)
+    key1 = torch.randint(0, q, (1024,), dtype=torch.int32, device=dev, generator=g).to(torch.int16)
+    for _ in range(5):
+        if what == "polymul1024":
+            p1.polymul(o1, a1, b1)
+        else:
+            p1.mul_key(o1, a1, key1)
