@@ -41,6 +41,27 @@ for q, n, tw in ((12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417,
         o = torch.empty((9000, k, n), dtype=torch.int32, device=dev)
         pl.matvec(o, torch.from_numpy(A).to(dev), torch.from_numpy(s).to(dev), k, k)
         torch.cuda.synchronize()
+# chunked work-counter claims: more than 10 grid-fulls of groups, so that claims of several groups AND the single-group
+# tail both run (warp32.cuh: Claim); fused product, canonical and variant-exact transforms
+for chunk in ("2", "4"):
+    os.environ["SCGPU_CLAIM_CHUNK"] = chunk
+    q, n, tw = 7681, 256, 16
+    w, r = O.tables(q, n, tw)
+    pl = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    rows = 130001
+    a = rng.integers(0, q, (rows, n)).astype(np.int32)
+    ta = torch.from_numpy(a).to(dev); out = torch.empty_like(ta)
+    pl.polymul(out, ta, ta)
+    pl.ntt_canonical(out, ta)
+    back = torch.empty_like(ta)
+    pl.ntt_canonical(back, out, inverse=True)
+    torch.cuda.synchronize()
+    ok &= bool(torch.equal(back, ta))
+    pe = sc.NttPlan(n, q, sc.AVX, w, r)
+    pe.batch(sc.OP_FWD, out, ta)
+    torch.cuda.synchronize()
+    ok &= np.array_equal(out.cpu().numpy()[-33:], O.port().ntt_batch(O.AVX, O.OP_FWD, n, q, tw, a[-33:], None, w, r))
+del os.environ["SCGPU_CLAIM_CHUNK"]
 gp = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0)
 seeds = torch.from_numpy(rng.integers(0, 256, (4000, 40)).astype(np.uint8)).to(dev)
 smp = torch.empty((4000, 64), dtype=torch.int32, device=dev)
