@@ -344,9 +344,19 @@ def main():
                         "note": "scgpu_polymul_batch without SCGPU_PLAN_INPUTS_IN_RANGE (any SINT32 input exact), same operands, same output"}
         shapes = {}
 
-        def put(name, units, secs, bytes_per_unit, unit):
+        def put(name, units, secs, bytes_per_unit, unit, ckey=None):
             shapes[name] = {"per_s": units / secs, "unit": unit + "/s", "units": units,
                             "hbm_frac": bytes_per_unit * units / secs / 1e9 / peak}
+            # the INT side of the roofline for the same leg: warp-instructions per unit (ncu count of the committed probe
+            # of this kernel, profiles/instr_counts_r2.json) x units / s against the hardware issue rate; where the capture
+            # shows one pipe busier than the issue slots (IMAD / IMAD.HI on the fma-heavy pipe of the 23-bit moduli) that
+            # pipe's utilisation under ncu is quoted beside it
+            c = counts.get(ckey) if ckey else None
+            if c and c.get("per_unit"):
+                shapes[name]["issue_frac"] = c["per_unit"] * units / secs / peak_issue
+                shapes[name]["warp_instr_per_unit"] = c["per_unit"]
+                if c.get("fmaheavy_pipe_pct"):
+                    shapes[name]["fmaheavy_pipe_pct_under_ncu"] = c["fmaheavy_pipe_pct"]
 
         for (qq, nn) in ((12289, 1024), (7681, 256)):
             ww, rr = O.tables(qq, nn, 16)
@@ -357,7 +367,8 @@ def main():
             xo = torch.empty_like(xa)
             put("polymul_n%d_q%d" % (nn, qq), bb, timed(lambda: pl.polymul(xo, xa, xb)), 12 * nn, "polymul")
             pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
-            put("polymul_n%d_q%d_inputs_in_range" % (nn, qq), bb, timed(lambda: pl.polymul(xo, xa, xb)), 12 * nn, "polymul")
+            put("polymul_n%d_q%d_inputs_in_range" % (nn, qq), bb, timed(lambda: pl.polymul(xo, xa, xb)), 12 * nn, "polymul",
+                ckey="k_polymul_w32_n1024_inrange" if nn == 1024 else "k_polymul_w32_n256_q7681_inrange")
             pl.set_flags(0)
             if nn == 256:
                 # Kyber module product t = A s, k = l = 3 (module_lwe.c:669-748), A in the NTT domain: 4 n (k^2 + 2 k) bytes
@@ -368,7 +379,8 @@ def main():
                 to = torch.empty((inst, k, nn), dtype=torch.int32, device=dev)
                 put("kyber_matvec_k3_n256_q7681", inst, timed(lambda: pl.matvec(to, A, sv, k, k)), 4 * nn * (k * k + 2 * k), "instance")
                 pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
-                put("kyber_matvec_k3_n256_q7681_inputs_in_range", inst, timed(lambda: pl.matvec(to, A, sv, k, k)), 4 * nn * (k * k + 2 * k), "instance")
+                put("kyber_matvec_k3_n256_q7681_inputs_in_range", inst, timed(lambda: pl.matvec(to, A, sv, k, k)), 4 * nn * (k * k + 2 * k), "instance",
+                    ckey="k_matvec16_w32_kyber_k3_inrange")
                 pl.set_flags(0)
                 # the same product with the matrix sampled on the device from a 32-byte seed per instance
                 # (create_rand_product_16_csprng): 4 n (l + k) + 32 bytes of HBM per instance, generator-bound
@@ -381,15 +393,16 @@ def main():
         # BLISS sign / verify core: v = INTT(NTT(t) o key), one shared SINT16 key (bliss_b.c:1378-1384): 8 n bytes
         key = torch.randint(0, Q, (N_COEF,), dtype=torch.int32, device=dev, generator=g).to(torch.int16)
         put("bliss_key_product_n512_q12289", BATCH, timed(lambda: plan_checked.mul_key(out, a, key)), 8 * N_COEF, "product")
-        put("bliss_key_product_n512_q12289_inputs_in_range", BATCH, timed(lambda: plan.mul_key(out, a, key)), 8 * N_COEF, "product")
+        put("bliss_key_product_n512_q12289_inputs_in_range", BATCH, timed(lambda: plan.mul_key(out, a, key)), 8 * N_COEF, "product",
+            ckey="k_polymul_w32_key16_n512_inrange")
         # single transforms with canonical output (normalize_32 o fwd_ntt, inv_ntt), n = 512: 8 n bytes each
-        put("fwd_ntt_canonical_n512_q12289", BATCH, timed(lambda: plan.ntt_canonical(out, a)), 8 * N_COEF, "ntt")
-        put("inv_ntt_canonical_n512_q12289", BATCH, timed(lambda: plan.ntt_canonical(out, a, inverse=True)), 8 * N_COEF, "ntt")
+        put("fwd_ntt_canonical_n512_q12289", BATCH, timed(lambda: plan.ntt_canonical(out, a)), 8 * N_COEF, "ntt", ckey="k_ntt_w32_fwd_n512_inrange")
+        put("inv_ntt_canonical_n512_q12289", BATCH, timed(lambda: plan.ntt_canonical(out, a, inverse=True)), 8 * N_COEF, "ntt", ckey="k_ntt_w32_inv_n512_inrange")
         # the members the drop-in table calls: the variant's own lazily reduced representative, bit for bit
         for vv, vname in ((sc.REFERENCE, "reference"), (sc.BARRETT, "barrett"), (sc.AVX, "avx")):
             pe = sc.NttPlan(N_COEF, Q, vv, w, r, device=local_rank)
-            put("exact_fwd_ntt_32_16_n512_%s" % vname, BATCH, timed(lambda: pe.batch(sc.OP_FWD, out, a)), 8 * N_COEF, "ntt")
-            put("exact_inv_ntt_32_16_n512_%s" % vname, BATCH, timed(lambda: pe.batch(sc.OP_INV, out, a)), 8 * N_COEF, "ntt")
+            put("exact_fwd_ntt_32_16_n512_%s" % vname, BATCH, timed(lambda: pe.batch(sc.OP_FWD, out, a)), 8 * N_COEF, "ntt", ckey="k_exact_w32_fwd_n512_%s" % vname)
+            put("exact_inv_ntt_32_16_n512_%s" % vname, BATCH, timed(lambda: pe.batch(sc.OP_INV, out, a)), 8 * N_COEF, "ntt", ckey="k_exact_w32_inv_n512_%s" % vname)
             del pe
         # Dilithium q = 8380417, n = 256 (32-bit tables): polymul and the k = 5, l = 4 module product
         qq, nn = 8380417, 256
@@ -400,6 +413,10 @@ def main():
         xb = torch.randint(0, qq, (bb, nn), dtype=torch.int32, device=dev, generator=g)
         xo = torch.empty_like(xa)
         put("polymul_n256_q8380417", bb, timed(lambda: pl.polymul(xo, xa, xb)), 12 * nn, "polymul")
+        pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+        put("polymul_n256_q8380417_inputs_in_range", bb, timed(lambda: pl.polymul(xo, xa, xb)), 12 * nn, "polymul",
+            ckey="k_polymul_w32_n256_q8380417_inrange")
+        pl.set_flags(0)
         del xa, xb, xo
         inst = 1 << 15
         A = torch.randint(0, qq, (inst, 20, nn), dtype=torch.int32, device=dev, generator=g)
@@ -407,7 +424,8 @@ def main():
         to = torch.empty((inst, 5, nn), dtype=torch.int32, device=dev)
         put("dilithium_matvec_k5_l4_n256", inst, timed(lambda: pl.matvec(to, A, sv, 5, 4)), 4 * nn * (20 + 4 + 5), "instance")
         pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
-        put("dilithium_matvec_k5_l4_n256_inputs_in_range", inst, timed(lambda: pl.matvec(to, A, sv, 5, 4)), 4 * nn * (20 + 4 + 5), "instance")
+        put("dilithium_matvec_k5_l4_n256_inputs_in_range", inst, timed(lambda: pl.matvec(to, A, sv, 5, 4)), 4 * nn * (20 + 4 + 5), "instance",
+            ckey="k_matvec_w32_dilithium_k5_l4_inrange")
         del A, sv, to, pl
 
     # ---- end-to-end leg: host buffers through the C-ABI ----------------------------------------------------

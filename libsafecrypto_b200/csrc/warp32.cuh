@@ -793,7 +793,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
     constexpr int AROW = N + T;                                      // staging row stride: T banks between instances
     constexpr uint32_t ROW_BYTES = (uint32_t)N * 4u;
     extern __shared__ __align__(16) int32_t dyn_tiles[];             // [l + 1][POLYS][TS], then [POLYS][AROW]
-    __shared__ __align__(8) uint64_t bars[kThreads32 / 32][2];       // [warp][0: s rows, 1: A row]
+    __shared__ __align__(8) uint64_t bars[kThreads32 / 32][3];       // [warp][0: s rows, 1: A rows in S, 2: A rows in X]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x / 32;
     const int tau = lane % T;
@@ -801,7 +801,13 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
     int32_t *xt = dyn_tiles + slot * C::TS;                          // exchange tile of the inverse transform
     int32_t *astage = dyn_tiles + (size_t)(l + 1) * C::POLYS * C::TS + slot * AROW;
     const int taurev = (int)(__brev((unsigned)tau) >> (32 - (LOGN - 5)));
-    uint32_t par_s = 0, par_a = 0;
+    // Two A rows in flight without more shared memory: even columns j of the matrix travel through the staging rows S,
+    // odd columns through X = the exchange tile of the inverse transform, which is idle while a row accumulates.  X takes
+    // its next row only after the inverse transform of the output row has finished (S carries the row in flight across
+    // it).  One row in flight left a warp waiting for DRAM in 21 % of its stall samples at 8 warps per SM
+    // (profiles/dil_matvec_r2_ncu.json); a second staging buffer proper costs a CTA per SM and was slower.
+    const int32_t *xstage = dyn_tiles + slot * AROW;
+    uint32_t par_s = 0, par_a0 = 0, par_a1 = 0;
 
     // lane 0: rows of the warp's PW instances (clamped to instance 0 beyond the batch)
     auto fetch_s = [&](size_t nbase) {
@@ -813,13 +819,13 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
                 bulk_g2s(dyn_tiles + ((size_t)(j + 1) * C::POLYS + warp * C::PW + p) * C::TS, s + (row * l + j) * N, ROW_BYTES, &bars[warp][0]);
         }
     };
-    auto fetch_a = [&](size_t nbase, int step) {
-        mbar_expect_tx(&bars[warp][1], ROW_BYTES * C::PW);
+    auto fetch_a = [&](size_t nbase, int step, int which) {
+        mbar_expect_tx(&bars[warp][1 + which], ROW_BYTES * C::PW);
+        int32_t *dst = which ? dyn_tiles : dyn_tiles + (size_t)(l + 1) * C::POLYS * C::TS;
         for (int p = 0; p < C::PW; p++) {
             size_t row = nbase + (size_t)warp * C::PW + p;
             if (row >= count) row = 0;
-            bulk_g2s(dyn_tiles + (size_t)(l + 1) * C::POLYS * C::TS + (warp * C::PW + p) * AROW,
-                     A + (row * k * l + step) * N, ROW_BYTES, &bars[warp][1]);
+            bulk_g2s(dst + (warp * C::PW + p) * AROW, A + (row * k * l + step) * N, ROW_BYTES, &bars[warp][1 + which]);
         }
     };
     const size_t first = (size_t)blockIdx.x * C::POLYS;
@@ -827,10 +833,11 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
         if (lane == 0) {
             mbar_init(&bars[warp][0], 1);
             mbar_init(&bars[warp][1], 1);
+            mbar_init(&bars[warp][2], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        if (lane == 0 && first < count) { fetch_s(first); fetch_a(first, 0); }
+        if (lane == 0 && first < count) { fetch_s(first); fetch_a(first, 0, 0); if (l >= 2) fetch_a(first, 1, 1); }
     }
 
     Claim cl;
@@ -879,20 +886,26 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
                 int32_t av[32];
                 bool wide = false;
                 if (TMA) {
-                    mbar_wait(&bars[warp][1], par_a); par_a ^= 1u;
+                    const int which = j & 1;
+                    if (which) { mbar_wait(&bars[warp][2], par_a1); par_a1 ^= 1u; }
+                    else       { mbar_wait(&bars[warp][1], par_a0); par_a0 ^= 1u; }
+                    const int32_t *arow = which ? xstage : astage;
 #pragma unroll
                     for (int e = 0; e < 32; e++) {
-                        av[e] = astage[taurev + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5))];
+                        av[e] = arow[taurev + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5))];
                         if (CHK) wide |= W::out_of_range(av[e], c);
                     }
-                    // the staging row is in registers: put the next row (this instance's next step, or step 0
-                    // of the warp's next instances) in flight before the arithmetic
+                    // the row is in registers: its buffer takes the next column of the same parity before the arithmetic;
+                    // past the end of the output row S takes column 0 of the next output row (or of the warp's next
+                    // instances), X waits for the inverse transform below
                     fence_proxy_async();
                     __syncwarp();
-                    const int step = i * l + j + 1;
                     if (lane == 0) {
-                        if (step < k * l) fetch_a(base, step);
-                        else if (nbase < count) fetch_a(nbase, 0);
+                        if (j + 2 < l) fetch_a(base, i * l + j + 2, which);
+                        else if (!which) {
+                            if (i + 1 < k) fetch_a(base, (i + 1) * l, 0);
+                            else if (nbase < count) fetch_a(nbase, 0, 0);
+                        }
                     }
                 } else {
                     const int32_t *arow = A + ((irow * k + i) * l + j) * N + taurev;
@@ -946,7 +959,17 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
                     for (int m = 0; m < 32; m++) orow[tau + m * T] = (int32_t)x[m];
                 }
             }
-            __syncwarp();
+            if (TMA && l >= 2) {
+                // the exchange tile is free again: column 1 of the next output row (or of the next instances) into X
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (i + 1 < k) fetch_a(base, (i + 1) * l + 1, 1);
+                    else if (nbase < count) fetch_a(nbase, 1, 1);
+                }
+            } else {
+                __syncwarp();
+            }
         }
         cl.advance(ctr);
     }

@@ -12,10 +12,11 @@ os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 log = os.path.join(ROOT, "gpurun_out", "instr_probe_ncu.csv")
 metrics = ("smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,"
            "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,"
+           "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed,"
            "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum")
 if "--parse-only" not in sys.argv:      # re-read an existing gpurun_out/instr_probe_ncu.csv (no GPU needed)
   subprocess.check_call(["ncu", "--metrics", metrics, "--clock-control", "none", "--csv", "--log-file", log,
-                       "-k", "regex:k_polymul_w32|k_ntt_w32|k_exact_w32|k_cdf_aes|k_cdf_chacha|k_stream_seq|k_ber_lanes",
+                       "-k", "regex:k_polymul_w32|k_ntt_w32|k_exact_w32|k_matvec|k_cdf_aes|k_cdf_chacha|k_stream_seq|k_ber_lanes",
                        sys.executable, os.path.join(ROOT, "tools", "instr_probe.py")])
 units = json.load(open(os.path.join(ROOT, "gpurun_out", "instr_probe_units.json")))
 rows = [r for r in csv.reader(open(log)) if len(r) > 10]
@@ -38,6 +39,7 @@ for kern, key, n in units:
                         "issue_active_pct": m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                         "alu_pipe_pct": m.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                         "fma_pipe_pct": m.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                        "fmaheavy_pipe_pct": m.get("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
                         "dram_bytes_per_unit": (m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)) / n,
                         "ns_under_ncu": m.get("gpu__time_duration.sum"),
                         "source": "profiles/instr_counts_r2.json: ncu counters of tools/instr_probe.py (tools/instr_counts.py)"}

@@ -33,6 +33,38 @@ for v, vn in ((sc.REFERENCE, "reference"), (sc.BARRETT, "barrett"), (sc.AVX, "av
     pe = sc.NttPlan(n, q, v, w, r)
     pe.batch(sc.OP_FWD, out, a); units.append(("k_exact_w32", "k_exact_w32_fwd_n512_%s" % vn, B))
     pe.batch(sc.OP_INV, out, a); units.append(("k_exact_w32", "k_exact_w32_inv_n512_%s" % vn, B))
+# the other shapes of bench.py's `other_shapes` (plans without range votes, as quoted there)
+plan.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+plan.mul_key(out, a, key); units.append(("k_polymul_w32", "k_polymul_w32_key16_n512_inrange", B))
+plan.ntt_canonical(out, a); units.append(("k_ntt_w32", "k_ntt_w32_fwd_n512_inrange", B))
+plan.ntt_canonical(out, a, inverse=True); units.append(("k_ntt_w32", "k_ntt_w32_inv_n512_inrange", B))
+plan.set_flags(0)
+w1, r1 = O.tables(q, 1024, 16)
+p1 = sc.NttPlan(1024, q, sc.REFERENCE, w1, r1); p1.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+a1, b1, o1 = a.view(B // 2, 1024), b.view(B // 2, 1024), out.view(B // 2, 1024)
+p1.polymul(o1, a1, b1); units.append(("k_polymul_w32", "k_polymul_w32_n1024_inrange", B // 2))
+w2, r2 = O.tables(7681, 256, 16)
+p2 = sc.NttPlan(256, 7681, sc.REFERENCE, w2, r2); p2.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+a2 = torch.randint(0, 7681, (B, 256), dtype=torch.int32, device=dev, generator=g)
+b2 = torch.randint(0, 7681, (B, 256), dtype=torch.int32, device=dev, generator=g)
+o2 = torch.empty_like(a2)
+p2.polymul(o2, a2, b2); units.append(("k_polymul_w32", "k_polymul_w32_n256_q7681_inrange", B))
+kk, inst = 3, 1 << 15
+A2 = torch.randint(0, 7681, (inst, kk * kk, 256), dtype=torch.int32, device=dev, generator=g)
+s2 = torch.randint(-4, 5, (inst, kk, 256), dtype=torch.int32, device=dev, generator=g)
+t2 = torch.empty((inst, kk, 256), dtype=torch.int32, device=dev)
+p2.matvec(t2, A2, s2, kk, kk); units.append(("k_matvec16_w32", "k_matvec16_w32_kyber_k3_inrange", inst))
+w3, r3 = O.tables(8380417, 256, 32)
+p3 = sc.NttPlan(256, 8380417, sc.REFERENCE, w3, r3); p3.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+a3 = torch.randint(0, 8380417, (B, 256), dtype=torch.int32, device=dev, generator=g)
+b3 = torch.randint(0, 8380417, (B, 256), dtype=torch.int32, device=dev, generator=g)
+p3.polymul(o2, a3, b3); units.append(("k_polymul_w32", "k_polymul_w32_n256_q8380417_inrange", B))
+inst3 = 1 << 14
+A3 = torch.randint(0, 8380417, (inst3, 20, 256), dtype=torch.int32, device=dev, generator=g)
+s3 = torch.randint(-2, 3, (inst3, 4, 256), dtype=torch.int32, device=dev, generator=g)
+t3 = torch.empty((inst3, 5, 256), dtype=torch.int32, device=dev)
+p3.matvec(t3, A3, s3, 5, 4); units.append(("k_matvec_w32", "k_matvec_w32_dilithium_k5_l4_inrange", inst3))
+del a2, b2, o2, a3, b3, A2, s2, t2, A3, s3, t3
 gp = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0)
 ns = 1 << 16
 seeds = torch.randint(0, 256, (ns, 40), dtype=torch.uint8, device=dev, generator=g)
