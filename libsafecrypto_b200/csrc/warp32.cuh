@@ -997,7 +997,7 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
     constexpr int SROW = 20 * T + T;                 // 16-bit stash row of one vector, in words (20 per thread)
     constexpr uint32_t ROW_BYTES = (uint32_t)N * 4u;
     extern __shared__ __align__(16) int32_t dyn_tiles[];             // [POLYS][TS] | [POLYS][AROW] | [l][POLYS][SROW]
-    __shared__ __align__(8) uint64_t bars[kThreads32 / 32];
+    __shared__ __align__(8) uint64_t bars[kThreads32 / 32][2];       // [warp][0: rows through S, 1: rows through X]
     // this kernel sits at its register cap (128): the claimed group index lives in shared memory, and the claim is
     // made where it is first needed (when the last row of an instance has been consumed) instead of a whole
     // iteration ahead -- one exposed atomic per instance group (~1 % of its time)
@@ -1011,27 +1011,33 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
     int32_t *stash0 = dyn_tiles + C::POLYS * (C::TS + AROW) + slot * SROW + 20 * tau;
     const int stash_stride = C::POLYS * SROW;                        // between vectors j
     const int taurev = (int)(__brev((unsigned)tau) >> (32 - (LOGN - 5)));
-    const int rows_per_inst = l + k * l;
-    uint32_t parity = 0;
+    // Rows travel through two buffers: S (the staging rows) takes the s rows and the even columns of the matrix, X (the
+    // exchange tile, idle while an output row accumulates) the odd columns -- two matrix rows in flight per instance in
+    // the same shared memory.  X is refilled only when the inverse transform (or, at the start of a group, the forward
+    // transforms) has released the tile.
+    const int32_t *xstage = dyn_tiles + slot * AROW;
+    uint32_t par_s = 0, par_x = 0;
 
     // lane 0: row r of the sequence for the warp's PW instances starting at nbase
-    auto fetch = [&](size_t nbase, int r) {
-        mbar_expect_tx(&bars[warp], ROW_BYTES * C::PW);
+    auto fetch = [&](size_t nbase, int r, int which) {
+        mbar_expect_tx(&bars[warp][which], ROW_BYTES * C::PW);
+        int32_t *dst = which ? dyn_tiles : dyn_tiles + C::POLYS * C::TS;
         for (int p = 0; p < C::PW; p++) {
             size_t inst = nbase + (size_t)warp * C::PW + p;
             if (inst >= count) inst = 0;
             const int32_t *src = r < l ? s + (inst * l + r) * N : A + (inst * k * l + (r - l)) * N;
-            bulk_g2s(dyn_tiles + C::POLYS * C::TS + (warp * C::PW + p) * AROW, src, ROW_BYTES, &bars[warp]);
+            bulk_g2s(dst + (warp * C::PW + p) * AROW, src, ROW_BYTES, &bars[warp][which]);
         }
     };
     const size_t first = (size_t)blockIdx.x * C::POLYS;
     if (TMA) {
         if (lane == 0) {
-            mbar_init(&bars[warp], 1);
+            mbar_init(&bars[warp][0], 1);
+            mbar_init(&bars[warp][1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        if (lane == 0 && first < count) fetch(first, 0);
+        if (lane == 0 && first < count) fetch(first, 0, 0);
     }
 
     for (unsigned g = blockIdx.x; (size_t)g * C::POLYS < count;) {
@@ -1039,20 +1045,20 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
         const size_t inst = base + slot;
         const bool live = inst < count;
         const size_t irow = live ? inst : 0;
-        int r = 0;                                                   // row of the sequence being consumed
-        // after the staging row has been read into registers: next row of this instance, or row 0 of the next
-        auto advance = [&]() {
+        // after a row of S has been read into registers: the next row of the S sequence (s rows, then the even columns
+        // output row by output row), or row 0 of the warp's next instances; nxt = that row's number in the instance's
+        // sequence (s rows 0 .. l-1, matrix rows l + i l + j), -1 = the instance has no further row for S
+        auto advance_s = [&](int nxt) {
             if (TMA) {
                 fence_proxy_async();
                 __syncwarp();
-                r++;
                 if (lane == 0) {
-                    if (r < rows_per_inst) fetch(base, r);
+                    if (nxt >= 0) fetch(base, nxt, 0);
                     else {
                         const unsigned gnext = claim_next(ctr, g, 0);
                         s_gnext[warp] = gnext;
                         const size_t nbase = (size_t)gnext * C::POLYS;
-                        if (nbase < count) fetch(nbase, 0);
+                        if (nbase < count) fetch(nbase, 0, 0);
                     }
                 }
             }
@@ -1061,9 +1067,9 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
         for (int j = 0; j < l; j++) {
             u32 x[32];
             if (TMA) {
-                mbar_wait(&bars[warp], parity); parity ^= 1u;
+                mbar_wait(&bars[warp][0], par_s); par_s ^= 1u;
                 W::template load_operand_staged<LOGN, CHK>(x, stage, tau, c);
-                advance();
+                advance_s(j + 1);                                    // s row j + 1, or matrix row (0, 0) = number l
             } else {
                 W::template load_operand<LOGN, CHK>(x, s + (irow * l + j) * N, tau, c);
             }
@@ -1090,6 +1096,12 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
             }
             __syncwarp();                                            // the exchange tile is reused by the next vector
         }
+        if (TMA && l >= 2) {
+            // the exchange tile is free until the first inverse transform: matrix row (0, 1) into X
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) fetch(base, l + 1, 1);
+        }
 #pragma unroll 1
         for (int i = 0; i < k; i++) {
             typename AR::Acc part[IACC ? 1 : 32];
@@ -1101,13 +1113,22 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
                 int32_t av[32];
                 bool wide = false;
                 if (TMA) {
-                    mbar_wait(&bars[warp], parity); parity ^= 1u;
+                    const int which = j & 1;
+                    if (which) { mbar_wait(&bars[warp][1], par_x); par_x ^= 1u; }
+                    else       { mbar_wait(&bars[warp][0], par_s); par_s ^= 1u; }
+                    const int32_t *arow = which ? xstage : stage;
 #pragma unroll
                     for (int e = 0; e < 32; e++) {
-                        av[e] = stage[taurev + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5))];
+                        av[e] = arow[taurev + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5))];
                         if (CHK) wide |= W::out_of_range(av[e], c);
                     }
-                    advance();
+                    if (!which) {
+                        advance_s(j + 2 < l ? l + i * l + j + 2 : (i + 1 < k ? l + (i + 1) * l : -1));
+                    } else if (j + 2 < l) {
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) fetch(base, l + i * l + j + 2, 1);
+                    }
                 } else {
                     const int32_t *arow = A + ((irow * k + i) * l + j) * N + taurev;
 #pragma unroll
@@ -1164,7 +1185,14 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
                     for (int m = 0; m < 32; m++) orow[tau + m * T] = (int32_t)x[m];
                 }
             }
-            __syncwarp();
+            if (TMA && l >= 2 && i + 1 < k) {
+                // the exchange tile is free again: column 1 of the next output row into X
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) fetch(base, l + (i + 1) * l + 1, 1);
+            } else {
+                __syncwarp();
+            }
         }
         if (!TMA && lane == 0) s_gnext[warp] = claim_next(ctr, g, 0);
         __syncwarp();
