@@ -587,15 +587,20 @@ def main():
                                                      "d2h_bytes_per_step": 4 * nstreams * n, "api": "scgpu_gauss_streams_host"}
         assert np.array_equal(ho_s[:4].numpy(), exp), "host-path sampler output differs from the oracle"
         del hs, ho_s
-    # Knuth-Yao-64 and Bernoulli-64 (the other two samplers north_star names), sigma 215, smaller batches
-    if rank == 0:
-        for sname, sid, ns in (("knuth_yao64", sc.SAMPLER_KNUTH_YAO, 1 << 17), ("bernoulli64", sc.SAMPLER_BERNOULLI, 1 << 17)):
-            gpx = sc.GaussPlan(sid, 64, 0, 13.42, 215.0, device=local_rank)
-            sx = torch.empty((ns, n), dtype=torch.int32, device=dev)
-            for prng_name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
-                secs = timed(lambda: gpx.streams(prng, seeds[:ns], n, sx), reps=3)
-                gauss["%s_sigma215_%s_samples_per_s" % (sname, prng_name)] = ns * n / secs
-            del gpx, sx
+    # Knuth-Yao-64 and Bernoulli-64 (the other two samplers north_star names), sigma 215, smaller batches; every rank its
+    # own streams, whole-job rate over the slowest rank like the CDF legs
+    for sname, sid, ns in (("knuth_yao64", sc.SAMPLER_KNUTH_YAO, 1 << 17), ("bernoulli64", sc.SAMPLER_BERNOULLI, 1 << 17)):
+        gpx = sc.GaussPlan(sid, 64, 0, 13.42, 215.0, device=local_rank)
+        sx = torch.empty((ns, n), dtype=torch.int32, device=dev)
+        for prng_name, prng in (("aes_ctr_drbg", sc.PRNG_AES_CTR_DRBG), ("chacha20", sc.PRNG_CHACHA)):
+            barrier()
+            secs = timed(lambda: gpx.streams(prng, seeds[:ns], n, sx), reps=3)
+            if world > 1:
+                t = torch.tensor([secs], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                secs = float(t.item())
+            gauss["%s_sigma215_%s_samples_per_s" % (sname, prng_name)] = world * ns * n / secs
+        del gpx, sx
     # the reference's own get_vector_32 (CDF-64 through create_sampler) on the host cores, both generators
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         chk, kind = (O.ref(), "reference") if O.ref_available() else (O.port(), "port")
