@@ -109,3 +109,14 @@ if what in ("polymul1024", "key1024"):
             p1.polymul(o1, a1, b1)
         else:
             p1.mul_key(o1, a1, key1)
+if what in ("kyber_matvec",):
+    qq, nn, kk = 7681, 256, 3
+    inst = 1 << 16
+    ww, rr = O.tables(qq, nn, 16)
+    pk = sc.NttPlan(nn, qq, sc.REFERENCE, ww, rr)
+    pk.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+    A2 = torch.randint(0, qq, (inst, kk * kk, nn), dtype=torch.int32, device=dev, generator=g)
+    s2 = torch.randint(-4, 5, (inst, kk, nn), dtype=torch.int32, device=dev, generator=g)
+    t2 = torch.empty((inst, kk, nn), dtype=torch.int32, device=dev)
+    for _ in range(5):
+        pk.matvec(t2, A2, s2, kk, kk)
