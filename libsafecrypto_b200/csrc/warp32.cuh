@@ -976,6 +976,185 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
 }
 
 
+// ---- mat-vec, one warp per OUTPUT ROW: the k warps of a CTA share the transformed vectors ------------------------
+// k_matvec_w32 keeps l full 32-bit tiles per instance for ONE warp: 8 one-warp CTAs per SM at l = 4, two warps per
+// scheduler, and the kernel is bound by fixed-latency dependencies (issue slots 41 % used, profiles/dil_matvec_r2g_ncu.json).
+// Here a CTA of k warps works on the same PW instances: the forward transforms of the l vectors are split over the warps,
+// a CTA barrier publishes the stash, then warp i accumulates and inverse-transforms output row i through its own
+// exchange tile and staging row (two matrix rows in flight per warp, as above).  Shared memory per warp falls from
+// l + 2 to l / k + 2 tiles: 15 warps per SM at k = 5, l = 4.  The s rows of the next group can only be requested after
+// every warp has left the stash (second barrier); the matrix rows of the next group are requested before it.
+template <class AR, int LOGN, bool CHK = true>
+__global__ void __launch_bounds__(256, 2)
+k_matvec_rows_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int32_t *__restrict__ s,
+                  int k, int l, size_t count, unsigned long long *ctr, const __grid_constant__ W32Const<AR> c)
+{
+    using C = Cfg32<LOGN>;
+    using W = W32<AR>;
+    constexpr int N = C::N, T = C::T, SUB = C::SUB, NSUB = C::NSUB, PW = C::PW;
+    constexpr int AROW = N + T;
+    constexpr int TILE = PW * C::TS;                                 // one tile per instance of the group
+    constexpr uint32_t ROW_BYTES = (uint32_t)N * 4u;
+    extern __shared__ __align__(16) int32_t dyn_tiles[];             // [l][PW][TS] stash | per warp: [PW][TS] | [PW][AROW]
+    __shared__ __align__(8) uint64_t bar_s;                          // the s rows of a group (whole CTA)
+    __shared__ __align__(8) uint64_t bars[8][2];                     // per warp: matrix rows in S, in X
+    __shared__ unsigned s_next[2];                                   // the group after the next one, from the counter (by iteration parity)
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x / 32;
+    const int nw = blockDim.x / 32;                                  // = k
+    const int tau = lane % T;
+    const int slot = lane / T;
+    int32_t *mine = dyn_tiles + (size_t)l * TILE + (size_t)warp * (TILE + PW * AROW);
+    int32_t *xt = mine + slot * C::TS;
+    const int32_t *astage = mine + TILE + slot * AROW;
+    const int32_t *xstage = mine + slot * AROW;
+    const int taurev = (int)(__brev((unsigned)tau) >> (32 - (LOGN - 5)));
+    uint32_t par_s = 0, par_a0 = 0, par_a1 = 0;
+
+    auto fetch_s = [&](size_t nbase) {                               // thread 0
+        mbar_expect_tx(&bar_s, ROW_BYTES * PW * (uint32_t)l);
+        for (int p = 0; p < PW; p++) {
+            size_t row = nbase + p;
+            if (row >= count) row = 0;
+            for (int j = 0; j < l; j++)
+                bulk_g2s(dyn_tiles + ((size_t)j * PW + p) * C::TS, s + (row * l + j) * N, ROW_BYTES, &bar_s);
+        }
+    };
+    auto fetch_a = [&](size_t nbase, int step, int which) {          // lane 0 of the warp
+        mbar_expect_tx(&bars[warp][which], ROW_BYTES * PW);
+        int32_t *dst = which ? mine : mine + TILE;
+        for (int p = 0; p < PW; p++) {
+            size_t row = nbase + p;
+            if (row >= count) row = 0;
+            bulk_g2s(dst + p * AROW, A + (row * k * l + step) * N, ROW_BYTES, &bars[warp][which]);
+        }
+    };
+    unsigned g = blockIdx.x, gn = blockIdx.x + gridDim.x, it = 0;
+    if (threadIdx.x == 0) mbar_init(&bar_s, 1);
+    if (lane == 0) {
+        mbar_init(&bars[warp][0], 1);
+        mbar_init(&bars[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if ((size_t)g * PW < count) {
+        if (threadIdx.x == 0) fetch_s((size_t)g * PW);
+        if (lane == 0) { fetch_a((size_t)g * PW, warp * l, 0); if (l >= 2) fetch_a((size_t)g * PW, warp * l + 1, 1); }
+    }
+
+    while ((size_t)g * PW < count) {
+        const size_t base = (size_t)g * PW;
+        const size_t nbase = (size_t)gn * PW;
+        const size_t inst = base + slot;
+        const bool live = inst < count;
+        // the group after the next one (read behind the second barrier of this iteration)
+        if (threadIdx.x == 0)
+            s_next[it & 1u] = ctr != nullptr ? atomicAdd(reinterpret_cast<unsigned *>(ctr), 1u) + 2u * gridDim.x : gn + gridDim.x;
+        mbar_wait(&bar_s, par_s); par_s ^= 1u;
+        // forward transforms of the vectors j = warp, warp + k, ... in place in their stash tiles
+#pragma unroll 1
+        for (int j = warp; j < l; j += nw) {
+            int32_t *tile = dyn_tiles + ((size_t)j * PW + slot) * C::TS;
+            {
+                u32 x[32];
+                W::template load_operand_staged<LOGN, CHK>(x, tile, tau, c);
+                __syncwarp();
+                W::fwd_pass0(x, c);
+                store_pass0<LOGN>(tile, x, tau);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int h = 0; h < NSUB; h++) {
+                u32 xa[SUB], xb[SUB];
+                int32_t *p = tile + 36 * tau + SUB * h;
+                load_sub<SUB>(p, xa);
+                W::template fwd_stages1<LOGN, C::S1, 1>(xa, xb, c, tau, h);
+#pragma unroll
+                for (int i = 0; i < SUB; i++) xa[i] = (u32)AR::dec(xa[i]);
+                store_sub<SUB>(p, xa);                               // lane `lane` of every warp reads it back
+            }
+        }
+        __syncthreads();                                             // the stash is complete
+        {
+            const int i = warp;                                      // this warp's output row
+            typename AR::Acc part[32];
+#pragma unroll
+            for (int e = 0; e < 32; e++) part[e] = AR::acc_zero();
+#pragma unroll 1
+            for (int j = 0; j < l; j++) {
+                int32_t av[32];
+                bool wide = false;
+                const int which = j & 1;
+                if (which) { mbar_wait(&bars[warp][1], par_a1); par_a1 ^= 1u; }
+                else       { mbar_wait(&bars[warp][0], par_a0); par_a0 ^= 1u; }
+                const int32_t *arow = which ? xstage : astage;
+#pragma unroll
+                for (int e = 0; e < 32; e++) {
+                    av[e] = arow[taurev + (int)((__brev((unsigned)e) >> 27) << (LOGN - 5))];
+                    if (CHK) wide |= W::out_of_range(av[e], c);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (j + 2 < l) fetch_a(base, i * l + j + 2, which);
+                    else if (!which && nbase < count) fetch_a(nbase, i * l, 0);      // this warp's row of the next group
+                }
+                if (CHK && __any_sync(0xFFFFFFFFu, wide)) {
+#pragma unroll
+                    for (int e = 0; e < 32; e++) av[e] = W::bred(av[e], c);
+                }
+                const int32_t *sp = dyn_tiles + ((size_t)j * PW + slot) * C::TS + 36 * tau;
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const int4 sv = *reinterpret_cast<const int4 *>(sp + e);
+                    AR::acc_add(part[e], av[e], sv.x, c.k);
+                    AR::acc_add(part[e + 1], av[e + 1], sv.y, c.k);
+                    AR::acc_add(part[e + 2], av[e + 2], sv.z, c.k);
+                    AR::acc_add(part[e + 3], av[e + 3], sv.w, c.k);
+                }
+            }
+            u32 acc[NSUB][SUB];
+#pragma unroll
+            for (int e = 0; e < 32; e++) acc[e / SUB][e % SUB] = AR::acc_fin(part[e], c.k);
+            // this warp has left the stash: announce it before the inverse transform, which needs only the warp's own tile
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0 && nbase < count) fetch_s(nbase);   // the next group's s rows travel during the inverse
+#pragma unroll
+            for (int h = 0; h < NSUB; h++) {
+                W::template inv_stages1<LOGN, LOGN - 1>(acc[h], c, tau, h);
+                store_sub<SUB>(xt + 36 * tau + SUB * h, acc[h]);
+            }
+            __syncwarp();
+            {
+                u32 x[32];
+                load_pass0<LOGN>(xt, x, tau);
+                if (c.r0) {
+#pragma unroll
+                    for (int m = 0; m < 32; m++) x[m] = AR::red(x[m], c.one, c.k);
+                }
+                W::inv_pass0(x, c);
+                if (live) {
+                    int32_t *orow = out + (inst * k + i) * N;
+#pragma unroll
+                    for (int m = 0; m < 32; m++) orow[tau + m * T] = (int32_t)x[m];
+                }
+            }
+            if (l >= 2) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && nbase < count) fetch_a(nbase, i * l + 1, 1);
+            } else {
+                __syncwarp();
+            }
+        }
+        g = gn;
+        gn = *reinterpret_cast<volatile unsigned *>(&s_next[it & 1u]);   // written before the barriers of this iteration; the slot
+        it++;                                                        // is rewritten two iterations (four barriers) later
+    }
+}
+
+
 // ---- mat-vec with a 16-bit stash (moduli below 2^15.8, policies with AR::STASH16) --------------------------------
 // The kernel above is limited to 8-9 warps per SM by the l full tiles it keeps per instance.  Here the transformed
 // vectors are reduced to |x| <= q/2 + and kept as int16 (20 words per thread: conflict-free 128-bit reads), the
@@ -1391,6 +1570,29 @@ int launch_matvec_w32(const W32Const<AR> &c, int sm_count, int32_t *out, const i
         count_launch();
         SCGPU_CUDA_CHECK(cudaGetLastError());
         return SCGPU_OK;
+    }
+    {
+        // one warp per output row (k_matvec_rows_w32): aligned rows, 2 <= k <= 8; SCGPU_MATVEC_ONE_WARP=1 keeps k_matvec_w32
+        const char *ow = getenv("SCGPU_MATVEC_ONE_WARP");
+        const size_t smem_rows = ((size_t)l * C::PW * C::TS + (size_t)k * (C::PW * C::TS + C::PW * (C::N + C::T))) * sizeof(int32_t);
+        if (tma && k >= 2 && k <= 8 && smem_rows <= 110 * 1024 && !(ow && atoi(ow) != 0)) {
+            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_rows_w32<AR, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SCGPU_CUDA_CHECK(cudaFuncSetAttribute(k_matvec_rows_w32<AR, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            const size_t rgroups = (count + C::PW - 1) / C::PW;
+            int per_sm = (int)((227 * 1024) / (smem_rows + 1024 + 256));
+            const int by_regs = 65536 / (k * 32 * 128);
+            if (per_sm > by_regs) per_sm = by_regs;
+            if (per_sm < 1) per_sm = 1;
+            size_t grid = (size_t)sms * per_sm;
+            if (grid > rgroups) grid = rgroups;
+            if (!groups_fit(rgroups, grid)) { set_error("batch of %zu rows is too large", count); return SCGPU_ERR_ARG; }
+            if (rgroups > grid) { const int e = next_work_counter(st, &ctr, 1); if (e != SCGPU_OK) return e; }
+            if (chk) k_matvec_rows_w32<AR, 8, true><<<(unsigned)grid, 32 * k, smem_rows, st>>>(out, A, s, k, l, count, ctr, c);
+            else     k_matvec_rows_w32<AR, 8, false><<<(unsigned)grid, 32 * k, smem_rows, st>>>(out, A, s, k, l, count, ctr, c);
+            count_launch();
+            SCGPU_CUDA_CHECK(cudaGetLastError());
+            return SCGPU_OK;
+        }
     }
     const size_t smem = ((size_t)(l + 1) * C::POLYS * C::TS + (tma ? (size_t)C::POLYS * (C::N + C::T) : 0)) * sizeof(int32_t);
     // per launch, not once: the attribute belongs to the current device's context and plans exist per device

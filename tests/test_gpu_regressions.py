@@ -128,3 +128,43 @@ def test_chunked_work_claims_cover_every_row_once(chunk, monkeypatch):
     pe.batch(sc.OP_FWD, out, a)
     exp = chk.ntt_batch(O.BARRETT, O.OP_FWD, n, q, 16, an, None, w, r, threads=8)
     assert np.array_equal(out.cpu().numpy(), exp)
+
+
+@pytest.mark.parametrize("k,l", [(2, 2), (3, 2), (4, 3), (5, 4), (6, 4), (8, 1), (2, 4)])
+def test_matvec_one_warp_per_output_row(k, l, monkeypatch):
+    """Module product for a 23-bit modulus (32-bit stash): the kernel whose k warps share the transformed vectors of an
+    instance group (k_matvec_rows_w32: CTA barriers, work counter per CTA, two matrix rows in flight per warp) against
+    the one-warp kernel on a ragged batch larger than one grid-full, and against the checker's composition
+    (module_lwe.c:588-748) on the first and last instances."""
+    q, n, tw = 8380417, 256, 32
+    w, r = O.tables(q, n, tw)
+    count = 7001
+    g = torch.Generator(device=DEV).manual_seed(100 * k + l)
+    A = torch.randint(0, q, (count, k * l, n), dtype=torch.int32, device=DEV, generator=g)
+    s = torch.randint(-5, 6, (count, l, n), dtype=torch.int32, device=DEV, generator=g)
+    outs = {}
+    for flags in (0, sc.PLAN_INPUTS_IN_RANGE):
+        plan = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+        if flags:
+            plan.set_flags(flags)
+        for mode in ("0", "1"):
+            monkeypatch.setenv("SCGPU_MATVEC_ONE_WARP", mode)
+            o = torch.full((count, k, n), -1, dtype=torch.int32, device=DEV)
+            plan.matvec(o, A, s, k, l)
+            torch.cuda.synchronize()
+            outs[(flags, mode)] = o
+    ref_out = outs[(0, "1")]
+    for key, o in outs.items():
+        assert torch.equal(o, ref_out), key
+    P = O.port()
+    sel = np.r_[0:6, count - 6:count]
+    An, sn = A[sel].cpu().numpy().reshape(len(sel), k, l, n), s[sel].cpu().numpy()
+    sh = P.ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, sn.reshape(-1, n), None, w, r).reshape(len(sel), l, n)
+    for i in range(k):
+        acc = np.zeros((len(sel), n), dtype=np.int64)
+        for j in range(l):
+            acc += P.ntt_batch(O.REFERENCE, O.OP_PW, n, q, tw, np.ascontiguousarray(An[:, i, j]), np.ascontiguousarray(sh[:, j]))
+        t = P.ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw, acc.astype(np.int32))
+        t = P.ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, t, None, w, r)
+        exp = P.ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw, t)
+        assert np.array_equal(ref_out[sel][:, i].cpu().numpy(), exp), i

@@ -57,5 +57,19 @@ for rep in range(3):
             os.environ["SCGPU_CLAIM_CHUNK"] = ck
             t = timeit(fn)
             res.setdefault((name, ck), []).append(units * bpu / t / 1e9 / 6550.4)
+# mat-vec with the 32-bit stash: one warp per output row (default) against one warp per instance group
+for rep in range(3):
+    for name, units, bpu, fn in legs:
+        if "dilithium" not in name:
+            continue
+        for tag, val in (("rows", "0"), ("one_warp", "1")):
+            os.environ["SCGPU_MATVEC_ONE_WARP"] = val
+            os.environ["SCGPU_CLAIM_CHUNK"] = "2"
+            t = timeit(fn)
+            res.setdefault((name, tag), []).append(units * bpu / t / 1e9 / 6550.4)
+os.environ["SCGPU_MATVEC_ONE_WARP"] = "0"
+for name, units, bpu, fn in legs:
+    if (name, "rows") in res:
+        print("%-32s" % name + "".join("  %s: %s" % (tag, " ".join("%.3f" % x for x in res[(name, tag)])) for tag in ("rows", "one_warp")), flush=True)
 for name, units, bpu, fn in legs:
     print("%-32s" % name + "".join("  chunk %s: %s" % (ck, " ".join("%.3f" % x for x in res[(name, ck)])) for ck in ("1", "2", "4")), flush=True)
