@@ -63,7 +63,7 @@ inst3 = 1 << 14
 A3 = torch.randint(0, 8380417, (inst3, 20, 256), dtype=torch.int32, device=dev, generator=g)
 s3 = torch.randint(-2, 3, (inst3, 4, 256), dtype=torch.int32, device=dev, generator=g)
 t3 = torch.empty((inst3, 5, 256), dtype=torch.int32, device=dev)
-p3.matvec(t3, A3, s3, 5, 4); units.append(("k_matvec_w32", "k_matvec_w32_dilithium_k5_l4_inrange", inst3))
+p3.matvec(t3, A3, s3, 5, 4); units.append(("k_matvec_rows_w32", "k_matvec_w32_dilithium_k5_l4_inrange", inst3))
 del a2, b2, o2, a3, b3, A2, s2, t2, A3, s3, t3
 gp = sc.GaussPlan(sc.SAMPLER_CDF, 64, 0, 13.42, 215.0)
 ns = 1 << 16
