@@ -168,3 +168,36 @@ def test_matvec_one_warp_per_output_row(k, l, monkeypatch):
         t = P.ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, t, None, w, r)
         exp = P.ntt_batch(O.REFERENCE, O.OP_NORMALIZE, n, q, tw, t)
         assert np.array_equal(ref_out[sel][:, i].cpu().numpy(), exp), i
+
+
+def test_matvec_rows_kernel_small_batches_and_graph_capture(monkeypatch):
+    """k_matvec_rows_w32 at the edges: fewer instances than one group, exactly one group, one more; and inside a CUDA
+    graph capture, where the launch keeps the static stride (no counter slot baked into the graph)."""
+    q, n, tw, k, l = 8380417, 256, 32, 5, 4
+    w, r = O.tables(q, n, tw)
+    plan = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    big = 9001
+    A = torch.randint(0, q, (big, k * l, n), dtype=torch.int32, device=DEV, generator=g)
+    s = torch.randint(-2, 3, (big, l, n), dtype=torch.int32, device=DEV, generator=g)
+    monkeypatch.setenv("SCGPU_MATVEC_ONE_WARP", "1")
+    ref = torch.empty((big, k, n), dtype=torch.int32, device=DEV)
+    plan.matvec(ref, A, s, k, l)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("SCGPU_MATVEC_ONE_WARP", "0")
+    for count in (1, 3, 4, 5, 8, 9):
+        o = torch.full((count, k, n), -1, dtype=torch.int32, device=DEV)
+        plan.matvec(o, A[:count], s[:count], k, l)
+        torch.cuda.synchronize()
+        assert torch.equal(o, ref[:count]), count
+    out = torch.zeros_like(ref)
+    graph = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream(device=DEV)
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(graph, stream=st):
+            plan.matvec(out, A, s, k, l, stream=st)
+    for _ in range(2):
+        out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
