@@ -837,8 +837,8 @@ struct ThreadCtx {
     int32_t *d_rc = nullptr;
     // Small calls go through one pinned, device-mapped buffer instead: the kernel reads its operands from host memory
     // and writes the result there, so a call is two host memcpy, one launch and one stream synchronisation -- no copy
-    // engine work (three cudaMemcpyAsync cost more than the kernel at these sizes: 31 us -> see
-    // profiles/dropin_latency_r2.txt).
+    // engine work (three cudaMemcpyAsync cost more than the kernel at these sizes: 21 -> 14 us per call,
+    // profiles/dropin_table_latency_r2.txt).
     char *h = nullptr, *h_dev = nullptr;
     size_t hcap = 0;
     int device = -1;
