@@ -169,7 +169,7 @@ ShConst32 sh32_const(const NttPlanDev &p, int r0)
 
 int build_sh32_tables(NttPlanDev &p, const int32_t *w_host)
 {
-    p.sh32_ok = 0; p.sh32_mv_ok = 0; p.sh32_tab = nullptr;
+    p.sh32_ok = 0; p.sh32_mv_ok = 0; p.sh32_mv_lmax = 0; p.sh32_tab = nullptr;
     if (p.logn < 8 || p.logn > 10) return SCGPU_OK;
     const int64_t q = p.rc.q;
     int r0 = 0; int32_t x0 = 0;
@@ -177,6 +177,13 @@ int build_sh32_tables(NttPlanDev &p, const int32_t *w_host)
     int r0_mv = 0; int32_t x0_mv = 0;
     p.sh32_mv_ok = analyse_sh(p.logn, q, 4, &r0_mv, &x0_mv) ? 1 : 0;
     p.sh32_r0_mv = r0_mv;
+    // Dilithium's largest set is k = 6, l = 5 (240 q < 2^31 for q = 8380417): accept every l the sum bound admits
+    p.sh32_mv_lmax = p.sh32_mv_ok ? 4 : 0;
+    for (int L = 5; L <= 8 && p.sh32_mv_ok; L++) {
+        int r0x = 0; int32_t x0x = 0;
+        if (!analyse_sh(p.logn, q, L, &r0x, &x0x) || r0x != r0_mv) break;
+        p.sh32_mv_lmax = L;
+    }
     const int n = p.n;
     const int64_t psi = (((int64_t)w_host[1] % q) + q) % q;
     if (powmod(psi, n, q) != q - 1) return SCGPU_OK;
@@ -226,7 +233,7 @@ void free_sh32_tables(NttPlanDev &p)
 int launch_matvec_sh32(const NttPlanDev &p, int32_t *out, const int32_t *A, const int32_t *s, int k, int l,
                        size_t count, cudaStream_t st)
 {
-    if (!p.sh32_ok || !p.sh32_mv_ok || p.logn != 8 || l > 4) return SCGPU_ERR_UNSUPPORTED;
+    if (!p.sh32_ok || !p.sh32_mv_ok || p.logn != 8 || l > p.sh32_mv_lmax) return SCGPU_ERR_UNSUPPORTED;
     return w32::launch_matvec_w32<ArSh>(sh32_const(p, p.sh32_r0_mv), p.sm_count, out, A, s, k, l, count, st, !p.inputs_in_range);
 }
 

@@ -62,6 +62,7 @@ struct NttPlanDev {
     int inputs_in_range;                 // SCGPU_PLAN_INPUTS_IN_RANGE: the fused products skip the range vote
     // Shoup / Montgomery arithmetic on the same schedule, for moduli up to 2^25 (ntt_fast_sh32.cu)
     int sh32_ok, sh32_r0, sh32_mv_ok, sh32_r0_mv;
+    int sh32_mv_lmax;          // largest l whose exact 64-bit sums stay inside the Montgomery range (analyse_sh)
     int32_t sh32_x0;
     void *sh32_tab;                      // forward [w | wp], inverse [w | wp], n words each
     alignas(16) unsigned char sh32_pass0[2 * 31 * 8], sh32_ninv[8], sh32_one[8];

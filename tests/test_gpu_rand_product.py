@@ -86,11 +86,13 @@ def test_kyber_products_against_the_reference(prng, k):
 
 @pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libscref.so not built")
 @pytest.mark.parametrize("prng", [O.PRNG_CHACHA, O.PRNG_AES_CTR_DRBG])
-def test_dilithium_product_against_the_reference(prng):
-    """q = 8380417, n = 256, k = 5, l = 4, 32-bit tables (dilithium.c:877-887): the matrix coefficients are 16-bit
-    values (uniform_random_ring_q_csprng reads UINT16 whatever q_bits is) -- reproduced, not corrected."""
-    q, n, k, l = 8380417, 256, 5, 4
-    rng = np.random.default_rng(77 + prng)
+@pytest.mark.parametrize("k,l", [(5, 4), (6, 5), (3, 2)])
+def test_dilithium_product_against_the_reference(prng, k, l):
+    """q = 8380417, n = 256, the (k, l) of Dilithium's parameter sets incl. the largest, k = 6, l = 5; 32-bit tables
+    (dilithium.c:877-887): the matrix coefficients are 16-bit values (uniform_random_ring_q_csprng reads UINT16
+    whatever q_bits is) -- reproduced, not corrected."""
+    q, n = 8380417, 256
+    rng = np.random.default_rng(77 + prng + 10 * k)
     seeds = rng.integers(0, 256, size=(33, 32)).astype(np.uint8)
     y = rng.integers(-5, 6, size=(33, l, n)).astype(np.int32)
     w, r = O.tables(q, n, 32)

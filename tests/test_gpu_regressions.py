@@ -130,7 +130,7 @@ def test_chunked_work_claims_cover_every_row_once(chunk, monkeypatch):
     assert np.array_equal(out.cpu().numpy(), exp)
 
 
-@pytest.mark.parametrize("k,l", [(2, 2), (3, 2), (4, 3), (5, 4), (6, 4), (8, 1), (2, 4)])
+@pytest.mark.parametrize("k,l", [(2, 2), (3, 2), (4, 3), (5, 4), (6, 4), (6, 5), (8, 1), (2, 4), (1, 5)])
 def test_matvec_one_warp_per_output_row(k, l, monkeypatch):
     """Module product for a 23-bit modulus (32-bit stash): the kernel whose k warps share the transformed vectors of an
     instance group (k_matvec_rows_w32: CTA barriers, work counter per CTA, two matrix rows in flight per warp) against
