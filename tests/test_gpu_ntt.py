@@ -786,3 +786,55 @@ def test_exact_transforms_when_q_divides_the_products(q, n, tw):
             for chk in checkers():
                 exp = chk.ntt_batch(variant, op, n, q, tw, a, None, w, r)
                 assert np.array_equal(got, exp), (O.VARIANT_NAMES[variant], op, chk.prefix, np.argwhere(got != exp)[:4])
+
+
+# the remaining moduli of the reference's parameter sets (ENS / DLP 5767169 and 10223617, Ring-TESLA 51750913 -- 26 bits,
+# beyond both fused arithmetics --, 4206593, 16813057), 32-bit tables
+OTHER_SCHEME_PARAMS = [(5767169, 512), (5767169, 1024), (10223617, 512), (10223617, 1024), (51750913, 512), (51750913, 1024),
+                       (4206593, 512), (16813057, 512)]
+
+
+@pytest.mark.parametrize("q,n", OTHER_SCHEME_PARAMS)
+def test_other_scheme_moduli(q, n):
+    """Every modulus the reference's schemes use beyond the headline sets: the variant-exact transforms and pointwise
+    product of every live variant against the checkers, the fused product / key product against the reference
+    composition, the canonical single transforms (which compose the exact kernels where no fused arithmetic serves)."""
+    tw = 32
+    rng = np.random.default_rng(q % 1000 + n)
+    w, r = O.tables(q, n, tw)
+    a = rand_inputs(rng, "uniform", q, (37, n))
+    b = rand_inputs(rng, "uniform", q, (37, n))
+    for v in (O.REFERENCE, O.BARRETT, O.FP, O.AVX):
+        for chk in checkers():
+            for op, second in ((O.OP_FWD, None), (O.OP_INV, None), (O.OP_PW, b), (O.OP_NORMALIZE, None)):
+                got, _ = run_gpu(q, n, tw, v, op, a, second)
+                assert np.array_equal(got, chk.ntt_batch(v, op, n, q, tw, a, second, w, r)), (v, op)
+        lz = rand_inputs(rng, "lazy", q, (9, n))
+        got, _ = run_gpu(q, n, tw, v, O.OP_FWD, lz)
+        assert np.array_equal(got, O.port().ntt_batch(v, O.OP_FWD, n, q, tw, lz, None, w, r)), v
+    p, _, _ = plan(q, n, tw, O.REFERENCE)
+    exp = O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a, b, w, r)
+    out = torch.full((37, n), -7, dtype=torch.int32, device=DEV)
+    p.polymul(out, dev(a), dev(b))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), exp)
+    big = rand_inputs(rng, "uniform", q, (20011, n))            # beyond one grid-full: the work counter
+    outb = torch.empty((20011, n), dtype=torch.int32, device=DEV)
+    p.polymul(outb, dev(big), dev(b[0]))
+    torch.cuda.synchronize()
+    sel = np.r_[0:5, 20000:20011]
+    assert np.array_equal(outb.cpu().numpy()[sel], O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, big[sel], np.tile(b[0], (len(sel), 1)), w, r))
+    fwd = torch.empty((37, n), dtype=torch.int32, device=DEV)
+    p.ntt_canonical(fwd, dev(a))
+    torch.cuda.synchronize()
+    assert np.array_equal(fwd.cpu().numpy(), np.mod(O.port().ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, a, None, w, r), q))
+    back = torch.empty_like(fwd)
+    p.ntt_canonical(back, fwd, inverse=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(back.cpu().numpy(), a)
+    key = rand_inputs(rng, "uniform", q, (n,))
+    p.mul_key(out, dev(a), dev(key))
+    torch.cuda.synchronize()
+    sh = O.port().ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, a, None, w, r)
+    pr = O.port().ntt_batch(O.REFERENCE, O.OP_PW, n, q, tw, sh, np.tile(key, (37, 1)), w, r)
+    assert np.array_equal(out.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, pr, None, w, r))
