@@ -118,8 +118,11 @@ double sh_bound(double b, double q) { return q * (1.0 + b / 8589934592.0) + 2.0;
 // Interval propagation over the schedule for this arithmetic; accumulate = pointwise products summed (mat-vec)
 bool analyse_sh(int logn, int64_t qi, int accumulate, int *r0_out, int32_t *x0_out)
 {
-    if ((qi & 1) == 0 || qi < 257 || qi >= (1ll << 25)) return false;
-    const double q = (double)qi, lim = 536870912.0 - 2.0;                // 2^29: quotient error < 1/16
+    if ((qi & 1) == 0 || qi < 257 || qi >= (1ll << 27)) return false;
+    // up to 2^25: every value below 2^29 (quotient error < 1/16, the bound the kernels were first proven with); the 26-bit
+    // moduli (Ring-TESLA's 51750913) use the whole signed range -- sh_bound() holds for any |x| < 2^31, the products stay
+    // inside (-q, 2 q), which is all canon() needs
+    const double q = (double)qi, lim = qi < (1ll << 25) ? 536870912.0 - 2.0 : 2147483648.0 - 67108864.0;
     const double x0 = 4.0 * q;
     double b = x0;
     for (int st = 0; st < logn; st++) {
@@ -127,8 +130,15 @@ bool analyse_sh(int logn, int64_t qi, int accumulate, int *r0_out, int32_t *x0_o
         b += sh_bound(b, q);
     }
     if (b >= lim) return false;
-    const double other = b > 32768.0 ? b : 32768.0;
-    if (b * other >= q * 2147483648.0) return false;                     // Montgomery product range
+    double other = b > 32768.0 ? b : 32768.0;
+    bool rb = false;
+    if (b * other >= q * 2147483648.0) {                                 // Montgomery product range
+        // reduce one operand first (bit 1 of the flag word): a Shoup product by 1 brings it to sh_bound(b)
+        if (accumulate > 1) return false;
+        rb = true;
+        other = sh_bound(b, q) > 32768.0 ? sh_bound(b, q) : 32768.0;
+        if (b * other >= q * 2147483648.0) return false;
+    }
     // mat-vec: `accumulate` products of a matrix coefficient (|a| <= x0) and a transformed vector coefficient (<= b)
     // are summed in 64 bits and reduced once: the sum must stay inside the Montgomery range; the result is in (-q, q)
     if (accumulate > 1 && (double)accumulate * x0 * b >= q * 2147483648.0) return false;
@@ -142,7 +152,7 @@ bool analyse_sh(int logn, int64_t qi, int accumulate, int *r0_out, int32_t *x0_o
             const double prod = sh_bound(d, q);
             v = (st == 0) ? prod : (d > prod ? d : prod);
         }
-        if (ok) { *r0_out = r0; *x0_out = (int32_t)x0; return true; }
+        if (ok) { *r0_out = r0 | (rb ? 2 : 0); *x0_out = (int32_t)x0; return true; }
     }
     return false;
 }

@@ -225,7 +225,8 @@ struct W32Const {
     typename AR::K k;
     int32_t q, nq, x0;
     uint32_t M;                                  // floor(2^32 / q): 32-bit Barrett of the out-of-range path
-    int r0;                                      // reduce every coefficient at the entry of inverse pass 0
+    int r0;                                      // bit 0: reduce every coefficient at the entry of inverse pass 0;
+                                                 // bit 1: reduce the second operand before the pointwise product
 };
 
 template <class AR>
@@ -558,6 +559,10 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
             } else if constexpr (MODE == FQ_POLYMUL) {
                 load_sub<SUB>(tb + 36 * tau + SUB * h, xb);
                 W::template fwd_stages1<LOGN, C::S1, 2>(xa, xb, c, tau, h);
+                if (c.r0 & 2) {                                      // 26-bit moduli: lazy x lazy leaves the Montgomery range
+#pragma unroll
+                    for (int i = 0; i < SUB; i++) xb[i] = AR::red(xb[i], c.one, c.k);
+                }
 #pragma unroll
                 for (int i = 0; i < SUB; i++)
                     xa[i] = AR::pw(xa[i], xb[i], c.k);
@@ -603,7 +608,7 @@ k_polymul_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, const vo
                 // every coefficient is in registers: ta takes the next product's b rows
                 if (lane == 0 && nbase < count) fetch(1, nbase, ta - (lane / T) * C::TS);
             }
-            if (c.r0) {
+            if (c.r0 & 1) {
 #pragma unroll
                 for (int m = 0; m < 32; m++) x[m] = AR::red(x[m], c.one, c.k);
             }
@@ -752,7 +757,7 @@ k_ntt_w32(int32_t *__restrict__ out, const int32_t *__restrict__ a, size_t count
             {
                 u32 x[32];
                 load_pass0<LOGN>(tile, x, tau);
-                if (c.r0) {
+                if (c.r0 & 1) {
 #pragma unroll
                     for (int m = 0; m < 32; m++) x[m] = AR::red(x[m], c.one, c.k);
                 }
@@ -948,7 +953,7 @@ k_matvec_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const int
             {
                 u32 x[32];
                 load_pass0<LOGN>(xt, x, tau);
-                if (c.r0) {
+                if (c.r0 & 1) {
 #pragma unroll
                     for (int m = 0; m < 32; m++) x[m] = AR::red(x[m], c.one, c.k);
                 }
@@ -1129,7 +1134,7 @@ k_matvec_rows_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, cons
             {
                 u32 x[32];
                 load_pass0<LOGN>(xt, x, tau);
-                if (c.r0) {
+                if (c.r0 & 1) {
 #pragma unroll
                     for (int m = 0; m < 32; m++) x[m] = AR::red(x[m], c.one, c.k);
                 }
@@ -1353,7 +1358,7 @@ k_matvec16_w32(int32_t *__restrict__ out, const int32_t *__restrict__ A, const i
             {
                 u32 x[32];
                 load_pass0<LOGN>(xt, x, tau);
-                if (c.r0) {
+                if (c.r0 & 1) {
 #pragma unroll
                     for (int m = 0; m < 32; m++) x[m] = AR::red(x[m], c.one, c.k);
                 }

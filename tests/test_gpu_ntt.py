@@ -818,6 +818,23 @@ def test_other_scheme_moduli(q, n):
     p.polymul(out, dev(a), dev(b))
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), exp)
+    for ka, kb, rows in (("lazy", "lazy", 64), ("extreme", "extreme", 129), ("signed", "small", 5)):
+        xa, xb = rand_inputs(rng, ka, q, (rows, n)), rand_inputs(rng, kb, q, (rows, n))
+        o2 = torch.full((rows, n), -7, dtype=torch.int32, device=DEV)
+        p.polymul(o2, dev(xa), dev(xb))
+        torch.cuda.synchronize()
+        assert np.array_equal(o2.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, xa, xb, w, r)), (ka, kb)
+        # inverse transform: inputs the reference itself handles without overflow (sums of n terms)
+        xi = rng.integers(-(2**31 // n) + 1, 2**31 // n, size=(rows, n)).astype(np.int32)
+        p.ntt_canonical(o2, dev(xi), inverse=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(o2.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, xi, None, w, r)), ka
+        kx = rand_inputs(rng, kb, q, (n,))
+        p.mul_key(o2, dev(xa), dev(kx))
+        torch.cuda.synchronize()
+        shx = O.port().ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, xa, None, w, r)
+        prx = O.port().ntt_batch(O.REFERENCE, O.OP_PW, n, q, tw, shx, np.tile(kx, (rows, 1)), w, r)
+        assert np.array_equal(o2.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, prx, None, w, r)), (ka, kb, "key")
     big = rand_inputs(rng, "uniform", q, (20011, n))            # beyond one grid-full: the work counter
     outb = torch.empty((20011, n), dtype=torch.int32, device=DEV)
     p.polymul(outb, dev(big), dev(b[0]))

@@ -92,5 +92,22 @@ for v, vn in ((sc.REFERENCE, "reference"), (sc.FP, "fp")):
 A, s = rnd(q, (1 << 15, 20, n)), torch.randint(-2, 3, (1 << 15, 4, n), dtype=torch.int32, device=dev, generator=g)
 o5 = torch.empty((1 << 15, 5, n), dtype=torch.int32, device=dev)
 report("C4 Dilithium mat-vec k=5 l=4", 1 << 15, timeit(lambda: pl.matvec(o5, A, s, 5, 4)), 4 * n * (20 + 4 + 5), "instance")
+A6, s6 = rnd(q, (1 << 14, 30, n)), torch.randint(-2, 3, (1 << 14, 5, n), dtype=torch.int32, device=dev, generator=g)
+o6 = torch.empty((1 << 14, 6, n), dtype=torch.int32, device=dev)
+report("C4 Dilithium mat-vec k=6 l=5", 1 << 14, timeit(lambda: pl.matvec(o6, A6, s6, 6, 5)), 4 * n * (30 + 5 + 6), "instance")
+del A, s, o5, A6, s6, o6, a, b, o
+# the other moduli of the reference's parameter sets (ENS / DLP, Ring-TESLA): 32-bit tables; 51750913 (26 bits) is beyond
+# both fused arithmetics and runs the Montgomery kernels of round 1
+for q, n in ((5767169, 512), (10223617, 1024), (51750913, 512), (51750913, 1024)):
+    B = (1 << 29) // (4 * n)
+    w, r = O.tables(q, n, 32)
+    pl = sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    if IN_RANGE: pl.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+    a, b, o = rnd(q, (B, n)), rnd(q, (B, n)), torch.empty((B, n), dtype=torch.int32, device=dev)
+    report("polymul n=%d q=%d" % (n, q), B, timeit(lambda: pl.polymul(o, a, b)), 12 * n)
+    report("canonical fwd NTT n=%d q=%d" % (n, q), B, timeit(lambda: pl.ntt_canonical(o, a)), 8 * n, "ntt")
+    pe = sc.NttPlan(n, q, sc.AVX, w, r)
+    report("exact fwd_ntt_32_32 n=%d q=%d avx" % (n, q), B, timeit(lambda: pe.batch(sc.OP_FWD, o, a)), 8 * n, "ntt")
+    del a, b, o
 if len(sys.argv) > 2 and sys.argv[1] == "--json":
     json.dump(res, open(sys.argv[2], "w"), indent=1)

@@ -14,7 +14,7 @@ rng = np.random.default_rng(seed)
 dev = "cuda:0"
 P = O.port()
 PARAMS = [(12289, 512, 16), (12289, 1024, 16), (7681, 256, 16), (8380417, 256, 32), (18433, 512, 16), (8399873, 512, 32),
-          (12289, 256, 16), (18433, 1024, 16)]
+          (12289, 256, 16), (18433, 1024, 16), (51750913, 512, 32), (51750913, 1024, 32), (5767169, 1024, 32), (10223617, 512, 32)]
 plans = {}
 
 
