@@ -855,3 +855,46 @@ def test_other_scheme_moduli(q, n):
     sh = O.port().ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, a, None, w, r)
     pr = O.port().ntt_batch(O.REFERENCE, O.OP_PW, n, q, tw, sh, np.tile(key, (37, 1)), w, r)
     assert np.array_equal(out.cpu().numpy(), O.port().ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, pr, None, w, r))
+
+
+@pytest.mark.parametrize("q,n", [(8380417, 256), (8399873, 512), (10223617, 1024), (51750913, 512), (51750913, 1024)])
+def test_large_modulus_inputs_at_the_proof_boundary(q, n):
+    """The Shoup-policy kernels at the edge of their interval analysis (analyse_sh: inputs up to 4 q, every intermediate
+    inside the signed 32-bit range -- for the 26-bit modulus the whole of it): constant and adversarially signed rows of
+    magnitude 4 q, through the default plan (range vote) and through a plan that declares them in range (no vote)."""
+    tw = 32
+    w, r = O.tables(q, n, tw)
+    rng = np.random.default_rng(q % 97 + n)
+    P = O.port()
+    checked, flagged = sc.NttPlan(n, q, sc.REFERENCE, w, r), sc.NttPlan(n, q, sc.REFERENCE, w, r)
+    flagged.set_flags(sc.PLAN_INPUTS_IN_RANGE)
+    cases = []
+    for mag in (4 * q, 4 * q - 1, q - 1):
+        cases.append(np.full((3, n), mag, dtype=np.int64))
+        cases.append(np.full((3, n), -mag, dtype=np.int64))
+        cases.append(mag * rng.choice([-1, 1], size=(3, n)))
+        alt = np.full((3, n), mag, dtype=np.int64)
+        alt[:, 1::2] = -mag
+        cases.append(alt)
+    for a in cases:
+        a = a.astype(np.int32)
+        for b in (a, np.ascontiguousarray(a[:, ::-1]), rng.integers(0, q, size=a.shape).astype(np.int32)):
+            exp = P.ntt_batch(O.REFERENCE, O.OP_POLYMUL, n, q, tw, a, b, w, r)
+            for p in (checked, flagged):
+                out = torch.empty((a.shape[0], n), dtype=torch.int32, device=DEV)
+                p.polymul(out, dev(a), dev(b))
+                torch.cuda.synchronize()
+                assert np.array_equal(out.cpu().numpy(), exp)
+        key = rng.integers(0, q, size=n).astype(np.int32)
+        sh = P.ntt_batch(O.REFERENCE, O.OP_FWD, n, q, tw, a, None, w, r)
+        pr = P.ntt_batch(O.REFERENCE, O.OP_PW, n, q, tw, sh, np.tile(key, (a.shape[0], 1)), w, r)
+        expk = P.ntt_batch(O.REFERENCE, O.OP_INV, n, q, tw, pr, None, w, r)
+        expf = np.mod(sh.astype(np.int64), q).astype(np.int32)
+        for p in (checked, flagged):
+            out = torch.empty((a.shape[0], n), dtype=torch.int32, device=DEV)
+            p.mul_key(out, dev(a), dev(key))
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), expk)
+            p.ntt_canonical(out, dev(a))
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), expf)
